@@ -1,0 +1,178 @@
+/*
+ * mewzoom_b200.h -- C ABI of the B200-native MewZoom.upscale hot path.
+ *
+ * The reference (andrewdalpino/UltraZoom) has NO native interface: its hot path
+ * is the Python method MewZoom.upscale (src/ultrazoom/model.py:166-179) which
+ * dispatches torch.nn modules.  Every entry point below therefore cites the
+ * reference *Python* symbol it replaces; the Python binding a maintainer would
+ * add is shown in INTEGRATION.md (ctypes, as ultrazoom_b200/_native.py does).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every function returns 0 on success, a negative mz_status otherwise;
+ *     mz_last_error() returns a thread-local message for the last failure.
+ *   - all `*_dev` pointers are DEVICE pointers on the model's GPU unless a
+ *     function name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     Nothing here synchronises the device or allocates on the hot call
+ *     (mz_upscale), except the *_host convenience entry points.
+ *   - there is no CPU fallback: without an sm_100 device every compute entry
+ *     point fails with MZ_ERR_CUDA / MZ_ERR_UNSUPPORTED.
+ */
+#ifndef MEWZOOM_B200_H_
+#define MEWZOOM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZ_ABI_VERSION 1
+
+typedef enum mz_status {
+  MZ_OK = 0,
+  MZ_ERR_INVALID = -1,     /* bad argument (the reference raises AssertionError) */
+  MZ_ERR_CUDA = -2,        /* CUDA runtime / driver error                        */
+  MZ_ERR_UNSUPPORTED = -3, /* shape or device not supported by the kernels       */
+  MZ_ERR_WORKSPACE = -4,   /* workspace too small                                */
+  MZ_ERR_STATE = -5        /* weights not (fully) set                            */
+} mz_status;
+
+/* flags for mz_upscale / mz_forward */
+#define MZ_FLAG_CLAMP01 1u        /* torch.clamp(z, 0, 1), model.py:177              */
+#define MZ_FLAG_SIMT_CONV 2u      /* diagnostic: SIMT direct conv instead of tcgen05  */
+#define MZ_FLAG_SKIP_FROM_BUFFER 4u /* head reads a precomputed bicubic image (mz_bicubic_f32 output in y) instead of recomputing it in its epilogue */
+
+/* Constructor kwargs of the 0.2.x-style MewZoom (README.md:254-258, model.py:52-69). */
+typedef struct mz_config {
+  int32_t upscale_ratio;      /* 2, 3 or 4   (SubpixelConv2d, model.py:894-898)      */
+  int32_t num_channels;       /* C           (README.md:37-42)                       */
+  int32_t hidden_ratio;       /* 1, 2 or 4   (InvertedBottleneck, model.py:738)      */
+  int32_t num_encoder_layers; /* L                                                   */
+  int32_t control_features;   /* 0 or 3      (ControlVector, README.md:118-122)      */
+  int32_t device;             /* CUDA device ordinal                                 */
+} mz_config;
+
+typedef struct mz_model mz_model; /* opaque */
+
+/* weight identifiers for mz_model_set_weight (state_dict keys of the Python module) */
+typedef enum mz_weight_kind {
+  MZ_W_STEM_WEIGHT = 0,  /* stem.conv.weight            (C,3,1,1)      model.py:224     */
+  MZ_W_STEM_BIAS = 1,    /* stem.conv.bias              (C,)           model.py:224     */
+  MZ_W_CONV1 = 2,        /* encoder.{l}.convnet.conv1.weight (hC,C,3,3) model.py:742-744 */
+  MZ_W_CONV2 = 3,        /* encoder.{l}.convnet.conv2.weight (C,hC,3,3) model.py:746-748 */
+  MZ_W_CTRL_WEIGHT = 4,  /* encoder.{l}.control.linear.weight (2hC,F)  (control.py, absent) */
+  MZ_W_CTRL_BIAS = 5,    /* encoder.{l}.control.linear.bias   (2hC,)                     */
+  MZ_W_HEAD = 6          /* head.conv.weight            (3r^2,C,3,3)   model.py:902-909 */
+} mz_weight_kind;
+
+const char* mz_last_error(void);
+int mz_abi_version(void);
+
+/* Number of visible CUDA devices with compute capability 10.x (0 if none / no driver). */
+int mz_device_count(void);
+
+/* ---- model lifetime: replaces MewZoom.__init__ / load_state_dict (model.py:52-92) ---- */
+int mz_model_create(const mz_config* cfg, mz_model** out);
+void mz_model_destroy(mz_model* m);
+
+/* Upload one fp32 HOST tensor in PyTorch layout (OIHW for convs); it is repacked to the
+ * bf16 K-major tap-blocked layout the tcgen05 kernels read.  `layer` is ignored for
+ * stem/head kinds.  `numel` must match the shape implied by the config. */
+int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* host_data, size_t numel);
+
+/* Bytes of device scratch mz_upscale needs for a (B,3,H,W) input. */
+int mz_workspace_bytes(const mz_model* m, int32_t B, int32_t H, int32_t W, size_t* bytes);
+
+/* ---- the hot path: replaces MewZoom.forward / MewZoom.upscale (model.py:149-179) ----
+ * x_dev : (B,3,H,W) fp32 NCHW in [0,1]
+ * c_dev : NULL for non-control models, else (B, control_features) fp32 (c_rows == B)
+ *         or (1, control_features) (c_rows == 1, broadcast) -- validate.py:73-94
+ * y_dev : (B,3,rH,rW) fp32 NCHW
+ * flags : MZ_FLAG_CLAMP01 => upscale(), 0 => forward()
+ */
+int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_rows, float* y_dev,
+               int32_t B, int32_t H, int32_t W, void* workspace_dev, size_t workspace_bytes,
+               uint32_t flags, void* stream);
+
+/* Same call with HOST buffers: H2D copy of x (and c), the kernels, D2H copy of y, stream
+ * synchronise.  Workspace and staging buffers are owned (and cached) by the model.  This is
+ * the end-to-end entry point bench.py times as `e2e`. */
+int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32_t c_rows,
+                    float* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags);
+
+/* ---- per-kernel entry points (unit tests, benches, partial pipelines) ---- */
+
+/* Tunables of the tcgen05 convolution kernel; every field 0 = let the library choose. */
+typedef struct mz_conv_tune {
+  int32_t rows;       /* image rows (accumulators) per patch, 1..4                                   */
+  int32_t acc_stages; /* TMEM accumulator stages, 1 or 2                                             */
+  int32_t kc;         /* channels per pipeline stage: 16, 32 or 64                                   */
+  int32_t halo_mode;  /* 0 one TMA per horizontal tap shift; 1 shared halo tile + shifted UMMA       */
+                      /* descriptors; 2 as 1 with the descriptor base_offset field set               */
+  int32_t b_stages;   /* weight ring depth                                                           */
+  int32_t a_stages;   /* activation ring depth                                                       */
+  int32_t max_ctas;   /* cap on the persistent grid                                                  */
+} mz_conv_tune;
+
+/* which = 0 conv1, 1 conv2, 2 head, -1 all.  Takes effect on the next mz_upscale. */
+int mz_model_set_tune(mz_model* m, int32_t which, const mz_conv_tune* tune);
+
+/* Upsample(scale_factor=r, mode="bicubic") -- model.py:71,156.  NCHW fp32, `planes` = B*3 planes. */
+int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, int32_t W, int32_t r,
+                   void* stream);
+
+/* FanOutProjection (model.py:212-242) fused with the NCHW->NHWC layout change:
+ * zf (B,H,W,Cp) fp32 residual stream and zb (B,H,W,Cp) bf16 MMA operand.
+ * w_dev is (Cp,3) fp32 and bias_dev (Cp,) fp32, zero-padded beyond the logical channel count. */
+int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev,
+                 int32_t B, int32_t H, int32_t W, int32_t Cp, void* stream);
+
+/* 3x3 / pad 1 / stride 1 / bias-free convolution on NHWC bf16 (model.py:742-748) with the
+ * fused epilogues of one encoder block.  `wpacked_dev` comes from mz_pack_conv_weight.
+ *   mode 0: out_bf16 = SiLU(scale[b,n]*acc + shift[b,n])   (conv1 + control + SiLU); film_dev is
+ *           (B,2,cout_p) fp32 -- scale row then shift row per image -- or NULL for scale 1, shift 0
+ *   mode 1: zf += acc ; out_bf16 = bf16(zf)                 (conv2 + ResidualConnection, model.py:789-792)
+ * use_tc = 1: tcgen05/TMEM/TMA kernel; 0: SIMT diagnostic kernel.  tune may be NULL. */
+int mz_conv3x3_bf16(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev,
+                    void* out_bf16_dev, float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p,
+                    int32_t cout_p, int32_t use_tc, const mz_conv_tune* tune, void* stream);
+
+/* SubpixelConv2d (model.py:885-930) + global skip (model.py:162) + optional clamp (:177):
+ * y = [clamp](skip + PixelShuffle_r(conv3x3(z))).  skip_mode 0: none, 1: read y_dev in place
+ * (precomputed bicubic), 2: recompute the bicubic from x_dev inside the epilogue.
+ * wpacked_dev has cout_p = mz_padded_channels(3*r*r) rows per tap. */
+int mz_head_shuffle_add(const void* zb_dev, const void* wpacked_dev, const float* x_dev, float* y_dev,
+                        int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t r, int32_t skip_mode,
+                        int32_t clamp01, int32_t use_tc, const mz_conv_tune* tune, void* stream);
+
+/* Repack OIHW fp32 (host) -> device bf16 [tap = ky*3+kx][cout_p][cin_p] (K-major rows; the TMA
+ * applies the shared-memory swizzle).  With dst_dev == NULL only *bytes is written. */
+int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t cout_p, int32_t cin_p,
+                        void* dst_dev, size_t* bytes);
+
+/* FiLM coefficients for every layer: film[l][b][0][n] = 1 + gamma, film[l][b][1][n] = beta,
+ * from c (B or 1 rows) and the per-layer Linear(F, 2hC) weights (control module; README.md:11,88). */
+int mz_control_film(const float* c_dev, int32_t c_rows, const float* w_dev /*L,2hC,F*/,
+                    const float* b_dev /*L,2hC*/, float* film_dev /*L,B,2,hCp*/, int32_t L, int32_t B,
+                    int32_t F, int32_t hC, int32_t hCp, void* stream);
+
+/* Hardware probes used by tests and DESIGN.md (not on the hot path).
+ * mz_probe_umma: one 128 x 64 x kc UMMA whose A descriptor starts `row_shift` rows into a
+ * TMA-swizzled tile; base_offset_mode 0 leaves the descriptor's base_offset 0, 1 sets it to
+ * (start >> 7) & 7.  Writes the max abs error against an exact host product.
+ * mz_probe_mma_rate: `iters` back-to-back 128 x n x 16 UMMAs per CTA on `ctas` CTAs; writes SM
+ * cycles per UMMA (mean over CTAs). */
+int mz_probe_umma(int32_t kc, int32_t row_shift, int32_t base_offset_mode, float* max_abs_err_out);
+int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_t distinct_a,
+                      float* cycles_per_mma_out);
+
+/* Padded channel counts the kernels use for a logical channel count. */
+int mz_padded_channels(int32_t c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEWZOOM_B200_H_ */

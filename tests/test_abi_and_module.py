@@ -1,0 +1,118 @@
+"""CPU: the C-ABI library loads and exports every symbol include/mewzoom_b200.h declares (no compute
+calls without a GPU), the Python boundary mirrors the reference's API and fails loudly without a B200."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import MODEL_CONFIGS as ORACLE_CONFIGS
+from oracle import OracleMewZoom, make_oracle
+from ultrazoom_b200 import MODEL_CONFIGS, ControlVector, MewZoom, ONNXModel, _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mewzoom_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mz_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load()
+    names = _declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _native.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_native.SIGNATURES) == names
+    assert lib.mz_abi_version() == 1
+
+
+def test_padded_channels_and_error_plumbing():
+    lib = _native.load()
+    assert [lib.mz_padded_channels(c) for c in (48, 54, 96, 108, 192, 12, 27)] == [48, 64, 96, 112, 192, 16, 32]
+    # invalid config -> MZ_ERR_INVALID with the reference's assertion wording (model.py:67-69)
+    cfg = _native.MzConfig(5, 48, 2, 20, 0, 0)
+    h = ctypes.c_void_p()
+    rc = lib.mz_model_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == _native.MZ_ERR_INVALID
+    assert "Upscale ratio" in _native.last_error()
+    with pytest.raises(AssertionError):
+        _native.check(rc)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly_no_fallback():
+    lib = _native.load()
+    assert lib.mz_device_count() == 0
+    cfg = _native.MzConfig(2, 48, 2, 20, 0, 0)
+    h = ctypes.c_void_p()
+    rc = lib.mz_model_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc in (_native.MZ_ERR_CUDA, _native.MZ_ERR_INVALID, _native.MZ_ERR_UNSUPPORTED) and not h.value
+    m = MewZoom(**MODEL_CONFIGS["MewZoom-2X"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.upscale(torch.rand(1, 3, 8, 8))
+
+
+def test_constructor_validation_matches_reference():
+    with pytest.raises(AssertionError):
+        MewZoom(5, 48, 2, 20)           # reference tests/test_model.py:69-73
+    with pytest.raises(AssertionError):
+        MewZoom(2, 48, 3, 20)           # model.py:738
+    with pytest.raises(AssertionError):
+        MewZoom(2, 48, 2, 0)
+    with pytest.raises(AssertionError):
+        MewZoom(2, 2, 2, 1)             # FanOutProjection model.py:218-222
+    m = MewZoom(2, 16, 2, 2, control_features=3)
+    x = torch.rand(2, 3, 8, 8)
+    with pytest.raises(AssertionError):
+        m._check_inputs(x, torch.rand(3, 3))      # tests/test_model.py:97-103
+    with pytest.raises(AssertionError):
+        m._check_inputs(x, torch.rand(2, 4))
+    with pytest.raises(AssertionError):
+        m._check_inputs(x, None)
+    with pytest.raises(AssertionError):
+        m._check_inputs(torch.rand(2, 1, 8, 8), torch.rand(2, 3))
+    assert m._check_inputs(x, torch.rand(3)).shape == (1, 3)
+    with pytest.raises(AssertionError):
+        MewZoom(2, 16, 2, 2)._check_inputs(x, torch.rand(2, 3))
+
+
+@pytest.mark.parametrize("name", sorted(MODEL_CONFIGS))
+def test_state_dict_is_interchangeable_with_oracle(name):
+    assert MODEL_CONFIGS[name] == ORACLE_CONFIGS[name]
+    torch.manual_seed(0)
+    m = MewZoom(**MODEL_CONFIGS[name])
+    o = make_oracle(name, seed=0)
+    sd_m, sd_o = m.state_dict(), o.state_dict()
+    assert list(sd_m.keys()) == list(sd_o.keys())
+    for k in sd_m:
+        assert torch.equal(sd_m[k], sd_o[k]), k      # same default init, same construction order
+    assert m.num_params == sum(p.numel() for p in o.parameters())
+    assert m.num_trainable_params == m.num_params
+    m.freeze_parameters()
+    assert m.num_trainable_params == 0
+    assert m.upscale_ratio == MODEL_CONFIGS[name]["upscale_ratio"]
+
+
+def test_save_and_from_pretrained_round_trip(tmp_path):
+    torch.manual_seed(3)
+    m = MewZoom(3, 16, 2, 2, control_features=3)
+    m.save_pretrained(str(tmp_path))
+    assert (tmp_path / "config.json").exists() and (tmp_path / "model.safetensors").exists()
+    m2 = MewZoom.from_pretrained(str(tmp_path))
+    assert m2.upscale_ratio == 3 and m2.control_features == 3 and m2.num_encoder_layers == 2
+    for (k1, v1), (k2, v2) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2)
+
+
+def test_control_vector():
+    c = ControlVector(gaussian_blur=0.5, gaussian_noise=0.2, jpeg_compression=0.3).to_tensor()   # README.md:118-122
+    assert c.dtype == torch.float32 and c.shape == (3,)
+    assert c.tolist() == pytest.approx([0.5, 0.2, 0.3])
+    with pytest.raises(AssertionError):
+        ControlVector(gaussian_noise=-0.1)
+    assert isinstance(ONNXModel(MewZoom(2, 16, 2, 1)), torch.nn.Module)

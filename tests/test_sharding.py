@@ -1,0 +1,107 @@
+"""CPU: host-side partitioning -- halo tiling is exact, frame-stream assignment is a partition, and the
+world_size-2 path works over gloo.  The compute function here is the oracle (tests may use it)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import make_oracle, max_abs_err
+from ultrazoom_b200.sharding import best_grid, frames_for_rank, halo_radius, plan_tiles, upscale_tiled
+
+CFG = dict(upscale_ratio=2, num_channels=16, hidden_ratio=2, num_encoder_layers=3, control_features=3)
+
+
+def test_frames_for_rank_is_a_partition():
+    for world in (1, 2, 4, 8):
+        seen = sorted(i for r in range(world) for i in frames_for_rank(64, r, world))
+        assert seen == list(range(64))
+    assert frames_for_rank(5, 3, 4) == [3]
+    assert frames_for_rank(2, 3, 4) == []          # ragged: more ranks than frames
+    with pytest.raises(AssertionError):
+        frames_for_rank(4, 4, 4)
+
+
+def test_plan_tiles_covers_image_and_clips_halo():
+    tiles = plan_tiles(1080, 1920, 2, 4, halo_radius(40))
+    assert len(tiles) == 8 and halo_radius(40) == 81
+    area = sum((t.y1 - t.y0) * (t.x1 - t.x0) for t in tiles)
+    assert area == 1080 * 1920
+    t0 = tiles[0]
+    assert (t0.hy0, t0.hx0) == (0, 0) and t0.hy1 == 540 + 81 and t0.hx1 == 480 + 81
+    executed = sum((t.hy1 - t.hy0) * (t.hx1 - t.hx0) for t in tiles) / area
+    assert 1.40 < executed < 1.48                   # 4 cols x 2 rows -> 1.44x
+    assert best_grid(1080, 1920, 8, 81) == (2, 4)
+    with pytest.raises(AssertionError):
+        plan_tiles(4, 4, 8, 1, 1)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (2, 2), (3, 2)])
+def test_tiled_inference_is_exact(rows, cols):
+    m = make_oracle(CFG, seed=5)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(2, 3, 37, 29, generator=g)
+    c = torch.rand(2, 3, generator=g)
+    full = m.upscale(x, c)
+    tiled = upscale_tiled(m.upscale, x, c, 2, CFG["num_encoder_layers"], rows, cols)
+    assert max_abs_err(full, tiled) <= 2e-6         # fp reassociation only
+
+
+def test_halo_one_short_is_not_exact():
+    import ultrazoom_b200.sharding as sh
+
+    m = make_oracle(CFG, seed=5)
+    x = torch.rand(1, 3, 40, 40, generator=torch.Generator().manual_seed(2))
+    c = torch.tensor([0.5, 0.2, 0.3])
+    full = m.upscale(x, c)
+    plan = plan_tiles(40, 40, 2, 2, halo_radius(3) - 1)
+    out = torch.zeros_like(full)
+    for t in plan:
+        sh.stitch(out, sh.run_tile(m.upscale, x, c, t, 2), t, 2)
+    assert max_abs_err(full, out) > 1e-5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = make_oracle(CFG, seed=5)
+        g = torch.Generator().manual_seed(9)
+        x = torch.rand(1, 3, 30, 34, generator=g)
+        c = torch.tensor([0.5, 0.2, 0.3])
+        mine = frames_for_rank(4, rank, world)
+        # each rank fills only its own tiles; the (test-only) sum over ranks stitches them
+        part = upscale_tiled(m.upscale, x, c, 2, CFG["num_encoder_layers"], 2, 2, tiles=mine)
+        dist.all_reduce(part)
+        full = m.upscale(x, c)
+        # frame-stream partition: every frame processed exactly once
+        count = torch.zeros(7)
+        for i in frames_for_rank(7, rank, world):
+            count[i] += 1
+        dist.all_reduce(count)
+        ret[rank] = (max_abs_err(full, part), count.tolist())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_two_gloo():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        for r in range(world):
+            err, count = ret[r]
+            assert err <= 2e-6
+            assert count == [1.0] * 7

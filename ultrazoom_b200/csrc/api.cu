@@ -1,0 +1,128 @@
+// api.cu -- extern "C" per-kernel entry points declared in include/mewzoom_b200.h.
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace mz {
+
+ConvTcTune to_tune(const mz_conv_tune* t) {
+  ConvTcTune o;
+  memset(&o, 0, sizeof(o));
+  if (t) {
+    o.rows = t->rows;
+    o.acc_stages = t->acc_stages;
+    o.kc = t->kc;
+    o.halo_mode = t->halo_mode;
+    o.b_stages = t->b_stages;
+    o.a_stages = t->a_stages;
+    o.max_ctas = t->max_ctas;
+  }
+  return o;
+}
+
+int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+
+// OIHW fp32 -> [tap][cout_p][cin_p] bf16 (zero padded), host side.
+void pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, std::vector<__nv_bfloat16>& out) {
+  out.assign(static_cast<size_t>(9) * cout_p * cin_p, __float2bfloat16_rn(0.f));
+  for (int o = 0; o < cout; ++o)
+    for (int i = 0; i < cin; ++i)
+      for (int t = 0; t < 9; ++t)
+        out[(static_cast<size_t>(t) * cout_p + o) * cin_p + i] =
+            __float2bfloat16_rn(w[(static_cast<size_t>(o) * cin + i) * 9 + t]);
+}
+
+}  // namespace mz
+
+using namespace mz;
+
+extern "C" {
+
+int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, int32_t W, int32_t r, void* stream) {
+  MZ_REQUIRE(x_dev && y_dev, "bicubic: null pointer");
+  return launch_bicubic(x_dev, y_dev, planes, H, W, r, static_cast<cudaStream_t>(stream));
+}
+
+int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev, int32_t B,
+                 int32_t H, int32_t W, int32_t Cp, void* stream) {
+  MZ_REQUIRE(x_dev && w_dev && bias_dev && zf_dev && zb_dev, "stem: null pointer");
+  return launch_stem(x_dev, w_dev, bias_dev, zf_dev, static_cast<__nv_bfloat16*>(zb_dev), B, H, W, Cp,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int mz_conv3x3_bf16(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev,
+                    void* out_bf16_dev, float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t cout_p,
+                    int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+  MZ_REQUIRE(in_dev && wpacked_dev && out_bf16_dev, "conv: null pointer");
+  MZ_REQUIRE(mode == 0 || mode == 1, "conv: mode must be 0 or 1, %d given", mode);
+  MZ_REQUIRE(mode == 0 || zf_dev, "conv: mode 1 needs the fp32 residual stream");
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = static_cast<const __nv_bfloat16*>(in_dev);
+  a.w = static_cast<const __nv_bfloat16*>(wpacked_dev);
+  a.cin_p = cin_p;
+  a.epi.mode = mode;
+  a.epi.B = B;
+  a.epi.H = H;
+  a.epi.W = W;
+  a.epi.n_pad = cout_p;
+  a.epi.film = film_dev;
+  a.epi.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16_dev);
+  a.epi.zf = zf_dev;
+  if (use_tc) return launch_conv_tc(a, to_tune(tune), current_device(), static_cast<cudaStream_t>(stream));
+  return launch_conv_simt(a, static_cast<cudaStream_t>(stream));
+}
+
+int mz_head_shuffle_add(const void* zb_dev, const void* wpacked_dev, const float* x_dev, float* y_dev, int32_t B,
+                        int32_t H, int32_t W, int32_t cin_p, int32_t r, int32_t skip_mode, int32_t clamp01,
+                        int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+  MZ_REQUIRE(zb_dev && wpacked_dev && y_dev, "head: null pointer");
+  MZ_REQUIRE(r == 2 || r == 3 || r == 4, "Upscale ratio must be either 2, 3, or 4, %d given.", r);
+  MZ_REQUIRE(skip_mode >= 0 && skip_mode <= 2, "head: skip_mode must be 0, 1 or 2, %d given", skip_mode);
+  MZ_REQUIRE(skip_mode != 2 || x_dev, "head: skip_mode 2 needs the LR image");
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = static_cast<const __nv_bfloat16*>(zb_dev);
+  a.w = static_cast<const __nv_bfloat16*>(wpacked_dev);
+  a.cin_p = cin_p;
+  a.epi.mode = 2;
+  a.epi.B = B;
+  a.epi.H = H;
+  a.epi.W = W;
+  a.epi.n_pad = mz_padded_channels(3 * r * r);
+  a.epi.x = x_dev;
+  a.epi.y = y_dev;
+  a.epi.r = r;
+  a.epi.skip_mode = skip_mode;
+  a.epi.clamp01 = clamp01;
+  make_bicubic_table(r, &a.epi.bt);
+  if (use_tc) return launch_conv_tc(a, to_tune(tune), current_device(), static_cast<cudaStream_t>(stream));
+  return launch_conv_simt(a, static_cast<cudaStream_t>(stream));
+}
+
+int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t cout_p, int32_t cin_p, void* dst_dev,
+                        size_t* bytes) {
+  MZ_REQUIRE(cout > 0 && cin > 0 && cout_p >= cout && cin_p >= cin, "pack: bad shape (%d,%d)->(%d,%d)", cout, cin,
+             cout_p, cin_p);
+  MZ_REQUIRE(cout_p % 16 == 0 && cin_p % 16 == 0, "pack: padded sizes must be multiples of 16");
+  const size_t n = static_cast<size_t>(9) * cout_p * cin_p * sizeof(__nv_bfloat16);
+  if (bytes) *bytes = n;
+  if (!dst_dev) return MZ_OK;
+  MZ_REQUIRE(w_host, "pack: null weight pointer");
+  std::vector<__nv_bfloat16> tmp;
+  pack_conv_weight_host(w_host, cout, cin, cout_p, cin_p, tmp);
+  MZ_CUDA(cudaMemcpy(dst_dev, tmp.data(), n, cudaMemcpyHostToDevice));
+  return MZ_OK;
+}
+
+int mz_control_film(const float* c_dev, int32_t c_rows, const float* w_dev, const float* b_dev, float* film_dev,
+                    int32_t L, int32_t B, int32_t F, int32_t hC, int32_t hCp, void* stream) {
+  MZ_REQUIRE(c_dev && w_dev && b_dev && film_dev, "film: null pointer");
+  return launch_film(c_dev, c_rows, w_dev, b_dev, film_dev, L, B, F, hC, hCp, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

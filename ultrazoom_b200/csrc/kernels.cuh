@@ -1,0 +1,182 @@
+// kernels.cuh -- internal launch interfaces and the fused epilogues shared by the tcgen05 and the
+// SIMT (diagnostic) convolution kernels.  Everything here is device code for sm_100a or plain
+// host structs; nothing is exported (the C ABI lives in api.cu / model.cu).
+#pragma once
+
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace mz {
+
+// ----------------------------------------------------------------------------------------------
+// Bicubic phase table -- Upsample(scale_factor=r, mode="bicubic"), reference model.py:71,156.
+// For integer r an output coordinate o has phase p = o % r; its four taps start at
+// (o / r) + off[p] - 1 and carry weights w[p][0..3] (Keys kernel, A = -0.75, half-pixel centres,
+// align_corners=False).  Tap indices are clamped to the image (no renormalisation).
+// ----------------------------------------------------------------------------------------------
+struct BicubicTable {
+  int r;
+  int off[4];
+  float w[4][4];
+};
+void make_bicubic_table(int r, BicubicTable* t);
+
+// ----------------------------------------------------------------------------------------------
+// Epilogue parameters.
+//   mode 0: hidden = SiLU(scale[b,n] * acc + shift[b,n])   -> bf16 NHWC      (conv1 + control + SiLU)
+//   mode 1: zf += acc ; zb = bf16(zf)                                         (conv2 + ResidualConnection)
+//   mode 2: y = [clamp](skip + PixelShuffle_r(acc))         -> fp32 NCHW      (SubpixelConv2d + skip)
+// ----------------------------------------------------------------------------------------------
+struct EpiParams {
+  int mode;
+  int B, H, W;
+  int n_pad;          // GEMM N (multiple of 16) == channel pitch of the bf16 / fp32 NHWC outputs
+  const float* film;  // mode 0: [B][2][n_pad] (scale row then shift row per image) or nullptr
+  __nv_bfloat16* out_bf16;  // mode 0: hidden; mode 1: zb
+  float* zf;                // mode 1: fp32 residual stream, updated in place
+  // mode 2
+  const float* x;  // LR image (B,3,H,W) fp32 -- only for skip_mode 2
+  float* y;        // HR image (B,3,rH,rW) fp32
+  int r;
+  int skip_mode;  // 0 none, 1 y already holds the bicubic image, 2 recompute bicubic from x
+  int clamp01;
+  BicubicTable bt;
+};
+
+// One 3x3 convolution launch (both kernels).
+struct ConvArgs {
+  const __nv_bfloat16* in;  // (B,H,W,cin_p) bf16
+  const __nv_bfloat16* w;   // [9][n_pad][cin_p] bf16, tap = ky*3+kx
+  int cin_p;
+  EpiParams epi;
+};
+
+// Tunables of the tcgen05 kernel (0 = let the launcher choose).
+struct ConvTcTune {
+  int rows;        // image rows per patch (accumulators per TMEM stage), 1..4
+  int acc_stages;  // 1 or 2 TMEM accumulator stages
+  int kc;          // K chunk per pipeline stage: 16, 32 or 64 channels
+  int halo_mode;   // 0: one TMA per horizontal tap shift (aligned descriptors)
+                   // 1: one shared halo tile, row-shifted UMMA descriptors, base_offset = 0
+                   // 2: as 1 with base_offset = (start >> 7) & 7
+  int b_stages;    // weight ring depth
+  int a_stages;    // activation ring depth
+  int max_ctas;    // cap on the persistent grid (0 = SM count)
+};
+
+int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
+int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaStream_t s);
+int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s);
+int launch_stem(const float* x, const float* w, const float* bias, float* zf, __nv_bfloat16* zb, int B, int H,
+                int W, int Cp, cudaStream_t s);
+int launch_film(const float* c, int c_rows, const float* w, const float* b, float* film, int L, int B, int F,
+                int hC, int hCp, cudaStream_t s);
+
+ConvTcTune to_tune(const mz_conv_tune* t);
+int current_device();
+// OIHW fp32 -> [tap = ky*3+kx][cout_p][cin_p] bf16, zero padded (host).
+void pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, std::vector<__nv_bfloat16>& out);
+
+#ifdef __CUDACC__
+// ----------------------------------------------------------------------------------------------
+// device-side epilogues
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// modes 0 and 1: sixteen consecutive output channels n0..n0+15 of pixel (b, y, x).
+template <int MODE>
+__device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, int x, int n0, float (&acc)[16]) {
+  const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
+  if (MODE == 0) {
+    if (p.film != nullptr) {
+      const float4* sc = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(b) * 2 * p.n_pad + n0);
+      const float4* sh = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(b) * 2 * p.n_pad + p.n_pad + n0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = __ldg(sc + q), c = __ldg(sh + q);
+        acc[4 * q + 0] = fmaf(acc[4 * q + 0], a.x, c.x);
+        acc[4 * q + 1] = fmaf(acc[4 * q + 1], a.y, c.y);
+        acc[4 * q + 2] = fmaf(acc[4 * q + 2], a.z, c.z);
+        acc[4 * q + 3] = fmaf(acc[4 * q + 3], a.w, c.w);
+      }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = pack_bf16x2(silu_f(acc[2 * q]), silu_f(acc[2 * q + 1]));
+    __nv_bfloat16* dst = p.out_bf16 + pix * p.n_pad + n0;
+    st_global_v4(dst, o[0], o[1], o[2], o[3]);
+    st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
+  } else {
+    float4* zf = reinterpret_cast<float4*>(p.zf + pix * p.n_pad + n0);
+    uint32_t o[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 z = zf[q];
+      z.x += acc[4 * q + 0];
+      z.y += acc[4 * q + 1];
+      z.z += acc[4 * q + 2];
+      z.w += acc[4 * q + 3];
+      zf[q] = z;
+      o[2 * q] = pack_bf16x2(z.x, z.y);
+      o[2 * q + 1] = pack_bf16x2(z.z, z.w);
+    }
+    __nv_bfloat16* dst = p.out_bf16 + pix * p.n_pad + n0;
+    st_global_v4(dst, o[0], o[1], o[2], o[3]);
+    st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
+  }
+}
+
+// Bicubic value of HR pixel (oy, ox) of one plane (H x W, fp32): 16 clamped taps, rows first.
+__device__ __forceinline__ float bicubic_at(const float* __restrict__ plane, int H, int W, const BicubicTable& bt,
+                                            int oy, int ox) {
+  const int r = bt.r;
+  const int py = oy % r, px = ox % r;
+  const int by = oy / r + bt.off[py] - 1, bx = ox / r + bt.off[px] - 1;
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int yy = min(max(by + k, 0), H - 1);
+    const float* row = plane + static_cast<size_t>(yy) * W;
+    float h = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int xx = min(max(bx + m, 0), W - 1);
+      h = fmaf(__ldg(row + xx), bt.w[px][m], h);
+    }
+    acc = fmaf(h, bt.w[py][k], acc);
+  }
+  return acc;
+}
+
+// mode 2: all head channels of LR pixel (b, y, x): acc[n], n = c*r*r + i*r + j  ->  y[b, c, y*r+i, x*r+j]
+// (PixelShuffle index rule, reference model.py:911,928) plus the global skip (model.py:162) and the clamp
+// of upscale() (model.py:177).
+template <int NMAX>
+__device__ __forceinline__ void epi_head(const EpiParams& p, int b, int y, int x, const float (&acc)[NMAX]) {
+  const int r = p.r, rr = r * r;
+  const int HR = p.H * r, WR = p.W * r;
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    if (n < 3 * rr) {
+      const int c = n / rr, i = (n % rr) / r, j = n % r;
+      const int oy = y * r + i, ox = x * r + j;
+      float* dst = p.y + ((static_cast<size_t>(b) * 3 + c) * HR + oy) * WR + ox;
+      float v = acc[n];
+      if (p.skip_mode == 1) {
+        v += *dst;
+      } else if (p.skip_mode == 2) {
+        v += bicubic_at(p.x + (static_cast<size_t>(b) * 3 + c) * p.H * p.W, p.H, p.W, p.bt, oy, ox);
+      }
+      if (p.clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+      *dst = v;
+    }
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace mz

@@ -1,0 +1,394 @@
+// model.cu -- mz_model: device-resident packed weights + the MewZoom forward schedule.
+//
+// Replaces MewZoom.__init__/load_state_dict (reference model.py:52-92) and MewZoom.forward/upscale
+// (model.py:149-179) for the flat 0.2.x architecture BASELINE.json names:
+//   film  = FiLM table from c                      (control modules)
+//   zf,zb = stem(x)                                (FanOutProjection + NCHW->NHWC)
+//   L x { h = SiLU(film . conv1(zb)) ; zf += conv2(h) ; zb = bf16(zf) }
+//   y     = [clamp](bicubic(x) + PixelShuffle(head(zb)))
+// 2L + 3 kernel launches on the caller's stream, no host synchronisation, no allocation.
+#include <stdlib.h>
+
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace mz;
+
+struct mz_model {
+  mz_config cfg;
+  int C, Cp, hC, hCp, L, r, F, headN, headNp;
+  float* stem_w = nullptr;  // (Cp,3)
+  float* stem_b = nullptr;  // (Cp)
+  __nv_bfloat16* conv1 = nullptr;  // L x [9][hCp][Cp]
+  __nv_bfloat16* conv2 = nullptr;  // L x [9][Cp][hCp]
+  __nv_bfloat16* head = nullptr;   // [9][headNp][Cp]
+  float* ctrl_w = nullptr;         // (L, 2hC, F)
+  float* ctrl_b = nullptr;         // (L, 2hC)
+  std::vector<uint8_t> have;       // per (kind, layer) upload flags
+  ConvTcTune tune[3];
+  // buffers owned for the *_host entry point
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  float* hx = nullptr;
+  float* hy = nullptr;
+  float* hc = nullptr;
+  size_t hx_bytes = 0, hy_bytes = 0, hc_bytes = 0;
+  cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+};
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsPlan {
+  size_t zf, zb, hid, film, total;
+};
+
+WsPlan plan_ws(const mz_model* m, int B, int H, int W) {
+  const size_t npix = static_cast<size_t>(B) * H * W;
+  WsPlan p;
+  size_t off = 0;
+  p.zf = off;
+  off = align_up(off + npix * m->Cp * sizeof(float), 1024);
+  p.zb = off;
+  off = align_up(off + npix * m->Cp * sizeof(__nv_bfloat16), 1024);
+  p.hid = off;
+  off = align_up(off + npix * m->hCp * sizeof(__nv_bfloat16), 1024);
+  p.film = off;
+  if (m->F > 0) off = align_up(off + static_cast<size_t>(m->L) * B * 2 * m->hCp * sizeof(float), 1024);
+  p.total = off;
+  return p;
+}
+
+int flag_index(const mz_model* m, int kind, int layer) {
+  switch (kind) {
+    case MZ_W_STEM_WEIGHT: return 0;
+    case MZ_W_STEM_BIAS: return 1;
+    case MZ_W_HEAD: return 2;
+    case MZ_W_CONV1: return 3 + layer;
+    case MZ_W_CONV2: return 3 + m->L + layer;
+    case MZ_W_CTRL_WEIGHT: return 3 + 2 * m->L + layer;
+    case MZ_W_CTRL_BIAS: return 3 + 3 * m->L + layer;
+  }
+  return -1;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mz_model_create(const mz_config* cfg, mz_model** out) {
+  MZ_REQUIRE(cfg && out, "model_create: null pointer");
+  *out = nullptr;
+  MZ_REQUIRE(cfg->upscale_ratio == 2 || cfg->upscale_ratio == 3 || cfg->upscale_ratio == 4,
+             "Upscale ratio must be one of {2, 3, 4}, but got %d.", cfg->upscale_ratio);
+  MZ_REQUIRE(cfg->num_channels > 3, "Output channels must be greater than input channels (3), %d given.",
+             cfg->num_channels);
+  MZ_REQUIRE(cfg->hidden_ratio == 1 || cfg->hidden_ratio == 2 || cfg->hidden_ratio == 4,
+             "Hidden ratio must be either 1, 2, or 4, %d given.", cfg->hidden_ratio);
+  MZ_REQUIRE(cfg->num_encoder_layers > 0, "Number of encoder layers must be greater than 0, %d given.",
+             cfg->num_encoder_layers);
+  MZ_REQUIRE(cfg->control_features >= 0 && cfg->control_features <= 64,
+             "control_features must be in [0, 64], %d given.", cfg->control_features);
+  const int hC = cfg->num_channels * cfg->hidden_ratio;
+  MZ_REQUIRE(mz_padded_channels(hC) <= 256, "hidden width %d exceeds the 256-channel limit of one UMMA tile", hC);
+
+  int ndev = 0;
+  MZ_CUDA(cudaGetDeviceCount(&ndev));
+  MZ_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device %d out of range (%d visible)", cfg->device, ndev);
+  int major = 0;
+  MZ_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+  if (major != 10) {
+    set_error("device %d has compute capability %d.x; this library is sm_100a only (no fallback)", cfg->device, major);
+    return MZ_ERR_UNSUPPORTED;
+  }
+
+  mz_model* m = new mz_model();
+  m->cfg = *cfg;
+  m->C = cfg->num_channels;
+  m->Cp = mz_padded_channels(m->C);
+  m->hC = hC;
+  m->hCp = mz_padded_channels(hC);
+  m->L = cfg->num_encoder_layers;
+  m->r = cfg->upscale_ratio;
+  m->F = cfg->control_features;
+  m->headN = 3 * m->r * m->r;
+  m->headNp = mz_padded_channels(m->headN);
+  m->have.assign(3 + 4 * m->L, 0);
+  memset(m->tune, 0, sizeof(m->tune));
+  const int hm = env_int("MZ_HALO_MODE", 0);
+  for (int i = 0; i < 3; ++i) m->tune[i].halo_mode = hm;
+
+  DeviceGuard g(cfg->device);
+  const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cp, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
+  };
+  alloc(reinterpret_cast<void**>(&m->stem_w), sizeof(float) * m->Cp * 3);
+  alloc(reinterpret_cast<void**>(&m->stem_b), sizeof(float) * m->Cp);
+  alloc(reinterpret_cast<void**>(&m->conv1), sizeof(__nv_bfloat16) * c1 * m->L);
+  alloc(reinterpret_cast<void**>(&m->conv2), sizeof(__nv_bfloat16) * c2 * m->L);
+  alloc(reinterpret_cast<void**>(&m->head), sizeof(__nv_bfloat16) * 9 * m->headNp * m->Cp);
+  if (m->F > 0) {
+    alloc(reinterpret_cast<void**>(&m->ctrl_w), sizeof(float) * m->L * 2 * m->hC * m->F);
+    alloc(reinterpret_cast<void**>(&m->ctrl_b), sizeof(float) * m->L * 2 * m->hC);
+  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    const int rc = cuda_fail(e, "model allocation", __FILE__, __LINE__);
+    mz_model_destroy(m);
+    return rc;
+  }
+  *out = m;
+  return MZ_OK;
+}
+
+void mz_model_destroy(mz_model* m) {
+  if (!m) return;
+  DeviceGuard g(m->cfg.device);
+  cudaFree(m->stem_w);
+  cudaFree(m->stem_b);
+  cudaFree(m->conv1);
+  cudaFree(m->conv2);
+  cudaFree(m->head);
+  cudaFree(m->ctrl_w);
+  cudaFree(m->ctrl_b);
+  cudaFree(m->ws);
+  cudaFree(m->hx);
+  cudaFree(m->hy);
+  cudaFree(m->hc);
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* host_data, size_t numel) {
+  MZ_REQUIRE(m && host_data, "set_weight: null pointer");
+  const bool per_layer =
+      kind == MZ_W_CONV1 || kind == MZ_W_CONV2 || kind == MZ_W_CTRL_WEIGHT || kind == MZ_W_CTRL_BIAS;
+  MZ_REQUIRE(!per_layer || (layer >= 0 && layer < m->L), "set_weight: layer %d out of range [0, %d)", layer, m->L);
+  MZ_REQUIRE((kind != MZ_W_CTRL_WEIGHT && kind != MZ_W_CTRL_BIAS) || m->F > 0,
+             "set_weight: this model has no control modules");
+  DeviceGuard g(m->cfg.device);
+  std::vector<__nv_bfloat16> packed;
+  switch (kind) {
+    case MZ_W_STEM_WEIGHT: {
+      MZ_REQUIRE(numel == static_cast<size_t>(m->C) * 3, "stem weight: expected %d elements, got %zu", m->C * 3,
+                 numel);
+      MZ_CUDA(cudaMemcpy(m->stem_w, host_data, sizeof(float) * numel, cudaMemcpyHostToDevice));
+      break;
+    }
+    case MZ_W_STEM_BIAS: {
+      MZ_REQUIRE(numel == static_cast<size_t>(m->C), "stem bias: expected %d elements, got %zu", m->C, numel);
+      MZ_CUDA(cudaMemcpy(m->stem_b, host_data, sizeof(float) * numel, cudaMemcpyHostToDevice));
+      break;
+    }
+    case MZ_W_CONV1: {
+      MZ_REQUIRE(numel == static_cast<size_t>(m->hC) * m->C * 9, "conv1 weight: expected %d elements, got %zu",
+                 m->hC * m->C * 9, numel);
+      pack_conv_weight_host(host_data, m->hC, m->C, m->hCp, m->Cp, packed);
+      MZ_CUDA(cudaMemcpy(m->conv1 + static_cast<size_t>(layer) * packed.size(), packed.data(),
+                         packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+      break;
+    }
+    case MZ_W_CONV2: {
+      MZ_REQUIRE(numel == static_cast<size_t>(m->hC) * m->C * 9, "conv2 weight: expected %d elements, got %zu",
+                 m->hC * m->C * 9, numel);
+      pack_conv_weight_host(host_data, m->C, m->hC, m->Cp, m->hCp, packed);
+      MZ_CUDA(cudaMemcpy(m->conv2 + static_cast<size_t>(layer) * packed.size(), packed.data(),
+                         packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+      break;
+    }
+    case MZ_W_HEAD: {
+      MZ_REQUIRE(numel == static_cast<size_t>(m->headN) * m->C * 9, "head weight: expected %d elements, got %zu",
+                 m->headN * m->C * 9, numel);
+      pack_conv_weight_host(host_data, m->headN, m->C, m->headNp, m->Cp, packed);
+      MZ_CUDA(cudaMemcpy(m->head, packed.data(), packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+      break;
+    }
+    case MZ_W_CTRL_WEIGHT: {
+      const size_t n = static_cast<size_t>(2) * m->hC * m->F;
+      MZ_REQUIRE(numel == n, "control weight: expected %zu elements, got %zu", n, numel);
+      MZ_CUDA(cudaMemcpy(m->ctrl_w + layer * n, host_data, sizeof(float) * n, cudaMemcpyHostToDevice));
+      break;
+    }
+    case MZ_W_CTRL_BIAS: {
+      const size_t n = static_cast<size_t>(2) * m->hC;
+      MZ_REQUIRE(numel == n, "control bias: expected %zu elements, got %zu", n, numel);
+      MZ_CUDA(cudaMemcpy(m->ctrl_b + layer * n, host_data, sizeof(float) * n, cudaMemcpyHostToDevice));
+      break;
+    }
+    default:
+      set_error("set_weight: unknown weight kind %d", kind);
+      return MZ_ERR_INVALID;
+  }
+  m->have[flag_index(m, kind, layer)] = 1;
+  return MZ_OK;
+}
+
+int mz_model_set_tune(mz_model* m, int32_t which, const mz_conv_tune* tune) {
+  MZ_REQUIRE(m, "set_tune: null model");
+  MZ_REQUIRE(which >= -1 && which <= 2, "set_tune: which must be -1..2, %d given", which);
+  const ConvTcTune t = to_tune(tune);
+  for (int i = 0; i < 3; ++i)
+    if (which < 0 || which == i) m->tune[i] = t;
+  return MZ_OK;
+}
+
+int mz_workspace_bytes(const mz_model* m, int32_t B, int32_t H, int32_t W, size_t* bytes) {
+  MZ_REQUIRE(m && bytes, "workspace_bytes: null pointer");
+  MZ_REQUIRE(B > 0 && H > 0 && W > 0, "workspace_bytes: empty input (B %d, H %d, W %d)", B, H, W);
+  *bytes = plan_ws(m, B, H, W).total;
+  return MZ_OK;
+}
+
+int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_rows, float* y_dev, int32_t B, int32_t H,
+               int32_t W, void* workspace_dev, size_t workspace_bytes, uint32_t flags, void* stream) {
+  MZ_REQUIRE(m && x_dev && y_dev && workspace_dev, "upscale: null pointer");
+  MZ_REQUIRE(B > 0 && H > 0 && W > 0, "upscale: empty input (B %d, H %d, W %d)", B, H, W);
+  if (m->F > 0) {
+    MZ_REQUIRE(c_dev != nullptr, "Control vector c is required for control models.");
+    MZ_REQUIRE(c_rows == 1 || c_rows == B, "Batch size of c (%d) must match x (%d).", c_rows, B);
+  } else {
+    MZ_REQUIRE(c_dev == nullptr, "This model has no control modules; c must be None.");
+  }
+  for (size_t i = 0; i < m->have.size(); ++i) {
+    const bool ctrl = i >= static_cast<size_t>(3 + 2 * m->L);
+    if (!m->have[i] && (!ctrl || m->F > 0)) {
+      set_error("upscale: weights not fully set (missing slot %zu)", i);
+      return MZ_ERR_STATE;
+    }
+  }
+  const WsPlan wp = plan_ws(m, B, H, W);
+  if (workspace_bytes < wp.total) {
+    set_error("upscale: workspace too small (%zu < %zu bytes)", workspace_bytes, wp.total);
+    return MZ_ERR_WORKSPACE;
+  }
+  MZ_REQUIRE((reinterpret_cast<uintptr_t>(workspace_dev) & 1023) == 0, "upscale: workspace must be 1024-byte aligned");
+
+  DeviceGuard g(m->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+  float* zf = reinterpret_cast<float*>(ws + wp.zf);
+  __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(ws + wp.zb);
+  __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(ws + wp.hid);
+  float* film = reinterpret_cast<float*>(ws + wp.film);
+  const bool simt = (flags & MZ_FLAG_SIMT_CONV) != 0;
+  int rc;
+
+  if (m->F > 0) {
+    rc = launch_film(c_dev, c_rows, m->ctrl_w, m->ctrl_b, film, m->L, B, m->F, m->hC, m->hCp, s);
+    if (rc != MZ_OK) return rc;
+  }
+  rc = launch_stem(x_dev, m->stem_w, m->stem_b, zf, zb, B, H, W, m->Cp, s);
+  if (rc != MZ_OK) return rc;
+
+  const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cp, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
+  for (int l = 0; l < m->L; ++l) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.in = zb;
+    a.w = m->conv1 + l * c1;
+    a.cin_p = m->Cp;
+    a.epi.mode = 0;
+    a.epi.B = B;
+    a.epi.H = H;
+    a.epi.W = W;
+    a.epi.n_pad = m->hCp;
+    a.epi.film = m->F > 0 ? film + static_cast<size_t>(l) * B * 2 * m->hCp : nullptr;
+    a.epi.out_bf16 = hid;
+    rc = simt ? launch_conv_simt(a, s) : launch_conv_tc(a, m->tune[0], m->cfg.device, s);
+    if (rc != MZ_OK) return rc;
+
+    memset(&a, 0, sizeof(a));
+    a.in = hid;
+    a.w = m->conv2 + l * c2;
+    a.cin_p = m->hCp;
+    a.epi.mode = 1;
+    a.epi.B = B;
+    a.epi.H = H;
+    a.epi.W = W;
+    a.epi.n_pad = m->Cp;
+    a.epi.out_bf16 = zb;
+    a.epi.zf = zf;
+    rc = simt ? launch_conv_simt(a, s) : launch_conv_tc(a, m->tune[1], m->cfg.device, s);
+    if (rc != MZ_OK) return rc;
+  }
+
+  int skip_mode = 2;
+  if (flags & MZ_FLAG_SKIP_FROM_BUFFER) {
+    rc = launch_bicubic(x_dev, y_dev, B * 3, H, W, m->r, s);
+    if (rc != MZ_OK) return rc;
+    skip_mode = 1;
+  }
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.in = zb;
+  a.w = m->head;
+  a.cin_p = m->Cp;
+  a.epi.mode = 2;
+  a.epi.B = B;
+  a.epi.H = H;
+  a.epi.W = W;
+  a.epi.n_pad = m->headNp;
+  a.epi.x = x_dev;
+  a.epi.y = y_dev;
+  a.epi.r = m->r;
+  a.epi.skip_mode = skip_mode;
+  a.epi.clamp01 = (flags & MZ_FLAG_CLAMP01) ? 1 : 0;
+  make_bicubic_table(m->r, &a.epi.bt);
+  return simt ? launch_conv_simt(a, s) : launch_conv_tc(a, m->tune[2], m->cfg.device, s);
+}
+
+int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32_t c_rows, float* y_host, int32_t B,
+                    int32_t H, int32_t W, uint32_t flags) {
+  MZ_REQUIRE(m && x_host && y_host, "upscale_host: null pointer");
+  MZ_REQUIRE(B > 0 && H > 0 && W > 0, "upscale_host: empty input (B %d, H %d, W %d)", B, H, W);
+  DeviceGuard g(m->cfg.device);
+  const size_t xb = sizeof(float) * 3 * B * H * W;
+  const size_t yb = xb * m->r * m->r;
+  const size_t cb = c_host ? sizeof(float) * c_rows * (m->F > 0 ? m->F : 1) : 0;
+  size_t wsb = 0;
+  int rc = mz_workspace_bytes(m, B, H, W, &wsb);
+  if (rc != MZ_OK) return rc;
+  auto ensure = [&](void** p, size_t* have, size_t need) -> int {
+    if (*have >= need) return MZ_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    MZ_CUDA(cudaMalloc(p, need));
+    *have = need;
+    return MZ_OK;
+  };
+  if ((rc = ensure(reinterpret_cast<void**>(&m->hx), &m->hx_bytes, xb)) != MZ_OK) return rc;
+  if ((rc = ensure(reinterpret_cast<void**>(&m->hy), &m->hy_bytes, yb)) != MZ_OK) return rc;
+  if (cb && (rc = ensure(reinterpret_cast<void**>(&m->hc), &m->hc_bytes, cb)) != MZ_OK) return rc;
+  if ((rc = ensure(&m->ws, &m->ws_bytes, wsb)) != MZ_OK) return rc;
+  MZ_CUDA(cudaMemcpyAsync(m->hx, x_host, xb, cudaMemcpyHostToDevice, m->stream));
+  if (cb) MZ_CUDA(cudaMemcpyAsync(m->hc, c_host, cb, cudaMemcpyHostToDevice, m->stream));
+  rc = mz_upscale(m, m->hx, cb ? m->hc : nullptr, c_rows, m->hy, B, H, W, m->ws, m->ws_bytes, flags, m->stream);
+  if (rc != MZ_OK) return rc;
+  MZ_CUDA(cudaMemcpyAsync(y_host, m->hy, yb, cudaMemcpyDeviceToHost, m->stream));
+  MZ_CUDA(cudaStreamSynchronize(m->stream));
+  return MZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+"""MewZoom -- drop-in for ``ultrazoom.model.MewZoom`` (reference src/ultrazoom/model.py:43-192, 0.2.x
+``upscale(x, c)`` signature per README.md:124) whose forward pass runs on hand-written sm_100a kernels.
+
+The ``torch.nn`` sub-modules below only *hold* the parameters (same shapes, same default initialisation and
+the same ``state_dict`` keys as the flat architecture BASELINE.json names); they are
+never called.  ``forward`` hands device pointers to the C ABI (include/mewzoom_b200.h) on the current CUDA
+stream.  There is no CPU / eager fallback: a non-CUDA input or a missing native library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import Tensor, nn
+
+try:  # the reference mixes this in (model.py:37,43); keep from_pretrained/save_pretrained working
+    from huggingface_hub import PyTorchModelHubMixin
+except Exception:  # pragma: no cover - hub not installed
+
+    class PyTorchModelHubMixin:  # type: ignore
+        pass
+
+
+from . import _native
+
+
+class FanOutProjection(nn.Module):
+    """Parameter holder for the 1x1 stem (reference model.py:212-242)."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        assert in_channels > 0, "Input channels must be greater than 0."
+        assert in_channels < out_channels, "Output channels must be greater than input channels."
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+
+
+class InvertedBottleneck(nn.Module):
+    """Parameter holder for conv3x3 -> SiLU -> conv3x3 (reference model.py:731-778)."""
+
+    def __init__(self, num_channels: int, hidden_ratio: int):
+        super().__init__()
+        assert num_channels > 0, "Number of channels must be greater than 0."
+        assert hidden_ratio in {1, 2, 4}, "Hidden ratio must be either 1, 2, or 4."
+        hidden = hidden_ratio * num_channels
+        self.conv1 = nn.Conv2d(num_channels, hidden, kernel_size=3, padding=1, bias=False)
+        self.conv2 = nn.Conv2d(hidden, num_channels, kernel_size=3, padding=1, bias=False)
+
+
+class ControlModule(nn.Module):
+    """Parameter holder for the per-layer FiLM control (restated)."""
+
+    def __init__(self, control_features: int, hidden_channels: int):
+        super().__init__()
+        assert control_features > 0, "Control features must be greater than 0."
+        self.linear = nn.Linear(control_features, 2 * hidden_channels, bias=True)
+
+
+class EncoderBlock(nn.Module):
+    """One residual block (reference model.py:487-511 with the plain ResidualConnection :781-792)."""
+
+    def __init__(self, num_channels: int, hidden_ratio: int, control_features: int):
+        super().__init__()
+        self.convnet = InvertedBottleneck(num_channels, hidden_ratio)
+        if control_features > 0:
+            self.control = ControlModule(control_features, hidden_ratio * num_channels)
+
+
+class SubpixelConv2d(nn.Module):
+    """Parameter holder for conv3x3 -> PixelShuffle (reference model.py:885-930)."""
+
+    def __init__(self, in_channels: int, out_channels: int, upscale_ratio: int):
+        super().__init__()
+        assert upscale_ratio in {2, 3, 4}, "Upscale ratio must be either 2, 3, or 4."
+        self.conv = nn.Conv2d(in_channels, out_channels * upscale_ratio**2, kernel_size=3, padding=1, bias=False)
+
+
+class _Engine:
+    """One native mz_model on one device + cached workspace."""
+
+    def __init__(self, owner: "MewZoom", device: torch.device):
+        self.lib = _native.load()
+        if self.lib.mz_device_count() == 0:
+            raise RuntimeError("no sm_100 (B200) device visible; ultrazoom_b200 has no CPU or non-Blackwell fallback")
+        self.device = device
+        cfg = _native.MzConfig(owner.upscale_ratio, owner.num_channels, owner.hidden_ratio,
+                               owner.num_encoder_layers, owner.control_features, device.index or 0)
+        handle = C.c_void_p()
+        _native.check(self.lib.mz_model_create(C.byref(cfg), C.byref(handle)))
+        self.handle = handle
+        self.versions = None
+        self.ws: Optional[Tensor] = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.mz_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def sync_weights(self, owner: "MewZoom") -> None:
+        versions = tuple((p.data_ptr(), p._version) for p in owner.parameters())
+        if versions == self.versions:
+            return
+        lib, h = self.lib, self.handle
+
+        def put(kind: int, layer: int, t: Tensor) -> None:
+            a = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            _native.check(lib.mz_model_set_weight(h, kind, layer, a.data_ptr(), a.numel()))
+
+        put(_native.W_STEM_WEIGHT, 0, owner.stem.conv.weight)
+        put(_native.W_STEM_BIAS, 0, owner.stem.conv.bias)
+        for l, blk in enumerate(owner.encoder):
+            put(_native.W_CONV1, l, blk.convnet.conv1.weight)
+            put(_native.W_CONV2, l, blk.convnet.conv2.weight)
+            if owner.control_features > 0:
+                put(_native.W_CTRL_WEIGHT, l, blk.control.linear.weight)
+                put(_native.W_CTRL_BIAS, l, blk.control.linear.bias)
+        put(_native.W_HEAD, 0, owner.head.conv.weight)
+        self.versions = versions
+
+    def workspace(self, B: int, H: int, W: int) -> Tensor:
+        need = C.c_size_t()
+        _native.check(self.lib.mz_workspace_bytes(self.handle, B, H, W, C.byref(need)))
+        if self.ws is None or self.ws.numel() < need.value:
+            self.ws = None
+            self.ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=self.device)
+        return self.ws
+
+
+class MewZoom(nn.Module, PyTorchModelHubMixin):
+    """Fast single-image super-resolution with optional control conditioning (B200-native forward)."""
+
+    AVAILABLE_UPSCALE_RATIOS = {2, 3, 4}
+
+    AVAILABLE_HIDDEN_RATIOS = {1, 2, 4}
+
+    def __init__(
+        self,
+        upscale_ratio: int,
+        num_channels: int,
+        hidden_ratio: int,
+        num_encoder_layers: int,
+        control_features: int = 0,
+    ):
+        super().__init__()
+        assert upscale_ratio in self.AVAILABLE_UPSCALE_RATIOS, (
+            f"Upscale ratio must be one of {self.AVAILABLE_UPSCALE_RATIOS}, but got {upscale_ratio}.")
+        assert hidden_ratio in self.AVAILABLE_HIDDEN_RATIOS, (
+            f"Hidden ratio must be one of {self.AVAILABLE_HIDDEN_RATIOS}, but got {hidden_ratio}.")
+        assert num_encoder_layers > 0, "Number of encoder layers must be greater than 0."
+        assert control_features >= 0, "Control features must not be negative."
+
+        self.stem = FanOutProjection(3, num_channels)
+        self.encoder = nn.ModuleList(
+            [EncoderBlock(num_channels, hidden_ratio, control_features) for _ in range(num_encoder_layers)])
+        self.head = SubpixelConv2d(num_channels, 3, upscale_ratio)
+
+        self.upscale_ratio = upscale_ratio
+        self.num_channels = num_channels
+        self.hidden_ratio = hidden_ratio
+        self.num_encoder_layers = num_encoder_layers
+        self.control_features = control_features
+        self._engines: dict = {}
+        self._flags_extra = 0
+
+    # ---- reference model.py:94-115 ----
+    @property
+    def num_params(self) -> int:
+        return sum(p.numel() for p in self.parameters())
+
+    @property
+    def num_trainable_params(self) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad)
+
+    def freeze_parameters(self) -> None:
+        for p in self.parameters():
+            p.requires_grad = False
+
+    # ---- native plumbing ----
+    def _engine(self, device: torch.device) -> _Engine:
+        key = (device.type, device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _Engine(self, device)
+            self._engines[key] = eng
+        eng.sync_weights(self)
+        return eng
+
+    def set_conv_tune(self, which: int = -1, device: Optional[torch.device] = None, **kw) -> None:
+        """Override the tcgen05 kernel's tunables (see mz_conv_tune); for benches and tests."""
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        eng = self._engine(dev)
+        t = _native.tune(**kw)
+        _native.check(eng.lib.mz_model_set_tune(eng.handle, which, C.byref(t)))
+
+    def _check_inputs(self, x: Tensor, c: Optional[Tensor]) -> Optional[Tensor]:
+        assert x.dim() == 4 and x.shape[1] == 3, f"Expected input of shape (B, 3, H, W), got {tuple(x.shape)}."
+        assert x.shape[0] > 0 and x.shape[2] > 0 and x.shape[3] > 0, "Input must not be empty."
+        if self.control_features == 0:
+            assert c is None, "This model has no control modules; c must be None."
+            return None
+        assert c is not None, "Control vector c is required for control models."
+        if c.dim() == 1:
+            c = c.unsqueeze(0)
+        assert c.dim() == 2 and c.shape[1] == self.control_features, (
+            f"Expected {self.control_features} control features, got {c.shape[-1]}.")
+        assert c.shape[0] in (1, x.shape[0]), "Batch size of c must match x."
+        return c
+
+    def _run(self, x: Tensor, c: Optional[Tensor], flags: int) -> Tensor:
+        c = self._check_inputs(x, c)
+        if not x.is_cuda:
+            raise RuntimeError("ultrazoom_b200.MewZoom runs on sm_100a CUDA kernels only; move the input to a "
+                               "B200 (`x.cuda()`). There is no CPU fallback.")
+        dev = x.device
+        eng = self._engine(dev)
+        x = x.detach().to(torch.float32).contiguous()
+        if c is not None:
+            c = c.detach().to(device=dev, dtype=torch.float32).contiguous()
+        B, _, H, W = x.shape
+        r = self.upscale_ratio
+        y = torch.empty((B, 3, H * r, W * r), dtype=torch.float32, device=dev)
+        ws = eng.workspace(B, H, W)
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _native.check(eng.lib.mz_upscale(
+            eng.handle, x.data_ptr(), c.data_ptr() if c is not None else None,
+            c.shape[0] if c is not None else 0, y.data_ptr(), B, H, W, ws_ptr, ws_bytes,
+            flags | self._flags_extra, stream))
+        return y
+
+    # ---- reference model.py:149-179 ----
+    def forward(self, x: Tensor, c: Optional[Tensor] = None) -> Tensor:
+        """bicubic(x) + residual network, un-clamped (reference model.py:149-164)."""
+        return self._run(x, c, 0)
+
+    @torch.inference_mode()
+    def upscale(self, x: Tensor, c: Optional[Tensor] = None) -> Tensor:
+        """``clamp(forward(x, c), 0, 1)`` (reference model.py:166-179); the clamp is fused in the head kernel."""
+        return self._run(x, c, _native.FLAG_CLAMP01)
+
+    @torch.inference_mode()
+    def upscale_host(self, x: Tensor, c: Optional[Tensor] = None, out: Optional[Tensor] = None,
+                     device: int = 0) -> Tensor:
+        """End-to-end call with HOST tensors: H2D copy, kernels, D2H copy (mz_upscale_host)."""
+        c = self._check_inputs(x, c)
+        assert not x.is_cuda, "upscale_host takes host tensors"
+        eng = self._engine(torch.device("cuda", device))
+        x = x.to(torch.float32).contiguous()
+        if c is not None:
+            c = c.to(device="cpu", dtype=torch.float32).contiguous()
+        B, _, H, W = x.shape
+        r = self.upscale_ratio
+        if out is None:
+            out = torch.empty((B, 3, H * r, W * r), dtype=torch.float32)
+        assert out.is_contiguous() and tuple(out.shape) == (B, 3, H * r, W * r) and out.dtype == torch.float32
+        _native.check(eng.lib.mz_upscale_host(
+            eng.handle, x.data_ptr(), c.data_ptr() if c is not None else None,
+            c.shape[0] if c is not None else 0, out.data_ptr(), B, H, W,
+            _native.FLAG_CLAMP01 | self._flags_extra))
+        return out
+
+
+class ONNXModel(nn.Module):
+    """Wrapper whose forward is ``model.upscale`` (reference model.py:195-209)."""
+
+    def __init__(self, model: MewZoom):
+        super().__init__()
+        self.model = model
+
+    def forward(self, x: Tensor, c: Optional[Tensor] = None) -> Tensor:
+        return self.model.upscale(x, c)

@@ -1,0 +1,110 @@
+"""Work partitioning for multi-GPU runs -- one process per GPU, NO collective on the hot path.
+
+Two partitionings:
+  * frame stream: frame i of a stream goes to rank ``i % world`` (``frames_for_rank``);
+  * spatial tiles with halo: one large image is cut into a cols x rows grid of LR tiles, each extended
+    by the network's receptive-field radius ``halo_radius(L) = 2L + 1`` LR pixels (every block has two
+    3x3 convs, the head one more); each rank runs the whole network on its haloed tile with ordinary
+    image-border semantics and keeps only the core (``plan_tiles`` / ``upscale_tiled``).
+    Tiles touching a true image border take no halo on that side, so zero padding (convs) and clamped
+    taps (bicubic) there are exactly the full-image ones.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+
+def halo_radius(num_encoder_layers: int) -> int:
+    """LR-pixel halo that makes tiled inference exact: 2 convs per block + the head conv.
+
+    The bicubic skip only needs 2 LR pixels, which this always covers."""
+    return 2 * num_encoder_layers + 1
+
+
+def frames_for_rank(num_frames: int, rank: int, world: int) -> List[int]:
+    assert world > 0 and 0 <= rank < world, f"bad rank {rank} / world {world}"
+    return list(range(rank, num_frames, world))
+
+
+@dataclass(frozen=True)
+class Tile:
+    index: int
+    # core region in LR pixels (what this tile contributes to the output)
+    y0: int
+    y1: int
+    x0: int
+    x1: int
+    # haloed region actually fed to the network
+    hy0: int
+    hy1: int
+    hx0: int
+    hx1: int
+
+
+def _splits(n: int, parts: int) -> List[Tuple[int, int]]:
+    base, extra = divmod(n, parts)
+    out, s = [], 0
+    for i in range(parts):
+        e = s + base + (1 if i < extra else 0)
+        out.append((s, e))
+        s = e
+    return out
+
+
+def plan_tiles(H: int, W: int, rows: int, cols: int, halo: int) -> List[Tile]:
+    assert rows > 0 and cols > 0 and rows <= H and cols <= W, f"bad grid {rows}x{cols} for a {H}x{W} image"
+    assert halo >= 0
+    tiles = []
+    for iy, (y0, y1) in enumerate(_splits(H, rows)):
+        for ix, (x0, x1) in enumerate(_splits(W, cols)):
+            tiles.append(Tile(iy * cols + ix, y0, y1, x0, x1,
+                              max(0, y0 - halo), min(H, y1 + halo), max(0, x0 - halo), min(W, x1 + halo)))
+    return tiles
+
+
+def best_grid(H: int, W: int, n_tiles: int, halo: int) -> Tuple[int, int]:
+    """rows x cols = n_tiles grid with the least executed work (haloed area)."""
+    best, best_cost = (1, n_tiles), None
+    for rows in range(1, n_tiles + 1):
+        if n_tiles % rows:
+            continue
+        cols = n_tiles // rows
+        if rows > H or cols > W:
+            continue
+        cost = sum((t.hy1 - t.hy0) * (t.hx1 - t.hx0) for t in plan_tiles(H, W, rows, cols, halo))
+        if best_cost is None or cost < best_cost:
+            best, best_cost = (rows, cols), cost
+    return best
+
+
+def run_tile(fn: Callable[[Tensor, Optional[Tensor]], Tensor], x: Tensor, c: Optional[Tensor], t: Tile,
+             r: int) -> Tensor:
+    """Run ``fn`` on the haloed tile and crop its HR core."""
+    y = fn(x[:, :, t.hy0:t.hy1, t.hx0:t.hx1].contiguous(), c)
+    oy, ox = (t.y0 - t.hy0) * r, (t.x0 - t.hx0) * r
+    return y[:, :, oy:oy + (t.y1 - t.y0) * r, ox:ox + (t.x1 - t.x0) * r]
+
+
+def stitch(out: Tensor, tile_out: Tensor, t: Tile, r: int) -> None:
+    out[:, :, t.y0 * r:t.y1 * r, t.x0 * r:t.x1 * r] = tile_out
+
+
+def upscale_tiled(fn: Callable[[Tensor, Optional[Tensor]], Tensor], x: Tensor, c: Optional[Tensor], r: int,
+                  num_encoder_layers: int, rows: int, cols: int, tiles: Optional[Sequence[int]] = None,
+                  out: Optional[Tensor] = None) -> Tensor:
+    """Tiled inference, exact w.r.t. the full-image result.  ``tiles`` selects which tile indices THIS
+    caller computes (e.g. ``frames_for_rank(rows*cols, rank, world)``); the others are left untouched in
+    ``out`` so ranks can fill disjoint parts of a shared / gathered buffer."""
+    B, _, H, W = x.shape
+    plan = plan_tiles(H, W, rows, cols, halo_radius(num_encoder_layers))
+    if out is None:
+        out = torch.zeros((B, 3, H * r, W * r), dtype=torch.float32, device=x.device)
+    for t in plan:
+        if tiles is not None and t.index not in tiles:
+            continue
+        stitch(out, run_tile(fn, x, c, t, r), t, r)
+    return out
