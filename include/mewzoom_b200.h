@@ -103,6 +103,13 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
 int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32_t c_rows,
                     float* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags);
 
+/* Optional timing of the encoder's convolution stack (the 2L launches of the dominant kernel):
+ * when enabled, mz_upscale records one CUDA event on `stream` before the first and one after the
+ * last encoder convolution.  mz_model_conv_stack_ms waits for those events and returns the mean
+ * elapsed milliseconds over the (up to 64 most recent) calls made since timing was enabled. */
+int mz_model_enable_timing(mz_model* m, int32_t enable);
+int mz_model_conv_stack_ms(mz_model* m, float* ms);
+
 /* ---- per-kernel entry points (unit tests, benches, partial pipelines) ---- */
 
 /* Tunables of the tcgen05 convolution kernel; every field 0 = let the library choose. */
@@ -110,8 +117,8 @@ typedef struct mz_conv_tune {
   int32_t rows;       /* image rows (accumulators) per patch, 1..4                                   */
   int32_t acc_stages; /* TMEM accumulator stages, 1 or 2                                             */
   int32_t kc;         /* channels per pipeline stage: 16, 32 or 64                                   */
-  int32_t halo_mode;  /* 0 one TMA per horizontal tap shift; 1 shared halo tile + shifted UMMA       */
-                      /* descriptors; 2 as 1 with the descriptor base_offset field set               */
+  int32_t halo_mode;  /* 0 one shared halo tile per K chunk + row-shifted UMMA descriptors (default);  */
+                      /* 1 three aligned TMA loads per chunk, one per horizontal tap shift (diagnostic) */
   int32_t b_stages;   /* weight ring depth                                                           */
   int32_t a_stages;   /* activation ring depth                                                       */
   int32_t max_ctas;   /* cap on the persistent grid                                                  */
@@ -163,11 +170,11 @@ int mz_control_film(const float* c_dev, int32_t c_rows, const float* w_dev /*L,2
  * mz_probe_umma: one 128 x 64 x kc UMMA whose A descriptor starts `row_shift` rows into a
  * TMA-swizzled tile; base_offset_mode 0 leaves the descriptor's base_offset 0, 1 sets it to
  * (start >> 7) & 7.  Writes the max abs error against an exact host product.
- * mz_probe_mma_rate: `iters` back-to-back 128 x n x 16 UMMAs per CTA on `ctas` CTAs; writes SM
- * cycles per UMMA (mean over CTAs). */
+ * mz_probe_mma_rate: `iters` back-to-back 128 x n x 16 UMMAs per CTA on `ctas` CTAs, cycling over
+ * `distinct_a` A tiles and `distinct_d` TMEM accumulators; writes SM cycles per UMMA (mean over CTAs). */
 int mz_probe_umma(int32_t kc, int32_t row_shift, int32_t base_offset_mode, float* max_abs_err_out);
 int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_t distinct_a,
-                      float* cycles_per_mma_out);
+                      int32_t distinct_d, float* cycles_per_mma_out);
 
 /* Padded channel counts the kernels use for a logical channel count. */
 int mz_padded_channels(int32_t c);

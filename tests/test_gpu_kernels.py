@@ -1,0 +1,192 @@
+"""GPU: every kernel behind the C ABI against a CPU fp32 reference computed on the SAME bf16-rounded operands
+(torch.nn.functional on the host), including the reference's edge cases: ragged widths (W not a multiple of the
+128-pixel tile), heights not a multiple of the patch rows, single-row images, padded channel counts (54 -> 64,
+108 -> 112), batch > 1, every upscale ratio, both halo modes, SIMT twin vs tcgen05 kernel."""
+import numpy as np
+import pytest
+import torch
+from torch.nn import functional as F
+
+from tests.helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+def _ops():
+    from ultrazoom_b200 import _native, ops
+
+    assert _native.load().mz_device_count() >= 1, "no sm_100 device: the CUDA path cannot run"
+    return ops, _native
+
+
+# Upsample(bicubic): r = 2, 4 have dyadic weights (bit-level agreement with ATen); for r = 3 ATen evaluates
+# t = fp32((ox + 0.5) / 3 - 0.5) per pixel, whose rounding error grows with ox (ulp(W) * slope), while the kernel
+# uses the exact 3-phase table -> tolerance 1e-4.
+@pytest.mark.parametrize("r,tol", [(2, 2e-6), (3, 1e-4), (4, 2e-6)])
+@pytest.mark.parametrize("shape", [(1, 3, 1, 1), (1, 3, 5, 7), (2, 3, 33, 61), (1, 3, 128, 256), (1, 1, 2, 300)])
+def test_bicubic_matches_torch(dev, r, tol, shape):
+    ops, _ = _ops()
+    x = torch.rand(shape, generator=torch.Generator().manual_seed(sum(shape) + r))
+    ref = F.interpolate(x, scale_factor=r, mode="bicubic")
+    got = ops.bicubic(x.to(dev), r).cpu()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("r,tol", [(2, 2e-6), (3, 2e-6), (4, 2e-6)])
+def test_bicubic_matches_reference_fixture(dev, r, tol):
+    ops, _ = _ops()
+    z = np.load(GOLDEN + "/leaf_ops.npz")
+    got = ops.bicubic(torch.from_numpy(z["x"]).to(dev), r).cpu()
+    assert (got - torch.from_numpy(z[f"bicubic_r{r}"])).abs().max().item() <= tol
+
+
+def test_bicubic_rejects_bad_ratio(dev):
+    ops, _ = _ops()
+    with pytest.raises(AssertionError, match="Upscale ratio"):
+        ops.bicubic(torch.rand(1, 3, 4, 4, device=dev), 5)
+
+
+@pytest.mark.parametrize("C", [16, 48, 54, 96])
+def test_stem_pack(dev, C):
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(C)
+    x = torch.rand(2, 3, 9, 11, generator=g)
+    w = torch.randn(C, 3, 1, 1, generator=g) * 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    ref = F.conv2d(x, w, b).permute(0, 2, 3, 1)
+    zf, zb = ops.stem_pack(x.to(dev), w, b)
+    zf, zb = zf.cpu(), zb.cpu().float()
+    assert (zf[..., :C] - ref).abs().max().item() <= 1e-5
+    assert torch.equal(zb, zf.to(torch.bfloat16).float())          # shadow copy is exactly bf16(zf)
+    if zf.shape[-1] > C:
+        assert zf[..., C:].abs().max().item() == 0.0               # padded channels stay zero
+
+
+def test_control_film(dev):
+    ops, _ = _ops()
+    g = torch.Generator().manual_seed(4)
+    L, B, Fc, hC = 3, 2, 3, 108
+    w, bb, c = torch.randn(L, 2 * hC, Fc, generator=g), torch.randn(L, 2 * hC, generator=g), torch.rand(B, Fc, generator=g)
+    gl = torch.einsum("bf,lnf->lbn", c, w) + bb[:, None, :]
+    for cc in (c, c[:1]):                                           # per-image and broadcast control vectors
+        film = ops.control_film(cc.to(dev), w.to(dev), bb.to(dev), B).cpu()
+        ref = gl if cc.shape[0] == B else gl[:, :1].expand(-1, B, -1)
+        assert (film[:, :, 0, :hC] - (1 + ref[..., :hC])).abs().max().item() <= 1e-5
+        assert (film[:, :, 1, :hC] - ref[..., hC:]).abs().max().item() <= 1e-5
+        assert bool((film[:, :, 0, hC:] == 1).all()) and bool((film[:, :, 1, hC:] == 0).all())
+    with pytest.raises(AssertionError, match="Batch size"):
+        ops.control_film(torch.rand(3, Fc, device=dev), w.to(dev), bb.to(dev), B)
+
+
+def _conv_operands(cin, cout, shape, seed, ops):
+    g = torch.Generator().manual_seed(seed)
+    B, H, W = shape
+    cin_p, cout_p = ops.padded_channels(cin), ops.padded_channels(cout)
+    inp = torch.zeros(B, H, W, cin_p, dtype=torch.bfloat16)
+    inp[..., :cin] = torch.randn(B, H, W, cin, generator=g).to(torch.bfloat16)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)
+    film = torch.ones(B, 2, cout_p)
+    film[:, 0, :cout] = 1 + 0.3 * torch.randn(B, cout, generator=g)
+    film[:, 1] = 0
+    film[:, 1, :cout] = 0.3 * torch.randn(B, cout, generator=g)
+    zf0 = torch.zeros(B, H, W, cout_p)
+    zf0[..., :cout] = torch.randn(B, H, W, cout, generator=g)
+    acc = F.conv2d(inp.float().permute(0, 3, 1, 2)[:, :cin], w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    return inp, w, film, zf0, acc
+
+
+CONV_CASES = [
+    # cin, cout, shape (B,H,W), tune
+    (16, 16, (1, 1, 128), dict(rows=1, acc_stages=1)),
+    (16, 32, (1, 1, 1), {}),
+    (32, 32, (1, 5, 130), dict(rows=1)),
+    (64, 64, (1, 5, 130), dict(rows=2)),
+    (48, 96, (2, 13, 150), {}),
+    (96, 192, (1, 21, 300), {}),
+    (54, 108, (1, 10, 70), {}),
+    (96, 192, (2, 30, 260), dict(max_ctas=3)),
+    (96, 192, (1, 9, 257), dict(kc=16, b_stages=2)),
+]
+
+
+@pytest.mark.parametrize("halo_mode", [0, 1])
+@pytest.mark.parametrize("cin,cout,shape,tune", CONV_CASES)
+def test_conv1_film_silu(dev, cin, cout, shape, tune, halo_mode):
+    ops, native = _ops()
+    inp, w, film, _, acc = _conv_operands(cin, cout, shape, 7, ops)
+    ref = F.silu(acc * film[:, 0][:, None, None, :cout] + film[:, 1][:, None, None, :cout])
+    wp = ops.pack_conv_weight(w, dev)
+    got = ops.conv3x3(inp.to(dev), wp, 0, film.to(dev), use_tc=True, tune=native.tune(halo_mode=halo_mode, **tune))
+    simt = ops.conv3x3(inp.to(dev), wp, 0, film.to(dev), use_tc=False)
+    got, simt = got.cpu().float(), simt.cpu().float()
+    tol = 2.0 ** -7 * max(1.0, ref.abs().max().item())           # one bf16 ulp of the largest output + accumulate order
+    assert (got[..., :cout] - ref).abs().max().item() <= tol
+    assert (simt[..., :cout] - ref).abs().max().item() <= tol
+    assert got[..., cout:].abs().max().item() == 0.0 if got.shape[-1] > cout else True
+    nofilm = ops.conv3x3(inp.to(dev), wp, 0, None, use_tc=True, tune=native.tune(halo_mode=halo_mode, **tune)).cpu().float()
+    assert (nofilm[..., :cout] - F.silu(acc)).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("halo_mode", [0, 1])
+@pytest.mark.parametrize("cin,cout,shape,tune", [
+    (96, 48, (2, 13, 150), {}), (192, 96, (1, 21, 300), {}), (108, 54, (1, 10, 70), {}),
+    (192, 96, (2, 30, 260), dict(max_ctas=3)), (32, 16, (1, 1, 5), {}), (192, 96, (1, 7, 129), dict(rows=1, acc_stages=1)),
+])
+def test_conv2_residual(dev, cin, cout, shape, tune, halo_mode):
+    ops, native = _ops()
+    inp, w, _, zf0, acc = _conv_operands(cin, cout, shape, 8, ops)
+    zref = zf0[..., :cout] + acc
+    wp = ops.pack_conv_weight(w, dev)
+    for use_tc in (True, False):
+        zf = zf0.to(dev).contiguous()
+        zb = ops.conv3x3(inp.to(dev), wp, 1, None, zf, use_tc=use_tc, tune=native.tune(halo_mode=halo_mode, **tune))
+        zf, zb = zf.cpu(), zb.cpu()
+        assert (zf[..., :cout] - zref).abs().max().item() <= 1e-4     # fp32 residual stream: accumulate-order noise only
+        assert torch.equal(zb, zf.to(torch.bfloat16))                 # shadow copy is exactly bf16(zf)
+        if zf.shape[-1] > cout:
+            assert zf[..., cout:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("use_tc", [True, False])
+@pytest.mark.parametrize("r,tol", [(2, 1e-4), (3, 2e-4), (4, 1e-4)])
+@pytest.mark.parametrize("cin,shape", [(48, (2, 7, 190)), (96, (1, 9, 129)), (54, (1, 1, 3))])
+def test_head_shuffle_skip_clamp(dev, r, tol, cin, shape, use_tc):
+    ops, native = _ops()
+    g = torch.Generator().manual_seed(9 + r)
+    B, H, W = shape
+    cin_p = ops.padded_channels(cin)
+    zb = torch.zeros(B, H, W, cin_p, dtype=torch.bfloat16)
+    zb[..., :cin] = torch.randn(B, H, W, cin, generator=g).to(torch.bfloat16)
+    w = torch.randn(3 * r * r, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)
+    x = torch.rand(B, 3, H, W, generator=g)
+    wp = ops.pack_conv_weight(w, dev)
+    u = F.pixel_shuffle(F.conv2d(zb.float().permute(0, 3, 1, 2)[:, :cin], w.to(torch.bfloat16).float(), padding=1), r)
+    s = F.interpolate(x, scale_factor=r, mode="bicubic")
+    # skip recomputed in the epilogue, clamped (upscale) and un-clamped (forward)
+    got = ops.head_shuffle_add(zb.to(dev), wp, r, x=x.to(dev), skip_mode=2, clamp01=True, use_tc=use_tc).cpu()
+    assert (got - (u + s).clamp(0, 1)).abs().max().item() <= tol
+    got = ops.head_shuffle_add(zb.to(dev), wp, r, x=x.to(dev), skip_mode=2, clamp01=False, use_tc=use_tc).cpu()
+    assert (got - (u + s)).abs().max().item() <= tol
+    # skip read from a precomputed bicubic buffer
+    y = ops.bicubic(x.to(dev), r)
+    got = ops.head_shuffle_add(zb.to(dev), wp, r, x=None, y=y, skip_mode=1, clamp01=False, use_tc=use_tc).cpu()
+    assert (got - (u + s)).abs().max().item() <= tol
+    # pixel shuffle only
+    got = ops.head_shuffle_add(zb.to(dev), wp, r, skip_mode=0, use_tc=use_tc).cpu()
+    assert (got - u).abs().max().item() <= tol
+
+
+def test_shifted_umma_descriptor_probe(dev):
+    """The hardware property the shared-halo conv relies on: a K-major swizzled A descriptor may
+    start at ANY row of a TMA-written tile when base_offset stays 0."""
+    ops, _ = _ops()
+    for kc in (64, 32, 16):
+        for shift in (0, 1, 2, 7, 130, 131, 132, 256):
+            assert ops.probe_umma(kc, shift, 0) == 0.0

@@ -60,6 +60,8 @@ SIGNATURES = {
     "mz_model_destroy": (None, [_P]),
     "mz_model_set_weight": (C.c_int, [_P, _I, _I, _P, C.c_size_t]),
     "mz_model_set_tune": (C.c_int, [_P, _I, C.POINTER(MzConvTune)]),
+    "mz_model_enable_timing": (C.c_int, [_P, _I]),
+    "mz_model_conv_stack_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "mz_workspace_bytes": (C.c_int, [_P, _I, _I, _I, C.POINTER(C.c_size_t)]),
     "mz_upscale": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _P, C.c_size_t, C.c_uint32, _P]),
     "mz_upscale_host": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, C.c_uint32]),
@@ -70,7 +72,7 @@ SIGNATURES = {
     "mz_pack_conv_weight": (C.c_int, [_P, _I, _I, _I, _I, _P, C.POINTER(C.c_size_t)]),
     "mz_control_film": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mz_probe_umma": (C.c_int, [_I, _I, _I, C.POINTER(C.c_float)]),
-    "mz_probe_mma_rate": (C.c_int, [_I, _I, _I, _I, _I, C.POINTER(C.c_float)]),
+    "mz_probe_mma_rate": (C.c_int, [_I, _I, _I, _I, _I, _I, C.POINTER(C.c_float)]),
     "mz_padded_channels": (C.c_int, [_I]),
 }
 

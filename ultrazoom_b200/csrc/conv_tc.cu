@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u);
         mbar_expect_tx(bar_a_full + 8 * sa, p.a_tx_bytes);
         const uint32_t dstA = a_base + sa * p.a_stage_bytes;
-        if (p.halo_mode == 0) {
+        if (p.halo_mode == 1) {
           const uint32_t per_dx = (p.rows + 2) * kTileW * row_bytes;
           for (int dx = 0; dx < 3; ++dx)
             tma_load_4d(dstA + dx * per_dx, &p.tmA, bar_a_full + 8 * sa, c * p.kc, x0 + dx - 1, y0 - 1, b);
@@ -158,18 +158,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_wait(bar_b_full + 8 * sb, pb);
           tc_fence_after();
           const uint32_t stageB = b_base + sb * p.b_stage_bytes;
-          for (int r = 0; r < p.rows; ++r) {
-            uint32_t a_off;
-            if (p.halo_mode == 0)
-              a_off = static_cast<uint32_t>((dx * (p.rows + 2) + r + dy) * kTileW) * row_bytes;
-            else
-              a_off = static_cast<uint32_t>((r + dy) * p.pw + dx) * row_bytes;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t a_addr = stageA + a_off + ks * 32;
-              const uint32_t b_addr = stageB + ks * 32;
-              const uint32_t bo = p.halo_mode == 2 ? ((a_addr >> 7) & 7u) : 0u;
-              const uint64_t adesc = umma_smem_desc(a_addr, sbo, lt, bo);
-              const uint64_t bdesc = umma_smem_desc(b_addr, sbo, lt, 0);
+          // ks outer / row inner: consecutive UMMAs hit different accumulators
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t b_addr = stageB + ks * 32;
+            const uint64_t bdesc = umma_smem_desc(b_addr, sbo, lt, 0);
+            for (int r = 0; r < p.rows; ++r) {
+              uint32_t a_off;
+              if (p.halo_mode == 1)
+                a_off = static_cast<uint32_t>((dx * (p.rows + 2) + r + dy) * kTileW) * row_bytes;
+              else
+                a_off = static_cast<uint32_t>((r + dy) * p.pw + dx) * row_bytes;
+              const uint64_t adesc = umma_smem_desc(stageA + a_off + ks * 32, sbo, lt, 0);
               umma_bf16(d_base + r * p.acc_stride, adesc, bdesc, p.idesc, (c | tap | ks) != 0 ? 1u : 0u);
             }
           }
@@ -269,8 +268,8 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   p.halo_mode = halo_mode;
   p.a_stages = a_stages;
   p.b_stages = b_stages;
-  p.pw = halo_mode == 0 ? kTileW : kTileW + 2;
-  const int a_bytes = (halo_mode == 0 ? 3 : 1) * (rows + 2) * p.pw * kc * 2;
+  p.pw = halo_mode == 1 ? kTileW : kTileW + 2;
+  const int a_bytes = (halo_mode == 1 ? 3 : 1) * (rows + 2) * p.pw * kc * 2;
   p.a_tx_bytes = a_bytes;
   p.a_stage_bytes = ((a_bytes + 1023) / 1024) * 1024;
   p.b_tx_bytes = p.epi.n_pad * kc * 2;
@@ -290,7 +289,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
              "conv: n_pad must be a multiple of 16 in [16, 256], %d given", e.n_pad);
   MZ_REQUIRE(e.mode >= 0 && e.mode <= 2, "conv: bad epilogue mode %d", e.mode);
   MZ_REQUIRE(e.mode != 2 || e.n_pad <= 48, "head conv: n_pad must be <= 48, %d given", e.n_pad);
-  MZ_REQUIRE(tune.halo_mode >= 0 && tune.halo_mode <= 2, "conv: bad halo_mode %d", tune.halo_mode);
+  MZ_REQUIRE(tune.halo_mode >= 0 && tune.halo_mode <= 1, "conv: bad halo_mode %d", tune.halo_mode);
   MZ_REQUIRE(tune.kc == 0 || ((tune.kc == 16 || tune.kc == 32 || tune.kc == 64) && a.cin_p % tune.kc == 0),
              "conv: kc %d does not divide cin_p %d (or is not 16/32/64)", tune.kc, a.cin_p);
 

@@ -59,9 +59,8 @@ struct ConvTcTune {
   int rows;        // image rows per patch (accumulators per TMEM stage), 1..4
   int acc_stages;  // 1 or 2 TMEM accumulator stages
   int kc;          // K chunk per pipeline stage: 16, 32 or 64 channels
-  int halo_mode;   // 0: one TMA per horizontal tap shift (aligned descriptors)
-                   // 1: one shared halo tile, row-shifted UMMA descriptors, base_offset = 0
-                   // 2: as 1 with base_offset = (start >> 7) & 7
+  int halo_mode;   // 0: one shared halo tile per K chunk, row-shifted UMMA descriptors (default)
+                   // 1: three TMA loads per chunk, one per horizontal tap shift (aligned descriptors; diagnostic)
   int b_stages;    // weight ring depth
   int a_stages;    // activation ring depth
   int max_ctas;    // cap on the persistent grid (0 = SM count)

@@ -35,7 +35,13 @@ struct mz_model {
   float* hc = nullptr;
   size_t hx_bytes = 0, hy_bytes = 0, hc_bytes = 0;
   cudaStream_t stream = nullptr;
+  // optional conv-stack timing
+  bool timing = false;
+  int timing_calls = 0;  // mz_upscale calls recorded since timing was enabled (ring of kTimingSlots)
+  std::vector<cudaEvent_t> ev;  // 2 * kTimingSlots events
 };
+
+static constexpr int kTimingSlots = 64;
 
 namespace {
 
@@ -133,7 +139,7 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   m->headNp = mz_padded_channels(m->headN);
   m->have.assign(3 + 4 * m->L, 0);
   memset(m->tune, 0, sizeof(m->tune));
-  const int hm = env_int("MZ_HALO_MODE", 0);
+  const int hm = env_int("MZ_HALO_MODE", 0);  // 1 = diagnostic per-dx loads
   for (int i = 0; i < 3; ++i) m->tune[i].halo_mode = hm;
 
   DeviceGuard g(cfg->device);
@@ -177,6 +183,7 @@ void mz_model_destroy(mz_model* m) {
   cudaFree(m->hy);
   cudaFree(m->hc);
   if (m->stream) cudaStreamDestroy(m->stream);
+  for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   delete m;
 }
 
@@ -253,6 +260,37 @@ int mz_model_set_tune(mz_model* m, int32_t which, const mz_conv_tune* tune) {
   return MZ_OK;
 }
 
+int mz_model_enable_timing(mz_model* m, int32_t enable) {
+  MZ_REQUIRE(m, "enable_timing: null model");
+  DeviceGuard g(m->cfg.device);
+  if (enable && m->ev.empty()) {
+    m->ev.resize(2 * kTimingSlots, nullptr);
+    for (auto& e : m->ev) MZ_CUDA(cudaEventCreate(&e));
+  }
+  m->timing = enable != 0;
+  m->timing_calls = 0;
+  return MZ_OK;
+}
+
+int mz_model_conv_stack_ms(mz_model* m, float* ms) {
+  MZ_REQUIRE(m && ms, "conv_stack_ms: null pointer");
+  if (!m->timing || m->timing_calls == 0) {
+    set_error("conv_stack_ms: timing is not enabled or no mz_upscale call has been made since");
+    return MZ_ERR_STATE;
+  }
+  DeviceGuard g(m->cfg.device);
+  const int n = m->timing_calls < kTimingSlots ? m->timing_calls : kTimingSlots;
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    float t = 0.f;
+    MZ_CUDA(cudaEventSynchronize(m->ev[2 * i + 1]));
+    MZ_CUDA(cudaEventElapsedTime(&t, m->ev[2 * i], m->ev[2 * i + 1]));
+    sum += t;
+  }
+  *ms = static_cast<float>(sum / n);
+  return MZ_OK;
+}
+
 int mz_workspace_bytes(const mz_model* m, int32_t B, int32_t H, int32_t W, size_t* bytes) {
   MZ_REQUIRE(m && bytes, "workspace_bytes: null pointer");
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "workspace_bytes: empty input (B %d, H %d, W %d)", B, H, W);
@@ -302,6 +340,8 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
   if (rc != MZ_OK) return rc;
 
   const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cp, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
+  const int slot = m->timing_calls % kTimingSlots;
+  if (m->timing) MZ_CUDA(cudaEventRecord(m->ev[2 * slot], s));
   for (int l = 0; l < m->L; ++l) {
     ConvArgs a;
     memset(&a, 0, sizeof(a));
@@ -331,6 +371,11 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     a.epi.zf = zf;
     rc = simt ? launch_conv_simt(a, s) : launch_conv_tc(a, m->tune[1], m->cfg.device, s);
     if (rc != MZ_OK) return rc;
+  }
+
+  if (m->timing) {
+    MZ_CUDA(cudaEventRecord(m->ev[2 * slot + 1], s));
+    ++m->timing_calls;
   }
 
   int skip_mode = 2;

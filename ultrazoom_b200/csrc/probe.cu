@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128, 1) probe_umma_kernel(const __grid_constan
 
 struct RateParams {
   float* out;  // cycles per MMA, one per CTA
-  int n, kc, iters, distinct_a;
+  int n, kc, iters, distinct_a, distinct_d;
   uint32_t tmem_cols;
 };
 
@@ -126,13 +126,14 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(const RateParams p) 
     for (int it = 0; it < p.iters; ++it) {
       const uint32_t a_tile = a_smem + (p.distinct_a > 1 ? (it % p.distinct_a) * 16384 : 0);
       for (int ks = 0; ks < ksteps; ++ks)
-        umma_bf16(tmem_base, umma_smem_desc(a_tile + ks * 32, sbo, lt, 0), umma_smem_desc(b_smem + ks * 32, sbo, lt, 0),
-                  idesc, 1u);
+        for (int d = 0; d < p.distinct_d; ++d)
+          umma_bf16(tmem_base + d * p.n, umma_smem_desc(a_tile + ks * 32, sbo, lt, 0),
+                    umma_smem_desc(b_smem + ks * 32, sbo, lt, 0), idesc, 1u);
     }
     umma_commit(bar_done);
     mbar_wait(bar_done, 0);
     const long long t1 = clock64();
-    p.out[blockIdx.x] = static_cast<float>(t1 - t0) / static_cast<float>(p.iters * ksteps);
+    p.out[blockIdx.x] = static_cast<float>(t1 - t0) / static_cast<float>(p.iters * ksteps * p.distinct_d);
   }
   tc_fence_before();
   __syncthreads();
@@ -226,12 +227,13 @@ int mz_probe_umma(int32_t kc, int32_t row_shift, int32_t base_offset_mode, float
   return rc;
 }
 
-int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_t distinct_a,
+int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_t distinct_a, int32_t distinct_d,
                       float* cycles_per_mma_out) {
   MZ_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "probe: n must be a multiple of 16 in [16, 256]");
   MZ_REQUIRE(kc == 16 || kc == 32 || kc == 64, "probe: kc must be 16, 32 or 64");
   MZ_REQUIRE(iters > 0 && iters <= (1 << 20) && ctas > 0 && ctas <= 4096, "probe: bad iters/ctas");
   MZ_REQUIRE(distinct_a >= 1 && distinct_a <= 8, "probe: distinct_a must be 1..8");
+  MZ_REQUIRE(distinct_d >= 1 && distinct_d * n <= 512, "probe: distinct_d * n must fit 512 TMEM columns");
   MZ_REQUIRE(cycles_per_mma_out, "probe: null output");
   float* dOut = nullptr;
   MZ_CUDA(cudaMalloc(&dOut, sizeof(float) * ctas));
@@ -241,8 +243,9 @@ int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_
   p.kc = kc;
   p.iters = iters;
   p.distinct_a = distinct_a;
+  p.distinct_d = distinct_d;
   p.tmem_cols = 32;
-  while (p.tmem_cols < static_cast<uint32_t>(n)) p.tmem_cols <<= 1;
+  while (p.tmem_cols < static_cast<uint32_t>(n * distinct_d)) p.tmem_cols <<= 1;
   const int smem = 1024 + 8 * 16384 + 32768 + 64;
   int rc = MZ_OK;
   cudaError_t e = cudaFuncSetAttribute(probe_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
