@@ -53,7 +53,15 @@ typedef struct mz_config {
   int32_t num_encoder_layers; /* L                                                   */
   int32_t control_features;   /* 0 or 3      (ControlVector, README.md:118-122)      */
   int32_t device;             /* CUDA device ordinal                                 */
+  int32_t operand_dtype;      /* MZ_DTYPE_F16 (default) or MZ_DTYPE_BF16: element type of  */
+                              /* the tensor-core operands (activations + weights).  Both run */
+                              /* at the same tcgen05 rate; accumulation and the residual     */
+                              /* stream are fp32 either way.  fp16's 10-bit mantissa keeps   */
+                              /* max|err| vs the fp32 reference ~8x smaller.     */
 } mz_config;
+
+#define MZ_DTYPE_F16 0
+#define MZ_DTYPE_BF16 1
 
 typedef struct mz_model mz_model; /* opaque */
 
@@ -79,7 +87,7 @@ int mz_model_create(const mz_config* cfg, mz_model** out);
 void mz_model_destroy(mz_model* m);
 
 /* Upload one fp32 HOST tensor in PyTorch layout (OIHW for convs); it is repacked to the
- * bf16 K-major tap-blocked layout the tcgen05 kernels read.  `layer` is ignored for
+ * 16-bit K-major per-tap layout the tcgen05 kernels read.  `layer` is ignored for
  * stem/head kinds.  `numel` must match the shape implied by the config. */
 int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* host_data, size_t numel);
 
@@ -132,20 +140,21 @@ int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, 
                    void* stream);
 
 /* FanOutProjection (model.py:212-242) fused with the NCHW->NHWC layout change:
- * zf (B,H,W,Cp) fp32 residual stream and zb (B,H,W,Cp) bf16 MMA operand.
+ * zf (B,H,W,Cp) fp32 residual stream and zb (B,H,W,Cp) 16-bit MMA operand (operand_dtype).
  * w_dev is (Cp,3) fp32 and bias_dev (Cp,) fp32, zero-padded beyond the logical channel count. */
 int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev,
-                 int32_t B, int32_t H, int32_t W, int32_t Cp, void* stream);
+                 int32_t B, int32_t H, int32_t W, int32_t Cp, int32_t operand_dtype, void* stream);
 
-/* 3x3 / pad 1 / stride 1 / bias-free convolution on NHWC bf16 (model.py:742-748) with the
- * fused epilogues of one encoder block.  `wpacked_dev` comes from mz_pack_conv_weight.
- *   mode 0: out_bf16 = SiLU(scale[b,n]*acc + shift[b,n])   (conv1 + control + SiLU); film_dev is
+/* 3x3 / pad 1 / stride 1 / bias-free convolution on NHWC 16-bit activations (model.py:742-748) with
+ * the fused epilogues of one encoder block.  `wpacked_dev` comes from mz_pack_conv_weight; input, weights
+ * and the 16-bit output all have element type operand_dtype.
+ *   mode 0: out16 = SiLU(scale[b,n]*acc + shift[b,n])   (conv1 + control + SiLU); film_dev is
  *           (B,2,cout_p) fp32 -- scale row then shift row per image -- or NULL for scale 1, shift 0
- *   mode 1: zf += acc ; out_bf16 = bf16(zf)                 (conv2 + ResidualConnection, model.py:789-792)
+ *   mode 1: zf += acc ; out16 = round16(zf)              (conv2 + ResidualConnection, model.py:789-792)
  * use_tc = 1: tcgen05/TMEM/TMA kernel; 0: SIMT diagnostic kernel.  tune may be NULL. */
-int mz_conv3x3_bf16(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev,
-                    void* out_bf16_dev, float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p,
-                    int32_t cout_p, int32_t use_tc, const mz_conv_tune* tune, void* stream);
+int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev,
+               void* out16_dev, float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t cout_p,
+               int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream);
 
 /* SubpixelConv2d (model.py:885-930) + global skip (model.py:162) + optional clamp (:177):
  * y = [clamp](skip + PixelShuffle_r(conv3x3(z))).  skip_mode 0: none, 1: read y_dev in place
@@ -153,12 +162,13 @@ int mz_conv3x3_bf16(const void* in_dev, const void* wpacked_dev, int32_t mode, c
  * wpacked_dev has cout_p = mz_padded_channels(3*r*r) rows per tap. */
 int mz_head_shuffle_add(const void* zb_dev, const void* wpacked_dev, const float* x_dev, float* y_dev,
                         int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t r, int32_t skip_mode,
-                        int32_t clamp01, int32_t use_tc, const mz_conv_tune* tune, void* stream);
+                        int32_t clamp01, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune,
+                        void* stream);
 
-/* Repack OIHW fp32 (host) -> device bf16 [tap = ky*3+kx][cout_p][cin_p] (K-major rows; the TMA
+/* Repack OIHW fp32 (host) -> device fp16|bf16 [tap = ky*3+kx][cout_p][cin_p] (K-major rows; the TMA
  * applies the shared-memory swizzle).  With dst_dev == NULL only *bytes is written. */
 int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t cout_p, int32_t cin_p,
-                        void* dst_dev, size_t* bytes);
+                        int32_t operand_dtype, void* dst_dev, size_t* bytes);
 
 /* FiLM coefficients for every layer: film[l][b][0][n] = 1 + gamma, film[l][b][1][n] = beta,
  * from c (B or 1 rows) and the per-layer Linear(F, 2hC) weights (control module; README.md:11,88). */

@@ -1,9 +1,13 @@
 """GPU parity proper: MewZoom (C ABI, sm_100a kernels) vs the oracle and vs fixtures made by the reference's own
-leaf classes.  Tolerances (BASELINE.json envelope: max-abs <= 2e-2 on [0,1] pixels, PSNR >= 45 dB), stated per config:
-    2X (48 ch / 20 layers):  max-abs <= 1.0e-2, PSNR >= 55 dB
-    3X (54 ch / 30 layers):  max-abs <= 1.5e-2, PSNR >= 52 dB
-    4X (96 ch / 40 layers):  max-abs <= 2.0e-2, PSNR >= 50 dB
-(bf16 MMA operands, fp32 accumulation, fp32 residual stream -- SURVEY.md Appendix B.2.)"""
+leaf classes.  BASELINE.json envelope: max-abs <= 2e-2 on [0,1] pixels, PSNR >= 45 dB.  Stated per config, for the
+default fp16 tensor-core operands (fp32 accumulation, fp32 residual stream), un-clamped forward AND clamped upscale,
+per-image random control vectors:
+    2X (48 ch / 20 layers):  max-abs <= 4e-3, PSNR >= 64 dB
+    3X (54 ch / 30 layers):  max-abs <= 6e-3, PSNR >= 62 dB
+    4X (96 ch / 40 layers):  max-abs <= 8e-3, PSNR >= 60 dB
+and for operand_dtype="bfloat16" (the type BASELINE.json's north_star names; 8x coarser mantissa), README control
+vector (0.5, 0.2, 0.3):   max-abs <= 2e-2, PSNR >= 50 dB on these test sizes -- at full frame size the 3X/4X
+bf16 variants exceed 2e-2 (CPU emulation: 0.0206 at 256x256 for 4X-Ctrl), which is why fp16 is the default."""
 import pytest
 import torch
 
@@ -12,7 +16,7 @@ from tests.helpers import CASES, load_case, oracle_from_case
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"MewZoom-2X": (1.0e-2, 55.0), "MewZoom-3X": (1.5e-2, 52.0), "MewZoom-4X": (2.0e-2, 50.0)}
+TOL = {"MewZoom-2X": (4e-3, 64.0), "MewZoom-3X": (6e-3, 62.0), "MewZoom-4X": (8e-3, 60.0)}
 
 
 @pytest.fixture(scope="module")
@@ -21,10 +25,10 @@ def dev():
     return torch.device("cuda", 0)
 
 
-def _model_from(cfg, sd, dev):
+def _model_from(cfg, sd, dev, operand_dtype="float16"):
     from ultrazoom_b200 import MewZoom
 
-    m = MewZoom(**cfg)
+    m = MewZoom(**cfg, operand_dtype=operand_dtype)
     m.load_state_dict(sd)
     return m.to(dev).eval()
 
@@ -36,8 +40,8 @@ def test_reference_fixtures(dev, name):
     cd = c.to(dev) if c is not None else None
     y = m.forward(x.to(dev), cd).cpu()
     yc = m.upscale(x.to(dev), cd).cpu()
-    assert max_abs_err(y, out["forward"]) <= 1e-2 and max_abs_err(yc, out["upscale"]) <= 1e-2
-    assert psnr(yc, out["upscale"]) >= 55.0
+    assert max_abs_err(y, out["forward"]) <= 2e-3 and max_abs_err(yc, out["upscale"]) <= 2e-3
+    assert psnr(yc, out["upscale"]) >= 70.0
     assert float(yc.min()) >= 0.0 and float(yc.max()) <= 1.0          # reference tests/test_model.py:161-169
     # SIMT twin and the diagnostic halo mode give the same answer within accumulate-order noise
     from ultrazoom_b200 import _native
@@ -47,9 +51,12 @@ def test_reference_fixtures(dev, name):
     m._flags_extra = _native.FLAG_SKIP_FROM_BUFFER
     yb = m.forward(x.to(dev), cd).cpu()
     m._flags_extra = 0
-    assert max_abs_err(ys, y) <= 5e-3 and max_abs_err(yb, y) <= 1e-5
+    assert max_abs_err(ys, y) <= 1e-3 and max_abs_err(yb, y) <= 1e-5
     m.set_conv_tune(-1, dev, halo_mode=1)
-    assert max_abs_err(m.forward(x.to(dev), cd).cpu(), y) <= 5e-3
+    assert max_abs_err(m.forward(x.to(dev), cd).cpu(), y) <= 1e-3
+    # bf16 operands: the coarser variant still reproduces the reference fixture within the envelope
+    mb = _model_from(cfg, sd, dev, "bfloat16")
+    assert max_abs_err(mb.upscale(x.to(dev), cd).cpu(), out["upscale"]) <= 1e-2
 
 
 @pytest.mark.parametrize("name,shape", [
@@ -73,6 +80,14 @@ def test_named_models_against_oracle(dev, name, shape):
     assert max_abs_err(got_f, ref_f) <= tol_abs, max_abs_err(got_f, ref_f)
     assert max_abs_err(got_u, ref_u) <= tol_abs
     assert psnr(got_u, ref_u) >= tol_psnr, psnr(got_u, ref_u)
+    if o.control_features:
+        mb = _model_from(dict(upscale_ratio=o.upscale_ratio, num_channels=o.num_channels, hidden_ratio=o.hidden_ratio,
+                              num_encoder_layers=o.num_encoder_layers, control_features=o.control_features),
+                         o.state_dict(), dev, "bfloat16")
+        cr = torch.tensor([[0.5, 0.2, 0.3]])
+        ref_b = o.upscale(x, cr)
+        got_b = mb.upscale(x.to(dev), cr.to(dev)).cpu()
+        assert max_abs_err(got_b, ref_b) <= 2e-2 and psnr(got_b, ref_b) >= 50.0
 
 
 def test_control_vector_broadcast_and_api(dev):
@@ -87,7 +102,7 @@ def test_control_vector_broadcast_and_api(dev):
     a = m.upscale(x.to(dev), c.to(dev)).cpu()                            # (3,) broadcast
     b = m.upscale(x.to(dev), c.repeat(2, 1).to(dev)).cpu()               # (B,3) as validate.py:73-94
     assert torch.equal(a, b)
-    assert max_abs_err(a, ref) <= 1e-2
+    assert max_abs_err(a, ref) <= 4e-3
     assert max_abs_err(ONNXModel(m)(x.to(dev), c.to(dev)).cpu(), a) == 0.0
     h = m.upscale_host(x, c)                                             # host-buffer entry point
     assert max_abs_err(h, a) == 0.0
@@ -122,4 +137,4 @@ def test_size_independent_properties_at_full_size(dev):
     R = 41
     crop = x[:1, :, :64 + R, :64 + R].cpu()
     ref = o.upscale(crop, c[:1].cpu())[:, :, :128, :128]
-    assert max_abs_err(y[:1, :, :128, :128].cpu(), ref) <= 1e-2
+    assert max_abs_err(y[:1, :, :128, :128].cpu(), ref) <= 4e-3

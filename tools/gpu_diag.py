@@ -116,7 +116,7 @@ def _conv_case(group, use_tc, tune_kw, cin, cout, mode, shape, gen, with_film=Tr
     inp = torch.zeros(B, H, W, cin_p, dtype=torch.bfloat16)
     inp[..., :cin] = _rand_bf16((B, H, W, cin), gen)
     w = torch.randn(cout, cin, 3, 3, generator=gen) / (3.0 * cin ** 0.5)
-    wp = ops.pack_conv_weight(w, dev)
+    wp = ops.pack_conv_weight(w, dev, dtype=torch.bfloat16)
     film = None
     if mode == 0 and with_film:
         film = torch.ones(B, 2, cout_p)
@@ -157,7 +157,7 @@ def _head_case(group, use_tc, tune_kw, cin, r, shape, gen, skip_mode, clamp):
     zb[..., :cin] = _rand_bf16((B, H, W, cin), gen)
     w = torch.randn(3 * r * r, cin, 3, 3, generator=gen) / (3.0 * cin ** 0.5)
     x = torch.rand(B, 3, H, W, generator=gen)
-    wp = ops.pack_conv_weight(w, dev)
+    wp = ops.pack_conv_weight(w, dev, dtype=torch.bfloat16)
     u = F.pixel_shuffle(F.conv2d(zb.float().permute(0, 3, 1, 2)[:, :cin], w.to(torch.bfloat16).float(), padding=1), r)
     s = F.interpolate(x, scale_factor=r, mode="bicubic")
     ref = u + (s if skip_mode else 0)

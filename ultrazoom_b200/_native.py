@@ -23,6 +23,8 @@ FLAG_CLAMP01 = 1
 FLAG_SIMT_CONV = 2
 FLAG_SKIP_FROM_BUFFER = 4
 
+DTYPE_F16, DTYPE_BF16 = 0, 1
+
 W_STEM_WEIGHT, W_STEM_BIAS, W_CONV1, W_CONV2, W_CTRL_WEIGHT, W_CTRL_BIAS, W_HEAD = range(7)
 
 
@@ -34,6 +36,7 @@ class MzConfig(C.Structure):
         ("num_encoder_layers", C.c_int32),
         ("control_features", C.c_int32),
         ("device", C.c_int32),
+        ("operand_dtype", C.c_int32),
     ]
 
 
@@ -66,10 +69,10 @@ SIGNATURES = {
     "mz_upscale": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _P, C.c_size_t, C.c_uint32, _P]),
     "mz_upscale_host": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, C.c_uint32]),
     "mz_bicubic_f32": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
-    "mz_stem_pack": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "mz_conv3x3_bf16": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
-    "mz_head_shuffle_add": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
-    "mz_pack_conv_weight": (C.c_int, [_P, _I, _I, _I, _I, _P, C.POINTER(C.c_size_t)]),
+    "mz_stem_pack": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mz_conv3x3": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
+    "mz_head_shuffle_add": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
+    "mz_pack_conv_weight": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, C.POINTER(C.c_size_t)]),
     "mz_control_film": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mz_probe_umma": (C.c_int, [_I, _I, _I, C.POINTER(C.c_float)]),
     "mz_probe_mma_rate": (C.c_int, [_I, _I, _I, _I, _I, _I, C.POINTER(C.c_float)]),
@@ -118,6 +121,16 @@ def check(rc: int) -> None:
     if rc == MZ_ERR_INVALID:
         raise AssertionError(msg)
     raise RuntimeError(f"mewzoom_b200 error {rc}: {msg}")
+
+
+def dtype_code(dt) -> int:
+    """torch.float16 / 'f16' -> MZ_DTYPE_F16, torch.bfloat16 / 'bf16' -> MZ_DTYPE_BF16."""
+    name = str(dt).replace("torch.", "")
+    if name in ("float16", "f16", "fp16", "half"):
+        return DTYPE_F16
+    if name in ("bfloat16", "bf16"):
+        return DTYPE_BF16
+    raise AssertionError(f"Operand dtype must be float16 or bfloat16, {dt} given.")
 
 
 def tune(**kw) -> MzConvTune:

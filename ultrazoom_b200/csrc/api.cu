@@ -26,15 +26,27 @@ int current_device() {
   return d;
 }
 
-// OIHW fp32 -> [tap][cout_p][cin_p] bf16 (zero padded), host side.
-void pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, std::vector<__nv_bfloat16>& out) {
-  out.assign(static_cast<size_t>(9) * cout_p * cin_p, __float2bfloat16_rn(0.f));
+// OIHW fp32 -> [tap][cout_p][cin_p] fp16 | bf16 bits (zero padded), host side.
+void pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, int bf16,
+                           std::vector<uint16_t>& out) {
+  out.assign(static_cast<size_t>(9) * cout_p * cin_p, 0);
   for (int o = 0; o < cout; ++o)
     for (int i = 0; i < cin; ++i)
-      for (int t = 0; t < 9; ++t)
-        out[(static_cast<size_t>(t) * cout_p + o) * cin_p + i] =
-            __float2bfloat16_rn(w[(static_cast<size_t>(o) * cin + i) * 9 + t]);
+      for (int t = 0; t < 9; ++t) {
+        const float v = w[(static_cast<size_t>(o) * cin + i) * 9 + t];
+        uint16_t bits;
+        if (bf16) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          memcpy(&bits, &h, 2);
+        } else {
+          const __half h = __float2half_rn(v);
+          memcpy(&bits, &h, 2);
+        }
+        out[(static_cast<size_t>(t) * cout_p + o) * cin_p + i] = bits;
+      }
 }
+
+bool dtype_ok(int d) { return d == MZ_DTYPE_F16 || d == MZ_DTYPE_BF16; }
 
 }  // namespace mz
 
@@ -48,30 +60,33 @@ int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, 
 }
 
 int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev, int32_t B,
-                 int32_t H, int32_t W, int32_t Cp, void* stream) {
+                 int32_t H, int32_t W, int32_t Cp, int32_t operand_dtype, void* stream) {
   MZ_REQUIRE(x_dev && w_dev && bias_dev && zf_dev && zb_dev, "stem: null pointer");
-  return launch_stem(x_dev, w_dev, bias_dev, zf_dev, static_cast<__nv_bfloat16*>(zb_dev), B, H, W, Cp,
+  MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
+  return launch_stem(x_dev, w_dev, bias_dev, zf_dev, static_cast<uint16_t*>(zb_dev), operand_dtype, B, H, W, Cp,
                      static_cast<cudaStream_t>(stream));
 }
 
-int mz_conv3x3_bf16(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev,
-                    void* out_bf16_dev, float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t cout_p,
-                    int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev, void* out_bf16_dev,
+               float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t cout_p, int32_t operand_dtype,
+               int32_t use_tc, const mz_conv_tune* tune, void* stream) {
   MZ_REQUIRE(in_dev && wpacked_dev && out_bf16_dev, "conv: null pointer");
+  MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
   MZ_REQUIRE(mode == 0 || mode == 1, "conv: mode must be 0 or 1, %d given", mode);
   MZ_REQUIRE(mode == 0 || zf_dev, "conv: mode 1 needs the fp32 residual stream");
   ConvArgs a;
   memset(&a, 0, sizeof(a));
-  a.in = static_cast<const __nv_bfloat16*>(in_dev);
-  a.w = static_cast<const __nv_bfloat16*>(wpacked_dev);
+  a.in = static_cast<const uint16_t*>(in_dev);
+  a.w = static_cast<const uint16_t*>(wpacked_dev);
   a.cin_p = cin_p;
+  a.epi.bf16 = operand_dtype == MZ_DTYPE_BF16;
   a.epi.mode = mode;
   a.epi.B = B;
   a.epi.H = H;
   a.epi.W = W;
   a.epi.n_pad = cout_p;
   a.epi.film = film_dev;
-  a.epi.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16_dev);
+  a.epi.out_bf16 = static_cast<uint16_t*>(out_bf16_dev);
   a.epi.zf = zf_dev;
   if (use_tc) return launch_conv_tc(a, to_tune(tune), current_device(), static_cast<cudaStream_t>(stream));
   return launch_conv_simt(a, static_cast<cudaStream_t>(stream));
@@ -79,16 +94,18 @@ int mz_conv3x3_bf16(const void* in_dev, const void* wpacked_dev, int32_t mode, c
 
 int mz_head_shuffle_add(const void* zb_dev, const void* wpacked_dev, const float* x_dev, float* y_dev, int32_t B,
                         int32_t H, int32_t W, int32_t cin_p, int32_t r, int32_t skip_mode, int32_t clamp01,
-                        int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+                        int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream) {
   MZ_REQUIRE(zb_dev && wpacked_dev && y_dev, "head: null pointer");
+  MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
   MZ_REQUIRE(r == 2 || r == 3 || r == 4, "Upscale ratio must be either 2, 3, or 4, %d given.", r);
   MZ_REQUIRE(skip_mode >= 0 && skip_mode <= 2, "head: skip_mode must be 0, 1 or 2, %d given", skip_mode);
   MZ_REQUIRE(skip_mode != 2 || x_dev, "head: skip_mode 2 needs the LR image");
   ConvArgs a;
   memset(&a, 0, sizeof(a));
-  a.in = static_cast<const __nv_bfloat16*>(zb_dev);
-  a.w = static_cast<const __nv_bfloat16*>(wpacked_dev);
+  a.in = static_cast<const uint16_t*>(zb_dev);
+  a.w = static_cast<const uint16_t*>(wpacked_dev);
   a.cin_p = cin_p;
+  a.epi.bf16 = operand_dtype == MZ_DTYPE_BF16;
   a.epi.mode = 2;
   a.epi.B = B;
   a.epi.H = H;
@@ -104,17 +121,18 @@ int mz_head_shuffle_add(const void* zb_dev, const void* wpacked_dev, const float
   return launch_conv_simt(a, static_cast<cudaStream_t>(stream));
 }
 
-int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t cout_p, int32_t cin_p, void* dst_dev,
-                        size_t* bytes) {
+int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t cout_p, int32_t cin_p,
+                        int32_t operand_dtype, void* dst_dev, size_t* bytes) {
+  MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
   MZ_REQUIRE(cout > 0 && cin > 0 && cout_p >= cout && cin_p >= cin, "pack: bad shape (%d,%d)->(%d,%d)", cout, cin,
              cout_p, cin_p);
   MZ_REQUIRE(cout_p % 16 == 0 && cin_p % 16 == 0, "pack: padded sizes must be multiples of 16");
-  const size_t n = static_cast<size_t>(9) * cout_p * cin_p * sizeof(__nv_bfloat16);
+  const size_t n = static_cast<size_t>(9) * cout_p * cin_p * sizeof(uint16_t);
   if (bytes) *bytes = n;
   if (!dst_dev) return MZ_OK;
   MZ_REQUIRE(w_host, "pack: null weight pointer");
-  std::vector<__nv_bfloat16> tmp;
-  pack_conv_weight_host(w_host, cout, cin, cout_p, cin_p, tmp);
+  std::vector<uint16_t> tmp;
+  pack_conv_weight_host(w_host, cout, cin, cout_p, cin_p, operand_dtype == MZ_DTYPE_BF16, tmp);
   MZ_CUDA(cudaMemcpy(dst_dev, tmp.data(), n, cudaMemcpyHostToDevice));
   return MZ_OK;
 }

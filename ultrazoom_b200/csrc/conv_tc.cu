@@ -1,6 +1,6 @@
 // conv_tc.cu -- 3x3 / pad 1 / stride 1 convolution as an implicit GEMM on the 5th-gen tensor cores.
 //
-//   D[128 pixels, N] += A[128 pixels, K = (tap, cin)] * W[N, K]^T        (bf16 x bf16 -> fp32 in TMEM)
+//   D[128 pixels, N] += A[128 pixels, K = (tap, cin)] * W[N, K]^T        (fp16 | bf16 operands -> fp32 in TMEM)
 //
 // Replaces InvertedBottleneck.conv1/conv2 (reference model.py:742-748,773-778) and
 // SubpixelConv2d.conv (model.py:902-909) with their elementwise successors fused in the epilogue.
@@ -57,7 +57,7 @@ __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
   return s;
 }
 
-template <int MODE>
+template <int MODE, int KSTEPS>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -107,9 +107,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int row_bytes = p.kc * 2;
   const int units_per_img = p.tiles_x * p.tiles_y;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0) {
     // =============================== TMA producer ===============================
+    // The whole warp walks the (uniform) loop so that addresses stay in uniform registers; lane 0 issues.
     uint32_t a_it = 0, b_it = 0;
+    const uint32_t per_dx = (p.rows + 2) * kTileW * row_bytes;
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
       const int b = unit / units_per_img;
       const int rem = unit - b * units_per_img;
@@ -118,30 +120,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int c = 0; c < p.n_chunks; ++c) {
         const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1u;
         mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u);
-        mbar_expect_tx(bar_a_full + 8 * sa, p.a_tx_bytes);
         const uint32_t dstA = a_base + sa * p.a_stage_bytes;
-        if (p.halo_mode == 1) {
-          const uint32_t per_dx = (p.rows + 2) * kTileW * row_bytes;
-          for (int dx = 0; dx < 3; ++dx)
-            tma_load_4d(dstA + dx * per_dx, &p.tmA, bar_a_full + 8 * sa, c * p.kc, x0 + dx - 1, y0 - 1, b);
-        } else {
-          tma_load_4d(dstA, &p.tmA, bar_a_full + 8 * sa, c * p.kc, x0 - 1, y0 - 1, b);
+        if (lane == 0) {
+          mbar_expect_tx(bar_a_full + 8 * sa, p.a_tx_bytes);
+          if (p.halo_mode == 1) {
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_4d(dstA + dx * per_dx, &p.tmA, bar_a_full + 8 * sa, c * p.kc, x0 + dx - 1, y0 - 1, b);
+          } else {
+            tma_load_4d(dstA, &p.tmA, bar_a_full + 8 * sa, c * p.kc, x0 - 1, y0 - 1, b);
+          }
         }
         ++a_it;
         for (int tap = 0; tap < 9; ++tap) {
           const uint32_t sb = b_it % p.b_stages, pb = (b_it / p.b_stages) & 1u;
           mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u);
-          mbar_expect_tx(bar_b_full + 8 * sb, p.b_tx_bytes);
-          tma_load_3d(b_base + sb * p.b_stage_bytes, &p.tmB, bar_b_full + 8 * sb, c * p.kc, 0, tap);
+          if (lane == 0) {
+            mbar_expect_tx(bar_b_full + 8 * sb, p.b_tx_bytes);
+            tma_load_3d(b_base + sb * p.b_stage_bytes, &p.tmB, bar_b_full + 8 * sb, c * p.kc, 0, tap);
+          }
           ++b_it;
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // =============================== MMA issuer ===============================
+    // Uniform loop over the whole warp, lane 0 issues tcgen05.mma / tcgen05.commit.  Descriptors are built once:
+    // the high word is constant, the low word (start address >> 4) advances by plain 32-bit adds.
     const uint32_t lt = umma_layout_type(p.kc);
     const uint32_t sbo = 8u * row_bytes;
-    const int ksteps = p.kc / 16;
+    const uint32_t desc_hi = static_cast<uint32_t>(umma_smem_desc(0, sbo, lt, 0) >> 32);
+    const uint32_t desc_lo0 = static_cast<uint32_t>(umma_smem_desc(0, sbo, lt, 0));
+    // tap (dy, dx) and accumulator row r start at dy * DY + dx * DX + r * RP sixteen-byte units into the A stage
+    uint32_t DY, DX, RP;
+    if (p.halo_mode == 1) {
+      DX = ((p.rows + 2) * kTileW * row_bytes) >> 4;
+      DY = (kTileW * row_bytes) >> 4;
+      RP = DY;
+    } else {
+      DX = row_bytes >> 4;
+      DY = (p.pw * row_bytes) >> 4;
+      RP = DY;
+    }
+    const bool leader = elect_one();  // the same lane issues every tcgen05.mma and tcgen05.commit
     uint32_t a_it = 0, b_it = 0, acc_it = 0;
     for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
       const uint32_t as = acc_it % p.acc_stages, pacc = (acc_it / p.acc_stages) & 1u;
@@ -151,36 +171,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int c = 0; c < p.n_chunks; ++c) {
         const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1u;
         mbar_wait(bar_a_full + 8 * sa, pa);
-        const uint32_t stageA = a_base + sa * p.a_stage_bytes;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3, dx = tap - dy * 3;
-          const uint32_t sb = b_it % p.b_stages, pb = (b_it / p.b_stages) & 1u;
-          mbar_wait(bar_b_full + 8 * sb, pb);
-          tc_fence_after();
-          const uint32_t stageB = b_base + sb * p.b_stage_bytes;
-          // ks outer / row inner: consecutive UMMAs hit different accumulators
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t b_addr = stageB + ks * 32;
-            const uint64_t bdesc = umma_smem_desc(b_addr, sbo, lt, 0);
-            for (int r = 0; r < p.rows; ++r) {
-              uint32_t a_off;
-              if (p.halo_mode == 1)
-                a_off = static_cast<uint32_t>((dx * (p.rows + 2) + r + dy) * kTileW) * row_bytes;
-              else
-                a_off = static_cast<uint32_t>((r + dy) * p.pw + dx) * row_bytes;
-              const uint64_t adesc = umma_smem_desc(stageA + a_off + ks * 32, sbo, lt, 0);
-              umma_bf16(d_base + r * p.acc_stride, adesc, bdesc, p.idesc, (c | tap | ks) != 0 ? 1u : 0u);
+        const uint32_t a_lo_stage = desc_lo0 + ((a_base + sa * p.a_stage_bytes) >> 4);
+        uint32_t first = c == 0 ? 0u : 1u;  // accumulate flag of the first UMMA of this tap
+        for (int dy = 0; dy < 3; ++dy) {
+          for (int dx = 0; dx < 3; ++dx) {
+            const uint32_t sb = b_it % p.b_stages, pb = (b_it / p.b_stages) & 1u;
+            mbar_wait(bar_b_full + 8 * sb, pb);
+            tc_fence_after();
+            const uint32_t b_lo = desc_lo0 + ((b_base + sb * p.b_stage_bytes) >> 4);
+            const uint32_t a_lo_tap = a_lo_stage + dy * DY + dx * DX;
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+              const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * ks);
+              uint32_t a_lo = a_lo_tap + 2 * ks;
+              uint32_t d = d_base;
+              const uint32_t accum = ks == 0 ? first : 1u;
+              for (int r = 0; r < p.rows; ++r) {
+                const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | a_lo;
+                if (leader) umma_bf16(d, adesc, bdesc, p.idesc, accum);
+                a_lo += RP;
+                d += p.acc_stride;
+              }
             }
+            if (leader) umma_commit(bar_b_empty + 8 * sb);
+            first = 1u;
+            ++b_it;
           }
-          umma_commit(bar_b_empty + 8 * sb);
-          ++b_it;
         }
-        umma_commit(bar_a_empty + 8 * sa);
+        if (leader) umma_commit(bar_a_empty + 8 * sa);
         ++a_it;
       }
-      umma_commit(bar_acc_full + 8 * as);
+      if (leader) umma_commit(bar_acc_full + 8 * as);
       ++acc_it;
     }
+    __syncwarp();
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
     const int q = warp - 4;  // TMEM lane quarter this warp may read (== warp % 4)
@@ -330,7 +354,8 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   const long long n_units = static_cast<long long>(e.B) * p.tiles_x * p.tiles_y;
   MZ_REQUIRE(n_units < (1LL << 31), "conv: too many patches (%lld)", n_units);
   p.n_units = static_cast<int>(n_units);
-  p.idesc = umma_idesc_bf16(128, e.n_pad);
+  p.idesc = e.bf16 ? umma_idesc_bf16(128, e.n_pad) : umma_idesc_f16(128, e.n_pad);
+  const CUtensorMapDataType tdt = e.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 
   const CUtensorMapSwizzle swz =
       p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -341,16 +366,14 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
                                  static_cast<uint64_t>(e.H) * e.W * a.cin_p * 2};
     const uint32_t box[4] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.pw),
                              static_cast<uint32_t>(p.rows + 2), 1u};
-    int rc = encode_tmap(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(a.in), dims, strides,
-                         box, swz);
+    int rc = encode_tmap(&p.tmA, tdt, 4, const_cast<uint16_t*>(a.in), dims, strides, box, swz);
     if (rc != MZ_OK) return rc;
   }
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(a.cin_p), static_cast<uint64_t>(e.n_pad), 9};
     const uint64_t strides[2] = {static_cast<uint64_t>(a.cin_p) * 2, static_cast<uint64_t>(e.n_pad) * a.cin_p * 2};
     const uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(e.n_pad), 1u};
-    int rc = encode_tmap(&p.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<__nv_bfloat16*>(a.w), dims, strides,
-                         box, swz);
+    int rc = encode_tmap(&p.tmB, tdt, 3, const_cast<uint16_t*>(a.w), dims, strides, box, swz);
     if (rc != MZ_OK) return rc;
   }
 
@@ -366,9 +389,10 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     MZ_CUDA(cudaGetLastError());
     return MZ_OK;
   };
-  if (e.mode == 0) return launch(conv_tc_kernel<0>);
-  if (e.mode == 1) return launch(conv_tc_kernel<1>);
-  return launch(conv_tc_kernel<2>);
+  const int ks = p.kc / 16;
+  if (e.mode == 0) return ks == 4 ? launch(conv_tc_kernel<0, 4>) : (ks == 2 ? launch(conv_tc_kernel<0, 2>) : launch(conv_tc_kernel<0, 1>));
+  if (e.mode == 1) return ks == 4 ? launch(conv_tc_kernel<1, 4>) : (ks == 2 ? launch(conv_tc_kernel<1, 2>) : launch(conv_tc_kernel<1, 1>));
+  return ks == 4 ? launch(conv_tc_kernel<2, 4>) : (ks == 2 ? launch(conv_tc_kernel<2, 2>) : launch(conv_tc_kernel<2, 1>));
 }
 
 }  // namespace mz

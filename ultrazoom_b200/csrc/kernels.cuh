@@ -33,9 +33,10 @@ void make_bicubic_table(int r, BicubicTable* t);
 struct EpiParams {
   int mode;
   int B, H, W;
-  int n_pad;          // GEMM N (multiple of 16) == channel pitch of the bf16 / fp32 NHWC outputs
+  int bf16;           // MMA-operand element type of every 16-bit tensor: 0 = fp16, 1 = bf16
+  int n_pad;          // GEMM N (multiple of 16) == channel pitch of the 16-bit / fp32 NHWC outputs
   const float* film;  // mode 0: [B][2][n_pad] (scale row then shift row per image) or nullptr
-  __nv_bfloat16* out_bf16;  // mode 0: hidden; mode 1: zb
+  uint16_t* out_bf16;       // mode 0: hidden; mode 1: zb (fp16 or bf16 bits)
   float* zf;                // mode 1: fp32 residual stream, updated in place
   // mode 2
   const float* x;  // LR image (B,3,H,W) fp32 -- only for skip_mode 2
@@ -48,8 +49,8 @@ struct EpiParams {
 
 // One 3x3 convolution launch (both kernels).
 struct ConvArgs {
-  const __nv_bfloat16* in;  // (B,H,W,cin_p) bf16
-  const __nv_bfloat16* w;   // [9][n_pad][cin_p] bf16, tap = ky*3+kx
+  const uint16_t* in;  // (B,H,W,cin_p) fp16 | bf16
+  const uint16_t* w;   // [9][n_pad][cin_p] fp16 | bf16, tap = ky*3+kx
   int cin_p;
   EpiParams epi;
 };
@@ -69,15 +70,17 @@ struct ConvTcTune {
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaStream_t s);
 int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s);
-int launch_stem(const float* x, const float* w, const float* bias, float* zf, __nv_bfloat16* zb, int B, int H,
+int launch_stem(const float* x, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16, int B, int H,
                 int W, int Cp, cudaStream_t s);
 int launch_film(const float* c, int c_rows, const float* w, const float* b, float* film, int L, int B, int F,
                 int hC, int hCp, cudaStream_t s);
 
 ConvTcTune to_tune(const mz_conv_tune* t);
 int current_device();
-// OIHW fp32 -> [tap = ky*3+kx][cout_p][cin_p] bf16, zero padded (host).
-void pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, std::vector<__nv_bfloat16>& out);
+bool dtype_ok(int d);
+// OIHW fp32 -> [tap = ky*3+kx][cout_p][cin_p] fp16 | bf16, zero padded (host).
+void pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, int bf16,
+                           std::vector<uint16_t>& out);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
@@ -106,8 +109,8 @@ __device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, in
     }
     uint32_t o[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) o[q] = pack_bf16x2(silu_f(acc[2 * q]), silu_f(acc[2 * q + 1]));
-    __nv_bfloat16* dst = p.out_bf16 + pix * p.n_pad + n0;
+    for (int q = 0; q < 8; ++q) o[q] = pack_op2(p.bf16, silu_f(acc[2 * q]), silu_f(acc[2 * q + 1]));
+    uint16_t* dst = p.out_bf16 + pix * p.n_pad + n0;
     st_global_v4(dst, o[0], o[1], o[2], o[3]);
     st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
   } else {
@@ -121,10 +124,10 @@ __device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, in
       z.z += acc[4 * q + 2];
       z.w += acc[4 * q + 3];
       zf[q] = z;
-      o[2 * q] = pack_bf16x2(z.x, z.y);
-      o[2 * q + 1] = pack_bf16x2(z.z, z.w);
+      o[2 * q] = pack_op2(p.bf16, z.x, z.y);
+      o[2 * q + 1] = pack_op2(p.bf16, z.z, z.w);
     }
-    __nv_bfloat16* dst = p.out_bf16 + pix * p.n_pad + n0;
+    uint16_t* dst = p.out_bf16 + pix * p.n_pad + n0;
     st_global_v4(dst, o[0], o[1], o[2], o[3]);
     st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
   }

@@ -17,12 +17,12 @@ using namespace mz;
 
 struct mz_model {
   mz_config cfg;
-  int C, Cp, hC, hCp, L, r, F, headN, headNp;
+  int C, Cp, hC, hCp, L, r, F, headN, headNp, bf16;
   float* stem_w = nullptr;  // (Cp,3)
   float* stem_b = nullptr;  // (Cp)
-  __nv_bfloat16* conv1 = nullptr;  // L x [9][hCp][Cp]
-  __nv_bfloat16* conv2 = nullptr;  // L x [9][Cp][hCp]
-  __nv_bfloat16* head = nullptr;   // [9][headNp][Cp]
+  uint16_t* conv1 = nullptr;  // L x [9][hCp][Cp]
+  uint16_t* conv2 = nullptr;  // L x [9][Cp][hCp]
+  uint16_t* head = nullptr;   // [9][headNp][Cp]
   float* ctrl_w = nullptr;         // (L, 2hC, F)
   float* ctrl_b = nullptr;         // (L, 2hC)
   std::vector<uint8_t> have;       // per (kind, layer) upload flags
@@ -69,9 +69,9 @@ WsPlan plan_ws(const mz_model* m, int B, int H, int W) {
   p.zf = off;
   off = align_up(off + npix * m->Cp * sizeof(float), 1024);
   p.zb = off;
-  off = align_up(off + npix * m->Cp * sizeof(__nv_bfloat16), 1024);
+  off = align_up(off + npix * m->Cp * sizeof(uint16_t), 1024);
   p.hid = off;
-  off = align_up(off + npix * m->hCp * sizeof(__nv_bfloat16), 1024);
+  off = align_up(off + npix * m->hCp * sizeof(uint16_t), 1024);
   p.film = off;
   if (m->F > 0) off = align_up(off + static_cast<size_t>(m->L) * B * 2 * m->hCp * sizeof(float), 1024);
   p.total = off;
@@ -113,6 +113,8 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
              cfg->num_encoder_layers);
   MZ_REQUIRE(cfg->control_features >= 0 && cfg->control_features <= 64,
              "control_features must be in [0, 64], %d given.", cfg->control_features);
+  MZ_REQUIRE(cfg->operand_dtype == MZ_DTYPE_F16 || cfg->operand_dtype == MZ_DTYPE_BF16,
+             "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given.", cfg->operand_dtype);
   const int hC = cfg->num_channels * cfg->hidden_ratio;
   MZ_REQUIRE(mz_padded_channels(hC) <= 256, "hidden width %d exceeds the 256-channel limit of one UMMA tile", hC);
 
@@ -137,6 +139,7 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   m->F = cfg->control_features;
   m->headN = 3 * m->r * m->r;
   m->headNp = mz_padded_channels(m->headN);
+  m->bf16 = cfg->operand_dtype == MZ_DTYPE_BF16;
   m->have.assign(3 + 4 * m->L, 0);
   memset(m->tune, 0, sizeof(m->tune));
   const int hm = env_int("MZ_HALO_MODE", 0);  // 1 = diagnostic per-dx loads
@@ -151,9 +154,9 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   };
   alloc(reinterpret_cast<void**>(&m->stem_w), sizeof(float) * m->Cp * 3);
   alloc(reinterpret_cast<void**>(&m->stem_b), sizeof(float) * m->Cp);
-  alloc(reinterpret_cast<void**>(&m->conv1), sizeof(__nv_bfloat16) * c1 * m->L);
-  alloc(reinterpret_cast<void**>(&m->conv2), sizeof(__nv_bfloat16) * c2 * m->L);
-  alloc(reinterpret_cast<void**>(&m->head), sizeof(__nv_bfloat16) * 9 * m->headNp * m->Cp);
+  alloc(reinterpret_cast<void**>(&m->conv1), sizeof(uint16_t) * c1 * m->L);
+  alloc(reinterpret_cast<void**>(&m->conv2), sizeof(uint16_t) * c2 * m->L);
+  alloc(reinterpret_cast<void**>(&m->head), sizeof(uint16_t) * 9 * m->headNp * m->Cp);
   if (m->F > 0) {
     alloc(reinterpret_cast<void**>(&m->ctrl_w), sizeof(float) * m->L * 2 * m->hC * m->F);
     alloc(reinterpret_cast<void**>(&m->ctrl_b), sizeof(float) * m->L * 2 * m->hC);
@@ -195,7 +198,7 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
   MZ_REQUIRE((kind != MZ_W_CTRL_WEIGHT && kind != MZ_W_CTRL_BIAS) || m->F > 0,
              "set_weight: this model has no control modules");
   DeviceGuard g(m->cfg.device);
-  std::vector<__nv_bfloat16> packed;
+  std::vector<uint16_t> packed;
   switch (kind) {
     case MZ_W_STEM_WEIGHT: {
       MZ_REQUIRE(numel == static_cast<size_t>(m->C) * 3, "stem weight: expected %d elements, got %zu", m->C * 3,
@@ -211,24 +214,24 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
     case MZ_W_CONV1: {
       MZ_REQUIRE(numel == static_cast<size_t>(m->hC) * m->C * 9, "conv1 weight: expected %d elements, got %zu",
                  m->hC * m->C * 9, numel);
-      pack_conv_weight_host(host_data, m->hC, m->C, m->hCp, m->Cp, packed);
+      pack_conv_weight_host(host_data, m->hC, m->C, m->hCp, m->Cp, m->bf16, packed);
       MZ_CUDA(cudaMemcpy(m->conv1 + static_cast<size_t>(layer) * packed.size(), packed.data(),
-                         packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+                         packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
       break;
     }
     case MZ_W_CONV2: {
       MZ_REQUIRE(numel == static_cast<size_t>(m->hC) * m->C * 9, "conv2 weight: expected %d elements, got %zu",
                  m->hC * m->C * 9, numel);
-      pack_conv_weight_host(host_data, m->C, m->hC, m->Cp, m->hCp, packed);
+      pack_conv_weight_host(host_data, m->C, m->hC, m->Cp, m->hCp, m->bf16, packed);
       MZ_CUDA(cudaMemcpy(m->conv2 + static_cast<size_t>(layer) * packed.size(), packed.data(),
-                         packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+                         packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
       break;
     }
     case MZ_W_HEAD: {
       MZ_REQUIRE(numel == static_cast<size_t>(m->headN) * m->C * 9, "head weight: expected %d elements, got %zu",
                  m->headN * m->C * 9, numel);
-      pack_conv_weight_host(host_data, m->headN, m->C, m->headNp, m->Cp, packed);
-      MZ_CUDA(cudaMemcpy(m->head, packed.data(), packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+      pack_conv_weight_host(host_data, m->headN, m->C, m->headNp, m->Cp, m->bf16, packed);
+      MZ_CUDA(cudaMemcpy(m->head, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
       break;
     }
     case MZ_W_CTRL_WEIGHT: {
@@ -326,8 +329,8 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
   float* zf = reinterpret_cast<float*>(ws + wp.zf);
-  __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(ws + wp.zb);
-  __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(ws + wp.hid);
+  uint16_t* zb = reinterpret_cast<uint16_t*>(ws + wp.zb);
+  uint16_t* hid = reinterpret_cast<uint16_t*>(ws + wp.hid);
   float* film = reinterpret_cast<float*>(ws + wp.film);
   const bool simt = (flags & MZ_FLAG_SIMT_CONV) != 0;
   int rc;
@@ -336,7 +339,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     rc = launch_film(c_dev, c_rows, m->ctrl_w, m->ctrl_b, film, m->L, B, m->F, m->hC, m->hCp, s);
     if (rc != MZ_OK) return rc;
   }
-  rc = launch_stem(x_dev, m->stem_w, m->stem_b, zf, zb, B, H, W, m->Cp, s);
+  rc = launch_stem(x_dev, m->stem_w, m->stem_b, zf, zb, m->bf16, B, H, W, m->Cp, s);
   if (rc != MZ_OK) return rc;
 
   const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cp, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
@@ -349,6 +352,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     a.w = m->conv1 + l * c1;
     a.cin_p = m->Cp;
     a.epi.mode = 0;
+    a.epi.bf16 = m->bf16;
     a.epi.B = B;
     a.epi.H = H;
     a.epi.W = W;
@@ -363,6 +367,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     a.w = m->conv2 + l * c2;
     a.cin_p = m->hCp;
     a.epi.mode = 1;
+    a.epi.bf16 = m->bf16;
     a.epi.B = B;
     a.epi.H = H;
     a.epi.W = W;
@@ -390,6 +395,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
   a.w = m->head;
   a.cin_p = m->Cp;
   a.epi.mode = 2;
+  a.epi.bf16 = m->bf16;
   a.epi.B = B;
   a.epi.H = H;
   a.epi.W = W;

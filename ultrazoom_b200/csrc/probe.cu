@@ -116,24 +116,36 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(const RateParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_gen;
-  if (threadIdx.x == 0) {
+  if (warp == 1) {
+    // warp-uniform issue loop (descriptor arithmetic in uniform registers), one elected lane issues
     const int row_bytes = p.kc * 2;
     const uint32_t lt = umma_layout_type(p.kc);
     const uint32_t sbo = 8u * row_bytes;
     const uint32_t idesc = umma_idesc_bf16(128, p.n);
+    const uint32_t hi = static_cast<uint32_t>(umma_smem_desc(0, sbo, lt, 0) >> 32);
+    const uint32_t lo0 = static_cast<uint32_t>(umma_smem_desc(0, sbo, lt, 0));
+    const uint32_t b_lo = lo0 + (b_smem >> 4);
+    const uint32_t a_lo0 = lo0 + (a_smem >> 4);
+    const uint32_t amask = static_cast<uint32_t>(p.distinct_a - 1);
+    const bool leader = elect_one();
     const int ksteps = p.kc / 16;
     const long long t0 = clock64();
     for (int it = 0; it < p.iters; ++it) {
-      const uint32_t a_tile = a_smem + (p.distinct_a > 1 ? (it % p.distinct_a) * 16384 : 0);
-      for (int ks = 0; ks < ksteps; ++ks)
-        for (int d = 0; d < p.distinct_d; ++d)
-          umma_bf16(tmem_base + d * p.n, umma_smem_desc(a_tile + ks * 32, sbo, lt, 0),
-                    umma_smem_desc(b_smem + ks * 32, sbo, lt, 0), idesc, 1u);
+      const uint32_t a_lo = a_lo0 + (static_cast<uint32_t>(it) & amask) * (16384u >> 4);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint64_t bdesc = (static_cast<uint64_t>(hi) << 32) | (b_lo + 2 * ks);
+        const uint64_t adesc = (static_cast<uint64_t>(hi) << 32) | (a_lo + 2 * ks);
+        uint32_t d = tmem_base;
+        for (int dd = 0; dd < p.distinct_d; ++dd) {
+          if (leader) umma_bf16(d, adesc, bdesc, idesc, 1u);
+          d += p.n;
+        }
+      }
     }
-    umma_commit(bar_done);
+    if (leader) umma_commit(bar_done);
     mbar_wait(bar_done, 0);
     const long long t1 = clock64();
-    p.out[blockIdx.x] = static_cast<float>(t1 - t0) / static_cast<float>(p.iters * ksteps * p.distinct_d);
+    if (leader) p.out[blockIdx.x] = static_cast<float>(t1 - t0) / static_cast<float>(p.iters * ksteps * p.distinct_d);
   }
   tc_fence_before();
   __syncthreads();
@@ -232,7 +244,7 @@ int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_
   MZ_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "probe: n must be a multiple of 16 in [16, 256]");
   MZ_REQUIRE(kc == 16 || kc == 32 || kc == 64, "probe: kc must be 16, 32 or 64");
   MZ_REQUIRE(iters > 0 && iters <= (1 << 20) && ctas > 0 && ctas <= 4096, "probe: bad iters/ctas");
-  MZ_REQUIRE(distinct_a >= 1 && distinct_a <= 8, "probe: distinct_a must be 1..8");
+  MZ_REQUIRE(distinct_a == 1 || distinct_a == 2 || distinct_a == 4 || distinct_a == 8, "probe: distinct_a must be 1, 2, 4 or 8");
   MZ_REQUIRE(distinct_d >= 1 && distinct_d * n <= 512, "probe: distinct_d * n must fit 512 TMEM columns");
   MZ_REQUIRE(cycles_per_mma_out, "probe: null output");
   float* dOut = nullptr;

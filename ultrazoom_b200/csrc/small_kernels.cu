@@ -120,7 +120,7 @@ int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cu
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ zf,
-                                                   __nv_bfloat16* __restrict__ zb, int B, int H, int W, int Cp) {
+                                                   uint16_t* __restrict__ zb, int bf16, int B, int H, int W, int Cp) {
   const int groups = Cp / 8;
   const long long npix = static_cast<long long>(B) * H * W;
   const long long total = npix * groups;
@@ -142,19 +142,19 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     float4* f = reinterpret_cast<float4*>(zf + static_cast<size_t>(pix) * Cp + g * 8);
     f[0] = make_float4(o[0], o[1], o[2], o[3]);
     f[1] = make_float4(o[4], o[5], o[6], o[7]);
-    st_global_v4(zb + static_cast<size_t>(pix) * Cp + g * 8, pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                 pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    st_global_v4(zb + static_cast<size_t>(pix) * Cp + g * 8, pack_op2(bf16, o[0], o[1]), pack_op2(bf16, o[2], o[3]),
+                 pack_op2(bf16, o[4], o[5]), pack_op2(bf16, o[6], o[7]));
   }
 }
 
-int launch_stem(const float* x, const float* w, const float* bias, float* zf, __nv_bfloat16* zb, int B, int H, int W,
-                int Cp, cudaStream_t s) {
+int launch_stem(const float* x, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16, int B, int H,
+                int W, int Cp, cudaStream_t s) {
   MZ_REQUIRE(Cp > 0 && Cp % 8 == 0, "stem: padded channel count must be a multiple of 8, %d given", Cp);
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "stem: empty input");
   const long long total = static_cast<long long>(B) * H * W * (Cp / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
-  stem_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, w, bias, zf, zb, B, H, W, Cp);
+  stem_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, w, bias, zf, zb, bf16, B, H, W, Cp);
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }
@@ -206,7 +206,7 @@ int launch_film(const float* c, int c_rows, const float* w, const float* b, floa
 }
 
 // ----------------------------------------------------------------------------------------------
-// SIMT direct convolution (diagnostic).  Same operands (bf16 NHWC activations, bf16 [tap][n][k]
+// SIMT direct convolution (diagnostic).  Same operands (16-bit NHWC activations, 16-bit [tap][n][k]
 // weights), fp32 accumulation, same epilogues -- so that a tcgen05 result can be bisected against
 // it on the GPU.  One thread -> 16 output channels of one pixel (modes 0/1) or the whole head.
 // ----------------------------------------------------------------------------------------------
@@ -235,13 +235,13 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvArgs a) {
       for (int kx = 0; kx < 3; ++kx) {
         const int xx = x + kx - 1;
         if (xx < 0 || xx >= p.W) continue;
-        const __nv_bfloat16* src = a.in + ((static_cast<size_t>(b) * p.H + yy) * p.W + xx) * a.cin_p;
-        const __nv_bfloat16* wt = a.w + (static_cast<size_t>(ky * 3 + kx) * p.n_pad + n0) * a.cin_p;
+        const uint16_t* src = a.in + ((static_cast<size_t>(b) * p.H + yy) * p.W + xx) * a.cin_p;
+        const uint16_t* wt = a.w + (static_cast<size_t>(ky * 3 + kx) * p.n_pad + n0) * a.cin_p;
         for (int k = 0; k < a.cin_p; ++k) {
-          const float v = __bfloat162float(src[k]);
+          const float v = op_to_float(p.bf16, src[k]);
 #pragma unroll
           for (int i = 0; i < NACC; ++i)
-            if (i < nlim) acc[i] = fmaf(v, __bfloat162float(wt[static_cast<size_t>(i) * a.cin_p + k]), acc[i]);
+            if (i < nlim) acc[i] = fmaf(v, op_to_float(p.bf16, wt[static_cast<size_t>(i) * a.cin_p + k]), acc[i]);
         }
       }
     }

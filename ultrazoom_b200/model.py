@@ -84,7 +84,8 @@ class _Engine:
             raise RuntimeError("no sm_100 (B200) device visible; ultrazoom_b200 has no CPU or non-Blackwell fallback")
         self.device = device
         cfg = _native.MzConfig(owner.upscale_ratio, owner.num_channels, owner.hidden_ratio,
-                               owner.num_encoder_layers, owner.control_features, device.index or 0)
+                               owner.num_encoder_layers, owner.control_features, device.index or 0,
+                               _native.dtype_code(owner.operand_dtype))
         handle = C.c_void_p()
         _native.check(self.lib.mz_model_create(C.byref(cfg), C.byref(handle)))
         self.handle = handle
@@ -143,8 +144,13 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         hidden_ratio: int,
         num_encoder_layers: int,
         control_features: int = 0,
+        operand_dtype: str = "float16",
     ):
+        """``operand_dtype``: element type of the tensor-core operands ("float16" default, or "bfloat16").
+        Both run at the same tcgen05 rate with fp32 accumulation and an fp32 residual stream; fp16's 10-bit
+        mantissa keeps max|err| vs the fp32 reference ~8x smaller ("Numerics")."""
         super().__init__()
+        _native.dtype_code(operand_dtype)
         assert upscale_ratio in self.AVAILABLE_UPSCALE_RATIOS, (
             f"Upscale ratio must be one of {self.AVAILABLE_UPSCALE_RATIOS}, but got {upscale_ratio}.")
         assert hidden_ratio in self.AVAILABLE_HIDDEN_RATIOS, (
@@ -162,6 +168,7 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         self.hidden_ratio = hidden_ratio
         self.num_encoder_layers = num_encoder_layers
         self.control_features = control_features
+        self.operand_dtype = str(operand_dtype).replace("torch.", "")
         self._engines: dict = {}
         self._flags_extra = 0
 

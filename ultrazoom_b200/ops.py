@@ -41,24 +41,25 @@ def bicubic(x: Tensor, r: int) -> Tensor:
 
 
 def pack_conv_weight(w: Tensor, device: torch.device, cout_p: Optional[int] = None,
-                     cin_p: Optional[int] = None) -> Tensor:
-    """OIHW fp32 -> device bf16 [9][cout_p][cin_p]."""
+                     cin_p: Optional[int] = None, dtype: torch.dtype = torch.float16) -> Tensor:
+    """OIHW fp32 -> device fp16|bf16 [9][cout_p][cin_p]."""
     lib = _native.load()
     w = w.detach().to(device="cpu", dtype=torch.float32).contiguous()
     cout, cin = w.shape[0], w.shape[1]
     assert tuple(w.shape[2:]) == (3, 3), "Expected a 3x3 kernel."
     cout_p = cout_p or lib.mz_padded_channels(cout)
     cin_p = cin_p or lib.mz_padded_channels(cin)
-    out = torch.empty((9, cout_p, cin_p), dtype=torch.bfloat16, device=device)
+    out = torch.empty((9, cout_p, cin_p), dtype=dtype, device=device)
     nbytes = C.c_size_t()
     with torch.cuda.device(device):
-        _native.check(lib.mz_pack_conv_weight(w.data_ptr(), cout, cin, cout_p, cin_p, out.data_ptr(), C.byref(nbytes)))
+        _native.check(lib.mz_pack_conv_weight(w.data_ptr(), cout, cin, cout_p, cin_p, _native.dtype_code(dtype),
+                                              out.data_ptr(), C.byref(nbytes)))
     assert nbytes.value == out.numel() * 2
     return out
 
 
-def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None):
-    """FanOutProjection + NCHW->NHWC: returns (zf fp32 (B,H,W,Cp), zb bf16 (B,H,W,Cp))."""
+def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None, dtype: torch.dtype = torch.float16):
+    """FanOutProjection + NCHW->NHWC: returns (zf fp32 (B,H,W,Cp), zb fp16|bf16 (B,H,W,Cp))."""
     _need_cuda(x)
     lib = _native.load()
     x = x.to(torch.float32).contiguous()
@@ -70,10 +71,10 @@ def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None)
     w[:Cc] = weight.detach().reshape(Cc, 3).to(x.device, torch.float32)
     b[:Cc] = bias.detach().to(x.device, torch.float32)
     zf = torch.empty((B, H, W, cp), dtype=torch.float32, device=x.device)
-    zb = torch.empty((B, H, W, cp), dtype=torch.bfloat16, device=x.device)
+    zb = torch.empty((B, H, W, cp), dtype=dtype, device=x.device)
     with torch.cuda.device(x.device):
         _native.check(lib.mz_stem_pack(x.data_ptr(), w.data_ptr(), b.data_ptr(), zf.data_ptr(), zb.data_ptr(),
-                                       B, H, W, cp, _stream(x)))
+                                       B, H, W, cp, _native.dtype_code(dtype), _stream(x)))
     return zf, zb
 
 
@@ -95,23 +96,23 @@ def control_film(c: Tensor, weight: Tensor, bias: Tensor, B: int, hcp: Optional[
 
 def conv3x3(inp: Tensor, wpacked: Tensor, mode: int, film: Optional[Tensor] = None, zf: Optional[Tensor] = None,
             use_tc: bool = True, tune: Optional[_native.MzConvTune] = None) -> Tensor:
-    """3x3 conv on NHWC bf16 with the fused block epilogues; returns the bf16 NHWC output.
+    """3x3 conv on NHWC fp16|bf16 with the fused block epilogues; returns the 16-bit NHWC output (dtype of `inp`).
 
-    mode 0: SiLU(scale*acc+shift) with film (B,2,cout_p) or None; mode 1: zf += acc (in place), returns bf16(zf)."""
+    mode 0: SiLU(scale*acc+shift) with film (B,2,cout_p) or None; mode 1: zf += acc (in place), returns round16(zf)."""
     _need_cuda(inp, wpacked)
-    assert inp.dtype == torch.bfloat16 and wpacked.dtype == torch.bfloat16
+    assert inp.dtype in (torch.float16, torch.bfloat16) and wpacked.dtype == inp.dtype
     inp = inp.contiguous()
     B, H, W, cin_p = inp.shape
     _, cout_p, cin_w = wpacked.shape
     assert cin_w == cin_p, "weight / activation channel mismatch"
-    out = torch.empty((B, H, W, cout_p), dtype=torch.bfloat16, device=inp.device)
+    out = torch.empty((B, H, W, cout_p), dtype=inp.dtype, device=inp.device)
     if mode == 1:
         assert zf is not None and zf.is_contiguous() and tuple(zf.shape) == (B, H, W, cout_p)
     with torch.cuda.device(inp.device):
-        _native.check(_native.load().mz_conv3x3_bf16(
+        _native.check(_native.load().mz_conv3x3(
             inp.data_ptr(), wpacked.data_ptr(), mode, film.data_ptr() if film is not None else None,
             out.data_ptr(), zf.data_ptr() if zf is not None else None, B, H, W, cin_p, cout_p,
-            1 if use_tc else 0, C.byref(tune) if tune is not None else None, _stream(inp)))
+            _native.dtype_code(inp.dtype), 1 if use_tc else 0, C.byref(tune) if tune is not None else None, _stream(inp)))
     return out
 
 
@@ -120,6 +121,7 @@ def head_shuffle_add(zb: Tensor, wpacked: Tensor, r: int, x: Optional[Tensor] = 
                      tune: Optional[_native.MzConvTune] = None) -> Tensor:
     """SubpixelConv2d + skip add (+ clamp): returns y (B,3,rH,rW) fp32 NCHW."""
     _need_cuda(zb, wpacked)
+    assert zb.dtype in (torch.float16, torch.bfloat16) and wpacked.dtype == zb.dtype
     zb = zb.contiguous()
     B, H, W, cin_p = zb.shape
     if y is None:
@@ -130,7 +132,7 @@ def head_shuffle_add(zb: Tensor, wpacked: Tensor, r: int, x: Optional[Tensor] = 
     with torch.cuda.device(zb.device):
         _native.check(_native.load().mz_head_shuffle_add(
             zb.data_ptr(), wpacked.data_ptr(), x.data_ptr() if x is not None else None, y.data_ptr(), B, H, W, cin_p,
-            r, skip_mode, 1 if clamp01 else 0, 1 if use_tc else 0, C.byref(tune) if tune is not None else None,
+            r, skip_mode, 1 if clamp01 else 0, _native.dtype_code(zb.dtype), 1 if use_tc else 0, C.byref(tune) if tune is not None else None,
             _stream(zb)))
     return y
 
