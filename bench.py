@@ -176,7 +176,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--halo-mode", type=int, default=None)
+    ap.add_argument("--operands", default="float16", choices=["float16", "bfloat16"])
+    ap.add_argument("--tune", default="", help="comma list k=v of mz_conv_tune fields, e.g. cluster=4,rows=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -204,9 +205,10 @@ def main():
     cfg = MODEL_CONFIGS[model_name]
     r = cfg["upscale_ratio"]
     torch.manual_seed(0)
-    model = MewZoom(**cfg).to(dev).eval()
-    if args.halo_mode is not None:
-        model.set_conv_tune(-1, dev, halo_mode=args.halo_mode)
+    model = MewZoom(**cfg, operand_dtype=args.operands).to(dev).eval()
+    tune_kw = {k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)}
+    if tune_kw:
+        model.set_conv_tune(-1, dev, **tune_kw)
     eng = model._engine(dev)
     g = torch.Generator().manual_seed(1234 + rank)
     x_host = torch.rand(B, 3, H, W, generator=g).pin_memory()
@@ -302,11 +304,12 @@ def main():
     line = {
         "metric": "output_mpx_per_s", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f16" if args.operands == "float16" else "bf16", "data": "synthetic",
         "config": {"workload": desc, "model": model_name, "batch_per_gpu": B, "lr_h": H, "lr_w": W,
                    "parallelism": f"replica per GPU x{world}, batch-sharded, no collective",
                    "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
-                   "weights": "random init (seed 0)", "residual_stream": "fp32", "mma_operands": "bf16"},
+                   "weights": "random init (seed 0)", "residual_stream": "fp32", "accumulate": "fp32", "mma_operands": args.operands,
+                   "tune": tune_kw},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         "ms_per_frame": ms_step / B,

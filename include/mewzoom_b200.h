@@ -130,6 +130,7 @@ typedef struct mz_conv_tune {
   int32_t b_stages;   /* weight ring depth                                                           */
   int32_t a_stages;   /* activation ring depth                                                       */
   int32_t max_ctas;   /* cap on the persistent grid                                                  */
+  int32_t cluster;    /* CTAs per cluster sharing the weight stream via TMA multicast: 1, 2 or 4       */
 } mz_conv_tune;
 
 /* which = 0 conv1, 1 conv2, 2 head, -1 all.  Takes effect on the next mz_upscale. */

@@ -121,6 +121,10 @@ CONV_CASES = [
     (54, 108, (1, 10, 70), {}),
     (96, 192, (2, 30, 260), dict(max_ctas=3)),
     (96, 192, (1, 9, 257), dict(kc=16, b_stages=2)),
+    (96, 192, (2, 30, 260), dict(max_ctas=3, cluster=1)),
+    (96, 192, (2, 30, 260), dict(cluster=4)),
+    (48, 96, (2, 13, 150), dict(cluster=4, max_ctas=6)),
+    (64, 64, (1, 3, 100), dict(cluster=4)),
 ]
 
 
@@ -148,6 +152,7 @@ def test_conv1_film_silu(dev, cin, cout, shape, tune, halo_mode, dt):
 @pytest.mark.parametrize("cin,cout,shape,tune", [
     (96, 48, (2, 13, 150), {}), (192, 96, (1, 21, 300), {}), (108, 54, (1, 10, 70), {}),
     (192, 96, (2, 30, 260), dict(max_ctas=3)), (32, 16, (1, 1, 5), {}), (192, 96, (1, 7, 129), dict(rows=1, acc_stages=1)),
+    (192, 96, (2, 30, 260), dict(cluster=4)), (192, 96, (2, 30, 260), dict(cluster=1)), (96, 48, (1, 5, 700), dict(cluster=2, max_ctas=5)),
 ])
 @pytest.mark.parametrize("dt", DTYPES)
 def test_conv2_residual(dev, cin, cout, shape, tune, halo_mode, dt):

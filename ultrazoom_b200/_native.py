@@ -49,6 +49,7 @@ class MzConvTune(C.Structure):
         ("b_stages", C.c_int32),
         ("a_stages", C.c_int32),
         ("max_ctas", C.c_int32),
+        ("cluster", C.c_int32),
     ]
 
 

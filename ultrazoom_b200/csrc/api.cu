@@ -16,6 +16,7 @@ ConvTcTune to_tune(const mz_conv_tune* t) {
     o.b_stages = t->b_stages;
     o.a_stages = t->a_stages;
     o.max_ctas = t->max_ctas;
+    o.cluster = t->cluster;
   }
   return o;
 }

@@ -37,7 +37,9 @@ struct TcParams {
   int a_stage_bytes, b_stage_bytes;
   int a_tx_bytes, b_tx_bytes;
   int pw;  // pixel rows per image row inside an A stage
-  int tiles_x, tiles_y, n_units;
+  int tiles_x, tiles_y, n_units, n_rounds;
+  int cluster;       // CTAs per cluster sharing the weight stream by TMA multicast (1, 2 or 4)
+  int b_slice_rows;  // n_pad / cluster: weight rows each CTA loads and multicasts per stage
   uint32_t idesc;
   uint32_t tmem_cols;
 };
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int i = 0; i < p.b_stages; ++i) {
       mbar_init(bar_b_full + 8 * i, 1);
-      mbar_init(bar_b_empty + 8 * i, 1);
+      mbar_init(bar_b_empty + 8 * i, p.cluster);  // one tcgen05.commit arrive per CTA sharing the stage
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
@@ -101,8 +103,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();  // peers' barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  const uint32_t cta_rank = p.cluster > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cta_mask = static_cast<uint16_t>((1u << p.cluster) - 1u);
 
   const int row_bytes = p.kc * 2;
   const int units_per_img = p.tiles_x * p.tiles_y;
@@ -112,7 +117,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // The whole warp walks the (uniform) loop so that addresses stay in uniform registers; lane 0 issues.
     uint32_t a_it = 0, b_it = 0;
     const uint32_t per_dx = (p.rows + 2) * kTileW * row_bytes;
-    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+    for (int round = 0; round < p.n_rounds; ++round) {
+      // every CTA of a cluster walks the same number of rounds (the weight stream is shared); a CTA whose unit
+      // index runs past the end recomputes the last unit and its epilogue stores nothing
+      const int unit = min(round * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x), p.n_units - 1);
       const int b = unit / units_per_img;
       const int rem = unit - b * units_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -136,7 +144,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u);
           if (lane == 0) {
             mbar_expect_tx(bar_b_full + 8 * sb, p.b_tx_bytes);
-            tma_load_3d(b_base + sb * p.b_stage_bytes, &p.tmB, bar_b_full + 8 * sb, c * p.kc, 0, tap);
+            if (p.cluster > 1)
+              tma_load_3d_mcast(b_base + sb * p.b_stage_bytes + cta_rank * p.b_slice_rows * row_bytes, &p.tmB,
+                                bar_b_full + 8 * sb, c * p.kc, cta_rank * p.b_slice_rows, tap, cta_mask);
+            else
+              tma_load_3d(b_base + sb * p.b_stage_bytes, &p.tmB, bar_b_full + 8 * sb, c * p.kc, 0, tap);
           }
           ++b_it;
         }
@@ -163,7 +175,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     const bool leader = elect_one();  // the same lane issues every tcgen05.mma and tcgen05.commit
     uint32_t a_it = 0, b_it = 0, acc_it = 0;
-    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+    for (int round = 0; round < p.n_rounds; ++round) {
       const uint32_t as = acc_it % p.acc_stages, pacc = (acc_it / p.acc_stages) & 1u;
       mbar_wait(bar_acc_empty + 8 * as, pacc ^ 1u);
       tc_fence_after();
@@ -193,7 +205,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 d += p.acc_stride;
               }
             }
-            if (leader) umma_commit(bar_b_empty + 8 * sb);
+            if (leader) {
+              if (p.cluster > 1)
+                umma_commit_mcast(bar_b_empty + 8 * sb, cta_mask);
+              else
+                umma_commit(bar_b_empty + 8 * sb);
+            }
             first = 1u;
             ++b_it;
           }
@@ -209,7 +226,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // =============================== epilogue ===============================
     const int q = warp - 4;  // TMEM lane quarter this warp may read (== warp % 4)
     uint32_t acc_it = 0;
-    for (int unit = blockIdx.x; unit < p.n_units; unit += gridDim.x) {
+    for (int round = 0; round < p.n_rounds; ++round) {
+      const int unit_raw = round * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
+      const bool unit_ok = unit_raw < p.n_units;  // CTA-uniform
+      const int unit = min(unit_raw, p.n_units - 1);
       const int b = unit / units_per_img;
       const int rem = unit - b * units_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -221,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_after();
       for (int r = 0; r < p.rows; ++r) {
         const int y = y0 + r;
-        if (y >= p.epi.H) break;  // warp-uniform
+        if (y >= p.epi.H || !unit_ok) break;  // warp-uniform
         const bool ok = x < p.epi.W;
         const uint32_t taddr =
             tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * p.rows + r) * p.acc_stride;
@@ -265,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
@@ -314,6 +335,8 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   MZ_REQUIRE(e.mode >= 0 && e.mode <= 2, "conv: bad epilogue mode %d", e.mode);
   MZ_REQUIRE(e.mode != 2 || e.n_pad <= 48, "head conv: n_pad must be <= 48, %d given", e.n_pad);
   MZ_REQUIRE(tune.halo_mode >= 0 && tune.halo_mode <= 1, "conv: bad halo_mode %d", tune.halo_mode);
+  MZ_REQUIRE(tune.cluster == 0 || tune.cluster == 1 || tune.cluster == 2 || tune.cluster == 4,
+             "conv: cluster must be 0 (auto), 1, 2 or 4, %d given", tune.cluster);
   MZ_REQUIRE(tune.kc == 0 || ((tune.kc == 16 || tune.kc == 32 || tune.kc == 64) && a.cin_p % tune.kc == 0),
              "conv: kc %d does not divide cin_p %d (or is not 16/32/64)", tune.kc, a.cin_p);
 
@@ -349,6 +372,13 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     return MZ_ERR_UNSUPPORTED;
   }
 
+  // cluster size: share the weight stream between k CTAs when the slices keep whole 8-row swizzle atoms
+  {
+    int k = tune.cluster ? tune.cluster : 2;
+    while (k > 1 && (e.n_pad % k != 0 || (e.n_pad / k) % 8 != 0)) k >>= 1;
+    p.cluster = k;
+    p.b_slice_rows = e.n_pad / k;
+  }
   p.tiles_x = ceil_div(e.W, kTileW);
   p.tiles_y = ceil_div(e.H, p.rows);
   const long long n_units = static_cast<long long>(e.B) * p.tiles_x * p.tiles_y;
@@ -372,7 +402,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(a.cin_p), static_cast<uint64_t>(e.n_pad), 9};
     const uint64_t strides[2] = {static_cast<uint64_t>(a.cin_p) * 2, static_cast<uint64_t>(e.n_pad) * a.cin_p * 2};
-    const uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(e.n_pad), 1u};
+    const uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.b_slice_rows), 1u};
     int rc = encode_tmap(&p.tmB, tdt, 3, const_cast<uint16_t*>(a.w), dims, strides, box, swz);
     if (rc != MZ_OK) return rc;
   }
@@ -380,13 +410,29 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   const uint32_t smem = plan_smem(p).total + 1024;
   int sms = sm_count(device);
   if (sms <= 0) sms = 148;
+  const int k = p.cluster;
   int grid = p.n_units < sms ? p.n_units : sms;
   if (tune.max_ctas > 0 && grid > tune.max_ctas) grid = tune.max_ctas;
+  grid = ceil_div(grid, k) * k;  // whole clusters (surplus CTAs recompute the last patch without storing)
+  if (grid > sms) grid = (sms / k) * k;
+  p.n_rounds = ceil_div(p.n_units, grid);
 
   auto launch = [&](auto kern) -> int {
     MZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    kern<<<grid, kThreads, smem, s>>>(p);
-    MZ_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = k;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = k > 1 ? 1 : 0;
+    MZ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     return MZ_OK;
   };
   const int ks = p.kc / 16;

@@ -65,6 +65,7 @@ struct ConvTcTune {
   int b_stages;    // weight ring depth
   int a_stages;    // activation ring depth
   int max_ctas;    // cap on the persistent grid (0 = SM count)
+  int cluster;     // CTAs per cluster sharing the weight stream through TMA multicast: 1, 2 or 4 (0 = auto)
 };
 
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
