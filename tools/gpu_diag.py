@@ -38,14 +38,13 @@ def g_probe():
 def g_rate():
     from ultrazoom_b200 import ops
 
-    for n in (48, 64, 96, 128, 192, 256):
+    for n in (48, 96, 128, 192, 256):
         for kc in (64, 32, 16):
-            for dd in (1, 2, 4):
+            for da, dd in ((1, 1), (2, 1), (1, 2), (2, 2)):
                 if n * dd > 512:
                     continue
-                cyc = ops.probe_mma_rate(n, kc, 4000, 148, 8, dd)
-                ideal = n / 2.0
-                _report("rate", f"n={n} kc={kc} distinct_d={dd}", f"cyc/mma={cyc:.1f} (N/2={ideal:.0f})", True)
+                cyc = ops.probe_mma_rate(n, kc, 4000, 148, da, dd)
+                _report("rate", f"n={n} kc={kc} distinct_a={da} distinct_d={dd}", f"cyc/mma={cyc:.1f} (N/2={n / 2:.0f})", True)
 
 
 def _rand_bf16(shape, gen, scale=1.0):

@@ -50,6 +50,7 @@ class MzConvTune(C.Structure):
         ("a_stages", C.c_int32),
         ("max_ctas", C.c_int32),
         ("cluster", C.c_int32),
+        ("dbg", C.c_int32),
     ]
 
 

@@ -17,6 +17,7 @@ ConvTcTune to_tune(const mz_conv_tune* t) {
     o.a_stages = t->a_stages;
     o.max_ctas = t->max_ctas;
     o.cluster = t->cluster;
+    o.dbg = t->dbg;
   }
   return o;
 }

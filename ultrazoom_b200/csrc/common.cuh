@@ -93,21 +93,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (launch failure reported to the host) instead of hanging
-// the GPU.  ~4 s at 2 GHz; never reached by a correct pipeline.
-#ifndef MZ_WAIT_LIMIT_CYCLES
-#define MZ_WAIT_LIMIT_CYCLES 8000000000ll
+// Bounded blocking wait.  The retry loop lives INSIDE the asm statement (PTX labels are scoped by the braces):
+// to the compiler the wait is one opaque convergent statement, so loop-carried ring state around it stays in
+// uniform registers -- a C-level polling loop makes every later value "divergent" and costs an R2UR / ELECT
+// waterfall per tcgen05.mma.  Each failed try_wait may suspend up to ~1 us (the hint) and is woken by the arrive;
+// after MZ_WAIT_LIMIT_TRIES failures (seconds) a protocol bug traps instead of hanging the GPU.
+#ifndef MZ_WAIT_LIMIT_TRIES
+#define MZ_WAIT_LIMIT_TRIES 4000000u
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > MZ_WAIT_LIMIT_CYCLES) {
-      printf("mz: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      ".reg .u32 tries;\n\t"
+      "mov.u32 tries, 0;\n\t"
+      "MZ_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra MZ_DONE;\n\t"
+      "add.u32 tries, tries, 1;\n\t"
+      "setp.lt.u32 P1, tries, %3;\n\t"
+      "@P1 bra MZ_WAIT;\n\t"
+      "trap;\n\t"
+      "MZ_DONE:\n\t"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(1000u), "r"(MZ_WAIT_LIMIT_TRIES)
+      : "memory");
 }
 
 // ---- TMA ----
@@ -183,6 +193,17 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// same with the accumulate input hard-wired on (no predicate register to set up per instruction)
+__device__ __forceinline__ void umma_acc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.u32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc)
       : "memory");
 }
 // mbarrier arrive when all previously issued MMAs of this thread have completed

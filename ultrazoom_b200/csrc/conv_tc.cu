@@ -40,12 +40,15 @@ struct TcParams {
   int tiles_x, tiles_y, n_units, n_rounds;
   int cluster;       // CTAs per cluster sharing the weight stream by TMA multicast (1, 2 or 4)
   int b_slice_rows;  // n_pad / cluster: weight rows each CTA loads and multicasts per stage
+  long long* prof;   // optional per-CTA role timers (clock64 ticks), [grid][3 roles][8]; nullptr = off
+  int dbg;           // timing experiments only (results are wrong): 1 skip weight loads, 2 skip activation loads,
+                     // 4 skip the epilogue body, 8 skip the MMAs
   uint32_t idesc;
   uint32_t tmem_cols;
 };
 
 struct SmemPlan {
-  uint32_t a, b, bars, tmem_ptr, total;
+  uint32_t a, b, bars, tmem_ptr, film, total;
 };
 
 __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
@@ -55,11 +58,24 @@ __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
   s.bars = s.b + p.b_stages * p.b_stage_bytes;
   const uint32_t nbars = 2 * p.a_stages + 2 * p.b_stages + 4;
   s.tmem_ptr = s.bars + nbars * 8;
-  s.total = s.tmem_ptr + 16;
+  s.film = s.tmem_ptr + 16;  // [2][n_pad <= 256] fp32: FiLM scale / shift rows of the current image
+  s.total = s.film + 2 * 256 * 4;
   return s;
 }
 
-template <int MODE, int KSTEPS>
+// role timers: accumulate clock64 ticks spent in a statement when profiling is on (warp-uniform flag)
+#define MZ_TIMED(slot, stmt)                         \
+  do {                                               \
+    if (prof_on) {                                   \
+      const long long _t = clock64();                \
+      stmt;                                          \
+      tick[slot] += clock64() - _t;                  \
+    } else {                                         \
+      stmt;                                          \
+    }                                                \
+  } while (0)
+
+template <int MODE, int KSTEPS, int ROWS>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -111,12 +127,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int row_bytes = p.kc * 2;
   const int units_per_img = p.tiles_x * p.tiles_y;
+  const bool prof_on = p.prof != nullptr;
+  long long tick[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_role0 = prof_on ? clock64() : 0;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     // The whole warp walks the (uniform) loop so that addresses stay in uniform registers; lane 0 issues.
-    uint32_t a_it = 0, b_it = 0;
-    const uint32_t per_dx = (p.rows + 2) * kTileW * row_bytes;
+    // Ring positions advance incrementally (no integer division in the hot loops).
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0;
+    bool a_wrapped = false, b_wrapped = false;
+    const uint32_t per_dx = (ROWS + 2) * kTileW * row_bytes;
+    const uint32_t tap_bytes = p.epi.n_pad * row_bytes;  // one tap's [N][kc] tile inside a weight stage
     for (int round = 0; round < p.n_rounds; ++round) {
       // every CTA of a cluster walks the same number of rounds (the weight stream is shared); a CTA whose unit
       // index runs past the end recomputes the last unit and its epilogue stores nothing
@@ -124,40 +146,60 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int b = unit / units_per_img;
       const int rem = unit - b * units_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int x0 = tx * kTileW, y0 = ty * p.rows;
+      const int x0 = tx * kTileW, y0 = ty * ROWS;
       for (int c = 0; c < p.n_chunks; ++c) {
-        const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1u;
-        mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u);
+        MZ_TIMED(0, mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u));
         const uint32_t dstA = a_base + sa * p.a_stage_bytes;
-        if (lane == 0) {
-          mbar_expect_tx(bar_a_full + 8 * sa, p.a_tx_bytes);
+        const uint32_t full_a = bar_a_full + 8 * sa;
+        if (lane == 0 && (p.dbg & 2) && a_wrapped) {
+          mbar_arrive(full_a);
+        } else if (lane == 0) {
+          mbar_expect_tx(full_a, p.a_tx_bytes);
           if (p.halo_mode == 1) {
             for (int dx = 0; dx < 3; ++dx)
-              tma_load_4d(dstA + dx * per_dx, &p.tmA, bar_a_full + 8 * sa, c * p.kc, x0 + dx - 1, y0 - 1, b);
+              tma_load_4d(dstA + dx * per_dx, &p.tmA, full_a, c * p.kc, x0 + dx - 1, y0 - 1, b);
           } else {
-            tma_load_4d(dstA, &p.tmA, bar_a_full + 8 * sa, c * p.kc, x0 - 1, y0 - 1, b);
+            tma_load_4d(dstA, &p.tmA, full_a, c * p.kc, x0 - 1, y0 - 1, b);
           }
         }
-        ++a_it;
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t sb = b_it % p.b_stages, pb = (b_it / p.b_stages) & 1u;
-          mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u);
-          if (lane == 0) {
-            mbar_expect_tx(bar_b_full + 8 * sb, p.b_tx_bytes);
-            if (p.cluster > 1)
-              tma_load_3d_mcast(b_base + sb * p.b_stage_bytes + cta_rank * p.b_slice_rows * row_bytes, &p.tmB,
-                                bar_b_full + 8 * sb, c * p.kc, cta_rank * p.b_slice_rows, tap, cta_mask);
-            else
-              tma_load_3d(b_base + sb * p.b_stage_bytes, &p.tmB, bar_b_full + 8 * sb, c * p.kc, 0, tap);
+        if (++sa == static_cast<uint32_t>(p.a_stages)) {
+          sa = 0;
+          pa ^= 1u;
+          a_wrapped = true;
+        }
+        // one weight stage = the three horizontal taps of filter row dy: [3][N][kc]
+        for (int dy = 0; dy < 3; ++dy) {
+          MZ_TIMED(1, mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u));
+          const uint32_t full_b = bar_b_full + 8 * sb;
+          const uint32_t dstB = b_base + sb * p.b_stage_bytes;
+          if (lane == 0 && (p.dbg & 1) && b_wrapped) {
+            mbar_arrive(full_b);
+          } else if (lane == 0) {
+            mbar_expect_tx(full_b, p.b_tx_bytes);
+            if (p.cluster > 1) {
+              for (int dx = 0; dx < 3; ++dx)
+                tma_load_3d_mcast(dstB + dx * tap_bytes + cta_rank * p.b_slice_rows * row_bytes, &p.tmB, full_b,
+                                  c * p.kc, cta_rank * p.b_slice_rows, dy * 3 + dx, cta_mask);
+            } else {
+              tma_load_3d(dstB, &p.tmB, full_b, c * p.kc, 0, dy * 3);
+            }
           }
-          ++b_it;
+          if (++sb == static_cast<uint32_t>(p.b_stages)) {
+            sb = 0;
+            pb ^= 1u;
+            b_wrapped = true;
+          }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    // Uniform loop over the whole warp, lane 0 issues tcgen05.mma / tcgen05.commit.  Descriptors are built once:
-    // the high word is constant, the low word (start address >> 4) advances by plain 32-bit adds.
+    // Uniform loop over the whole warp; one elected lane issues tcgen05.mma / tcgen05.commit.  Per weight stage
+    // (filter row dy) all 3 * KSTEPS * ROWS UMMAs are issued back to back from ONE predicated region: the
+    // descriptor high word is constant, the low words are uniform 32-bit adds computed outside the region, so the
+    // SASS is a run of UTCHMMA with ~2 uniform instructions each (an earlier version spent ~100 issue cycles per
+    // UMMA on descriptor construction, integer division and R2UR/ELECT waterfalls -- more than the 48..96 cycles a
+    // 128 x N x 16 UMMA takes).
     const uint32_t lt = umma_layout_type(p.kc);
     const uint32_t sbo = 8u * row_bytes;
     const uint32_t desc_hi = static_cast<uint32_t>(umma_smem_desc(0, sbo, lt, 0) >> 32);
@@ -165,7 +207,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // tap (dy, dx) and accumulator row r start at dy * DY + dx * DX + r * RP sixteen-byte units into the A stage
     uint32_t DY, DX, RP;
     if (p.halo_mode == 1) {
-      DX = ((p.rows + 2) * kTileW * row_bytes) >> 4;
+      DX = ((ROWS + 2) * kTileW * row_bytes) >> 4;
       DY = (kTileW * row_bytes) >> 4;
       RP = DY;
     } else {
@@ -173,59 +215,78 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       DY = (p.pw * row_bytes) >> 4;
       RP = DY;
     }
+    const uint32_t TB = (p.epi.n_pad * row_bytes) >> 4;  // tap pitch inside a weight stage
     const bool leader = elect_one();  // the same lane issues every tcgen05.mma and tcgen05.commit
-    uint32_t a_it = 0, b_it = 0, acc_it = 0;
+    const bool issue = leader && !(p.dbg & 8);
+    const uint32_t idesc = p.idesc;
+    const uint32_t acc_stride = p.acc_stride;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
     for (int round = 0; round < p.n_rounds; ++round) {
-      const uint32_t as = acc_it % p.acc_stages, pacc = (acc_it / p.acc_stages) & 1u;
-      mbar_wait(bar_acc_empty + 8 * as, pacc ^ 1u);
+      MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * as, pacc ^ 1u));
       tc_fence_after();
-      const uint32_t d_base = tmem_base + as * p.rows * p.acc_stride;
+      const uint32_t d_base = tmem_base + as * ROWS * acc_stride;
       for (int c = 0; c < p.n_chunks; ++c) {
-        const uint32_t sa = a_it % p.a_stages, pa = (a_it / p.a_stages) & 1u;
-        mbar_wait(bar_a_full + 8 * sa, pa);
+        MZ_TIMED(1, mbar_wait(bar_a_full + 8 * sa, pa));
         const uint32_t a_lo_stage = desc_lo0 + ((a_base + sa * p.a_stage_bytes) >> 4);
-        uint32_t first = c == 0 ? 0u : 1u;  // accumulate flag of the first UMMA of this tap
-        for (int dy = 0; dy < 3; ++dy) {
-          for (int dx = 0; dx < 3; ++dx) {
-            const uint32_t sb = b_it % p.b_stages, pb = (b_it / p.b_stages) & 1u;
-            mbar_wait(bar_b_full + 8 * sb, pb);
-            tc_fence_after();
-            const uint32_t b_lo = desc_lo0 + ((b_base + sb * p.b_stage_bytes) >> 4);
-            const uint32_t a_lo_tap = a_lo_stage + dy * DY + dx * DX;
 #pragma unroll
-            for (int ks = 0; ks < KSTEPS; ++ks) {
-              const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * ks);
-              uint32_t a_lo = a_lo_tap + 2 * ks;
-              uint32_t d = d_base;
-              const uint32_t accum = ks == 0 ? first : 1u;
-              for (int r = 0; r < p.rows; ++r) {
-                const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | a_lo;
-                if (leader) umma_bf16(d, adesc, bdesc, p.idesc, accum);
-                a_lo += RP;
-                d += p.acc_stride;
+        for (int dy = 0; dy < 3; ++dy) {
+          MZ_TIMED(2, mbar_wait(bar_b_full + 8 * sb, pb));
+          tc_fence_after();
+          const uint32_t b_lo_stage = desc_lo0 + ((b_base + sb * p.b_stage_bytes) >> 4);
+          const uint32_t a_lo_dy = a_lo_stage + dy * DY;
+          const uint32_t first = (c == 0 && dy == 0) ? 0u : 1u;  // 0: overwrite the accumulator
+          if (issue) {
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+              for (int ks = 0; ks < KSTEPS; ++ks) {
+                const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_stage + dx * TB + 2 * ks);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                  const uint64_t adesc =
+                      (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_dy + dx * DX + r * RP + 2 * ks);
+                  if (dx == 0 && ks == 0)
+                    umma_bf16(d_base + r * acc_stride, adesc, bdesc, idesc, first);
+                  else
+                    umma_acc(d_base + r * acc_stride, adesc, bdesc, idesc);
+                }
               }
             }
-            if (leader) {
-              if (p.cluster > 1)
-                umma_commit_mcast(bar_b_empty + 8 * sb, cta_mask);
-              else
-                umma_commit(bar_b_empty + 8 * sb);
-            }
-            first = 1u;
-            ++b_it;
+          }
+          if (leader) {
+            if (p.cluster > 1)
+              umma_commit_mcast(bar_b_empty + 8 * sb, cta_mask);
+            else
+              umma_commit(bar_b_empty + 8 * sb);
+          }
+          if (++sb == static_cast<uint32_t>(p.b_stages)) {
+            sb = 0;
+            pb ^= 1u;
           }
         }
         if (leader) umma_commit(bar_a_empty + 8 * sa);
-        ++a_it;
+        if (++sa == static_cast<uint32_t>(p.a_stages)) {
+          sa = 0;
+          pa ^= 1u;
+        }
       }
       if (leader) umma_commit(bar_acc_full + 8 * as);
-      ++acc_it;
+      if (++as == static_cast<uint32_t>(p.acc_stages)) {
+        as = 0;
+        pacc ^= 1u;
+      }
     }
     __syncwarp();
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
+    // Everything an accumulator row needs from global memory is fetched BEFORE the accumulator is waited for:
+    // the FiLM rows of the image go to shared memory once per image, the fp32 residual row of a pixel goes to
+    // registers -- so no load latency sits between tcgen05.ld and the stores.
     const int q = warp - 4;  // TMEM lane quarter this warp may read (== warp % 4)
-    uint32_t acc_it = 0;
+    float* film_s = reinterpret_cast<float*>(gen_base + sp.film);
+    int film_b = -1;
+    uint32_t as = 0, pacc = 0;
+    constexpr int kPre = 24;  // float4 registers of residual prefetch: the first 96 channels of a pixel
     for (int round = 0; round < p.n_rounds; ++round) {
       const int unit_raw = round * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
       const bool unit_ok = unit_raw < p.n_units;  // CTA-uniform
@@ -234,17 +295,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int rem = unit - b * units_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int x = tx * kTileW + q * 32 + lane;
-      const int y0 = ty * p.rows;
-      const uint32_t as = acc_it % p.acc_stages, pacc = (acc_it / p.acc_stages) & 1u;
-      mbar_wait(bar_acc_full + 8 * as, pacc);
+      const int y0 = ty * ROWS;
+      const bool ok = x < p.epi.W;
+
+      if (MODE == 0 && b != film_b) {  // CTA-uniform: all four epilogue warps take it together
+        named_bar_sync(1, 128);        // nobody still reads the previous image's rows
+        for (int i = threadIdx.x - 128; i < 2 * p.epi.n_pad; i += 128) {
+          float v = i < p.epi.n_pad ? 1.f : 0.f;
+          if (p.epi.film != nullptr) v = __ldg(p.epi.film + static_cast<size_t>(b) * 2 * p.epi.n_pad + i);
+          film_s[i] = v;
+        }
+        named_bar_sync(1, 128);
+        film_b = b;
+      }
+
+      float4 zpre[kPre];
+      auto prefetch_residual = [&](int y) {
+        if (MODE == 1 && ok && y < p.epi.H) {
+          const float4* src = reinterpret_cast<const float4*>(
+              p.epi.zf + ((static_cast<size_t>(b) * p.epi.H + y) * p.epi.W + x) * p.epi.n_pad);
+#pragma unroll
+          for (int i = 0; i < kPre; ++i)
+            if (i * 4 < p.epi.n_pad) zpre[i] = src[i];
+        }
+      };
+      if (!(p.dbg & 4)) prefetch_residual(y0);
+
+      MZ_TIMED(0, mbar_wait(bar_acc_full + 8 * as, pacc));
       __syncwarp();
       tc_fence_after();
-      for (int r = 0; r < p.rows; ++r) {
+      for (int r = 0; r < ROWS; ++r) {
         const int y = y0 + r;
-        if (y >= p.epi.H || !unit_ok) break;  // warp-uniform
-        const bool ok = x < p.epi.W;
+        if (y >= p.epi.H || !unit_ok || (p.dbg & 4)) break;  // warp-uniform
+        if (r > 0) prefetch_residual(y);
         const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * p.rows + r) * p.acc_stride;
+            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * ROWS + r) * p.acc_stride;
         if (MODE == 2) {
           float acc[48];
           uint32_t v[16];
@@ -261,6 +346,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
           }
           if (ok) epi_head<48>(p.epi, b, y, x, acc);
+        } else if (MODE == 1) {
+#pragma unroll
+          for (int j = 0; j < kPre / 4; ++j) {
+            if (j * 16 < p.epi.n_pad) {  // warp-uniform
+              uint32_t v[16];
+              tmem_ld16(taddr + j * 16, v);
+              tmem_ld_wait();
+              if (ok) {
+                float acc[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
+                epi_residual16(p.epi, b, y, x, j * 16, acc, &zpre[j * 4]);
+              }
+            }
+          }
+          for (int n0 = kPre * 4; n0 < p.epi.n_pad; n0 += 16) {  // channels beyond the prefetch window
+            uint32_t v[16];
+            tmem_ld16(taddr + n0, v);
+            tmem_ld_wait();
+            if (ok) {
+              float acc[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
+              epi_store16<1>(p.epi, b, y, x, n0, acc, nullptr);
+            }
+          }
         } else {
           for (int n0 = 0; n0 < p.epi.n_pad; n0 += 16) {
             uint32_t v[16];
@@ -270,8 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               float acc[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
-              constexpr int M01 = MODE == 2 ? 0 : MODE;
-              epi_store16<M01>(p.epi, b, y, x, n0, acc);
+              epi_store16<0>(p.epi, b, y, x, n0, acc, film_s);
             }
           }
         }
@@ -279,10 +389,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
-      ++acc_it;
+      if (++as == static_cast<uint32_t>(p.acc_stages)) {
+        as = 0;
+        pacc ^= 1u;
+      }
     }
   }
 
+  if (prof_on && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
+    const int role = warp == 4 ? 2 : warp;
+    long long* dst = p.prof + (static_cast<size_t>(blockIdx.x) * 3 + role) * 8;
+    tick[7] = clock64() - t_role0;  // whole role
+    for (int i = 0; i < 8; ++i) dst[i] = tick[i];
+  }
   tc_fence_before();
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it
@@ -317,7 +436,7 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   const int a_bytes = (halo_mode == 1 ? 3 : 1) * (rows + 2) * p.pw * kc * 2;
   p.a_tx_bytes = a_bytes;
   p.a_stage_bytes = ((a_bytes + 1023) / 1024) * 1024;
-  p.b_tx_bytes = p.epi.n_pad * kc * 2;
+  p.b_tx_bytes = 3 * p.epi.n_pad * kc * 2;  // the three horizontal taps of one filter row
   p.b_stage_bytes = ((p.b_tx_bytes + 1023) / 1024) * 1024;
   p.tmem_cols = pow2_cols(static_cast<uint32_t>(acc_stages * rows * p.acc_stride));
 }
@@ -337,6 +456,8 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   MZ_REQUIRE(tune.halo_mode >= 0 && tune.halo_mode <= 1, "conv: bad halo_mode %d", tune.halo_mode);
   MZ_REQUIRE(tune.cluster == 0 || tune.cluster == 1 || tune.cluster == 2 || tune.cluster == 4,
              "conv: cluster must be 0 (auto), 1, 2 or 4, %d given", tune.cluster);
+  MZ_REQUIRE(tune.rows == 0 || tune.rows == 1 || tune.rows == 2 || tune.rows == 4,
+             "conv: rows must be 0 (auto), 1, 2 or 4, %d given", tune.rows);
   MZ_REQUIRE(tune.kc == 0 || ((tune.kc == 16 || tune.kc == 32 || tune.kc == 64) && a.cin_p % tune.kc == 0),
              "conv: kc %d does not divide cin_p %d (or is not 16/32/64)", tune.kc, a.cin_p);
 
@@ -354,6 +475,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     if (rmax > e.H) rmax = e.H;
     if (tune.rows) rmax = tune.rows;
     for (int rows = rmax; rows >= 1 && !found; --rows) {
+      if (rows == 3) continue;  // instantiated for 1, 2 and 4 accumulator rows
       for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {
         for (int bs = tune.b_stages ? tune.b_stages : 4; bs >= 2 && !found; --bs) {
           fill_geometry(p, a.cin_p, kc, rows, acc_stages, tune.halo_mode, tune.a_stages ? tune.a_stages : 2, bs);
@@ -378,6 +500,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     while (k > 1 && (e.n_pad % k != 0 || (e.n_pad / k) % 8 != 0)) k >>= 1;
     p.cluster = k;
     p.b_slice_rows = e.n_pad / k;
+    p.dbg = (tune.dbg & 1) && k > 1 ? (tune.dbg & ~1) : tune.dbg;  // skipping multicast loads would deadlock peers
   }
   p.tiles_x = ceil_div(e.W, kTileW);
   p.tiles_y = ceil_div(e.H, p.rows);
@@ -402,7 +525,8 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   {
     const uint64_t dims[3] = {static_cast<uint64_t>(a.cin_p), static_cast<uint64_t>(e.n_pad), 9};
     const uint64_t strides[2] = {static_cast<uint64_t>(a.cin_p) * 2, static_cast<uint64_t>(e.n_pad) * a.cin_p * 2};
-    const uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.b_slice_rows), 1u};
+    const uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.b_slice_rows),
+                             p.cluster > 1 ? 1u : 3u};
     int rc = encode_tmap(&p.tmB, tdt, 3, const_cast<uint16_t*>(a.w), dims, strides, box, swz);
     if (rc != MZ_OK) return rc;
   }
@@ -416,6 +540,14 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   grid = ceil_div(grid, k) * k;  // whole clusters (surplus CTAs recompute the last patch without storing)
   if (grid > sms) grid = (sms / k) * k;
   p.n_rounds = ceil_div(p.n_units, grid);
+
+  static long long* g_prof = nullptr;
+  if (tune.dbg & 16) {
+    if (!g_prof) MZ_CUDA(cudaMalloc(&g_prof, sizeof(long long) * 4096 * 24));
+    MZ_CUDA(cudaMemsetAsync(g_prof, 0, sizeof(long long) * 4096 * 24, s));
+    p.prof = g_prof;
+    p.dbg &= ~16;
+  }
 
   auto launch = [&](auto kern) -> int {
     MZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
@@ -433,12 +565,38 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     cfg.attrs = attr;
     cfg.numAttrs = k > 1 ? 1 : 0;
     MZ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    if (p.prof) {  // diagnostic: synchronise and print mean ticks per role (stderr)
+      MZ_CUDA(cudaStreamSynchronize(s));
+      std::vector<long long> h(static_cast<size_t>(grid) * 24);
+      MZ_CUDA(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      double m[24] = {0};
+      for (int c = 0; c < grid; ++c)
+        for (int i = 0; i < 24; ++i) m[i] += static_cast<double>(h[static_cast<size_t>(c) * 24 + i]) / grid;
+      fprintf(stderr,
+              "[mz prof] mode %d rows %d kc %d n %d rounds %d | producer: wait_a_empty %.0f wait_b_empty %.0f total %.0f | "
+              "mma: wait_acc_empty %.0f wait_a_full %.0f wait_b_full %.0f total %.0f | epilogue: wait_acc_full %.0f total %.0f\n",
+              e.mode, p.rows, p.kc, e.n_pad, p.n_rounds, m[0], m[1], m[7], m[8], m[9], m[10], m[15], m[16], m[23]);
+    }
     return MZ_OK;
   };
   const int ks = p.kc / 16;
-  if (e.mode == 0) return ks == 4 ? launch(conv_tc_kernel<0, 4>) : (ks == 2 ? launch(conv_tc_kernel<0, 2>) : launch(conv_tc_kernel<0, 1>));
-  if (e.mode == 1) return ks == 4 ? launch(conv_tc_kernel<1, 4>) : (ks == 2 ? launch(conv_tc_kernel<1, 2>) : launch(conv_tc_kernel<1, 1>));
-  return ks == 4 ? launch(conv_tc_kernel<2, 4>) : (ks == 2 ? launch(conv_tc_kernel<2, 2>) : launch(conv_tc_kernel<2, 1>));
+#define MZ_DISPATCH_ROWS(M, K)                              \
+  switch (p.rows) {                                         \
+    case 1: return launch(conv_tc_kernel<M, K, 1>);         \
+    case 2: return launch(conv_tc_kernel<M, K, 2>);         \
+    default: return launch(conv_tc_kernel<M, K, 4>);        \
+  }
+#define MZ_DISPATCH_KS(M)                                   \
+  switch (ks) {                                             \
+    case 4: MZ_DISPATCH_ROWS(M, 4)                          \
+    case 2: MZ_DISPATCH_ROWS(M, 2)                          \
+    default: MZ_DISPATCH_ROWS(M, 1)                         \
+  }
+  if (e.mode == 0) MZ_DISPATCH_KS(0)
+  if (e.mode == 1) MZ_DISPATCH_KS(1)
+  MZ_DISPATCH_KS(2)
+#undef MZ_DISPATCH_KS
+#undef MZ_DISPATCH_ROWS
 }
 
 }  // namespace mz

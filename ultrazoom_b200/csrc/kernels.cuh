@@ -66,6 +66,8 @@ struct ConvTcTune {
   int a_stages;    // activation ring depth
   int max_ctas;    // cap on the persistent grid (0 = SM count)
   int cluster;     // CTAs per cluster sharing the weight stream through TMA multicast: 1, 2 or 4 (0 = auto)
+  int dbg;         // timing experiments only (WRONG results): 1 skip weight loads, 2 skip activation loads,
+                   // 4 skip the epilogue body, 8 skip the MMAs
 };
 
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
@@ -91,17 +93,42 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
   asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// modes 0 and 1: sixteen consecutive output channels n0..n0+15 of pixel (b, y, x).
+// mode 1 with the residual row already in registers: zf += acc ; zb = round16(zf) for channels n0..n0+15.
+__device__ __forceinline__ void epi_residual16(const EpiParams& p, int b, int y, int x, int n0, const float (&acc)[16],
+                                               const float4* zin) {
+  const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
+  float4* zf = reinterpret_cast<float4*>(p.zf + pix * p.n_pad + n0);
+  uint32_t o[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 z = zin[q];
+    z.x += acc[4 * q + 0];
+    z.y += acc[4 * q + 1];
+    z.z += acc[4 * q + 2];
+    z.w += acc[4 * q + 3];
+    zf[q] = z;
+    o[2 * q] = pack_op2(p.bf16, z.x, z.y);
+    o[2 * q + 1] = pack_op2(p.bf16, z.z, z.w);
+  }
+  uint16_t* dst = p.out_bf16 + pix * p.n_pad + n0;
+  st_global_v4(dst, o[0], o[1], o[2], o[3]);
+  st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
+}
+
+// modes 0 and 1: sixteen consecutive output channels n0..n0+15 of pixel (b, y, x).  `film_rows` (mode 0) points at
+// [scale row | shift row], each n_pad floats, of image b -- shared memory in the tcgen05 kernel, global otherwise;
+// nullptr = identity.
 template <int MODE>
-__device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, int x, int n0, float (&acc)[16]) {
+__device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, int x, int n0, float (&acc)[16],
+                                            const float* film_rows) {
   const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
   if (MODE == 0) {
-    if (p.film != nullptr) {
-      const float4* sc = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(b) * 2 * p.n_pad + n0);
-      const float4* sh = reinterpret_cast<const float4*>(p.film + static_cast<size_t>(b) * 2 * p.n_pad + p.n_pad + n0);
+    if (film_rows != nullptr) {
+      const float4* sc = reinterpret_cast<const float4*>(film_rows + n0);
+      const float4* sh = reinterpret_cast<const float4*>(film_rows + p.n_pad + n0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 a = __ldg(sc + q), c = __ldg(sh + q);
+        const float4 a = sc[q], c = sh[q];
         acc[4 * q + 0] = fmaf(acc[4 * q + 0], a.x, c.x);
         acc[4 * q + 1] = fmaf(acc[4 * q + 1], a.y, c.y);
         acc[4 * q + 2] = fmaf(acc[4 * q + 2], a.z, c.z);
@@ -115,22 +142,11 @@ __device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, in
     st_global_v4(dst, o[0], o[1], o[2], o[3]);
     st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
   } else {
-    float4* zf = reinterpret_cast<float4*>(p.zf + pix * p.n_pad + n0);
-    uint32_t o[8];
+    const float4* zf = reinterpret_cast<const float4*>(p.zf + pix * p.n_pad + n0);
+    float4 zin[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 z = zf[q];
-      z.x += acc[4 * q + 0];
-      z.y += acc[4 * q + 1];
-      z.z += acc[4 * q + 2];
-      z.w += acc[4 * q + 3];
-      zf[q] = z;
-      o[2 * q] = pack_op2(p.bf16, z.x, z.y);
-      o[2 * q + 1] = pack_op2(p.bf16, z.z, z.w);
-    }
-    uint16_t* dst = p.out_bf16 + pix * p.n_pad + n0;
-    st_global_v4(dst, o[0], o[1], o[2], o[3]);
-    st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
+    for (int q = 0; q < 4; ++q) zin[q] = zf[q];
+    epi_residual16(p, b, y, x, n0, acc, zin);
   }
 }
 

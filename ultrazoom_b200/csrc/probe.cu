@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(const RateParams p) 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_gen;
   if (warp == 1) {
-    // warp-uniform issue loop (descriptor arithmetic in uniform registers), one elected lane issues
+    // warp-uniform issue loop: 8 fully unrolled UMMAs per iteration, descriptors precomputed
     const int row_bytes = p.kc * 2;
     const uint32_t lt = umma_layout_type(p.kc);
     const uint32_t sbo = 8u * row_bytes;
@@ -125,27 +125,23 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(const RateParams p) 
     const uint32_t hi = static_cast<uint32_t>(umma_smem_desc(0, sbo, lt, 0) >> 32);
     const uint32_t lo0 = static_cast<uint32_t>(umma_smem_desc(0, sbo, lt, 0));
     const uint32_t b_lo = lo0 + (b_smem >> 4);
-    const uint32_t a_lo0 = lo0 + (a_smem >> 4);
-    const uint32_t amask = static_cast<uint32_t>(p.distinct_a - 1);
+    const uint32_t a_lo = lo0 + (a_smem >> 4);
+    const uint32_t a_step = p.distinct_a > 1 ? (16384u >> 4) : 0u;
+    const uint32_t d_step = p.distinct_d > 1 ? static_cast<uint32_t>(p.n) : 0u;
     const bool leader = elect_one();
-    const int ksteps = p.kc / 16;
     const long long t0 = clock64();
     for (int it = 0; it < p.iters; ++it) {
-      const uint32_t a_lo = a_lo0 + (static_cast<uint32_t>(it) & amask) * (16384u >> 4);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t bdesc = (static_cast<uint64_t>(hi) << 32) | (b_lo + 2 * ks);
-        const uint64_t adesc = (static_cast<uint64_t>(hi) << 32) | (a_lo + 2 * ks);
-        uint32_t d = tmem_base;
-        for (int dd = 0; dd < p.distinct_d; ++dd) {
-          if (leader) umma_bf16(d, adesc, bdesc, idesc, 1u);
-          d += p.n;
-        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint64_t adesc = (static_cast<uint64_t>(hi) << 32) | (a_lo + (j & 1) * a_step + 2 * (j >> 1));
+        const uint64_t bdesc = (static_cast<uint64_t>(hi) << 32) | (b_lo + 2 * (j >> 1));
+        if (leader) umma_acc(tmem_base + (j & 1) * d_step, adesc, bdesc, idesc);
       }
     }
     if (leader) umma_commit(bar_done);
     mbar_wait(bar_done, 0);
     const long long t1 = clock64();
-    if (leader) p.out[blockIdx.x] = static_cast<float>(t1 - t0) / static_cast<float>(p.iters * ksteps * p.distinct_d);
+    if (leader) p.out[blockIdx.x] = static_cast<float>(t1 - t0) / static_cast<float>(p.iters * 8);
   }
   tc_fence_before();
   __syncthreads();

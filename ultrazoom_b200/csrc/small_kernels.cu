@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvArgs a) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) h[i] = acc[i];
       constexpr int M01 = MODE == 2 ? 0 : MODE;
-      epi_store16<M01>(p, b, y, x, n0, h);
+      epi_store16<M01>(p, b, y, x, n0, h,
+                       p.film != nullptr ? p.film + static_cast<size_t>(b) * 2 * p.n_pad : nullptr);
     }
   }
 }
