@@ -29,6 +29,10 @@ constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 struct TcParams {
   CUtensorMap tmA;  // activations: (cin_p, W, H, B) bf16
   CUtensorMap tmB;  // weights:     (cin_p, n_pad, 9) bf16
+  CUtensorMap tmO;  // 16-bit output (hidden | zb): (n_pad, W, H, B), box (e16, 32 px, 1, 1), swizzled
+  CUtensorMap tmZ;  // fp32 residual stream (mode 1): (n_pad, W, H, B), box (e32, 32 px, 1, 1), swizzled
+  int e16, e32;     // channels per output box: box rows are 128 / 64 / 32 bytes
+  int stage_bytes;  // epilogue staging (all four warps)
   EpiParams epi;
   int kc, n_chunks;
   int rows, acc_stages, acc_stride;
@@ -48,7 +52,7 @@ struct TcParams {
 };
 
 struct SmemPlan {
-  uint32_t a, b, bars, tmem_ptr, film, total;
+  uint32_t a, b, bars, tmem_ptr, film, stage, total;
 };
 
 __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
@@ -56,10 +60,11 @@ __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
   s.a = 0;
   s.b = s.a + p.a_stages * p.a_stage_bytes;
   s.bars = s.b + p.b_stages * p.b_stage_bytes;
-  const uint32_t nbars = 2 * p.a_stages + 2 * p.b_stages + 4;
+  const uint32_t nbars = 2 * p.a_stages + 2 * p.b_stages + 4 + 4;  // + one residual-load barrier per epilogue warp
   s.tmem_ptr = s.bars + nbars * 8;
   s.film = s.tmem_ptr + 16;  // [2][n_pad <= 256] fp32: FiLM scale / shift rows of the current image
-  s.total = s.film + 2 * 256 * 4;
+  s.stage = (s.film + 2 * 256 * 4 + 1023u) & ~1023u;  // epilogue staging: swizzled boxes for TMA store / load
+  s.total = s.stage + p.stage_bytes;
   return s;
 }
 
@@ -91,6 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t bar_b_empty = bar_b_full + 8 * p.b_stages;
   const uint32_t bar_acc_full = bar_b_empty + 8 * p.b_stages;
   const uint32_t bar_acc_empty = bar_acc_full + 16;
+  const uint32_t bar_res = bar_acc_empty + 16;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen_base + sp.tmem_ptr);
 
   const int warp = threadIdx.x >> 5;
@@ -99,6 +105,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    if (MODE != 2) tma_prefetch_desc(&p.tmO);
+    if (MODE == 1) tma_prefetch_desc(&p.tmZ);
     for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(bar_a_full + 8 * i, 1);
       mbar_init(bar_a_empty + 8 * i, 1);
@@ -111,6 +119,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bar_acc_full + 8 * i, 1);
       mbar_init(bar_acc_empty + 8 * i, 4);  // one arrive per epilogue warp
     }
+    for (int i = 0; i < 4; ++i) mbar_init(bar_res + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -279,14 +288,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     __syncwarp();
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
-    // Everything an accumulator row needs from global memory is fetched BEFORE the accumulator is waited for:
-    // the FiLM rows of the image go to shared memory once per image, the fp32 residual row of a pixel goes to
-    // registers -- so no load latency sits between tcgen05.ld and the stores.
+    // Each warp owns 32 pixels (its TMEM lane quarter).  Nothing goes to or from global memory through the LSU:
+    // results are written as swizzled 16-byte chunks into warp-private staging boxes and leave by TMA store
+    // (coalesced, asynchronous); the fp32 residual row-tile arrives by TMA load before the accumulator is waited
+    // for.  (Per-thread 16-byte global accesses at a 384-byte lane stride cost 32 sectors per instruction and made
+    // the epilogue, not the tensor pipe, the bottleneck.)
     const int q = warp - 4;  // TMEM lane quarter this warp may read (== warp % 4)
     float* film_s = reinterpret_cast<float*>(gen_base + sp.film);
     int film_b = -1;
-    uint32_t as = 0, pacc = 0;
-    constexpr int kPre = 24;  // float4 registers of residual prefetch: the first 96 channels of a pixel
+    uint32_t as = 0, pacc = 0, rpar = 0, ring = 0;
+    const uint32_t n_pad = p.epi.n_pad;
+    const uint32_t row16 = p.e16 * 2, row32 = p.e32 * 4;          // staging row bytes (= TMA box inner extent)
+    const uint32_t box16 = 32 * row16, box32 = 32 * row32;        // one warp-box: 32 pixels
+    const uint32_t nb16 = n_pad / p.e16, nb32 = n_pad / p.e32;
+    const uint32_t sh16 = 31 - __clz(p.e16), sh32 = 31 - __clz(p.e32);  // box widths are powers of two
+    // warp-private staging: mode 0 -> ring of two 16-bit boxes; mode 1 -> whole fp32 row-tile + whole 16-bit row-tile
+    const uint32_t st_base = base + sp.stage + q * (MODE == 0 ? 2 * box16 : 32 * n_pad * 6);
+    const uint32_t st_z = st_base, st_o = MODE == 0 ? st_base : st_base + 32 * n_pad * 4;
+    const uint32_t my_res = bar_res + 8 * q;
     for (int round = 0; round < p.n_rounds; ++round) {
       const int unit_raw = round * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
       const bool unit_ok = unit_raw < p.n_units;  // CTA-uniform
@@ -294,9 +313,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int b = unit / units_per_img;
       const int rem = unit - b * units_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int x = tx * kTileW + q * 32 + lane;
+      const int xw = tx * kTileW + q * 32;  // first pixel of this warp
+      const int x = xw + lane;
       const int y0 = ty * ROWS;
       const bool ok = x < p.epi.W;
+      const bool live = unit_ok && !(p.dbg & 4);
 
       if (MODE == 0 && b != film_b) {  // CTA-uniform: all four epilogue warps take it together
         named_bar_sync(1, 128);        // nobody still reads the previous image's rows
@@ -309,27 +330,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         film_b = b;
       }
 
-      float4 zpre[kPre];
-      auto prefetch_residual = [&](int y) {
-        if (MODE == 1 && ok && y < p.epi.H) {
-          const float4* src = reinterpret_cast<const float4*>(
-              p.epi.zf + ((static_cast<size_t>(b) * p.epi.H + y) * p.epi.W + x) * p.epi.n_pad);
-#pragma unroll
-          for (int i = 0; i < kPre; ++i)
-            if (i * 4 < p.epi.n_pad) zpre[i] = src[i];
+      // residual row-tile of accumulator row r: TMA load into this warp's staging (after its previous stores have
+      // finished reading it)
+      auto load_residual = [&](int y) {
+        if (MODE == 1 && live && y < p.epi.H && lane == 0) {
+          bulk_wait_read<0>();
+          mbar_expect_tx(my_res, 32 * n_pad * 4);
+          for (uint32_t bx = 0; bx < nb32; ++bx) tma_load_4d(st_z + bx * box32, &p.tmZ, my_res, bx * p.e32, xw, y, b);
         }
       };
-      if (!(p.dbg & 4)) prefetch_residual(y0);
+      load_residual(y0);
 
       MZ_TIMED(0, mbar_wait(bar_acc_full + 8 * as, pacc));
       __syncwarp();
       tc_fence_after();
       for (int r = 0; r < ROWS; ++r) {
         const int y = y0 + r;
-        if (y >= p.epi.H || !unit_ok || (p.dbg & 4)) break;  // warp-uniform
-        if (r > 0) prefetch_residual(y);
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * ROWS + r) * p.acc_stride;
+        if (y >= p.epi.H || !live) break;  // warp-uniform
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * ROWS + r) * p.acc_stride;
         if (MODE == 2) {
           float acc[48];
           uint32_t v[16];
@@ -347,41 +365,75 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           if (ok) epi_head<48>(p.epi, b, y, x, acc);
         } else if (MODE == 1) {
-#pragma unroll
-          for (int j = 0; j < kPre / 4; ++j) {
-            if (j * 16 < p.epi.n_pad) {  // warp-uniform
-              uint32_t v[16];
-              tmem_ld16(taddr + j * 16, v);
-              tmem_ld_wait();
-              if (ok) {
-                float acc[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
-                epi_residual16(p.epi, b, y, x, j * 16, acc, &zpre[j * 4]);
-              }
-            }
-          }
-          for (int n0 = kPre * 4; n0 < p.epi.n_pad; n0 += 16) {  // channels beyond the prefetch window
+          if (r > 0) load_residual(y);
+          mbar_wait(my_res, rpar);
+          rpar ^= 1u;
+          for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) {
             uint32_t v[16];
             tmem_ld16(taddr + n0, v);
             tmem_ld_wait();
-            if (ok) {
-              float acc[16];
+            const uint32_t bz = n0 >> sh32, cz = (n0 - (bz << sh32)) >> 2;  // fp32 box, first 16-byte chunk in its row
+            const uint32_t zrow = st_z + bz * box32 + lane * row32;
+            uint32_t o[8];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
-              epi_store16<1>(p.epi, b, y, x, n0, acc, nullptr);
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t addr = zrow + swz_chunk(lane, cz + k, row32) * 16;
+              float4 z = lds128f(addr);
+              z.x += __uint_as_float(v[4 * k + 0]);
+              z.y += __uint_as_float(v[4 * k + 1]);
+              z.z += __uint_as_float(v[4 * k + 2]);
+              z.w += __uint_as_float(v[4 * k + 3]);
+              sts128(addr, __float_as_uint(z.x), __float_as_uint(z.y), __float_as_uint(z.z), __float_as_uint(z.w));
+              o[2 * k] = pack_op2(p.epi.bf16, z.x, z.y);
+              o[2 * k + 1] = pack_op2(p.epi.bf16, z.z, z.w);
             }
+            const uint32_t bo = n0 >> sh16, co = (n0 - (bo << sh16)) >> 3;
+            const uint32_t orow = st_o + bo * box16 + lane * row16;
+            sts128(orow + swz_chunk(lane, co, row16) * 16, o[0], o[1], o[2], o[3]);
+            sts128(orow + swz_chunk(lane, co + 1, row16) * 16, o[4], o[5], o[6], o[7]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            for (uint32_t bx = 0; bx < nb32; ++bx) tma_store_4d(&p.tmZ, st_z + bx * box32, bx * p.e32, xw, y, b);
+            for (uint32_t bx = 0; bx < nb16; ++bx) tma_store_4d(&p.tmO, st_o + bx * box16, bx * p.e16, xw, y, b);
+            bulk_commit();
           }
         } else {
-          for (int n0 = 0; n0 < p.epi.n_pad; n0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + n0, v);
-            tmem_ld_wait();
-            if (ok) {
+          for (uint32_t bx = 0; bx < nb16; ++bx) {
+            const uint32_t buf = st_o + (ring & 1u) * box16;
+            ++ring;
+            if (lane == 0) bulk_wait_read<1>();  // the store issued two boxes ago has finished reading this buffer
+            __syncwarp();
+            const uint32_t orow = buf + lane * row16;
+            for (uint32_t sub = 0; sub < static_cast<uint32_t>(p.e16); sub += 16) {
+              const uint32_t n0 = bx * p.e16 + sub;
+              uint32_t v[16];
+              tmem_ld16(taddr + n0, v);
+              tmem_ld_wait();
               float acc[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
-              epi_store16<0>(p.epi, b, y, x, n0, acc, film_s);
+              const float4* sc = reinterpret_cast<const float4*>(film_s + n0);
+              const float4* sh = reinterpret_cast<const float4*>(film_s + n_pad + n0);
+              uint32_t o[8];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 g = sc[k], h = sh[k];
+                const float a0 = silu_f(fmaf(acc[4 * k + 0], g.x, h.x)), a1 = silu_f(fmaf(acc[4 * k + 1], g.y, h.y));
+                const float a2 = silu_f(fmaf(acc[4 * k + 2], g.z, h.z)), a3 = silu_f(fmaf(acc[4 * k + 3], g.w, h.w));
+                o[2 * k] = pack_op2(p.epi.bf16, a0, a1);
+                o[2 * k + 1] = pack_op2(p.epi.bf16, a2, a3);
+              }
+              const uint32_t co = sub >> 3;
+              sts128(orow + swz_chunk(lane, co, row16) * 16, o[0], o[1], o[2], o[3]);
+              sts128(orow + swz_chunk(lane, co + 1, row16) * 16, o[4], o[5], o[6], o[7]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&p.tmO, buf, bx * p.e16, xw, y, b);
+              bulk_commit();
             }
           }
         }
@@ -394,6 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         pacc ^= 1u;
       }
     }
+    if (lane == 0) bulk_wait_all();  // every TMA store of this warp has landed before the CTA exits
   }
 
   if (prof_on && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
@@ -439,6 +492,10 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   p.b_tx_bytes = 3 * p.epi.n_pad * kc * 2;  // the three horizontal taps of one filter row
   p.b_stage_bytes = ((p.b_tx_bytes + 1023) / 1024) * 1024;
   p.tmem_cols = pow2_cols(static_cast<uint32_t>(acc_stages * rows * p.acc_stride));
+  const int n = p.epi.n_pad;
+  p.e16 = n % 64 == 0 ? 64 : (n % 32 == 0 ? 32 : 16);
+  p.e32 = n % 32 == 0 ? 32 : 16;
+  p.stage_bytes = p.epi.mode == 0 ? 4 * 2 * 32 * p.e16 * 2 : (p.epi.mode == 1 ? 4 * 32 * n * 6 : 0);
 }
 
 static bool fits(const TcParams& p) {
@@ -529,6 +586,27 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
                              p.cluster > 1 ? 1u : 3u};
     int rc = encode_tmap(&p.tmB, tdt, 3, const_cast<uint16_t*>(a.w), dims, strides, box, swz);
     if (rc != MZ_OK) return rc;
+  }
+
+  auto swz_of = [](int row_bytes) {
+    return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  };
+  if (e.mode != 2) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(e.n_pad), static_cast<uint64_t>(e.W), static_cast<uint64_t>(e.H),
+                              static_cast<uint64_t>(e.B)};
+    const uint64_t st16[3] = {static_cast<uint64_t>(e.n_pad) * 2, static_cast<uint64_t>(e.W) * e.n_pad * 2,
+                              static_cast<uint64_t>(e.H) * e.W * e.n_pad * 2};
+    const uint32_t box16[4] = {static_cast<uint32_t>(p.e16), 32u, 1u, 1u};
+    int rc = encode_tmap(&p.tmO, tdt, 4, e.out_bf16, dims, st16, box16, swz_of(p.e16 * 2));
+    if (rc != MZ_OK) return rc;
+    if (e.mode == 1) {
+      const uint64_t st32[3] = {static_cast<uint64_t>(e.n_pad) * 4, static_cast<uint64_t>(e.W) * e.n_pad * 4,
+                                static_cast<uint64_t>(e.H) * e.W * e.n_pad * 4};
+      const uint32_t box32[4] = {static_cast<uint32_t>(p.e32), 32u, 1u, 1u};
+      rc = encode_tmap(&p.tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e.zf, dims, st32, box32, swz_of(p.e32 * 4));
+      if (rc != MZ_OK) return rc;
+    }
   }
 
   const uint32_t smem = plan_smem(p).total + 1024;
