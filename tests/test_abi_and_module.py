@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_padded_channels_and_error_plumbing():
     lib = _native.load()
-    assert [lib.mz_padded_channels(c) for c in (48, 54, 96, 108, 192, 12, 27)] == [48, 64, 96, 112, 192, 16, 32]
+    assert [lib.mz_padded_channels(c) for c in (48, 54, 96, 108, 192, 12, 27)] == [48, 64, 96, 128, 192, 16, 32]
     # invalid config -> MZ_ERR_INVALID with the reference's assertion wording (model.py:67-69)
     cfg = _native.MzConfig(5, 48, 2, 20, 0, 0)
     h = ctypes.c_void_p()

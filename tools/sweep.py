@@ -44,8 +44,12 @@ def main():
     w2 = ops.pack_conv_weight(torch.randn(C, 2 * C, 3, 3, generator=g) * 0.02, dev)
     film = torch.ones(B, 2, hCp, device=dev)
     print(f"C={C} {W}x{H} B={B}: {flops / 1e9:.1f} GFLOP per conv; 100% of 1644 TF = {flops / 1644e12 * 1e6:.1f} us")
-    grid = list(itertools.product((1,), (0, 1, 2), (0, 32, 64), (0,)))
-    dbgs = (0,)
+    if os.environ.get("SWEEP") == "dbg":
+        grid = list(itertools.product((1,), (0,), (0,), (0,)))
+        dbgs = (0, 4, 8, 12, 3, 7)
+    else:
+        grid = list(itertools.product((1,), (0, 1, 2, 4), (0,), (0,)))
+        dbgs = (0,)
     extra = os.environ.get("SWEEP_EXTRA")
     for which, (inp, wp, mode, fl, z) in (("conv1", (zb, w1, 0, film, None)), ("conv2", (hid, w2, 1, None, zf))):
         for cluster, rows, kc, bs in grid:

@@ -93,13 +93,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe of a barrier phase.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded blocking wait.  The retry loop lives INSIDE the asm statement (PTX labels are scoped by the braces):
 // to the compiler the wait is one opaque convergent statement, so loop-carried ring state around it stays in
 // uniform registers -- a C-level polling loop makes every later value "divergent" and costs an R2UR / ELECT
-// waterfall per tcgen05.mma.  Each failed try_wait may suspend up to ~1 us (the hint) and is woken by the arrive;
-// after MZ_WAIT_LIMIT_TRIES failures (seconds) a protocol bug traps instead of hanging the GPU.
+// waterfall per tcgen05.mma.  A failed try_wait suspends the thread for a hardware-chosen interval and is woken by
+// the arrive (an explicit suspend-time hint compiles to NANOSLEEP and adds up to that much latency to every
+// wait, so none is given); after MZ_WAIT_LIMIT_TRIES failures a protocol bug traps instead of hanging the GPU.
 #ifndef MZ_WAIT_LIMIT_TRIES
-#define MZ_WAIT_LIMIT_TRIES 4000000u
+#define MZ_WAIT_LIMIT_TRIES 20000000u
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -108,15 +123,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       ".reg .u32 tries;\n\t"
       "mov.u32 tries, 0;\n\t"
       "MZ_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra MZ_DONE;\n\t"
       "add.u32 tries, tries, 1;\n\t"
-      "setp.lt.u32 P1, tries, %3;\n\t"
+      "setp.lt.u32 P1, tries, %2;\n\t"
       "@P1 bra MZ_WAIT;\n\t"
       "trap;\n\t"
       "MZ_DONE:\n\t"
       "}\n" ::"r"(bar),
-      "r"(parity), "r"(1000u), "r"(MZ_WAIT_LIMIT_TRIES)
+      "r"(parity), "r"(MZ_WAIT_LIMIT_TRIES)
       : "memory");
 }
 

@@ -34,7 +34,10 @@ struct TcParams {
   int e16, e32;     // channels per output box: box rows are 128 / 64 / 32 bytes
   int stage_bytes;  // epilogue staging (all four warps)
   EpiParams epi;
-  int kc, n_chunks;
+  int kc, n_chunks;  // channels per swizzled sub-tile; pipeline chunks per patch (each = subs sub-tiles)
+  int subs;          // 16-channel sub-tiles fused into one stage (3 for Cin = 48), else 1
+  int a_kp, b_kp;    // k-step pitch inside a stage in 16-byte units (A / B): 2 within a swizzled row, else the sub-tile pitch
+  int b_tap;         // tap pitch inside a weight stage in 16-byte units
   int rows, acc_stages, acc_stride;
   int halo_mode;
   int a_stages, b_stages;
@@ -80,7 +83,7 @@ __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
     }                                                \
   } while (0)
 
-template <int MODE, int KSTEPS, int ROWS>
+template <int MODE, int KT, int ROWS>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -148,6 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     bool a_wrapped = false, b_wrapped = false;
     const uint32_t per_dx = (ROWS + 2) * kTileW * row_bytes;
     const uint32_t tap_bytes = p.epi.n_pad * row_bytes;  // one tap's [N][kc] tile inside a weight stage
+    const uint32_t a_sub_bytes = static_cast<uint32_t>(p.a_kp) << 4;  // one 16-channel sub-tile of a fused stage
     for (int round = 0; round < p.n_rounds; ++round) {
       // every CTA of a cluster walks the same number of rounds (the weight stream is shared); a CTA whose unit
       // index runs past the end recomputes the last unit and its epilogue stores nothing
@@ -168,7 +172,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int dx = 0; dx < 3; ++dx)
               tma_load_4d(dstA + dx * per_dx, &p.tmA, full_a, c * p.kc, x0 + dx - 1, y0 - 1, b);
           } else {
-            tma_load_4d(dstA, &p.tmA, full_a, c * p.kc, x0 - 1, y0 - 1, b);
+            for (int sub = 0; sub < p.subs; ++sub)
+              tma_load_4d(dstA + sub * a_sub_bytes, &p.tmA, full_a, (c * p.subs + sub) * p.kc, x0 - 1, y0 - 1, b);
           }
         }
         if (++sa == static_cast<uint32_t>(p.a_stages)) {
@@ -190,7 +195,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 tma_load_3d_mcast(dstB + dx * tap_bytes + cta_rank * p.b_slice_rows * row_bytes, &p.tmB, full_b,
                                   c * p.kc, cta_rank * p.b_slice_rows, dy * 3 + dx, cta_mask);
             } else {
-              tma_load_3d(dstB, &p.tmB, full_b, c * p.kc, 0, dy * 3);
+              for (int sub = 0; sub < p.subs; ++sub)  // stage layout [sub][3 taps][N][kc]
+                tma_load_3d(dstB + sub * 3 * tap_bytes, &p.tmB, full_b, (c * p.subs + sub) * p.kc, 0, dy * 3);
             }
           }
           if (++sb == static_cast<uint32_t>(p.b_stages)) {
@@ -224,67 +230,114 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       DY = (p.pw * row_bytes) >> 4;
       RP = DY;
     }
-    const uint32_t TB = (p.epi.n_pad * row_bytes) >> 4;  // tap pitch inside a weight stage
+    const uint32_t TB = p.b_tap;  // tap pitch inside a weight stage
     const bool leader = elect_one();  // the same lane issues every tcgen05.mma and tcgen05.commit
     const bool issue = leader && !(p.dbg & 8);
     const uint32_t idesc = p.idesc;
     const uint32_t acc_stride = p.acc_stride;
+    const uint32_t a_kp = p.a_kp, b_kp = p.b_kp;
+    // One tap (dx) of the current weight stage: KT k-steps x ROWS accumulators, all descriptor words uniform.
+#define MZ_ISSUE_TAP(DXV)                                                                                         \
+  if (issue) {                                                                                                    \
+    _Pragma("unroll") for (int t = 0; t < KT; ++t) {                                                              \
+      const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_stage + (DXV) * TB + t * b_kp);        \
+      _Pragma("unroll") for (int r = 0; r < ROWS; ++r) {                                                          \
+        const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_dy + (DXV) * DX + r * RP + t * a_kp); \
+        if ((DXV) == 0 && t == 0)                                                                                 \
+          umma_bf16(d_base + r * acc_stride, adesc, bdesc, idesc, first);                                         \
+        else                                                                                                      \
+          umma_acc(d_base + r * acc_stride, adesc, bdesc, idesc);                                                 \
+      }                                                                                                           \
+    }                                                                                                             \
+  }
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+    // Barrier state of the NEXT step is sampled (non-blocking mbarrier.test_wait) in the middle of the current
+    // step, so in the common case -- the producer is ahead -- the blocking wait and its latency are skipped and
+    // the tensor pipe never drains between stages.  The commit of the current stage is NOT delayed by this.
+    auto test_uniform = [&](uint32_t bar, uint32_t parity) -> bool { return __all_sync(0xffffffffu, mbar_test(bar, parity)); };
+    const bool la_acc = p.acc_stages > 1;
+    MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * as, pacc ^ 1u));
+    MZ_TIMED(1, mbar_wait(bar_a_full + 8 * sa, pa));
+    MZ_TIMED(2, mbar_wait(bar_b_full + 8 * sb, pb));
+    tc_fence_after();
     for (int round = 0; round < p.n_rounds; ++round) {
-      MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * as, pacc ^ 1u));
-      tc_fence_after();
       const uint32_t d_base = tmem_base + as * ROWS * acc_stride;
       for (int c = 0; c < p.n_chunks; ++c) {
-        MZ_TIMED(1, mbar_wait(bar_a_full + 8 * sa, pa));
         const uint32_t a_lo_stage = desc_lo0 + ((a_base + sa * p.a_stage_bytes) >> 4);
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-          MZ_TIMED(2, mbar_wait(bar_b_full + 8 * sb, pb));
-          tc_fence_after();
           const uint32_t b_lo_stage = desc_lo0 + ((b_base + sb * p.b_stage_bytes) >> 4);
           const uint32_t a_lo_dy = a_lo_stage + dy * DY;
           const uint32_t first = (c == 0 && dy == 0) ? 0u : 1u;  // 0: overwrite the accumulator
-          if (issue) {
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-              for (int ks = 0; ks < KSTEPS; ++ks) {
-                const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_stage + dx * TB + 2 * ks);
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) {
-                  const uint64_t adesc =
-                      (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_dy + dx * DX + r * RP + 2 * ks);
-                  if (dx == 0 && ks == 0)
-                    umma_bf16(d_base + r * acc_stride, adesc, bdesc, idesc, first);
-                  else
-                    umma_acc(d_base + r * acc_stride, adesc, bdesc, idesc);
+          MZ_ISSUE_TAP(0)
+          MZ_ISSUE_TAP(1)
+          // ---- sample the barriers of the next step ----
+          const bool last_chunk = c == p.n_chunks - 1;
+          const bool last_step = dy == 2 && last_chunk && round == p.n_rounds - 1;
+          uint32_t nsb = sb + 1, npb = pb, nsa = sa, npa = pa, nas = as, npacc = pacc;
+          if (nsb == static_cast<uint32_t>(p.b_stages)) {
+            nsb = 0;
+            npb ^= 1u;
+          }
+          bool b_ready = true, a_ready = true, acc_ready = true;
+          if (!last_step) {
+            b_ready = test_uniform(bar_b_full + 8 * nsb, npb);
+            if (dy == 2) {
+              if (++nsa == static_cast<uint32_t>(p.a_stages)) {
+                nsa = 0;
+                npa ^= 1u;
+              }
+              a_ready = test_uniform(bar_a_full + 8 * nsa, npa);
+              if (last_chunk && la_acc) {
+                if (++nas == static_cast<uint32_t>(p.acc_stages)) {
+                  nas = 0;
+                  npacc ^= 1u;
                 }
+                acc_ready = test_uniform(bar_acc_empty + 8 * nas, npacc ^ 1u);
               }
             }
           }
+          MZ_ISSUE_TAP(2)
           if (leader) {
             if (p.cluster > 1)
               umma_commit_mcast(bar_b_empty + 8 * sb, cta_mask);
             else
               umma_commit(bar_b_empty + 8 * sb);
+            if (dy == 2) umma_commit(bar_a_empty + 8 * sa);
+            if (dy == 2 && last_chunk) umma_commit(bar_acc_full + 8 * as);
           }
-          if (++sb == static_cast<uint32_t>(p.b_stages)) {
-            sb = 0;
-            pb ^= 1u;
+          // ---- now block on whatever was not ready when sampled ----
+          if (!last_step) {
+            if (dy == 2 && last_chunk) {
+              if (la_acc) {
+                if (!acc_ready) MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * nas, npacc ^ 1u));
+              } else {
+                uint32_t was = as + 1, wp = pacc;  // single TMEM stage: released by the epilogue of THIS patch
+                if (was == static_cast<uint32_t>(p.acc_stages)) {
+                  was = 0;
+                  wp ^= 1u;
+                }
+                MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * was, wp ^ 1u));
+              }
+            }
+            if (dy == 2 && !a_ready) MZ_TIMED(1, mbar_wait(bar_a_full + 8 * nsa, npa));
+            if (!b_ready) MZ_TIMED(2, mbar_wait(bar_b_full + 8 * nsb, npb));
+            tc_fence_after();
           }
+          sb = nsb;
+          pb = npb;
         }
-        if (leader) umma_commit(bar_a_empty + 8 * sa);
         if (++sa == static_cast<uint32_t>(p.a_stages)) {
           sa = 0;
           pa ^= 1u;
         }
       }
-      if (leader) umma_commit(bar_acc_full + 8 * as);
       if (++as == static_cast<uint32_t>(p.acc_stages)) {
         as = 0;
         pacc ^= 1u;
       }
     }
+#undef MZ_ISSUE_TAP
     __syncwarp();
   } else if (warp >= 4) {
     // =============================== epilogue ===============================
@@ -363,7 +416,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               for (int i = 0; i < 16; ++i) acc[j * 16 + i] = 0.f;
             }
           }
-          if (ok) epi_head<48>(p.epi, b, y, x, acc);
+          if (ok) {
+            if (p.epi.r == 4)
+              epi_head_r<4>(p.epi, b, y, x, acc);
+            else if (p.epi.r == 2)
+              epi_head_r<2>(p.epi, b, y, x, acc);
+            else
+              epi_head_r<3>(p.epi, b, y, x, acc);
+          }
         } else if (MODE == 1) {
           if (r > 0) load_residual(y);
           mbar_wait(my_res, rpar);
@@ -478,7 +538,10 @@ static uint32_t pow2_cols(uint32_t c) {
 static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stages, int halo_mode, int a_stages,
                           int b_stages) {
   p.kc = kc;
-  p.n_chunks = cin_p / kc;
+  // 16-channel sub-tiles are fused into one pipeline stage when the whole K extent is small (Cin = 48): three times
+  // the UMMAs per barrier round trip
+  p.subs = (kc == 16 && halo_mode == 0 && cin_p / 16 <= 3 && p.cluster <= 1) ? cin_p / 16 : 1;
+  p.n_chunks = cin_p / (kc * p.subs);
   p.rows = rows;
   p.acc_stages = acc_stages;
   p.acc_stride = ((p.epi.n_pad + 31) / 32) * 32;
@@ -486,11 +549,16 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   p.a_stages = a_stages;
   p.b_stages = b_stages;
   p.pw = halo_mode == 1 ? kTileW : kTileW + 2;
-  const int a_bytes = (halo_mode == 1 ? 3 : 1) * (rows + 2) * p.pw * kc * 2;
-  p.a_tx_bytes = a_bytes;
+  int a_sub = (rows + 2) * p.pw * kc * 2;
+  if (p.subs > 1) a_sub = ((a_sub + 1023) / 1024) * 1024;  // each sub-tile is its own TMA destination / swizzle frame
+  const int a_bytes = (halo_mode == 1 ? 3 : p.subs) * a_sub;
+  p.a_tx_bytes = (halo_mode == 1 ? 3 : p.subs) * (rows + 2) * p.pw * kc * 2;
   p.a_stage_bytes = ((a_bytes + 1023) / 1024) * 1024;
-  p.b_tx_bytes = 3 * p.epi.n_pad * kc * 2;  // the three horizontal taps of one filter row
+  p.b_tx_bytes = p.subs * 3 * p.epi.n_pad * kc * 2;  // the three horizontal taps of one filter row
   p.b_stage_bytes = ((p.b_tx_bytes + 1023) / 1024) * 1024;
+  p.b_tap = (p.epi.n_pad * kc * 2) >> 4;
+  p.a_kp = p.subs > 1 ? a_sub >> 4 : 2;
+  p.b_kp = p.subs > 1 ? (3 * p.epi.n_pad * kc * 2) >> 4 : 2;
   p.tmem_cols = pow2_cols(static_cast<uint32_t>(acc_stages * rows * p.acc_stride));
   const int n = p.epi.n_pad;
   p.e16 = n % 64 == 0 ? 64 : (n % 32 == 0 ? 32 : 16);
@@ -522,6 +590,14 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   memset(&p, 0, sizeof(p));
   p.epi = e;
 
+  // cluster size: share the weight stream between k CTAs when the slices keep whole 8-row swizzle atoms
+  {
+    int k = tune.cluster ? tune.cluster : 1;  // multicast is opt-in: L2 is not the limiter at these tile sizes
+    while (k > 1 && (e.n_pad % k != 0 || (e.n_pad / k) % 8 != 0)) k >>= 1;
+    p.cluster = k;
+    p.b_slice_rows = e.n_pad / k;
+    p.dbg = (tune.dbg & 1) && k > 1 ? (tune.dbg & ~1) : tune.dbg;  // skipping multicast loads would deadlock peers
+  }
   // ---- choose the patch geometry: largest patch that keeps two TMEM stages and fits shared memory ----
   const int acc_stride = ((e.n_pad + 31) / 32) * 32;
   bool found = false;
@@ -551,14 +627,6 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     return MZ_ERR_UNSUPPORTED;
   }
 
-  // cluster size: share the weight stream between k CTAs when the slices keep whole 8-row swizzle atoms
-  {
-    int k = tune.cluster ? tune.cluster : 2;
-    while (k > 1 && (e.n_pad % k != 0 || (e.n_pad / k) % 8 != 0)) k >>= 1;
-    p.cluster = k;
-    p.b_slice_rows = e.n_pad / k;
-    p.dbg = (tune.dbg & 1) && k > 1 ? (tune.dbg & ~1) : tune.dbg;  // skipping multicast loads would deadlock peers
-  }
   p.tiles_x = ceil_div(e.W, kTileW);
   p.tiles_y = ceil_div(e.H, p.rows);
   const long long n_units = static_cast<long long>(e.B) * p.tiles_x * p.tiles_y;
@@ -657,7 +725,8 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     }
     return MZ_OK;
   };
-  const int ks = p.kc / 16;
+  const int ks = p.subs > 1 ? p.subs : p.kc / 16;  // k-steps per stage and tap
+  MZ_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "conv: the look-ahead issue loop needs at least two A and two B stages");
 #define MZ_DISPATCH_ROWS(M, K)                              \
   switch (p.rows) {                                         \
     case 1: return launch(conv_tc_kernel<M, K, 1>);         \
@@ -667,6 +736,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
 #define MZ_DISPATCH_KS(M)                                   \
   switch (ks) {                                             \
     case 4: MZ_DISPATCH_ROWS(M, 4)                          \
+    case 3: MZ_DISPATCH_ROWS(M, 3)                          \
     case 2: MZ_DISPATCH_ROWS(M, 2)                          \
     default: MZ_DISPATCH_ROWS(M, 1)                         \
   }

@@ -95,6 +95,12 @@ int mz_device_count(void) {
   return ok;
 }
 
-int mz_padded_channels(int32_t c) { return c <= 0 ? 0 : ((c + 15) / 16) * 16; }
+// Channel counts are padded to a multiple of 16 (one UMMA k-step); beyond 64 to a multiple of 32 so that a K chunk
+// is at least a 64-byte swizzled row (108 -> 128 rather than 112 = 7 x 16).
+int mz_padded_channels(int32_t c) {
+  if (c <= 0) return 0;
+  const int p16 = ((c + 15) / 16) * 16;
+  return p16 <= 64 ? p16 : ((c + 31) / 32) * 32;
+}
 
 }  // extern "C"
