@@ -180,6 +180,7 @@ def main():
     ap.add_argument("--tune", default="", help="comma list k=v of mz_conv_tune fields, e.g. cluster=4,rows=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary MewZoom-4X-Ctrl measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least three warm-up steps
@@ -201,75 +202,119 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    model_name, B, H, W, desc = WORKLOADS[args.workload]
-    cfg = MODEL_CONFIGS[model_name]
-    r = cfg["upscale_ratio"]
-    torch.manual_seed(0)
-    model = MewZoom(**cfg, operand_dtype=args.operands).to(dev).eval()
+    import ctypes as C
+
     tune_kw = {k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)}
-    if tune_kw:
-        model.set_conv_tune(-1, dev, **tune_kw)
-    eng = model._engine(dev)
-    g = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.rand(B, 3, H, W, generator=g).pin_memory()
-    c_host = torch.tensor([[0.5, 0.2, 0.3]]).pin_memory() if cfg["control_features"] else None
-    x = x_host.to(dev)
-    c = c_host.to(dev) if c_host is not None else None
-    out_px = B * H * r * W * r
-    npix = B * H * W
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    import ctypes as C
-
-    for _ in range(args.warmup):
-        y = model.upscale(x, c)
-    barrier()
-    _native.check(eng.lib.mz_model_enable_timing(eng.handle, 1))
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        y = model.upscale(x, c)
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
-    conv_ms = C.c_float()
-    _native.check(eng.lib.mz_model_conv_stack_ms(eng.handle, C.byref(conv_ms)))
-    _native.check(eng.lib.mz_model_enable_timing(eng.handle, 0))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * out_px / (ms_step * 1e-3) / 1e6
-
-    # ---- end to end through the public API with HOST buffers (H2D + kernels + D2H inside the timed region) ----
-    e2e = None
-    if not args.no_e2e:
-        out_host = torch.empty((B, 3, H * r, W * r), dtype=torch.float32).pin_memory()
-        for _ in range(2):
-            model.upscale_host(x_host, c_host, out=out_host, device=local_rank)
+    def measure(workload: str, steps: int, warmup: int, want_e2e: bool, sample_clocks: bool):
+        """W untimed + exactly K timed steps (CUDA events on the launching stream, barrier + synchronize on both
+        sides, max over ranks) of one workload; optionally the end-to-end leg with host buffers."""
+        model_name, B, H, W, desc = WORKLOADS[workload]
+        cfg = MODEL_CONFIGS[model_name]
+        r = cfg["upscale_ratio"]
+        torch.manual_seed(0)
+        model = MewZoom(**cfg, operand_dtype=args.operands).to(dev).eval()
+        if tune_kw:
+            model.set_conv_tune(-1, dev, **tune_kw)
+        eng = model._engine(dev)
+        g = torch.Generator().manual_seed(1234 + rank)
+        x_host = torch.rand(B, 3, H, W, generator=g).pin_memory()
+        c_host = torch.tensor([[0.5, 0.2, 0.3]]).pin_memory() if cfg["control_features"] else None
+        x = x_host.to(dev)
+        c = c_host.to(dev) if c_host is not None else None
+        out_px = B * H * r * W * r
+        for _ in range(warmup):
+            model.upscale(x, c)
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            model.upscale_host(x_host, c_host, out=out_host, device=local_rank)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        _native.check(eng.lib.mz_model_enable_timing(eng.handle, 1))
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            model.upscale(x, c)
+        ev1.record()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+        conv_ms = C.c_float()
+        _native.check(eng.lib.mz_model_conv_stack_ms(eng.handle, C.byref(conv_ms)))
+        _native.check(eng.lib.mz_model_enable_timing(eng.handle, 0))
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-        e2e = {"value": world * out_px * args.steps / dt / 1e6, "unit": "Mpx/s",
-               "h2d_bytes_per_step": x_host.numel() * 4 + (c_host.numel() * 4 if c_host is not None else 0),
-               "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": 1e3 * dt / args.steps,
-               "api": "MewZoom.upscale_host -> mz_upscale_host (pinned host buffers)"}
+        ms_step = float(t.item()) / steps
+        res = {"model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc, "ms_step": ms_step,
+               "conv_ms": conv_ms.value, "clocks": clocks, "value": world * out_px / (ms_step * 1e-3) / 1e6,
+               "e2e": None}
+        # ---- end to end through the public API with HOST buffers (H2D + kernels + D2H inside the timed region) ----
+        if want_e2e:
+            out_host = torch.empty((B, 3, H * r, W * r), dtype=torch.float32).pin_memory()
+            for _ in range(2):
+                model.upscale_host(x_host, c_host, out=out_host, device=local_rank)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                model.upscale_host(x_host, c_host, out=out_host, device=local_rank)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            res["e2e"] = {"value": world * out_px * steps / dt / 1e6, "unit": "Mpx/s",
+                          "h2d_bytes_per_step": x_host.numel() * 4 + (c_host.numel() * 4 if c_host is not None else 0),
+                          "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": 1e3 * dt / steps,
+                          "api": "MewZoom.upscale_host -> mz_upscale_host (pinned host buffers)"}
+        del model, eng, x, c
+        torch.cuda.empty_cache()
+        return res
+
+    def roofline_of(res, peaks):
+        """Roofline of the dominant kernel (one encoder convolution launch; conv1 and conv2 alternate, so per-launch
+        figures are their mean).  Algorithmic work per launch, unpadded:
+          flops = 2 * 9 * C * hC per LR pixel (conv1 == conv2)
+          bytes = mean of conv1 (read zb 2C, write hidden 2hC) and conv2 (read hidden 2hC + zf 4C, write zf 4C + zb 2C)
+        The bound is whichever of flops/peak_tensor and bytes/peak_hbm is the longer time."""
+        cfg, npix = res["cfg"], res["B"] * res["H"] * res["W"]
+        L, C_ = cfg["num_encoder_layers"], cfg["num_channels"]
+        hC = C_ * cfg["hidden_ratio"]
+        conv_launch_ms = res["conv_ms"] / (2 * L)
+        conv_flops = conv_flops_per_launch(cfg, npix)
+        conv_bytes = 0.5 * ((2 * C_ + 2 * hC) + (2 * hC + 4 * C_ + 4 * C_ + 2 * C_)) * npix
+        t_tensor = conv_flops / (peaks["bf16_sustained"] * 1e12)
+        t_hbm = conv_bytes / (peaks["hbm"] * 1e9)
+        tf = conv_flops / (conv_launch_ms * 1e-3) / 1e12
+        gbs = conv_bytes / (conv_launch_ms * 1e-3) / 1e9
+        total_flops = algorithmic_flops_per_lr_px(cfg) * npix
+        common = {
+            "kernel": "conv_tc_kernel (3x3 implicit GEMM, tcgen05)", "traffic": None,
+            "flops_per_launch": conv_flops, "bytes_per_launch": conv_bytes, "ms_per_launch": conv_launch_ms,
+            "launches_per_step": 2 * L, "conv_share_of_step": res["conv_ms"] / res["ms_step"],
+            "tensor": {"achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                       "frac": tf / peaks["bf16_sustained"], "frac_of_burst_peak": tf / peaks["bf16_burst"]},
+            "hbm": {"achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"]},
+            "whole_step_tflops": total_flops / (res["ms_step"] * 1e-3) / 1e12,
+            "peak_source": peaks["source"] + "; tensor = sustained 16-bit dense (kernel timed inside a long step)",
+        }
+        if t_hbm > t_tensor:
+            return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                    **common}
+        return {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": tf / peaks["bf16_sustained"], **common}
+
+    main_res = measure(args.workload, args.steps, args.warmup, not args.no_e2e, True)
+    # The north_star's efficiency target is stated on MewZoom-4X-Ctrl: measure that frame too (same protocol) so the
+    # one JSON line carries both the configs[1] headline and the 4X-Ctrl roofline fraction.
+    also_res = None
+    if args.workload == "cfg2" and not args.no_also:
+        also_res = measure("cfg4a", max(3, args.steps), args.warmup, False, False)
 
     if rank != 0:
         if world > 1:
@@ -277,21 +322,12 @@ def main():
         return
 
     peaks = load_peaks()
+    res = main_res
+    model_name, cfg, B, H, W, desc = res["model_name"], res["cfg"], res["B"], res["H"], res["W"], res["desc"]
+    ms_step, value, e2e, clocks = res["ms_step"], res["value"], res["e2e"], res["clocks"]
     L = cfg["num_encoder_layers"]
     launches_per_step = 2 * L + 2 + (1 if cfg["control_features"] else 0)
-    conv_launch_ms = conv_ms.value / (2 * L)
-    conv_flops = conv_flops_per_launch(cfg, npix)
-    achieved = conv_flops / (conv_launch_ms * 1e-3) / 1e12
-    total_flops = algorithmic_flops_per_lr_px(cfg) * npix
-    roofline = {
-        "bound": "tensor", "kernel": "conv_tc_kernel (3x3 implicit GEMM, tcgen05)", "achieved": achieved,
-        "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-        "traffic": None, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-        "frac_of_burst_peak": achieved / peaks["bf16_burst"], "flops_per_launch": conv_flops,
-        "ms_per_launch": conv_launch_ms, "launches_per_step": 2 * L,
-        "conv_share_of_step": conv_ms.value / ms_step,
-        "whole_step_tflops": total_flops / (ms_step * 1e-3) / 1e12,
-    }
+    roofline = roofline_of(res, peaks)
     cpu_baseline = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -314,6 +350,10 @@ def main():
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         "ms_per_frame": ms_step / B,
     }
+    if also_res is not None:
+        ar = roofline_of(also_res, peaks)
+        line["also"] = {"cfg4a": {"workload": also_res["desc"], "value": also_res["value"], "unit": "Mpx/s",
+                                  "ms_per_frame": also_res["ms_step"], "roofline": ar}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

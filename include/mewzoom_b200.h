@@ -143,10 +143,11 @@ int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, 
                    void* stream);
 
 /* FanOutProjection (model.py:212-242) fused with the NCHW->NHWC layout change:
- * zf (B,H,W,Cp) fp32 residual stream and zb (B,H,W,Cp) 16-bit MMA operand (operand_dtype).
+ * zf (B,H,W,Cp) fp32 residual stream and zb (B,H,W,zb_pitch) 16-bit MMA operand (operand_dtype);
+ * zb_pitch = 0 means Cp, a larger pitch is zero-filled (mz_zb_pitch gives the pitch mz_upscale uses).
  * w_dev is (Cp,3) fp32 and bias_dev (Cp,) fp32, zero-padded beyond the logical channel count. */
 int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev,
-                 int32_t B, int32_t H, int32_t W, int32_t Cp, int32_t operand_dtype, void* stream);
+                 int32_t B, int32_t H, int32_t W, int32_t Cp, int32_t zb_pitch, int32_t operand_dtype, void* stream);
 
 /* 3x3 / pad 1 / stride 1 / bias-free convolution on NHWC 16-bit activations (model.py:742-748) with
  * the fused epilogues of one encoder block.  `wpacked_dev` comes from mz_pack_conv_weight; input, weights
@@ -154,10 +155,11 @@ int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, 
  *   mode 0: out16 = SiLU(scale[b,n]*acc + shift[b,n])   (conv1 + control + SiLU); film_dev is
  *           (B,2,cout_p) fp32 -- scale row then shift row per image -- or NULL for scale 1, shift 0
  *   mode 1: zf += acc ; out16 = round16(zf)              (conv2 + ResidualConnection, model.py:789-792)
+ * out_pitch: channel pitch of out16 in elements (0 = cout_p); channels beyond cout_p are left untouched.
  * use_tc = 1: tcgen05/TMEM/TMA kernel; 0: SIMT diagnostic kernel.  tune may be NULL. */
 int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev,
                void* out16_dev, float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t cout_p,
-               int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream);
+               int32_t out_pitch, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream);
 
 /* SubpixelConv2d (model.py:885-930) + global skip (model.py:162) + optional clamp (:177):
  * y = [clamp](skip + PixelShuffle_r(conv3x3(z))).  skip_mode 0: none, 1: read y_dev in place
@@ -191,6 +193,10 @@ int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_
 
 /* Padded channel counts the kernels use for a logical channel count. */
 int mz_padded_channels(int32_t c);
+
+/* Channel pitch of the 16-bit shadow `zb` of the residual stream for a padded channel count: 48 -> 64 (so that a
+ * pixel is one 128-byte TMA row instead of three 32-byte ones), otherwise unchanged. */
+int mz_zb_pitch(int32_t cp);
 
 #ifdef __cplusplus
 }

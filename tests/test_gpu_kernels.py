@@ -70,6 +70,32 @@ def test_stem_pack(dev, C):
             assert zf[..., C:].abs().max().item() == 0.0           # padded channels stay zero
 
 
+def test_stem_pack_with_padded_shadow_pitch(dev):
+    """48-channel models keep zb at a 64-channel pitch (one 128-byte TMA row per pixel); the pad must be zero."""
+    ops, native = _ops()
+    assert native.load().mz_zb_pitch(48) == 64 and native.load().mz_zb_pitch(96) == 96
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1, 3, 6, 7, generator=g)
+    w, b = torch.randn(48, 3, 1, 1, generator=g) * 0.5, torch.randn(48, generator=g) * 0.1
+    ref = F.conv2d(x, w, b).permute(0, 2, 3, 1)
+    zf, zb = ops.stem_pack(x.to(dev), w, b, zb_pitch=64)
+    assert tuple(zf.shape) == (1, 6, 7, 48) and tuple(zb.shape) == (1, 6, 7, 64)
+    assert (zf.cpu() - ref).abs().max().item() <= 1e-5
+    assert torch.equal(zb.cpu()[..., :48], zf.cpu().to(torch.float16)) and zb.cpu()[..., 48:].abs().max().item() == 0.0
+
+
+def test_conv2_writes_shadow_at_padded_pitch(dev):
+    ops, native = _ops()
+    inp, w, _, zf0, acc = _conv_operands(96, 48, (2, 9, 140), 21, ops, torch.float16)
+    wp = ops.pack_conv_weight(w, dev)
+    for use_tc in (True, False):
+        zf = zf0.to(dev).contiguous()
+        zb = ops.conv3x3(inp.to(dev), wp, 1, None, zf, use_tc=use_tc, out_pitch=64).cpu()
+        assert tuple(zb.shape) == (2, 9, 140, 64)
+        assert torch.equal(zb[..., :48], zf.cpu().to(torch.float16)) and zb[..., 48:].abs().max().item() == 0.0
+        assert (zf.cpu() - (zf0 + acc)).abs().max().item() <= 1e-4
+
+
 def test_control_film(dev):
     ops, _ = _ops()
     g = torch.Generator().manual_seed(4)

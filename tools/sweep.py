@@ -46,7 +46,7 @@ def main():
     print(f"C={C} {W}x{H} B={B}: {flops / 1e9:.1f} GFLOP per conv; 100% of 1644 TF = {flops / 1644e12 * 1e6:.1f} us")
     if os.environ.get("SWEEP") == "dbg":
         grid = list(itertools.product((1,), (0,), (0,), (0,)))
-        dbgs = (0, 4, 8, 12, 3, 7)
+        dbgs = (0, 16, 16, 4, 8, 12, 3, 7)
     else:
         grid = list(itertools.product((1,), (0, 1, 2, 4), (0,), (0,)))
         dbgs = (0,)

@@ -71,14 +71,15 @@ SIGNATURES = {
     "mz_upscale": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _P, C.c_size_t, C.c_uint32, _P]),
     "mz_upscale_host": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, C.c_uint32]),
     "mz_bicubic_f32": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
-    "mz_stem_pack": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "mz_conv3x3": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
+    "mz_stem_pack": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "mz_conv3x3": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
     "mz_head_shuffle_add": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
     "mz_pack_conv_weight": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, C.POINTER(C.c_size_t)]),
     "mz_control_film": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mz_probe_umma": (C.c_int, [_I, _I, _I, C.POINTER(C.c_float)]),
     "mz_probe_mma_rate": (C.c_int, [_I, _I, _I, _I, _I, _I, C.POINTER(C.c_float)]),
     "mz_padded_channels": (C.c_int, [_I]),
+    "mz_zb_pitch": (C.c_int, [_I]),
 }
 
 _lib = None

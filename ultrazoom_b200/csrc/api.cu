@@ -62,16 +62,17 @@ int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, 
 }
 
 int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev, int32_t B,
-                 int32_t H, int32_t W, int32_t Cp, int32_t operand_dtype, void* stream) {
+                 int32_t H, int32_t W, int32_t Cp, int32_t zb_pitch, int32_t operand_dtype, void* stream) {
   MZ_REQUIRE(x_dev && w_dev && bias_dev && zf_dev && zb_dev, "stem: null pointer");
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
-  return launch_stem(x_dev, w_dev, bias_dev, zf_dev, static_cast<uint16_t*>(zb_dev), operand_dtype, B, H, W, Cp,
+  return launch_stem(x_dev, w_dev, bias_dev, zf_dev, static_cast<uint16_t*>(zb_dev), operand_dtype, B, H, W, Cp, zb_pitch,
                      static_cast<cudaStream_t>(stream));
 }
 
 int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev, void* out_bf16_dev,
-               float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t cout_p, int32_t operand_dtype,
-               int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+               float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t cout_p, int32_t out_pitch,
+               int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+  MZ_REQUIRE(out_pitch == 0 || (out_pitch >= cout_p && out_pitch % 8 == 0), "conv: out_pitch %d must be 0 or a multiple of 8 >= cout_p", out_pitch);
   MZ_REQUIRE(in_dev && wpacked_dev && out_bf16_dev, "conv: null pointer");
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
   MZ_REQUIRE(mode == 0 || mode == 1, "conv: mode must be 0 or 1, %d given", mode);
@@ -89,6 +90,7 @@ int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const 
   a.epi.n_pad = cout_p;
   a.epi.film = film_dev;
   a.epi.out_bf16 = static_cast<uint16_t*>(out_bf16_dev);
+  a.epi.out_pitch = out_pitch;
   a.epi.zf = zf_dev;
   if (use_tc) return launch_conv_tc(a, to_tune(tune), current_device(), static_cast<cudaStream_t>(stream));
   return launch_conv_simt(a, static_cast<cudaStream_t>(stream));

@@ -33,6 +33,8 @@ struct TcParams {
   CUtensorMap tmZ;  // fp32 residual stream (mode 1): (n_pad, W, H, B), box (e32, 32 px, 1, 1), swizzled
   int e16, e32;     // channels per output box: box rows are 128 / 64 / 32 bytes
   int stage_bytes;  // epilogue staging (all four warps)
+  int o_ring;       // mode 0: warp-private ring of output boxes (2 or 4)
+  int res_rows;     // mode 1: accumulator rows whose residual / output staging is resident at once (1 or ROWS)
   EpiParams epi;
   int kc, n_chunks;  // channels per swizzled sub-tile; pipeline chunks per patch (each = subs sub-tiles)
   int subs;          // 16-channel sub-tiles fused into one stage (3 for Cin = 48), else 1
@@ -356,8 +358,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t nb16 = n_pad / p.e16, nb32 = n_pad / p.e32;
     const uint32_t sh16 = 31 - __clz(p.e16), sh32 = 31 - __clz(p.e32);  // box widths are powers of two
     // warp-private staging: mode 0 -> ring of two 16-bit boxes; mode 1 -> whole fp32 row-tile + whole 16-bit row-tile
-    const uint32_t st_base = base + sp.stage + q * (MODE == 0 ? 2 * box16 : 32 * n_pad * 6);
-    const uint32_t st_z = st_base, st_o = MODE == 0 ? st_base : st_base + 32 * n_pad * 4;
+    const uint32_t row_stage = 32 * n_pad * 6;  // mode 1: one accumulator row of this warp: fp32 tile + 16-bit tile
+    const uint32_t st_base = base + sp.stage + q * (MODE == 0 ? p.o_ring * box16 : p.res_rows * row_stage);
+    const bool all_rows = p.res_rows > 1;
     const uint32_t my_res = bar_res + 8 * q;
     for (int round = 0; round < p.n_rounds; ++round) {
       const int unit_raw = round * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
@@ -383,16 +386,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         film_b = b;
       }
 
-      // residual row-tile of accumulator row r: TMA load into this warp's staging (after its previous stores have
-      // finished reading it)
-      auto load_residual = [&](int y) {
-        if (MODE == 1 && live && y < p.epi.H && lane == 0) {
-          bulk_wait_read<0>();
-          mbar_expect_tx(my_res, 32 * n_pad * 4);
-          for (uint32_t bx = 0; bx < nb32; ++bx) tma_load_4d(st_z + bx * box32, &p.tmZ, my_res, bx * p.e32, xw, y, b);
+      // residual row-tiles: TMA load into this warp's staging once its previous stores have finished reading it.
+      // With staging for every accumulator row (res_rows == ROWS) all rows of the patch are requested up front on
+      // one barrier; otherwise row r is requested when row r-1 has been stored.
+      auto load_residual = [&](int r_lo, int r_hi) {
+        if (MODE == 1 && live && lane == 0) {
+          int nrows = 0;
+          for (int r = r_lo; r < r_hi; ++r) nrows += (y0 + r < p.epi.H) ? 1 : 0;
+          if (nrows > 0) {
+            bulk_wait_read<0>();
+            mbar_expect_tx(my_res, nrows * 32 * n_pad * 4);
+            for (int r = r_lo; r < r_hi; ++r) {
+              if (y0 + r >= p.epi.H) break;
+              const uint32_t dst = st_base + (all_rows ? r : 0) * row_stage;
+              for (uint32_t bx = 0; bx < nb32; ++bx) tma_load_4d(dst + bx * box32, &p.tmZ, my_res, bx * p.e32, xw, y0 + r, b);
+            }
+          }
         }
       };
-      load_residual(y0);
+      load_residual(0, all_rows ? ROWS : 1);
 
       MZ_TIMED(0, mbar_wait(bar_acc_full + 8 * as, pacc));
       __syncwarp();
@@ -425,9 +437,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               epi_head_r<3>(p.epi, b, y, x, acc);
           }
         } else if (MODE == 1) {
-          if (r > 0) load_residual(y);
-          mbar_wait(my_res, rpar);
-          rpar ^= 1u;
+          if (r > 0 && !all_rows) load_residual(r, r + 1);
+          if (r == 0 || !all_rows) {
+            mbar_wait(my_res, rpar);
+            rpar ^= 1u;
+          }
+          const uint32_t st_z = st_base + (all_rows ? r : 0) * row_stage, st_o = st_z + 32 * n_pad * 4;
           for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) {
             uint32_t v[16];
             tmem_ld16(taddr + n0, v);
@@ -461,9 +476,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         } else {
           for (uint32_t bx = 0; bx < nb16; ++bx) {
-            const uint32_t buf = st_o + (ring & 1u) * box16;
+            const uint32_t buf = st_base + (ring & static_cast<uint32_t>(p.o_ring - 1)) * box16;
             ++ring;
-            if (lane == 0) bulk_wait_read<1>();  // the store issued two boxes ago has finished reading this buffer
+            if (lane == 0) {  // the store issued o_ring boxes ago has finished reading this buffer
+              if (p.o_ring == 4)
+                bulk_wait_read<3>();
+              else
+                bulk_wait_read<1>();
+            }
             __syncwarp();
             const uint32_t orow = buf + lane * row16;
             for (uint32_t sub = 0; sub < static_cast<uint32_t>(p.e16); sub += 16) {
@@ -536,7 +556,9 @@ static uint32_t pow2_cols(uint32_t c) {
 }
 
 static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stages, int halo_mode, int a_stages,
-                          int b_stages) {
+                          int b_stages, bool rich_staging) {
+  p.o_ring = rich_staging ? 4 : 2;
+  p.res_rows = rich_staging ? rows : 1;
   p.kc = kc;
   // 16-channel sub-tiles are fused into one pipeline stage when the whole K extent is small (Cin = 48): three times
   // the UMMAs per barrier round trip
@@ -563,7 +585,7 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   const int n = p.epi.n_pad;
   p.e16 = n % 64 == 0 ? 64 : (n % 32 == 0 ? 32 : 16);
   p.e32 = n % 32 == 0 ? 32 : 16;
-  p.stage_bytes = p.epi.mode == 0 ? 4 * 2 * 32 * p.e16 * 2 : (p.epi.mode == 1 ? 4 * 32 * n * 6 : 0);
+  p.stage_bytes = p.epi.mode == 0 ? 4 * p.o_ring * 32 * p.e16 * 2 : (p.epi.mode == 1 ? 4 * p.res_rows * 32 * n * 6 : 0);
 }
 
 static bool fits(const TcParams& p) {
@@ -611,8 +633,12 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
       if (rows == 3) continue;  // instantiated for 1, 2 and 4 accumulator rows
       for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {
         for (int bs = tune.b_stages ? tune.b_stages : 4; bs >= 2 && !found; --bs) {
-          fill_geometry(p, a.cin_p, kc, rows, acc_stages, tune.halo_mode, tune.a_stages ? tune.a_stages : 2, bs);
-          if (fits(p)) found = true;
+          // deeper epilogue staging (more TMA stores / residual loads in flight) when shared memory allows
+          for (int rich = 1; rich >= 0 && !found; --rich) {
+            fill_geometry(p, a.cin_p, kc, rows, acc_stages, tune.halo_mode, tune.a_stages ? tune.a_stages : 2, bs,
+                          rich != 0);
+            if (fits(p)) found = true;
+          }
           if (tune.b_stages) break;
         }
         if (tune.kc) break;
@@ -663,8 +689,8 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   if (e.mode != 2) {
     const uint64_t dims[4] = {static_cast<uint64_t>(e.n_pad), static_cast<uint64_t>(e.W), static_cast<uint64_t>(e.H),
                               static_cast<uint64_t>(e.B)};
-    const uint64_t st16[3] = {static_cast<uint64_t>(e.n_pad) * 2, static_cast<uint64_t>(e.W) * e.n_pad * 2,
-                              static_cast<uint64_t>(e.H) * e.W * e.n_pad * 2};
+    const uint64_t op = e.out_pitch ? e.out_pitch : e.n_pad;
+    const uint64_t st16[3] = {op * 2, static_cast<uint64_t>(e.W) * op * 2, static_cast<uint64_t>(e.H) * e.W * op * 2};
     const uint32_t box16[4] = {static_cast<uint32_t>(p.e16), 32u, 1u, 1u};
     int rc = encode_tmap(&p.tmO, tdt, 4, e.out_bf16, dims, st16, box16, swz_of(p.e16 * 2));
     if (rc != MZ_OK) return rc;

@@ -103,4 +103,6 @@ int mz_padded_channels(int32_t c) {
   return p16 <= 64 ? p16 : ((c + 31) / 32) * 32;
 }
 
+int mz_zb_pitch(int32_t cp) { return cp == 48 ? 64 : cp; }
+
 }  // extern "C"

@@ -37,6 +37,8 @@ struct EpiParams {
   int n_pad;          // GEMM N (multiple of 16) == channel pitch of the 16-bit / fp32 NHWC outputs
   const float* film;  // mode 0: [B][2][n_pad] (scale row then shift row per image) or nullptr
   uint16_t* out_bf16;       // mode 0: hidden; mode 1: zb (fp16 or bf16 bits)
+  int out_pitch;            // channel pitch of out_bf16 in elements (0 = n_pad); > n_pad when the consumer wants
+                            // zero-padded channels (48-channel zb is kept at pitch 64: 128-byte TMA rows)
   float* zf;                // mode 1: fp32 residual stream, updated in place
   // mode 2
   const float* x;  // LR image (B,3,H,W) fp32 -- only for skip_mode 2
@@ -74,7 +76,7 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaStream_t s);
 int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s);
 int launch_stem(const float* x, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16, int B, int H,
-                int W, int Cp, cudaStream_t s);
+                int W, int Cp, int zb_pitch, cudaStream_t s);
 int launch_film(const float* c, int c_rows, const float* w, const float* b, float* film, int L, int B, int F,
                 int hC, int hCp, cudaStream_t s);
 
@@ -110,7 +112,7 @@ __device__ __forceinline__ void epi_residual16(const EpiParams& p, int b, int y,
     o[2 * q] = pack_op2(p.bf16, z.x, z.y);
     o[2 * q + 1] = pack_op2(p.bf16, z.z, z.w);
   }
-  uint16_t* dst = p.out_bf16 + pix * p.n_pad + n0;
+  uint16_t* dst = p.out_bf16 + pix * (p.out_pitch ? p.out_pitch : p.n_pad) + n0;
   st_global_v4(dst, o[0], o[1], o[2], o[3]);
   st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
 }
@@ -138,7 +140,7 @@ __device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, in
     uint32_t o[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) o[q] = pack_op2(p.bf16, silu_f(acc[2 * q]), silu_f(acc[2 * q + 1]));
-    uint16_t* dst = p.out_bf16 + pix * p.n_pad + n0;
+    uint16_t* dst = p.out_bf16 + pix * (p.out_pitch ? p.out_pitch : p.n_pad) + n0;
     st_global_v4(dst, o[0], o[1], o[2], o[3]);
     st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
   } else {

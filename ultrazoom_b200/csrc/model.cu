@@ -17,7 +17,7 @@ using namespace mz;
 
 struct mz_model {
   mz_config cfg;
-  int C, Cp, hC, hCp, L, r, F, headN, headNp, bf16;
+  int C, Cp, Cz, hC, hCp, L, r, F, headN, headNp, bf16;  // Cz: channel pitch of zb (>= Cp, zero padded)
   float* stem_w = nullptr;  // (Cp,3)
   float* stem_b = nullptr;  // (Cp)
   uint16_t* conv1 = nullptr;  // L x [9][hCp][Cp]
@@ -69,7 +69,7 @@ WsPlan plan_ws(const mz_model* m, int B, int H, int W) {
   p.zf = off;
   off = align_up(off + npix * m->Cp * sizeof(float), 1024);
   p.zb = off;
-  off = align_up(off + npix * m->Cp * sizeof(uint16_t), 1024);
+  off = align_up(off + npix * m->Cz * sizeof(uint16_t), 1024);
   p.hid = off;
   off = align_up(off + npix * m->hCp * sizeof(uint16_t), 1024);
   p.film = off;
@@ -132,6 +132,7 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   m->cfg = *cfg;
   m->C = cfg->num_channels;
   m->Cp = mz_padded_channels(m->C);
+  m->Cz = mz_zb_pitch(m->Cp);
   m->hC = hC;
   m->hCp = mz_padded_channels(hC);
   m->L = cfg->num_encoder_layers;
@@ -146,7 +147,7 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   for (int i = 0; i < 3; ++i) m->tune[i].halo_mode = hm;
 
   DeviceGuard g(cfg->device);
-  const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cp, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
+  const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cz, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
@@ -156,7 +157,7 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   alloc(reinterpret_cast<void**>(&m->stem_b), sizeof(float) * m->Cp);
   alloc(reinterpret_cast<void**>(&m->conv1), sizeof(uint16_t) * c1 * m->L);
   alloc(reinterpret_cast<void**>(&m->conv2), sizeof(uint16_t) * c2 * m->L);
-  alloc(reinterpret_cast<void**>(&m->head), sizeof(uint16_t) * 9 * m->headNp * m->Cp);
+  alloc(reinterpret_cast<void**>(&m->head), sizeof(uint16_t) * 9 * m->headNp * m->Cz);
   if (m->F > 0) {
     alloc(reinterpret_cast<void**>(&m->ctrl_w), sizeof(float) * m->L * 2 * m->hC * m->F);
     alloc(reinterpret_cast<void**>(&m->ctrl_b), sizeof(float) * m->L * 2 * m->hC);
@@ -214,7 +215,7 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
     case MZ_W_CONV1: {
       MZ_REQUIRE(numel == static_cast<size_t>(m->hC) * m->C * 9, "conv1 weight: expected %d elements, got %zu",
                  m->hC * m->C * 9, numel);
-      pack_conv_weight_host(host_data, m->hC, m->C, m->hCp, m->Cp, m->bf16, packed);
+      pack_conv_weight_host(host_data, m->hC, m->C, m->hCp, m->Cz, m->bf16, packed);
       MZ_CUDA(cudaMemcpy(m->conv1 + static_cast<size_t>(layer) * packed.size(), packed.data(),
                          packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
       break;
@@ -230,7 +231,7 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
     case MZ_W_HEAD: {
       MZ_REQUIRE(numel == static_cast<size_t>(m->headN) * m->C * 9, "head weight: expected %d elements, got %zu",
                  m->headN * m->C * 9, numel);
-      pack_conv_weight_host(host_data, m->headN, m->C, m->headNp, m->Cp, m->bf16, packed);
+      pack_conv_weight_host(host_data, m->headN, m->C, m->headNp, m->Cz, m->bf16, packed);
       MZ_CUDA(cudaMemcpy(m->head, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
       break;
     }
@@ -339,10 +340,10 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     rc = launch_film(c_dev, c_rows, m->ctrl_w, m->ctrl_b, film, m->L, B, m->F, m->hC, m->hCp, s);
     if (rc != MZ_OK) return rc;
   }
-  rc = launch_stem(x_dev, m->stem_w, m->stem_b, zf, zb, m->bf16, B, H, W, m->Cp, s);
+  rc = launch_stem(x_dev, m->stem_w, m->stem_b, zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s);
   if (rc != MZ_OK) return rc;
 
-  const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cp, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
+  const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cz, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
   const int slot = m->timing_calls % kTimingSlots;
   if (m->timing) MZ_CUDA(cudaEventRecord(m->ev[2 * slot], s));
   for (int l = 0; l < m->L; ++l) {
@@ -350,7 +351,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     memset(&a, 0, sizeof(a));
     a.in = zb;
     a.w = m->conv1 + l * c1;
-    a.cin_p = m->Cp;
+    a.cin_p = m->Cz;
     a.epi.mode = 0;
     a.epi.bf16 = m->bf16;
     a.epi.B = B;
@@ -373,6 +374,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     a.epi.W = W;
     a.epi.n_pad = m->Cp;
     a.epi.out_bf16 = zb;
+    a.epi.out_pitch = m->Cz;
     a.epi.zf = zf;
     rc = simt ? launch_conv_simt(a, s) : launch_conv_tc(a, m->tune[1], m->cfg.device, s);
     if (rc != MZ_OK) return rc;
@@ -393,7 +395,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
   memset(&a, 0, sizeof(a));
   a.in = zb;
   a.w = m->head;
-  a.cin_p = m->Cp;
+  a.cin_p = m->Cz;
   a.epi.mode = 2;
   a.epi.bf16 = m->bf16;
   a.epi.B = B;

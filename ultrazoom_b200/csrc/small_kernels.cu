@@ -120,8 +120,9 @@ int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cu
 // ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ zf,
-                                                   uint16_t* __restrict__ zb, int bf16, int B, int H, int W, int Cp) {
-  const int groups = Cp / 8;
+                                                   uint16_t* __restrict__ zb, int bf16, int B, int H, int W, int Cp,
+                                                   int Cz) {
+  const int groups = Cz / 8;
   const long long npix = static_cast<long long>(B) * H * W;
   const long long total = npix * groups;
   const size_t plane = static_cast<size_t>(H) * W;
@@ -129,32 +130,36 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int g = static_cast<int>(idx % groups);
     const long long pix = idx / groups;
-    const long long b = pix / static_cast<long long>(plane);
-    const size_t sp = static_cast<size_t>(pix - b * static_cast<long long>(plane));
-    const float* xb = x + static_cast<size_t>(b) * 3 * plane + sp;
-    const float r0 = __ldg(xb), r1 = __ldg(xb + plane), r2 = __ldg(xb + 2 * plane);
-    float o[8];
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (g * 8 < Cp) {  // channels beyond Cp exist only in the 16-bit shadow (zero padding up to its pitch)
+      const long long b = pix / static_cast<long long>(plane);
+      const size_t sp = static_cast<size_t>(pix - b * static_cast<long long>(plane));
+      const float* xb = x + static_cast<size_t>(b) * 3 * plane + sp;
+      const float r0 = __ldg(xb), r1 = __ldg(xb + plane), r2 = __ldg(xb + 2 * plane);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int n = g * 8 + i;
-      o[i] = fmaf(__ldg(w + n * 3 + 2), r2, fmaf(__ldg(w + n * 3 + 1), r1, fmaf(__ldg(w + n * 3), r0, __ldg(bias + n))));
+      for (int i = 0; i < 8; ++i) {
+        const int n = g * 8 + i;
+        o[i] = fmaf(__ldg(w + n * 3 + 2), r2, fmaf(__ldg(w + n * 3 + 1), r1, fmaf(__ldg(w + n * 3), r0, __ldg(bias + n))));
+      }
+      float4* f = reinterpret_cast<float4*>(zf + static_cast<size_t>(pix) * Cp + g * 8);
+      f[0] = make_float4(o[0], o[1], o[2], o[3]);
+      f[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
-    float4* f = reinterpret_cast<float4*>(zf + static_cast<size_t>(pix) * Cp + g * 8);
-    f[0] = make_float4(o[0], o[1], o[2], o[3]);
-    f[1] = make_float4(o[4], o[5], o[6], o[7]);
-    st_global_v4(zb + static_cast<size_t>(pix) * Cp + g * 8, pack_op2(bf16, o[0], o[1]), pack_op2(bf16, o[2], o[3]),
+    st_global_v4(zb + static_cast<size_t>(pix) * Cz + g * 8, pack_op2(bf16, o[0], o[1]), pack_op2(bf16, o[2], o[3]),
                  pack_op2(bf16, o[4], o[5]), pack_op2(bf16, o[6], o[7]));
   }
 }
 
 int launch_stem(const float* x, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16, int B, int H,
-                int W, int Cp, cudaStream_t s) {
+                int W, int Cp, int zb_pitch, cudaStream_t s) {
   MZ_REQUIRE(Cp > 0 && Cp % 8 == 0, "stem: padded channel count must be a multiple of 8, %d given", Cp);
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "stem: empty input");
-  const long long total = static_cast<long long>(B) * H * W * (Cp / 8);
+  const int Cz = zb_pitch ? zb_pitch : Cp;
+  MZ_REQUIRE(Cz >= Cp && Cz % 8 == 0, "stem: zb pitch %d must be a multiple of 8 and >= %d", Cz, Cp);
+  const long long total = static_cast<long long>(B) * H * W * (Cz / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;
-  stem_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, w, bias, zf, zb, bf16, B, H, W, Cp);
+  stem_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, w, bias, zf, zb, bf16, B, H, W, Cp, Cz);
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }

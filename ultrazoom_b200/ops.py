@@ -58,8 +58,9 @@ def pack_conv_weight(w: Tensor, device: torch.device, cout_p: Optional[int] = No
     return out
 
 
-def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None, dtype: torch.dtype = torch.float16):
-    """FanOutProjection + NCHW->NHWC: returns (zf fp32 (B,H,W,Cp), zb fp16|bf16 (B,H,W,Cp))."""
+def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None, dtype: torch.dtype = torch.float16,
+              zb_pitch: int = 0):
+    """FanOutProjection + NCHW->NHWC: returns (zf fp32 (B,H,W,Cp), zb fp16|bf16 (B,H,W,zb_pitch or Cp))."""
     _need_cuda(x)
     lib = _native.load()
     x = x.to(torch.float32).contiguous()
@@ -71,10 +72,10 @@ def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None,
     w[:Cc] = weight.detach().reshape(Cc, 3).to(x.device, torch.float32)
     b[:Cc] = bias.detach().to(x.device, torch.float32)
     zf = torch.empty((B, H, W, cp), dtype=torch.float32, device=x.device)
-    zb = torch.empty((B, H, W, cp), dtype=dtype, device=x.device)
+    zb = torch.empty((B, H, W, zb_pitch or cp), dtype=dtype, device=x.device)
     with torch.cuda.device(x.device):
         _native.check(lib.mz_stem_pack(x.data_ptr(), w.data_ptr(), b.data_ptr(), zf.data_ptr(), zb.data_ptr(),
-                                       B, H, W, cp, _native.dtype_code(dtype), _stream(x)))
+                                       B, H, W, cp, zb_pitch, _native.dtype_code(dtype), _stream(x)))
     return zf, zb
 
 
@@ -95,7 +96,7 @@ def control_film(c: Tensor, weight: Tensor, bias: Tensor, B: int, hcp: Optional[
 
 
 def conv3x3(inp: Tensor, wpacked: Tensor, mode: int, film: Optional[Tensor] = None, zf: Optional[Tensor] = None,
-            use_tc: bool = True, tune: Optional[_native.MzConvTune] = None) -> Tensor:
+            use_tc: bool = True, tune: Optional[_native.MzConvTune] = None, out_pitch: int = 0) -> Tensor:
     """3x3 conv on NHWC fp16|bf16 with the fused block epilogues; returns the 16-bit NHWC output (dtype of `inp`).
 
     mode 0: SiLU(scale*acc+shift) with film (B,2,cout_p) or None; mode 1: zf += acc (in place), returns round16(zf)."""
@@ -105,14 +106,15 @@ def conv3x3(inp: Tensor, wpacked: Tensor, mode: int, film: Optional[Tensor] = No
     B, H, W, cin_p = inp.shape
     _, cout_p, cin_w = wpacked.shape
     assert cin_w == cin_p, "weight / activation channel mismatch"
-    out = torch.empty((B, H, W, cout_p), dtype=inp.dtype, device=inp.device)
+    alloc = torch.zeros if out_pitch > cout_p else torch.empty   # pad channels are never written by the kernel
+    out = alloc((B, H, W, out_pitch or cout_p), dtype=inp.dtype, device=inp.device)
     if mode == 1:
         assert zf is not None and zf.is_contiguous() and tuple(zf.shape) == (B, H, W, cout_p)
     with torch.cuda.device(inp.device):
         _native.check(_native.load().mz_conv3x3(
             inp.data_ptr(), wpacked.data_ptr(), mode, film.data_ptr() if film is not None else None,
             out.data_ptr(), zf.data_ptr() if zf is not None else None, B, H, W, cin_p, cout_p,
-            _native.dtype_code(inp.dtype), 1 if use_tc else 0, C.byref(tune) if tune is not None else None, _stream(inp)))
+            out_pitch, _native.dtype_code(inp.dtype), 1 if use_tc else 0, C.byref(tune) if tune is not None else None, _stream(inp)))
     return out
 
 
