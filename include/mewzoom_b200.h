@@ -133,6 +133,7 @@ typedef struct mz_conv_tune {
   int32_t cluster;    /* CTAs per cluster sharing the weight stream via TMA multicast: 1, 2 or 4       */
   int32_t dbg;        /* timing experiments ONLY (results are wrong): 1 skip weight loads, 2 skip        */
                       /* activation loads, 4 skip the epilogue body, 8 skip the MMAs                     */
+  int32_t pair;       /* 1: CTA pairs issue M = 256 UMMAs (cta_group::2), weights split between the two  */
 } mz_conv_tune;
 
 /* which = 0 conv1, 1 conv2, 2 head, -1 all.  Takes effect on the next mz_upscale. */

@@ -151,6 +151,10 @@ CONV_CASES = [
     (96, 192, (2, 30, 260), dict(cluster=4)),
     (48, 96, (2, 13, 150), dict(cluster=4, max_ctas=6)),
     (64, 64, (1, 3, 100), dict(cluster=4)),
+    (96, 192, (1, 21, 300), dict(pair=1)),
+    (96, 192, (2, 30, 260), dict(pair=1, max_ctas=4)),
+    (64, 64, (1, 5, 130), dict(pair=1)),
+    (64, 128, (1, 1, 100), dict(pair=1)),
 ]
 
 
@@ -179,6 +183,7 @@ def test_conv1_film_silu(dev, cin, cout, shape, tune, halo_mode, dt):
     (96, 48, (2, 13, 150), {}), (192, 96, (1, 21, 300), {}), (108, 54, (1, 10, 70), {}),
     (192, 96, (2, 30, 260), dict(max_ctas=3)), (32, 16, (1, 1, 5), {}), (192, 96, (1, 7, 129), dict(rows=1, acc_stages=1)),
     (192, 96, (2, 30, 260), dict(cluster=4)), (192, 96, (2, 30, 260), dict(cluster=1)), (96, 48, (1, 5, 700), dict(cluster=2, max_ctas=5)),
+    (192, 96, (1, 21, 300), dict(pair=1)), (192, 96, (2, 30, 260), dict(pair=1, max_ctas=4)), (128, 64, (1, 3, 129), dict(pair=1)),
 ])
 @pytest.mark.parametrize("dt", DTYPES)
 def test_conv2_residual(dev, cin, cout, shape, tune, halo_mode, dt):

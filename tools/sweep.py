@@ -48,7 +48,7 @@ def main():
         grid = list(itertools.product((1,), (0,), (0,), (0,)))
         dbgs = (0, 16, 16, 4, 8, 12, 3, 7)
     else:
-        grid = list(itertools.product((1,), (0, 1, 2, 4), (0,), (0,)))
+        grid = list(itertools.product((1,), (0, 1, 2), (0, 32, 64), (0, 3, 6)))
         dbgs = (0,)
     extra = os.environ.get("SWEEP_EXTRA")
     for which, (inp, wp, mode, fl, z) in (("conv1", (zb, w1, 0, film, None)), ("conv2", (hid, w2, 1, None, zf))):
@@ -57,7 +57,7 @@ def main():
             if kc and cin % kc:
                 continue
             for dbg in dbgs:
-                kw = dict(cluster=cluster, rows=rows, kc=kc, b_stages=bs, dbg=dbg)
+                kw = dict(cluster=cluster, rows=rows, kc=kc, b_stages=bs, dbg=dbg, pair=int(os.environ.get("PAIR", "0")))
                 try:
                     us = time_conv(inp, wp, mode, fl, z, _native.tune(**kw))
                     print(f"{which} {kw}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)

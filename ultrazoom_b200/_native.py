@@ -51,6 +51,7 @@ class MzConvTune(C.Structure):
         ("max_ctas", C.c_int32),
         ("cluster", C.c_int32),
         ("dbg", C.c_int32),
+        ("pair", C.c_int32),
     ]
 
 

@@ -18,6 +18,7 @@ ConvTcTune to_tune(const mz_conv_tune* t) {
     o.max_ctas = t->max_ctas;
     o.cluster = t->cluster;
     o.dbg = t->dbg;
+    o.pair = t->pair;
   }
   return o;
 }

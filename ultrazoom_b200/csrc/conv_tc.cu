@@ -48,6 +48,7 @@ struct TcParams {
   int pw;  // pixel rows per image row inside an A stage
   int tiles_x, tiles_y, n_units, n_rounds;
   int cluster;       // CTAs per cluster sharing the weight stream by TMA multicast (1, 2 or 4)
+  int pair;          // 1: CTA pairs issue M = 256 UMMAs (cta_group::2), weights split N/2 + N/2 between them
   int b_slice_rows;  // n_pad / cluster: weight rows each CTA loads and multicasts per stage
   long long* prof;   // optional per-CTA role timers (clock64 ticks), [grid][3 roles][8]; nullptr = off
   int dbg;           // timing experiments only (results are wrong): 1 skip weight loads, 2 skip activation loads,
@@ -85,7 +86,10 @@ __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
     }                                                \
   } while (0)
 
-template <int MODE, int KT, int ROWS>
+// PAIR: the CTA pair of a cluster works as one 256-row UMMA (cta_group::2): the leader CTA issues M = 256 UMMAs whose
+// A operand is each CTA's own 128-pixel tile and whose B operand is split -- each CTA holds N/2 weight rows -- so
+// per CTA the weight stream (TMA writes AND tensor-core operand reads from shared memory) is halved.
+template <int MODE, int KT, int ROWS, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -122,21 +126,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, 4);  // one arrive per epilogue warp
+      mbar_init(bar_acc_empty + 8 * i, PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int i = 0; i < 4; ++i) mbar_init(bar_res + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(base + sp.tmem_ptr, p.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(base + sp.tmem_ptr, p.tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(base + sp.tmem_ptr, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster > 1) cluster_sync_all();  // peers' barriers must be initialised before anything is multicast to them
+  if (PAIR || p.cluster > 1) cluster_sync_all();  // peers' barriers must be initialised before anything is signalled to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
-  const uint32_t cta_rank = p.cluster > 1 ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = (PAIR || p.cluster > 1) ? cluster_ctarank() : 0u;
   const uint16_t cta_mask = static_cast<uint16_t>((1u << p.cluster) - 1u);
 
   const int row_bytes = p.kc * 2;
@@ -166,7 +175,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         MZ_TIMED(0, mbar_wait(bar_a_empty + 8 * sa, pa ^ 1u));
         const uint32_t dstA = a_base + sa * p.a_stage_bytes;
         const uint32_t full_a = bar_a_full + 8 * sa;
-        if (lane == 0 && (p.dbg & 2) && a_wrapped) {
+        if (PAIR) {
+          // both CTAs' bytes complete on the LEADER's barrier, which the leader arms for the pair
+          if (lane == 0) {
+            if (cta_rank == 0) mbar_expect_tx(full_a, 2 * p.a_tx_bytes);
+            tma2_load_4d(dstA, &p.tmA, mapa_u32(full_a, 0), c * p.kc, x0 - 1, y0 - 1, b);
+          }
+        } else if (lane == 0 && (p.dbg & 2) && a_wrapped) {
           mbar_arrive(full_a);
         } else if (lane == 0) {
           mbar_expect_tx(full_a, p.a_tx_bytes);
@@ -188,7 +203,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           MZ_TIMED(1, mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u));
           const uint32_t full_b = bar_b_full + 8 * sb;
           const uint32_t dstB = b_base + sb * p.b_stage_bytes;
-          if (lane == 0 && (p.dbg & 1) && b_wrapped) {
+          if (PAIR) {
+            if (lane == 0) {  // this CTA's half of the weight rows; stage layout [3 taps][N/2][kc]
+              if (cta_rank == 0) mbar_expect_tx(full_b, 2 * p.b_tx_bytes);
+              tma2_load_3d(dstB, &p.tmB, mapa_u32(full_b, 0), c * p.kc, cta_rank * p.b_slice_rows, dy * 3);
+            }
+          } else if (lane == 0 && (p.dbg & 1) && b_wrapped) {
             mbar_arrive(full_b);
           } else if (lane == 0) {
             mbar_expect_tx(full_b, p.b_tx_bytes);
@@ -209,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && (!PAIR || cta_rank == 0)) {
     // =============================== MMA issuer ===============================
     // Uniform loop over the whole warp; one elected lane issues tcgen05.mma / tcgen05.commit.  Per weight stage
     // (filter row dy) all 3 * KSTEPS * ROWS UMMAs are issued back to back from ONE predicated region: the
@@ -245,10 +265,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_stage + (DXV) * TB + t * b_kp);        \
       _Pragma("unroll") for (int r = 0; r < ROWS; ++r) {                                                          \
         const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_dy + (DXV) * DX + r * RP + t * a_kp); \
-        if ((DXV) == 0 && t == 0)                                                                                 \
+        if (PAIR) {                                                                                               \
+          if ((DXV) == 0 && t == 0)                                                                               \
+            umma2_bf16(d_base + r * acc_stride, adesc, bdesc, idesc, first);                                      \
+          else                                                                                                    \
+            umma2_acc(d_base + r * acc_stride, adesc, bdesc, idesc);                                              \
+        } else if ((DXV) == 0 && t == 0) {                                                                        \
           umma_bf16(d_base + r * acc_stride, adesc, bdesc, idesc, first);                                         \
-        else                                                                                                      \
+        } else {                                                                                                  \
           umma_acc(d_base + r * acc_stride, adesc, bdesc, idesc);                                                 \
+        }                                                                                                         \
       }                                                                                                           \
     }                                                                                                             \
   }
@@ -301,12 +327,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           MZ_ISSUE_TAP(2)
           if (leader) {
-            if (p.cluster > 1)
-              umma_commit_mcast(bar_b_empty + 8 * sb, cta_mask);
-            else
-              umma_commit(bar_b_empty + 8 * sb);
-            if (dy == 2) umma_commit(bar_a_empty + 8 * sa);
-            if (dy == 2 && last_chunk) umma_commit(bar_acc_full + 8 * as);
+            if (PAIR) {  // release / signal in BOTH CTAs of the pair
+              umma2_commit_mcast(bar_b_empty + 8 * sb, 3);
+              if (dy == 2) umma2_commit_mcast(bar_a_empty + 8 * sa, 3);
+              if (dy == 2 && last_chunk) umma2_commit_mcast(bar_acc_full + 8 * as, 3);
+            } else {
+              if (p.cluster > 1)
+                umma_commit_mcast(bar_b_empty + 8 * sb, cta_mask);
+              else
+                umma_commit(bar_b_empty + 8 * sb);
+              if (dy == 2) umma_commit(bar_a_empty + 8 * sa);
+              if (dy == 2 && last_chunk) umma_commit(bar_acc_full + 8 * as);
+            }
           }
           // ---- now block on whatever was not ready when sampled ----
           if (!last_step) {
@@ -520,7 +552,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_acc_empty + 8 * as);
+      if (lane == 0) {
+        if (PAIR)
+          mbar_arrive_cluster(mapa_u32(bar_acc_empty + 8 * as, 0));  // the leader's issuer waits for both CTAs
+        else
+          mbar_arrive(bar_acc_empty + 8 * as);
+      }
       if (++as == static_cast<uint32_t>(p.acc_stages)) {
         as = 0;
         pacc ^= 1u;
@@ -537,10 +574,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into it
+  if (PAIR || p.cluster > 1) cluster_sync_all();  // no CTA may exit while a peer can still signal into it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR)
+      tmem_dealloc2(tmem_base, p.tmem_cols);
+    else
+      tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -562,7 +602,7 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   p.kc = kc;
   // 16-channel sub-tiles are fused into one pipeline stage when the whole K extent is small (Cin = 48): three times
   // the UMMAs per barrier round trip
-  p.subs = (kc == 16 && halo_mode == 0 && cin_p / 16 <= 3 && p.cluster <= 1) ? cin_p / 16 : 1;
+  p.subs = (kc == 16 && halo_mode == 0 && cin_p / 16 <= 3 && p.cluster <= 1 && !p.pair) ? cin_p / 16 : 1;
   p.n_chunks = cin_p / (kc * p.subs);
   p.rows = rows;
   p.acc_stages = acc_stages;
@@ -576,11 +616,12 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   const int a_bytes = (halo_mode == 1 ? 3 : p.subs) * a_sub;
   p.a_tx_bytes = (halo_mode == 1 ? 3 : p.subs) * (rows + 2) * p.pw * kc * 2;
   p.a_stage_bytes = ((a_bytes + 1023) / 1024) * 1024;
-  p.b_tx_bytes = p.subs * 3 * p.epi.n_pad * kc * 2;  // the three horizontal taps of one filter row
+  const int n_local = p.pair ? p.epi.n_pad / 2 : p.epi.n_pad;  // weight rows held by this CTA
+  p.b_tx_bytes = p.subs * 3 * n_local * kc * 2;  // the three horizontal taps of one filter row
   p.b_stage_bytes = ((p.b_tx_bytes + 1023) / 1024) * 1024;
-  p.b_tap = (p.epi.n_pad * kc * 2) >> 4;
+  p.b_tap = (n_local * kc * 2) >> 4;
   p.a_kp = p.subs > 1 ? a_sub >> 4 : 2;
-  p.b_kp = p.subs > 1 ? (3 * p.epi.n_pad * kc * 2) >> 4 : 2;
+  p.b_kp = p.subs > 1 ? (3 * n_local * kc * 2) >> 4 : 2;
   p.tmem_cols = pow2_cols(static_cast<uint32_t>(acc_stages * rows * p.acc_stride));
   const int n = p.epi.n_pad;
   p.e16 = n % 64 == 0 ? 64 : (n % 32 == 0 ? 32 : 16);
@@ -618,6 +659,12 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     while (k > 1 && (e.n_pad % k != 0 || (e.n_pad / k) % 8 != 0)) k >>= 1;
     p.cluster = k;
     p.b_slice_rows = e.n_pad / k;
+    // CTA pairs: opt-in (tune.pair), for the encoder convolutions whose weight rows split into two 8-row multiples
+    p.pair = (tune.pair == 1 && k == 1 && e.mode != 2 && tune.halo_mode == 0 && (e.n_pad / 2) % 8 == 0 &&
+              a.cin_p % 32 == 0)
+                 ? 1
+                 : 0;
+    if (p.pair) p.b_slice_rows = e.n_pad / 2;
     p.dbg = (tune.dbg & 1) && k > 1 ? (tune.dbg & ~1) : tune.dbg;  // skipping multicast loads would deadlock peers
   }
   // ---- choose the patch geometry: largest patch that keeps two TMEM stages and fits shared memory ----
@@ -628,6 +675,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     int rmax = 512 / (acc_stages * acc_stride);
     if (rmax > 4) rmax = 4;
     if (rmax > e.H) rmax = e.H;
+    if (p.pair && rmax > 2) rmax = 2;  // pair kernels are instantiated for one and two accumulator rows
     if (tune.rows) rmax = tune.rows;
     for (int rows = rmax; rows >= 1 && !found; --rows) {
       if (rows == 3) continue;  // instantiated for 1, 2 and 4 accumulator rows
@@ -658,7 +706,8 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   const long long n_units = static_cast<long long>(e.B) * p.tiles_x * p.tiles_y;
   MZ_REQUIRE(n_units < (1LL << 31), "conv: too many patches (%lld)", n_units);
   p.n_units = static_cast<int>(n_units);
-  p.idesc = e.bf16 ? umma_idesc_bf16(128, e.n_pad) : umma_idesc_f16(128, e.n_pad);
+  const int mma_m = p.pair ? 256 : 128;
+  p.idesc = e.bf16 ? umma_idesc_bf16(mma_m, e.n_pad) : umma_idesc_f16(mma_m, e.n_pad);
   const CUtensorMapDataType tdt = e.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 
   const CUtensorMapSwizzle swz =
@@ -677,7 +726,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     const uint64_t dims[3] = {static_cast<uint64_t>(a.cin_p), static_cast<uint64_t>(e.n_pad), 9};
     const uint64_t strides[2] = {static_cast<uint64_t>(a.cin_p) * 2, static_cast<uint64_t>(e.n_pad) * a.cin_p * 2};
     const uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.b_slice_rows),
-                             p.cluster > 1 ? 1u : 3u};
+                             p.cluster > 1 ? 1u : 3u};  // pair: this CTA's N/2 rows of all three taps
     int rc = encode_tmap(&p.tmB, tdt, 3, const_cast<uint16_t*>(a.w), dims, strides, box, swz);
     if (rc != MZ_OK) return rc;
   }
@@ -706,7 +755,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   const uint32_t smem = plan_smem(p).total + 1024;
   int sms = sm_count(device);
   if (sms <= 0) sms = 148;
-  const int k = p.cluster;
+  const int k = p.pair ? 2 : p.cluster;
   int grid = p.n_units < sms ? p.n_units : sms;
   if (tune.max_ctas > 0 && grid > tune.max_ctas) grid = tune.max_ctas;
   grid = ceil_div(grid, k) * k;  // whole clusters (surplus CTAs recompute the last patch without storing)
@@ -753,11 +802,23 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   };
   const int ks = p.subs > 1 ? p.subs : p.kc / 16;  // k-steps per stage and tap
   MZ_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "conv: the look-ahead issue loop needs at least two A and two B stages");
-#define MZ_DISPATCH_ROWS(M, K)                              \
-  switch (p.rows) {                                         \
-    case 1: return launch(conv_tc_kernel<M, K, 1>);         \
-    case 2: return launch(conv_tc_kernel<M, K, 2>);         \
-    default: return launch(conv_tc_kernel<M, K, 4>);        \
+  if (p.pair) {  // instantiated for the shapes the 64/96/128-channel encoders use
+    if (e.mode == 0 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<0, 2, 1, true>);
+    if (e.mode == 0 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<0, 2, 2, true>);
+    if (e.mode == 0 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<0, 4, 1, true>);
+    if (e.mode == 0 && ks == 4 && p.rows == 2) return launch(conv_tc_kernel<0, 4, 2, true>);
+    if (e.mode == 1 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<1, 2, 1, true>);
+    if (e.mode == 1 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<1, 2, 2, true>);
+    if (e.mode == 1 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<1, 4, 1, true>);
+    if (e.mode == 1 && ks == 4 && p.rows == 2) return launch(conv_tc_kernel<1, 4, 2, true>);
+    set_error("conv: no CTA-pair kernel for mode %d, %d k-steps, %d rows", e.mode, ks, p.rows);
+    return MZ_ERR_UNSUPPORTED;
+  }
+#define MZ_DISPATCH_ROWS(M, K)                                     \
+  switch (p.rows) {                                                \
+    case 1: return launch(conv_tc_kernel<M, K, 1, false>);         \
+    case 2: return launch(conv_tc_kernel<M, K, 2, false>);         \
+    default: return launch(conv_tc_kernel<M, K, 4, false>);        \
   }
 #define MZ_DISPATCH_KS(M)                                   \
   switch (ks) {                                             \

@@ -68,6 +68,7 @@ struct ConvTcTune {
   int a_stages;    // activation ring depth
   int max_ctas;    // cap on the persistent grid (0 = SM count)
   int cluster;     // CTAs per cluster sharing the weight stream through TMA multicast: 1, 2 or 4 (0 = auto)
+  int pair;        // 1: CTA pairs issue M = 256 UMMAs (cta_group::2), each CTA holding half of the weight rows
   int dbg;         // timing experiments only (WRONG results): 1 skip weight loads, 2 skip activation loads,
                    // 4 skip the epilogue body, 8 skip the MMAs
 };
