@@ -134,6 +134,8 @@ typedef struct mz_conv_tune {
   int32_t dbg;        /* timing experiments ONLY (results are wrong): 1 skip weight loads, 2 skip        */
                       /* activation loads, 4 skip the epilogue body, 8 skip the MMAs                     */
   int32_t pair;       /* 1: CTA pairs issue M = 256 UMMAs (cta_group::2), weights split between the two  */
+  int32_t resident;   /* filter bank resident in shared memory: 0 when it fits, 1 require, 2 never       */
+  int32_t epi_warps;  /* epilogue warps per CTA: 0 auto (8), 4 or 8                                      */
 } mz_conv_tune;
 
 /* which = 0 conv1, 1 conv2, 2 head, -1 all.  Takes effect on the next mz_upscale. */
@@ -187,10 +189,11 @@ int mz_control_film(const float* c_dev, int32_t c_rows, const float* w_dev /*L,2
  * TMA-swizzled tile; base_offset_mode 0 leaves the descriptor's base_offset 0, 1 sets it to
  * (start >> 7) & 7.  Writes the max abs error against an exact host product.
  * mz_probe_mma_rate: `iters` back-to-back 128 x n x 16 UMMAs per CTA on `ctas` CTAs, cycling over
- * `distinct_a` A tiles and `distinct_d` TMEM accumulators; writes SM cycles per UMMA (mean over CTAs). */
+ * `distinct_a` A tiles and `distinct_d` TMEM accumulators, the A descriptor starting `a_row_shift` rows into its
+ * tile (the shared-halo conv's shifted taps); writes SM cycles per UMMA (mean over CTAs). */
 int mz_probe_umma(int32_t kc, int32_t row_shift, int32_t base_offset_mode, float* max_abs_err_out);
 int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_t distinct_a,
-                      int32_t distinct_d, float* cycles_per_mma_out);
+                      int32_t distinct_d, int32_t a_row_shift, float* cycles_per_mma_out);
 
 /* Padded channel counts the kernels use for a logical channel count. */
 int mz_padded_channels(int32_t c);

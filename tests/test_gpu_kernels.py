@@ -155,6 +155,18 @@ CONV_CASES = [
     (96, 192, (2, 30, 260), dict(pair=1, max_ctas=4)),
     (64, 64, (1, 5, 130), dict(pair=1)),
     (64, 128, (1, 1, 100), dict(pair=1)),
+    # filter bank resident in shared memory (the default when it fits) vs streamed per patch
+    (48, 96, (2, 13, 150), dict(resident=1)),
+    (48, 96, (2, 13, 150), dict(resident=2)),
+    (48, 96, (2, 40, 300), dict(resident=1, max_ctas=3)),
+    (64, 128, (1, 9, 257), dict(resident=1, max_ctas=2)),
+    (64, 128, (1, 9, 257), dict(resident=2)),
+    (96, 192, (2, 30, 260), dict(pair=1, resident=1, max_ctas=4)),
+    (96, 192, (1, 21, 300), dict(pair=1, resident=2)),
+    # four epilogue warps (one per TMEM lane quarter) instead of the default eight
+    (48, 96, (2, 13, 150), dict(epi_warps=4)),
+    (96, 192, (1, 21, 300), dict(epi_warps=4, resident=2)),
+    (64, 64, (1, 5, 130), dict(epi_warps=4, rows=1)),
 ]
 
 
@@ -163,6 +175,8 @@ CONV_CASES = [
 @pytest.mark.parametrize("cin,cout,shape,tune", CONV_CASES)
 def test_conv1_film_silu(dev, cin, cout, shape, tune, halo_mode, dt):
     ops, native = _ops()
+    if halo_mode == 1 and tune.get("resident") == 1:
+        pytest.skip("the resident filter bank is a shared-halo (halo_mode 0) configuration")
     inp, w, film, _, acc = _conv_operands(cin, cout, shape, 7, ops, dt)
     ref = F.silu(acc * film[:, 0][:, None, None, :cout] + film[:, 1][:, None, None, :cout])
     wp = ops.pack_conv_weight(w, dev, dtype=dt)
@@ -184,10 +198,16 @@ def test_conv1_film_silu(dev, cin, cout, shape, tune, halo_mode, dt):
     (192, 96, (2, 30, 260), dict(max_ctas=3)), (32, 16, (1, 1, 5), {}), (192, 96, (1, 7, 129), dict(rows=1, acc_stages=1)),
     (192, 96, (2, 30, 260), dict(cluster=4)), (192, 96, (2, 30, 260), dict(cluster=1)), (96, 48, (1, 5, 700), dict(cluster=2, max_ctas=5)),
     (192, 96, (1, 21, 300), dict(pair=1)), (192, 96, (2, 30, 260), dict(pair=1, max_ctas=4)), (128, 64, (1, 3, 129), dict(pair=1)),
+    (96, 48, (2, 13, 150), dict(resident=1)), (96, 48, (2, 40, 300), dict(resident=1, max_ctas=3)), (96, 48, (2, 13, 150), dict(resident=2)),
+    (128, 64, (1, 9, 257), dict(resident=1, max_ctas=2)), (192, 96, (1, 21, 300), dict(resident=2)),
+    (96, 48, (2, 13, 150), dict(epi_warps=4)), (192, 96, (1, 21, 300), dict(epi_warps=4)), (96, 48, (2, 40, 300), dict(epi_warps=4, rows=4, max_ctas=3)),
+    (96, 48, (2, 40, 300), dict(rows=4, resident=2, max_ctas=3)), (96, 48, (1, 7, 129), dict(rows=1)),
 ])
 @pytest.mark.parametrize("dt", DTYPES)
 def test_conv2_residual(dev, cin, cout, shape, tune, halo_mode, dt):
     ops, native = _ops()
+    if halo_mode == 1 and tune.get("resident") == 1:
+        pytest.skip("the resident filter bank is a shared-halo (halo_mode 0) configuration")
     inp, w, _, zf0, acc = _conv_operands(cin, cout, shape, 8, ops, dt)
     zref = zf0[..., :cout] + acc
     wp = ops.pack_conv_weight(w, dev, dtype=dt)

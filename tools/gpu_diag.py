@@ -47,6 +47,16 @@ def g_rate():
                 _report("rate", f"n={n} kc={kc} distinct_a={da} distinct_d={dd}", f"cyc/mma={cyc:.1f} (N/2={n / 2:.0f})", True)
 
 
+def g_shift():
+    """UMMA rate when the A descriptor starts a few rows into the swizzled tile (the shared-halo taps)."""
+    from ultrazoom_b200 import ops
+
+    for n in (48, 96, 192):
+        for kc in (64, 32, 16):
+            row = " ".join(f"{s}:{ops.probe_mma_rate(n, kc, 4000, 148, 1, 2, s):.1f}" for s in (0, 1, 2, 3, 4, 8, 10, 16))
+            _report("shift", f"n={n} kc={kc}", f"cyc/mma by a_row_shift  {row}", True)
+
+
 def _rand_bf16(shape, gen, scale=1.0):
     import torch
 
@@ -276,6 +286,8 @@ def main():
         g_probe()
     elif what == "rate":
         g_rate()
+    elif what == "shift":
+        g_shift()
     elif what == "small":
         g_small()
     elif what == "simt":

@@ -36,33 +36,38 @@ def main():
     dev = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(0)
     Cp, hCp = ops.padded_channels(C), ops.padded_channels(2 * C)
+    Cz = int(os.environ.get("ZP", Cp))        # channel pitch of zb (the model keeps 48-channel zb at pitch 64)
     flops = 2.0 * 9 * C * 2 * C * B * H * W
-    zb = torch.randn(B, H, W, Cp, generator=g).to(torch.float16).to(dev)
-    hid = torch.randn(B, H, W, hCp, generator=g).to(torch.float16).to(dev)
+    dt = torch.bfloat16 if os.environ.get("DT") == "bf16" else torch.float16
+    zb = torch.zeros(B, H, W, Cz, dtype=dt)
+    zb[..., :Cp] = torch.randn(B, H, W, Cp, generator=g).to(dt)
+    zb = zb.to(dev)
+    hid = torch.randn(B, H, W, hCp, generator=g).to(dt).to(dev)
     zf = torch.zeros(B, H, W, Cp, device=dev)
-    w1 = ops.pack_conv_weight(torch.randn(2 * C, C, 3, 3, generator=g) * 0.02, dev)
-    w2 = ops.pack_conv_weight(torch.randn(C, 2 * C, 3, 3, generator=g) * 0.02, dev)
+    w1 = ops.pack_conv_weight(torch.randn(2 * C, C, 3, 3, generator=g) * 0.02, dev, cin_p=Cz, dtype=dt)
+    w2 = ops.pack_conv_weight(torch.randn(C, 2 * C, 3, 3, generator=g) * 0.02, dev, dtype=dt)
     film = torch.ones(B, 2, hCp, device=dev)
     print(f"C={C} {W}x{H} B={B}: {flops / 1e9:.1f} GFLOP per conv; 100% of 1644 TF = {flops / 1644e12 * 1e6:.1f} us")
-    if os.environ.get("SWEEP") == "dbg":
-        grid = list(itertools.product((1,), (0,), (0,), (0,)))
-        dbgs = (0, 16, 16, 4, 8, 12, 3, 7)
+    base = dict(pair=int(os.environ.get("PAIR", "0")))
+    if os.environ.get("SWEEP_CFGS"):        # e.g. SWEEP_CFGS="[dict(resident=1), dict(resident=2, rows=2)]"
+        cfgs = [dict(base, **c) for c in eval(os.environ["SWEEP_CFGS"], {"dict": dict})]
+    elif os.environ.get("SWEEP") == "dbg":
+        cfgs = [dict(base, dbg=d) for d in (0, 16, 16, 4, 8, 12, 3, 7)]
     else:
-        grid = list(itertools.product((1,), (0, 1, 2), (0, 32, 64), (0, 3, 6)))
-        dbgs = (0,)
-    extra = os.environ.get("SWEEP_EXTRA")
+        cfgs = [dict(base, resident=r, rows=rows) for r in (0, 2) for rows in (0, 1, 2, 4)]
+    only = os.environ.get("ONLY")
     for which, (inp, wp, mode, fl, z) in (("conv1", (zb, w1, 0, film, None)), ("conv2", (hid, w2, 1, None, zf))):
-        for cluster, rows, kc, bs in grid:
+        if only and only != which:
+            continue
+        for kw in cfgs:
             cin = inp.shape[-1]
-            if kc and cin % kc:
+            if kw.get("kc") and cin % kw["kc"]:
                 continue
-            for dbg in dbgs:
-                kw = dict(cluster=cluster, rows=rows, kc=kc, b_stages=bs, dbg=dbg, pair=int(os.environ.get("PAIR", "0")))
-                try:
-                    us = time_conv(inp, wp, mode, fl, z, _native.tune(**kw))
-                    print(f"{which} {kw}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
-                except Exception as e:  # noqa: BLE001
-                    print(f"{which} {kw}: {str(e)[:100]}", flush=True)
+            try:
+                us = time_conv(inp, wp, mode, fl, z, _native.tune(**kw))
+                print(f"{which} {kw}: {us:8.1f} us  {flops / us / 1e6:7.1f} TFLOP/s", flush=True)
+            except Exception as e:  # noqa: BLE001
+                print(f"{which} {kw}: {str(e)[:100]}", flush=True)
 
 
 if __name__ == "__main__":

@@ -19,6 +19,8 @@ ConvTcTune to_tune(const mz_conv_tune* t) {
     o.cluster = t->cluster;
     o.dbg = t->dbg;
     o.pair = t->pair;
+    o.resident = t->resident;
+    o.epi_warps = t->epi_warps;
   }
   return o;
 }

@@ -18,12 +18,14 @@
 //   warp 2             TMEM allocator.
 //   warps 4..7         epilogue: tcgen05.ld -> FiLM scale/shift + SiLU -> bf16 | residual add | pixel-shuffle.
 //                      With two TMEM stages the epilogue of patch i overlaps the MMAs of patch i+1.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace mz {
 
 constexpr int kTileW = 128;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + up to 8 epilogue warps
 constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
 struct TcParams {
@@ -34,7 +36,8 @@ struct TcParams {
   int e16, e32;     // channels per output box: box rows are 128 / 64 / 32 bytes
   int stage_bytes;  // epilogue staging (all four warps)
   int o_ring;       // mode 0: warp-private ring of output boxes (2 or 4)
-  int res_rows;     // mode 1: accumulator rows whose residual / output staging is resident at once (1 or ROWS)
+  int res_rows;     // mode 1: row buffers (fp32 residual tile + 16-bit tile) per epilogue warp: 1, or all its rows
+  int epi_warps;    // 4 or 8 epilogue warps; with 8, two warps share a TMEM lane quarter and split the rows / boxes
   EpiParams epi;
   int kc, n_chunks;  // channels per swizzled sub-tile; pipeline chunks per patch (each = subs sub-tiles)
   int subs;          // 16-channel sub-tiles fused into one stage (3 for Cin = 48), else 1
@@ -50,6 +53,8 @@ struct TcParams {
   int cluster;       // CTAs per cluster sharing the weight stream by TMA multicast (1, 2 or 4)
   int pair;          // 1: CTA pairs issue M = 256 UMMAs (cta_group::2), weights split N/2 + N/2 between them
   int b_slice_rows;  // n_pad / cluster: weight rows each CTA loads and multicasts per stage
+  int res_b;         // 1: the whole filter bank stays resident in shared memory (b_stages == 3 * n_chunks): it is
+                     // loaded during the first patch and never again -- the persistent CTA then streams activations only
   long long* prof;   // optional per-CTA role timers (clock64 ticks), [grid][3 roles][8]; nullptr = off
   int dbg;           // timing experiments only (results are wrong): 1 skip weight loads, 2 skip activation loads,
                      // 4 skip the epilogue body, 8 skip the MMAs
@@ -66,7 +71,7 @@ __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
   s.a = 0;
   s.b = s.a + p.a_stages * p.a_stage_bytes;
   s.bars = s.b + p.b_stages * p.b_stage_bytes;
-  const uint32_t nbars = 2 * p.a_stages + 2 * p.b_stages + 4 + 4;  // + one residual-load barrier per epilogue warp
+  const uint32_t nbars = 2 * p.a_stages + 2 * p.b_stages + 4 + 8;  // + one residual-load barrier per epilogue warp
   s.tmem_ptr = s.bars + nbars * 8;
   s.film = s.tmem_ptr + 16;  // [2][n_pad <= 256] fp32: FiLM scale / shift rows of the current image
   s.stage = (s.film + 2 * 256 * 4 + 1023u) & ~1023u;  // epilogue staging: swizzled boxes for TMA store / load
@@ -126,9 +131,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar_acc_full + 8 * i, 1);
-      mbar_init(bar_acc_empty + 8 * i, PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(bar_acc_empty + 8 * i, (PAIR ? 2 : 1) * p.epi_warps);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    for (int i = 0; i < 4; ++i) mbar_init(bar_res + 8 * i, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(bar_res + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -200,7 +205,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         // one weight stage = the three horizontal taps of filter row dy: [3][N][kc]
         for (int dy = 0; dy < 3; ++dy) {
-          MZ_TIMED(1, mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u));
+          if (p.res_b) {
+            if (round > 0) break;  // resident filter bank: stage (c, dy) was filled during the first patch
+          } else {
+            MZ_TIMED(1, mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u));
+          }
           const uint32_t full_b = bar_b_full + 8 * sb;
           const uint32_t dstB = b_base + sb * p.b_stage_bytes;
           if (PAIR) {
@@ -252,12 +261,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       DY = (p.pw * row_bytes) >> 4;
       RP = DY;
     }
-    const uint32_t TB = p.b_tap;  // tap pitch inside a weight stage
+    if (p.dbg & 32) DY = DX = RP = 0;  // timing experiment: every UMMA reads the same A rows
+    const uint32_t TB = (p.dbg & 32) ? 0u : p.b_tap;  // tap pitch inside a weight stage
     const bool leader = elect_one();  // the same lane issues every tcgen05.mma and tcgen05.commit
     const bool issue = leader && !(p.dbg & 8);
     const uint32_t idesc = p.idesc;
     const uint32_t acc_stride = p.acc_stride;
-    const uint32_t a_kp = p.a_kp, b_kp = p.b_kp;
+    const uint32_t a_kp = (p.dbg & 64) ? 0u : p.a_kp, b_kp = (p.dbg & 64) ? 0u : p.b_kp;  // 64: same k-step
     // One tap (dx) of the current weight stage: KT k-steps x ROWS accumulators, all descriptor words uniform.
 #define MZ_ISSUE_TAP(DXV)                                                                                         \
   if (issue) {                                                                                                    \
@@ -288,6 +298,91 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     MZ_TIMED(1, mbar_wait(bar_a_full + 8 * sa, pa));
     MZ_TIMED(2, mbar_wait(bar_b_full + 8 * sb, pb));
     tc_fence_after();
+    long long t_gap = 0;
+    if (p.res_b) {
+      // ---- resident filter bank: one hand-off per K chunk, all nine taps issued back to back ----
+      // The UMMA queue is shallow: once the last UMMA of a burst is issued only a few hundred cycles of tensor work
+      // remain queued, and everything the issuer does before the next burst beyond that is a tensor-pipe bubble
+      // (measured: ~600 cycles per hand-off with the bookkeeping at the end of the burst).  So ALL bookkeeping of the
+      // next step -- ring positions, descriptor bases, barrier sampling -- happens between the second and the third
+      // filter row of the current step; what is left after the last UMMA is two commits, two (normally not taken)
+      // waits and a fence.  The weight stages are waited for once, during the first patch.
+      uint32_t cur_a_lo = desc_lo0 + (a_base >> 4);
+      uint32_t cur_d = tmem_base;
+      uint32_t cur_b_lo = desc_lo0 + (b_base >> 4);
+      const uint32_t a_stage_u = static_cast<uint32_t>(p.a_stage_bytes) >> 4, b_stage_u = static_cast<uint32_t>(p.b_stage_bytes) >> 4;
+      const int n_chunks = p.n_chunks;
+      const int total_steps = p.n_rounds * n_chunks;
+      int c = 0;
+      bool first_round = true;
+      for (int step = 0; step < total_steps; ++step) {
+        const bool last_chunk = c == n_chunks - 1;
+        const bool last_step = step == total_steps - 1;
+        const uint32_t d_base = cur_d;
+        uint32_t nsa = sa, npa = pa, nas = as, npacc = pacc, n_a_lo = cur_a_lo, n_d = cur_d, n_b_lo = cur_b_lo;
+        bool a_ready = true, acc_ready = true;
+        if (prof_on && t_gap != 0) tick[3] += clock64() - t_gap;  // issuer time between two bursts
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const uint32_t b_lo_stage = cur_b_lo + dy * b_stage_u;
+          if (first_round && step + dy > 0) {  // (stage 0 was waited for before the loop)
+            MZ_TIMED(2, mbar_wait(bar_b_full + 8 * (c * 3 + dy), 0));
+            tc_fence_after();
+          }
+          const uint32_t a_lo_dy = cur_a_lo + dy * DY;
+          const uint32_t first = (c == 0 && dy == 0) ? 0u : 1u;  // 0: overwrite the accumulator
+          if (dy == 2) {
+            // ---- bookkeeping of the NEXT step, two filter rows of tensor work still queued behind us ----
+            if (++nsa == static_cast<uint32_t>(p.a_stages)) {
+              nsa = 0;
+              npa ^= 1u;
+            }
+            n_a_lo = desc_lo0 + (a_base >> 4) + nsa * a_stage_u;
+            n_b_lo = last_chunk ? desc_lo0 + (b_base >> 4) : cur_b_lo + 3 * b_stage_u;
+            if (last_chunk) {
+              if (++nas == static_cast<uint32_t>(p.acc_stages)) {
+                nas = 0;
+                npacc ^= 1u;
+              }
+              n_d = tmem_base + nas * ROWS * acc_stride;
+            }
+            if (!last_step) {
+              a_ready = test_uniform(bar_a_full + 8 * nsa, npa);
+              if (last_chunk) acc_ready = test_uniform(bar_acc_empty + 8 * nas, npacc ^ 1u);
+            }
+          }
+          MZ_ISSUE_TAP(0)
+          MZ_ISSUE_TAP(1)
+          MZ_ISSUE_TAP(2)
+        }
+        if (prof_on) t_gap = clock64();
+        if (leader) {
+          if (PAIR) {
+            umma2_commit_mcast(bar_a_empty + 8 * sa, 3);
+            if (last_chunk) umma2_commit_mcast(bar_acc_full + 8 * as, 3);
+          } else {
+            umma_commit(bar_a_empty + 8 * sa);
+            if (last_chunk) umma_commit(bar_acc_full + 8 * as);
+          }
+        }
+        if (!acc_ready) MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * nas, npacc ^ 1u));
+        if (!a_ready) MZ_TIMED(1, mbar_wait(bar_a_full + 8 * nsa, npa));
+        tc_fence_after();
+        sa = nsa;
+        pa = npa;
+        as = nas;
+        pacc = npacc;
+        cur_a_lo = n_a_lo;
+        cur_d = n_d;
+        cur_b_lo = n_b_lo;
+        if (last_chunk) {
+          c = 0;
+          first_round = false;
+        } else {
+          ++c;
+        }
+      }
+    } else
     for (int round = 0; round < p.n_rounds; ++round) {
       const uint32_t d_base = tmem_base + as * ROWS * acc_stride;
       for (int c = 0; c < p.n_chunks; ++c) {
@@ -305,7 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           uint32_t nsb = sb + 1, npb = pb, nsa = sa, npa = pa, nas = as, npacc = pacc;
           if (nsb == static_cast<uint32_t>(p.b_stages)) {
             nsb = 0;
-            npb ^= 1u;
+            if (!p.res_b) npb ^= 1u;  // resident stages complete once (phase 0) and stay complete
           }
           bool b_ready = true, a_ready = true, acc_ready = true;
           if (!last_step) {
@@ -328,13 +423,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           MZ_ISSUE_TAP(2)
           if (leader) {
             if (PAIR) {  // release / signal in BOTH CTAs of the pair
-              umma2_commit_mcast(bar_b_empty + 8 * sb, 3);
+              if (!p.res_b) umma2_commit_mcast(bar_b_empty + 8 * sb, 3);
               if (dy == 2) umma2_commit_mcast(bar_a_empty + 8 * sa, 3);
               if (dy == 2 && last_chunk) umma2_commit_mcast(bar_acc_full + 8 * as, 3);
             } else {
               if (p.cluster > 1)
                 umma_commit_mcast(bar_b_empty + 8 * sb, cta_mask);
-              else
+              else if (!p.res_b)
                 umma_commit(bar_b_empty + 8 * sb);
               if (dy == 2) umma_commit(bar_a_empty + 8 * sa);
               if (dy == 2 && last_chunk) umma_commit(bar_acc_full + 8 * as);
@@ -373,14 +468,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
 #undef MZ_ISSUE_TAP
     __syncwarp();
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + p.epi_warps) {
     // =============================== epilogue ===============================
-    // Each warp owns 32 pixels (its TMEM lane quarter).  Nothing goes to or from global memory through the LSU:
-    // results are written as swizzled 16-byte chunks into warp-private staging boxes and leave by TMA store
-    // (coalesced, asynchronous); the fp32 residual row-tile arrives by TMA load before the accumulator is waited
-    // for.  (Per-thread 16-byte global accesses at a 384-byte lane stride cost 32 sectors per instruction and made
-    // the epilogue, not the tensor pipe, the bottleneck.)
-    const int q = warp - 4;  // TMEM lane quarter this warp may read (== warp % 4)
+    // Warp w owns the 32 pixels of TMEM lane quarter w % 4.  With eight epilogue warps two warps share a quarter and
+    // split the work of a patch -- (row, output box) items in mode 0, accumulator rows in modes 1 and 2 -- so each SM
+    // sub-partition has two warps to hide tcgen05.ld / MUFU / fence latencies behind one another.
+    // Nothing goes to or from global memory through the LSU: results are written as swizzled 16-byte chunks into
+    // warp-private staging boxes and leave by TMA store (coalesced, asynchronous); the fp32 residual row-tile arrives
+    // by TMA load before the accumulator is waited for, and the tiles of the NEXT patch are prefetched into L2 a whole
+    // patch ahead.  (Per-thread 16-byte global accesses at a 384-byte lane stride cost 32 sectors per instruction
+    // and made the epilogue, not the tensor pipe, the bottleneck.)
+    const int q = warp & 3;          // TMEM lane quarter this warp may read (== warp % 4)
+    const int ew = warp - 4;         // staging slot / residual barrier of this warp
+    const int half = ew >> 2;        // 0 | 1: which share of a patch this warp takes
+    const int nh = p.epi_warps >> 2;  // warps per lane quarter (1 | 2)
     float* film_s = reinterpret_cast<float*>(gen_base + sp.film);
     int film_b = -1;
     uint32_t as = 0, pacc = 0, rpar = 0, ring = 0;
@@ -389,11 +490,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t box16 = 32 * row16, box32 = 32 * row32;        // one warp-box: 32 pixels
     const uint32_t nb16 = n_pad / p.e16, nb32 = n_pad / p.e32;
     const uint32_t sh16 = 31 - __clz(p.e16), sh32 = 31 - __clz(p.e32);  // box widths are powers of two
-    // warp-private staging: mode 0 -> ring of two 16-bit boxes; mode 1 -> whole fp32 row-tile + whole 16-bit row-tile
+    // warp-private staging: mode 0 -> ring of 16-bit boxes; mode 1 -> res_rows x (fp32 row-tile + 16-bit row-tile)
     const uint32_t row_stage = 32 * n_pad * 6;  // mode 1: one accumulator row of this warp: fp32 tile + 16-bit tile
-    const uint32_t st_base = base + sp.stage + q * (MODE == 0 ? p.o_ring * box16 : p.res_rows * row_stage);
+    const uint32_t st_base = base + sp.stage + ew * (MODE == 0 ? p.o_ring * box16 : p.res_rows * row_stage);
     const bool all_rows = p.res_rows > 1;
-    const uint32_t my_res = bar_res + 8 * q;
+    const uint32_t my_res = bar_res + 8 * ew;
+    const int n_epi_threads = p.epi_warps * 32;
     for (int round = 0; round < p.n_rounds; ++round) {
       const int unit_raw = round * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
       const bool unit_ok = unit_raw < p.n_units;  // CTA-uniform
@@ -407,41 +509,58 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool ok = x < p.epi.W;
       const bool live = unit_ok && !(p.dbg & 4);
 
-      if (MODE == 0 && b != film_b) {  // CTA-uniform: all four epilogue warps take it together
-        named_bar_sync(1, 128);        // nobody still reads the previous image's rows
-        for (int i = threadIdx.x - 128; i < 2 * p.epi.n_pad; i += 128) {
+      if (MODE == 0 && b != film_b) {  // CTA-uniform: all epilogue warps take it together
+        named_bar_sync(1, n_epi_threads);  // nobody still reads the previous image's rows
+        for (int i = threadIdx.x - 128; i < 2 * p.epi.n_pad; i += n_epi_threads) {
           float v = i < p.epi.n_pad ? 1.f : 0.f;
           if (p.epi.film != nullptr) v = __ldg(p.epi.film + static_cast<size_t>(b) * 2 * p.epi.n_pad + i);
           film_s[i] = v;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, n_epi_threads);
         film_b = b;
       }
 
-      // residual row-tiles: TMA load into this warp's staging once its previous stores have finished reading it.
-      // With staging for every accumulator row (res_rows == ROWS) all rows of the patch are requested up front on
-      // one barrier; otherwise row r is requested when row r-1 has been stored.
-      auto load_residual = [&](int r_lo, int r_hi) {
+      // residual row-tiles of this warp's rows (r = half, half + nh, ...): TMA load into the warp's staging once its
+      // previous stores have finished reading it.  With a buffer per row (res_rows > 1) all of them are requested up
+      // front on one barrier; otherwise row k+1 is requested when row k has been stored.
+      auto load_residual = [&](int k_lo, int k_hi) {  // k indexes this warp's rows: r = half + k * nh
         if (MODE == 1 && live && lane == 0) {
           int nrows = 0;
-          for (int r = r_lo; r < r_hi; ++r) nrows += (y0 + r < p.epi.H) ? 1 : 0;
+          for (int k = k_lo; k < k_hi; ++k) nrows += (half + k * nh < ROWS && y0 + half + k * nh < p.epi.H) ? 1 : 0;
           if (nrows > 0) {
             bulk_wait_read<0>();
             mbar_expect_tx(my_res, nrows * 32 * n_pad * 4);
-            for (int r = r_lo; r < r_hi; ++r) {
-              if (y0 + r >= p.epi.H) break;
-              const uint32_t dst = st_base + (all_rows ? r : 0) * row_stage;
+            for (int k = k_lo; k < k_hi; ++k) {
+              const int r = half + k * nh;
+              if (r >= ROWS || y0 + r >= p.epi.H) break;
+              const uint32_t dst = st_base + (all_rows ? k : 0) * row_stage;
               for (uint32_t bx = 0; bx < nb32; ++bx) tma_load_4d(dst + bx * box32, &p.tmZ, my_res, bx * p.e32, xw, y0 + r, b);
             }
           }
         }
       };
-      load_residual(0, all_rows ? ROWS : 1);
+      constexpr int kMyRowsMax = ROWS;  // upper bound of rows per warp
+      load_residual(0, all_rows ? kMyRowsMax : 1);
+      if (MODE == 1 && lane == 0 && !(p.dbg & 4)) {
+        // L2 prefetch of the residual tiles this warp will need for the NEXT patch: by then they are an L2 hit
+        // (~0.5 us) instead of an HBM round trip that a single row buffer cannot hide
+        const int nunit = unit_raw + static_cast<int>(gridDim.x);
+        if (nunit < p.n_units) {
+          const int nb = nunit / units_per_img;
+          const int nrem = nunit - nb * units_per_img;
+          const int nty = nrem / p.tiles_x, ntx = nrem - nty * p.tiles_x;
+          for (int r = half; r < ROWS; r += nh) {
+            if (nty * ROWS + r >= p.epi.H) break;
+            for (uint32_t bx = 0; bx < nb32; ++bx)
+              tma_prefetch_4d(&p.tmZ, bx * p.e32, ntx * kTileW + q * 32, nty * ROWS + r, nb);
+          }
+        }
+      }
 
       MZ_TIMED(0, mbar_wait(bar_acc_full + 8 * as, pacc));
       __syncwarp();
       tc_fence_after();
-      for (int r = 0; r < ROWS; ++r) {
+      for (int r = (MODE == 0 ? 0 : half), k = 0; r < ROWS; r += (MODE == 0 ? 1 : nh), ++k) {
         const int y = y0 + r;
         if (y >= p.epi.H || !live) break;  // warp-uniform
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * ROWS + r) * p.acc_stride;
@@ -469,12 +588,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               epi_head_r<3>(p.epi, b, y, x, acc);
           }
         } else if (MODE == 1) {
-          if (r > 0 && !all_rows) load_residual(r, r + 1);
-          if (r == 0 || !all_rows) {
+          if (k > 0 && !all_rows) load_residual(k, k + 1);
+          if (k == 0 || !all_rows) {
             mbar_wait(my_res, rpar);
             rpar ^= 1u;
           }
-          const uint32_t st_z = st_base + (all_rows ? r : 0) * row_stage, st_o = st_z + 32 * n_pad * 4;
+          const uint32_t st_z = st_base + (all_rows ? k : 0) * row_stage, st_o = st_z + 32 * n_pad * 4;
           for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) {
             uint32_t v[16];
             tmem_ld16(taddr + n0, v);
@@ -483,16 +602,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t zrow = st_z + bz * box32 + lane * row32;
             uint32_t o[8];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t addr = zrow + swz_chunk(lane, cz + k, row32) * 16;
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t addr = zrow + swz_chunk(lane, cz + kk, row32) * 16;
               float4 z = lds128f(addr);
-              z.x += __uint_as_float(v[4 * k + 0]);
-              z.y += __uint_as_float(v[4 * k + 1]);
-              z.z += __uint_as_float(v[4 * k + 2]);
-              z.w += __uint_as_float(v[4 * k + 3]);
+              z.x += __uint_as_float(v[4 * kk + 0]);
+              z.y += __uint_as_float(v[4 * kk + 1]);
+              z.z += __uint_as_float(v[4 * kk + 2]);
+              z.w += __uint_as_float(v[4 * kk + 3]);
               sts128(addr, __float_as_uint(z.x), __float_as_uint(z.y), __float_as_uint(z.z), __float_as_uint(z.w));
-              o[2 * k] = pack_op2(p.epi.bf16, z.x, z.y);
-              o[2 * k + 1] = pack_op2(p.epi.bf16, z.z, z.w);
+              o[2 * kk] = pack_op2(p.epi.bf16, z.x, z.y);
+              o[2 * kk + 1] = pack_op2(p.epi.bf16, z.z, z.w);
             }
             const uint32_t bo = n0 >> sh16, co = (n0 - (bo << sh16)) >> 3;
             const uint32_t orow = st_o + bo * box16 + lane * row16;
@@ -508,6 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         } else {
           for (uint32_t bx = 0; bx < nb16; ++bx) {
+            if (nh == 2 && ((static_cast<uint32_t>(r) * nb16 + bx) & 1u) != static_cast<uint32_t>(half)) continue;
             const uint32_t buf = st_base + (ring & static_cast<uint32_t>(p.o_ring - 1)) * box16;
             ++ring;
             if (lane == 0) {  // the store issued o_ring boxes ago has finished reading this buffer
@@ -530,12 +650,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const float4* sh = reinterpret_cast<const float4*>(film_s + n_pad + n0);
               uint32_t o[8];
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float4 g = sc[k], h = sh[k];
-                const float a0 = silu_f(fmaf(acc[4 * k + 0], g.x, h.x)), a1 = silu_f(fmaf(acc[4 * k + 1], g.y, h.y));
-                const float a2 = silu_f(fmaf(acc[4 * k + 2], g.z, h.z)), a3 = silu_f(fmaf(acc[4 * k + 3], g.w, h.w));
-                o[2 * k] = pack_op2(p.epi.bf16, a0, a1);
-                o[2 * k + 1] = pack_op2(p.epi.bf16, a2, a3);
+              for (int kk = 0; kk < 4; ++kk) {
+                const float4 g = sc[kk], h = sh[kk];
+                const float a0 = silu_f(fmaf(acc[4 * kk + 0], g.x, h.x)), a1 = silu_f(fmaf(acc[4 * kk + 1], g.y, h.y));
+                const float a2 = silu_f(fmaf(acc[4 * kk + 2], g.z, h.z)), a3 = silu_f(fmaf(acc[4 * kk + 3], g.w, h.w));
+                o[2 * kk] = pack_op2(p.epi.bf16, a0, a1);
+                o[2 * kk + 1] = pack_op2(p.epi.bf16, a2, a3);
               }
               const uint32_t co = sub >> 3;
               sts128(orow + swz_chunk(lane, co, row16) * 16, o[0], o[1], o[2], o[3]);
@@ -595,10 +715,14 @@ static uint32_t pow2_cols(uint32_t c) {
   return v;
 }
 
+// staging: 2 = deep (four output boxes / every accumulator row's residual in flight per warp), 1 = two boxes / one row,
+// 0 = slim (two boxes of at most 32 channels) -- what is left beside a resident filter bank
 static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stages, int halo_mode, int a_stages,
-                          int b_stages, bool rich_staging) {
-  p.o_ring = rich_staging ? 4 : 2;
-  p.res_rows = rich_staging ? rows : 1;
+                          int b_stages, int staging, bool res_b) {
+  const int nh = p.epi_warps / 4;
+  p.o_ring = staging == 2 ? 4 : 2;
+  p.res_rows = staging == 2 ? (rows + nh - 1) / nh : 1;
+  p.res_b = res_b ? 1 : 0;
   p.kc = kc;
   // 16-channel sub-tiles are fused into one pipeline stage when the whole K extent is small (Cin = 48): three times
   // the UMMAs per barrier round trip
@@ -609,7 +733,7 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   p.acc_stride = ((p.epi.n_pad + 31) / 32) * 32;
   p.halo_mode = halo_mode;
   p.a_stages = a_stages;
-  p.b_stages = b_stages;
+  p.b_stages = res_b ? 3 * p.n_chunks : b_stages;
   p.pw = halo_mode == 1 ? kTileW : kTileW + 2;
   int a_sub = (rows + 2) * p.pw * kc * 2;
   if (p.subs > 1) a_sub = ((a_sub + 1023) / 1024) * 1024;  // each sub-tile is its own TMA destination / swizzle frame
@@ -624,9 +748,10 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   p.b_kp = p.subs > 1 ? (3 * n_local * kc * 2) >> 4 : 2;
   p.tmem_cols = pow2_cols(static_cast<uint32_t>(acc_stages * rows * p.acc_stride));
   const int n = p.epi.n_pad;
-  p.e16 = n % 64 == 0 ? 64 : (n % 32 == 0 ? 32 : 16);
+  p.e16 = (n % 64 == 0 && staging > 0) ? 64 : (n % 32 == 0 ? 32 : 16);
   p.e32 = n % 32 == 0 ? 32 : 16;
-  p.stage_bytes = p.epi.mode == 0 ? 4 * p.o_ring * 32 * p.e16 * 2 : (p.epi.mode == 1 ? 4 * p.res_rows * 32 * n * 6 : 0);
+  p.stage_bytes = p.epi.mode == 0 ? p.epi_warps * p.o_ring * 32 * p.e16 * 2
+                                  : (p.epi.mode == 1 ? p.epi_warps * p.res_rows * 32 * n * 6 : 0);
 }
 
 static bool fits(const TcParams& p) {
@@ -649,9 +774,13 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   MZ_REQUIRE(tune.kc == 0 || ((tune.kc == 16 || tune.kc == 32 || tune.kc == 64) && a.cin_p % tune.kc == 0),
              "conv: kc %d does not divide cin_p %d (or is not 16/32/64)", tune.kc, a.cin_p);
 
+  MZ_REQUIRE(tune.epi_warps == 0 || tune.epi_warps == 4 || tune.epi_warps == 8,
+             "conv: epi_warps must be 0 (auto), 4 or 8, %d given", tune.epi_warps);
+
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.epi = e;
+  p.epi_warps = tune.epi_warps ? tune.epi_warps : 8;
 
   // cluster size: share the weight stream between k CTAs when the slices keep whole 8-row swizzle atoms
   {
@@ -667,27 +796,63 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     if (p.pair) p.b_slice_rows = e.n_pad / 2;
     p.dbg = (tune.dbg & 1) && k > 1 ? (tune.dbg & ~1) : tune.dbg;  // skipping multicast loads would deadlock peers
   }
-  // ---- choose the patch geometry: largest patch that keeps two TMEM stages and fits shared memory ----
+  // ---- choose the patch geometry ----
+  // First choice: the whole filter bank resident in shared memory (the persistent CTA then streams activations only;
+  // re-streaming 83..332 KB of weights per patch is what saturates the L2 -> SM path otherwise).  It needs two TMEM
+  // stages and room for at least two activation stages beside the bank.
   const int acc_stride = ((e.n_pad + 31) / 32) * 32;
   bool found = false;
   const int kc_first = tune.kc ? tune.kc : pick_kc(a.cin_p);
-  for (int acc_stages = tune.acc_stages ? tune.acc_stages : 2; acc_stages >= 1 && !found; --acc_stages) {
+  auto rows_cap = [&](int acc_stages) {
     int rmax = 512 / (acc_stages * acc_stride);
     if (rmax > 4) rmax = 4;
     if (rmax > e.H) rmax = e.H;
     if (p.pair && rmax > 2) rmax = 2;  // pair kernels are instantiated for one and two accumulator rows
     if (tune.rows) rmax = tune.rows;
+    return rmax;
+  };
+  // epilogue warps: eight (two per TMEM lane quarter) unless their staging does not fit beside the operand rings
+  const int ew_first = tune.epi_warps ? tune.epi_warps : 8, ew_last = tune.epi_warps ? tune.epi_warps : 4;
+  if (tune.resident != 2 && p.cluster == 1 && tune.halo_mode == 0 && (tune.acc_stages == 0 || tune.acc_stages == 2)) {
+    for (int rows = rows_cap(2); rows >= 1 && !found; --rows) {
+      if (rows == 3) continue;
+      for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {
+        for (int ew = ew_first; ew >= ew_last && !found; ew -= 4) {
+          p.epi_warps = ew;
+          for (int as = tune.a_stages ? tune.a_stages : 3; as >= 2 && !found; --as) {
+            for (int staging = 2; staging >= 0 && !found; --staging) {
+              fill_geometry(p, a.cin_p, kc, rows, 2, 0, as, 0, staging, true);
+              if (fits(p)) found = true;
+            }
+            if (tune.a_stages) break;
+          }
+        }
+        if (tune.kc) break;
+      }
+      if (tune.rows) break;
+    }
+  }
+  if (!found && tune.resident == 1) {
+    set_error("conv: the filter bank (cin_p %d, n_pad %d) does not fit resident in shared memory", a.cin_p, e.n_pad);
+    return MZ_ERR_UNSUPPORTED;
+  }
+  // Otherwise stream the weights per patch: largest patch that keeps two TMEM stages and fits shared memory.
+  for (int acc_stages = tune.acc_stages ? tune.acc_stages : 2; acc_stages >= 1 && !found; --acc_stages) {
+    const int rmax = rows_cap(acc_stages);
     for (int rows = rmax; rows >= 1 && !found; --rows) {
       if (rows == 3) continue;  // instantiated for 1, 2 and 4 accumulator rows
       for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {
-        for (int bs = tune.b_stages ? tune.b_stages : 4; bs >= 2 && !found; --bs) {
-          // deeper epilogue staging (more TMA stores / residual loads in flight) when shared memory allows
-          for (int rich = 1; rich >= 0 && !found; --rich) {
-            fill_geometry(p, a.cin_p, kc, rows, acc_stages, tune.halo_mode, tune.a_stages ? tune.a_stages : 2, bs,
-                          rich != 0);
-            if (fits(p)) found = true;
+        for (int ew = ew_first; ew >= ew_last && !found; ew -= 4) {
+          p.epi_warps = ew;
+          for (int bs = tune.b_stages ? tune.b_stages : 4; bs >= 2 && !found; --bs) {
+            // deeper epilogue staging (more TMA stores / residual loads in flight) when shared memory allows
+            for (int staging = 2; staging >= 1 && !found; --staging) {
+              fill_geometry(p, a.cin_p, kc, rows, acc_stages, tune.halo_mode, tune.a_stages ? tune.a_stages : 2, bs,
+                            staging, false);
+              if (fits(p)) found = true;
+            }
+            if (tune.b_stages) break;
           }
-          if (tune.b_stages) break;
         }
         if (tune.kc) break;
       }
@@ -762,6 +927,15 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   if (grid > sms) grid = (sms / k) * k;
   p.n_rounds = ceil_div(p.n_units, grid);
 
+  {
+    static const bool verbose = getenv("MZ_VERBOSE") != nullptr;
+    if (verbose)
+      fprintf(stderr,
+              "[mz conv] mode %d cin_p %d n %d | rows %d kc %d subs %d chunks %d a_stages %d b_stages %d resident %d pair %d "
+              "cluster %d epi_warps %d o_ring %d res_rows %d e16 %d e32 %d acc_stages %d smem %u grid %d rounds %d\n",
+              e.mode, a.cin_p, e.n_pad, p.rows, p.kc, p.subs, p.n_chunks, p.a_stages, p.b_stages, p.res_b, p.pair,
+              p.cluster, p.epi_warps, p.o_ring, p.res_rows, p.e16, p.e32, p.acc_stages, smem, grid, p.n_rounds);
+  }
   static long long* g_prof = nullptr;
   if (tune.dbg & 16) {
     if (!g_prof) MZ_CUDA(cudaMalloc(&g_prof, sizeof(long long) * 4096 * 24));
@@ -795,14 +969,18 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
         for (int i = 0; i < 24; ++i) m[i] += static_cast<double>(h[static_cast<size_t>(c) * 24 + i]) / grid;
       fprintf(stderr,
               "[mz prof] mode %d rows %d kc %d n %d rounds %d | producer: wait_a_empty %.0f wait_b_empty %.0f total %.0f | "
-              "mma: wait_acc_empty %.0f wait_a_full %.0f wait_b_full %.0f total %.0f | epilogue: wait_acc_full %.0f total %.0f\n",
-              e.mode, p.rows, p.kc, e.n_pad, p.n_rounds, m[0], m[1], m[7], m[8], m[9], m[10], m[15], m[16], m[23]);
+              "mma: wait_acc_empty %.0f wait_a_full %.0f wait_b_full %.0f gaps %.0f total %.0f | epilogue: wait_acc_full %.0f total %.0f\n",
+              e.mode, p.rows, p.kc, e.n_pad, p.n_rounds, m[0], m[1], m[7], m[8], m[9], m[10], m[11], m[15], m[16], m[23]);
     }
     return MZ_OK;
   };
   const int ks = p.subs > 1 ? p.subs : p.kc / 16;  // k-steps per stage and tap
   MZ_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "conv: the look-ahead issue loop needs at least two A and two B stages");
   if (p.pair) {  // instantiated for the shapes the 64/96/128-channel encoders use
+    if (e.mode == 0 && ks == 1 && p.rows == 1) return launch(conv_tc_kernel<0, 1, 1, true>);
+    if (e.mode == 0 && ks == 1 && p.rows == 2) return launch(conv_tc_kernel<0, 1, 2, true>);
+    if (e.mode == 1 && ks == 1 && p.rows == 1) return launch(conv_tc_kernel<1, 1, 1, true>);
+    if (e.mode == 1 && ks == 1 && p.rows == 2) return launch(conv_tc_kernel<1, 1, 2, true>);
     if (e.mode == 0 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<0, 2, 1, true>);
     if (e.mode == 0 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<0, 2, 2, true>);
     if (e.mode == 0 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<0, 4, 1, true>);

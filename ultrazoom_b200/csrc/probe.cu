@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128, 1) probe_umma_kernel(const __grid_constan
 
 struct RateParams {
   float* out;  // cycles per MMA, one per CTA
-  int n, kc, iters, distinct_a, distinct_d;
+  int n, kc, iters, distinct_a, distinct_d, a_row_shift;
   uint32_t tmem_cols;
 };
 
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(const RateParams p) 
     const uint32_t hi = static_cast<uint32_t>(umma_smem_desc(0, sbo, lt, 0) >> 32);
     const uint32_t lo0 = static_cast<uint32_t>(umma_smem_desc(0, sbo, lt, 0));
     const uint32_t b_lo = lo0 + (b_smem >> 4);
-    const uint32_t a_lo = lo0 + (a_smem >> 4);
+    const uint32_t a_lo = lo0 + ((a_smem + static_cast<uint32_t>(p.a_row_shift * row_bytes)) >> 4);
     const uint32_t a_step = p.distinct_a > 1 ? (16384u >> 4) : 0u;
     const uint32_t d_step = p.distinct_d > 1 ? static_cast<uint32_t>(p.n) : 0u;
     const bool leader = elect_one();
@@ -236,7 +236,8 @@ int mz_probe_umma(int32_t kc, int32_t row_shift, int32_t base_offset_mode, float
 }
 
 int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_t distinct_a, int32_t distinct_d,
-                      float* cycles_per_mma_out) {
+                      int32_t a_row_shift, float* cycles_per_mma_out) {
+  MZ_REQUIRE(a_row_shift >= 0 && a_row_shift <= 64, "probe: a_row_shift must be in [0, 64]");
   MZ_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0, "probe: n must be a multiple of 16 in [16, 256]");
   MZ_REQUIRE(kc == 16 || kc == 32 || kc == 64, "probe: kc must be 16, 32 or 64");
   MZ_REQUIRE(iters > 0 && iters <= (1 << 20) && ctas > 0 && ctas <= 4096, "probe: bad iters/ctas");
@@ -252,6 +253,7 @@ int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_
   p.iters = iters;
   p.distinct_a = distinct_a;
   p.distinct_d = distinct_d;
+  p.a_row_shift = a_row_shift;
   p.tmem_cols = 32;
   while (p.tmem_cols < static_cast<uint32_t>(n * distinct_d)) p.tmem_cols <<= 1;
   const int smem = 1024 + 8 * 16384 + 32768 + 64;

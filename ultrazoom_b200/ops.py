@@ -146,7 +146,8 @@ def probe_umma(kc: int, row_shift: int, base_offset_mode: int) -> float:
 
 
 def probe_mma_rate(n: int, kc: int, iters: int = 2000, ctas: int = 1, distinct_a: int = 1,
-                   distinct_d: int = 1) -> float:
+                   distinct_d: int = 1, a_row_shift: int = 0) -> float:
     cyc = C.c_float()
-    _native.check(_native.load().mz_probe_mma_rate(n, kc, iters, ctas, distinct_a, distinct_d, C.byref(cyc)))
+    _native.check(_native.load().mz_probe_mma_rate(n, kc, iters, ctas, distinct_a, distinct_d, a_row_shift,
+                                                   C.byref(cyc)))
     return cyc.value
