@@ -133,7 +133,8 @@ typedef struct mz_conv_tune {
   int32_t cluster;    /* CTAs per cluster sharing the weight stream via TMA multicast: 1, 2 or 4       */
   int32_t dbg;        /* timing experiments ONLY (results are wrong): 1 skip weight loads, 2 skip        */
                       /* activation loads, 4 skip the epilogue body, 8 skip the MMAs                     */
-  int32_t pair;       /* 1: CTA pairs issue M = 256 UMMAs (cta_group::2), weights split between the two  */
+  int32_t pair;       /* CTA pairs issue M = 256 UMMAs (cta_group::2), weights split between the two:    */
+                      /* 0 only when that makes the filter bank resident, 1 always, 2 never              */
   int32_t resident;   /* filter bank resident in shared memory: 0 when it fits, 1 require, 2 never       */
   int32_t epi_warps;  /* epilogue warps per CTA: 0 auto (8), 4 or 8                                      */
 } mz_conv_tune;
@@ -192,6 +193,10 @@ int mz_control_film(const float* c_dev, int32_t c_rows, const float* w_dev /*L,2
  * `distinct_a` A tiles and `distinct_d` TMEM accumulators, the A descriptor starting `a_row_shift` rows into its
  * tile (the shared-halo conv's shifted taps); writes SM cycles per UMMA (mean over CTAs). */
 int mz_probe_umma(int32_t kc, int32_t row_shift, int32_t base_offset_mode, float* max_abs_err_out);
+/* mz_probe_set_gap: subsequent mz_probe_mma_rate calls idle the issuing thread for `gap_cycles` (after a
+ * tcgen05.commit when commit_in_gap != 0) between bursts of 8 * burst_iters UMMAs (0 = no gaps): measures how much
+ * issuer-side bookkeeping the UMMA queue hides. */
+int mz_probe_set_gap(int32_t burst_iters, int32_t gap_cycles, int32_t commit_in_gap);
 int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_t distinct_a,
                       int32_t distinct_d, int32_t a_row_shift, float* cycles_per_mma_out);
 

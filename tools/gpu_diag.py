@@ -47,6 +47,23 @@ def g_rate():
                 _report("rate", f"n={n} kc={kc} distinct_a={da} distinct_d={dd}", f"cyc/mma={cyc:.1f} (N/2={n / 2:.0f})", True)
 
 
+def g_gap():
+    """How long may the issuing thread stay away between two bursts before the tensor pipe runs dry?"""
+    from ultrazoom_b200 import _native, ops
+
+    lib = _native.load()
+    for n in (48, 96, 192):
+        for burst in (4, 8):                      # 32 / 64 UMMAs per burst
+            for commit in (0, 1):
+                row = []
+                for gap in (0, 50, 100, 150, 200, 300, 400, 600):
+                    lib.mz_probe_set_gap(burst, gap, commit)
+                    cyc = ops.probe_mma_rate(n, 32, 4000, 148, 2, 2, 0)
+                    row.append(f"{gap}:{cyc * 8 * burst:.0f}")
+                _report("gap", f"n={n} burst={8 * burst} commit={commit}", "cycles per burst by gap  " + " ".join(row), True)
+    lib.mz_probe_set_gap(0, 0, 0)
+
+
 def g_shift():
     """UMMA rate when the A descriptor starts a few rows into the swizzled tile (the shared-halo taps)."""
     from ultrazoom_b200 import ops
@@ -288,6 +305,8 @@ def main():
         g_rate()
     elif what == "shift":
         g_shift()
+    elif what == "gap":
+        g_gap()
     elif what == "small":
         g_small()
     elif what == "simt":

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mz_pack_conv_weight": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, C.POINTER(C.c_size_t)]),
     "mz_control_film": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mz_probe_umma": (C.c_int, [_I, _I, _I, C.POINTER(C.c_float)]),
+    "mz_probe_set_gap": (C.c_int, [_I, _I, _I]),
     "mz_probe_mma_rate": (C.c_int, [_I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_float)]),
     "mz_padded_channels": (C.c_int, [_I]),
     "mz_zb_pitch": (C.c_int, [_I]),

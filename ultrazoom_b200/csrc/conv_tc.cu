@@ -298,30 +298,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     MZ_TIMED(1, mbar_wait(bar_a_full + 8 * sa, pa));
     MZ_TIMED(2, mbar_wait(bar_b_full + 8 * sb, pb));
     tc_fence_after();
-    long long t_gap = 0;
     if (p.res_b) {
       // ---- resident filter bank: one hand-off per K chunk, all nine taps issued back to back ----
-      // The UMMA queue is shallow: once the last UMMA of a burst is issued only a few hundred cycles of tensor work
-      // remain queued, and everything the issuer does before the next burst beyond that is a tensor-pipe bubble
-      // (measured: ~600 cycles per hand-off with the bookkeeping at the end of the burst).  So ALL bookkeeping of the
-      // next step -- ring positions, descriptor bases, barrier sampling -- happens between the second and the third
-      // filter row of the current step; what is left after the last UMMA is two commits, two (normally not taken)
-      // waits and a fence.  The weight stages are waited for once, during the first patch.
-      uint32_t cur_a_lo = desc_lo0 + (a_base >> 4);
-      uint32_t cur_d = tmem_base;
-      uint32_t cur_b_lo = desc_lo0 + (b_base >> 4);
+      // Measured with mz_probe_set_gap (tools/gpu_diag.py gap): for the operand-fetch-bound UMMA shapes (N <= 128 at
+      // M = 128) the tensor pipe has NO slack -- every cycle the issuing thread spends away from the next tcgen05.mma
+      // beyond one UMMA time (44 / 56 cycles at N = 48 / 96) is a bubble.  So all bookkeeping of the next step (ring
+      // positions, descriptor bases, commit addresses, barrier sampling, the after-sync fence) runs between the second
+      // and the third filter row of the current step, and what follows the last UMMA of a step is two commits and one
+      // normally-not-taken branch.  The weight stages are waited for once, during the first patch.
       const uint32_t a_stage_u = static_cast<uint32_t>(p.a_stage_bytes) >> 4, b_stage_u = static_cast<uint32_t>(p.b_stage_bytes) >> 4;
+      const uint32_t a_lo0 = desc_lo0 + (a_base >> 4), b_lo0 = desc_lo0 + (b_base >> 4);
+      const uint32_t n_a_stages = static_cast<uint32_t>(p.a_stages), acc_cols = ROWS * acc_stride;
       const int n_chunks = p.n_chunks;
       const int total_steps = p.n_rounds * n_chunks;
+      uint32_t cur_a_lo = a_lo0, cur_b_lo = b_lo0, cur_d = tmem_base;
+      uint32_t cur_commit_a = bar_a_empty, cur_commit_acc = n_chunks == 1 ? bar_acc_full : 0u;
+      uint32_t cur_first = 0u;  // 0: the first UMMA of the step overwrites the accumulator (first chunk of a patch)
       int c = 0;
       bool first_round = true;
       for (int step = 0; step < total_steps; ++step) {
-        const bool last_chunk = c == n_chunks - 1;
-        const bool last_step = step == total_steps - 1;
         const uint32_t d_base = cur_d;
-        uint32_t nsa = sa, npa = pa, nas = as, npacc = pacc, n_a_lo = cur_a_lo, n_d = cur_d, n_b_lo = cur_b_lo;
-        bool a_ready = true, acc_ready = true;
-        if (prof_on && t_gap != 0) tick[3] += clock64() - t_gap;  // issuer time between two bursts
+        uint32_t n_a_lo = 0, n_b_lo = 0, n_d = 0, n_commit_a = 0, n_commit_acc = 0, n_first = 0;
+        uint32_t nsa = sa, npa = pa, nas = as, npacc = pacc;
+        bool ready = true;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
           const uint32_t b_lo_stage = cur_b_lo + dy * b_stage_u;
@@ -330,57 +329,66 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tc_fence_after();
           }
           const uint32_t a_lo_dy = cur_a_lo + dy * DY;
-          const uint32_t first = (c == 0 && dy == 0) ? 0u : 1u;  // 0: overwrite the accumulator
+          const uint32_t first = dy == 0 ? cur_first : 1u;
           if (dy == 2) {
-            // ---- bookkeeping of the NEXT step, two filter rows of tensor work still queued behind us ----
-            if (++nsa == static_cast<uint32_t>(p.a_stages)) {
+            // ---- bookkeeping of the NEXT step, one filter row of tensor work still to be issued after it ----
+            const bool last_chunk = c == n_chunks - 1;
+            if (++nsa == n_a_stages) {
               nsa = 0;
               npa ^= 1u;
             }
-            n_a_lo = desc_lo0 + (a_base >> 4) + nsa * a_stage_u;
-            n_b_lo = last_chunk ? desc_lo0 + (b_base >> 4) : cur_b_lo + 3 * b_stage_u;
+            n_a_lo = a_lo0 + nsa * a_stage_u;
+            n_commit_a = bar_a_empty + 8 * nsa;
             if (last_chunk) {
               if (++nas == static_cast<uint32_t>(p.acc_stages)) {
                 nas = 0;
                 npacc ^= 1u;
               }
-              n_d = tmem_base + nas * ROWS * acc_stride;
+              n_b_lo = b_lo0;
+              n_first = 0u;
+              c = 0;
+              first_round = false;
+            } else {
+              n_b_lo = cur_b_lo + 3 * b_stage_u;
+              n_first = 1u;
+              ++c;
             }
-            if (!last_step) {
-              a_ready = test_uniform(bar_a_full + 8 * nsa, npa);
-              if (last_chunk) acc_ready = test_uniform(bar_acc_empty + 8 * nas, npacc ^ 1u);
+            n_d = tmem_base + nas * acc_cols;
+            n_commit_acc = c == n_chunks - 1 ? bar_acc_full + 8 * nas : 0u;  // (c is already the next step's chunk)
+            if (step + 1 < total_steps) {
+              ready = test_uniform(bar_a_full + 8 * nsa, npa);
+              if (last_chunk) ready = test_uniform(bar_acc_empty + 8 * nas, npacc ^ 1u) && ready;
+              tc_fence_after();
             }
           }
           MZ_ISSUE_TAP(0)
           MZ_ISSUE_TAP(1)
           MZ_ISSUE_TAP(2)
         }
-        if (prof_on) t_gap = clock64();
         if (leader) {
           if (PAIR) {
-            umma2_commit_mcast(bar_a_empty + 8 * sa, 3);
-            if (last_chunk) umma2_commit_mcast(bar_acc_full + 8 * as, 3);
+            umma2_commit_mcast(cur_commit_a, 3);
+            if (cur_commit_acc != 0u) umma2_commit_mcast(cur_commit_acc, 3);
           } else {
-            umma_commit(bar_a_empty + 8 * sa);
-            if (last_chunk) umma_commit(bar_acc_full + 8 * as);
+            umma_commit(cur_commit_a);
+            if (cur_commit_acc != 0u) umma_commit(cur_commit_acc);
           }
         }
-        if (!acc_ready) MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * nas, npacc ^ 1u));
-        if (!a_ready) MZ_TIMED(1, mbar_wait(bar_a_full + 8 * nsa, npa));
-        tc_fence_after();
+        if (!ready) {  // rare: the producer or the epilogue is behind
+          if (n_first == 0u) MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * nas, npacc ^ 1u));
+          MZ_TIMED(1, mbar_wait(bar_a_full + 8 * nsa, npa));
+          tc_fence_after();
+        }
         sa = nsa;
         pa = npa;
         as = nas;
         pacc = npacc;
         cur_a_lo = n_a_lo;
-        cur_d = n_d;
         cur_b_lo = n_b_lo;
-        if (last_chunk) {
-          c = 0;
-          first_round = false;
-        } else {
-          ++c;
-        }
+        cur_d = n_d;
+        cur_commit_a = n_commit_a;
+        cur_commit_acc = n_commit_acc;
+        cur_first = n_first;
       }
     } else
     for (int round = 0; round < p.n_rounds; ++round) {
@@ -788,21 +796,24 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     while (k > 1 && (e.n_pad % k != 0 || (e.n_pad / k) % 8 != 0)) k >>= 1;
     p.cluster = k;
     p.b_slice_rows = e.n_pad / k;
-    // CTA pairs: opt-in (tune.pair), for the encoder convolutions whose weight rows split into two 8-row multiples
-    p.pair = (tune.pair == 1 && k == 1 && e.mode != 2 && tune.halo_mode == 0 && (e.n_pad / 2) % 8 == 0 &&
-              a.cin_p % 32 == 0)
-                 ? 1
-                 : 0;
-    if (p.pair) p.b_slice_rows = e.n_pad / 2;
     p.dbg = (tune.dbg & 1) && k > 1 ? (tune.dbg & ~1) : tune.dbg;  // skipping multicast loads would deadlock peers
   }
   // ---- choose the patch geometry ----
   // First choice: the whole filter bank resident in shared memory (the persistent CTA then streams activations only;
   // re-streaming 83..332 KB of weights per patch is what saturates the L2 -> SM path otherwise).  It needs two TMEM
-  // stages and room for at least two activation stages beside the bank.
+  // stages, two-row patches (unless TMEM only holds one-row stages) and at least two activation stages beside the
+  // bank.  A bank that does not fit one CTA is split between the two CTAs of a pair (cta_group::2, M = 256 UMMAs:
+  // each CTA holds N/2 weight rows).  Otherwise the weights are streamed per patch.
+  // tune.pair: 0 = pair only when that makes the bank resident, 1 = always pair, 2 = never.
   const int acc_stride = ((e.n_pad + 31) / 32) * 32;
   bool found = false;
   const int kc_first = tune.kc ? tune.kc : pick_kc(a.cin_p);
+  const bool pair_ok = p.cluster == 1 && e.mode != 2 && tune.halo_mode == 0 && (e.n_pad / 2) % 8 == 0 &&
+                       a.cin_p % 32 == 0 && tune.pair != 2;
+  auto set_pair = [&](int on) {
+    p.pair = on;
+    p.b_slice_rows = on ? e.n_pad / 2 : e.n_pad / p.cluster;
+  };
   auto rows_cap = [&](int acc_stages) {
     int rmax = 512 / (acc_stages * acc_stride);
     if (rmax > 4) rmax = 4;
@@ -813,12 +824,16 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   };
   // epilogue warps: eight (two per TMEM lane quarter) unless their staging does not fit beside the operand rings
   const int ew_first = tune.epi_warps ? tune.epi_warps : 8, ew_last = tune.epi_warps ? tune.epi_warps : 4;
-  if (tune.resident != 2 && p.cluster == 1 && tune.halo_mode == 0 && (tune.acc_stages == 0 || tune.acc_stages == 2)) {
-    for (int rows = rows_cap(2); rows >= 1 && !found; --rows) {
-      if (rows == 3) continue;
-      for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {
-        for (int ew = ew_first; ew >= ew_last && !found; ew -= 4) {
-          p.epi_warps = ew;
+  auto try_resident = [&]() {
+    if (tune.resident == 2 || p.cluster != 1 || tune.halo_mode != 0 || !(tune.acc_stages == 0 || tune.acc_stages == 2))
+      return;
+    const int rcap = rows_cap(2);
+    const int rmin = (rcap >= 2 && !tune.rows) ? 2 : 1;  // a one-row patch reads every activation row three times
+    for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {  // wide K chunks first: fewer hand-offs per patch
+      for (int ew = ew_first; ew >= ew_last && !found; ew -= 4) {
+        p.epi_warps = ew;
+        for (int rows = rcap; rows >= rmin && !found; --rows) {
+          if (rows == 3) continue;
           for (int as = tune.a_stages ? tune.a_stages : 3; as >= 2 && !found; --as) {
             for (int staging = 2; staging >= 0 && !found; --staging) {
               fill_geometry(p, a.cin_p, kc, rows, 2, 0, as, 0, staging, true);
@@ -826,40 +841,54 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
             }
             if (tune.a_stages) break;
           }
+          if (tune.rows) break;
         }
-        if (tune.kc) break;
       }
-      if (tune.rows) break;
+      if (tune.kc) break;
+    }
+  };
+  auto try_stream = [&]() {
+    for (int acc_stages = tune.acc_stages ? tune.acc_stages : 2; acc_stages >= 1 && !found; --acc_stages) {
+      const int rmax = rows_cap(acc_stages);
+      for (int rows = rmax; rows >= 1 && !found; --rows) {
+        if (rows == 3) continue;  // instantiated for 1, 2 and 4 accumulator rows
+        for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {
+          for (int ew = ew_first; ew >= ew_last && !found; ew -= 4) {
+            p.epi_warps = ew;
+            for (int bs = tune.b_stages ? tune.b_stages : 4; bs >= 2 && !found; --bs) {
+              // deeper epilogue staging (more TMA stores / residual loads in flight) when shared memory allows
+              for (int staging = 2; staging >= 1 && !found; --staging) {
+                fill_geometry(p, a.cin_p, kc, rows, acc_stages, tune.halo_mode, tune.a_stages ? tune.a_stages : 2, bs,
+                              staging, false);
+                if (fits(p)) found = true;
+              }
+              if (tune.b_stages) break;
+            }
+          }
+          if (tune.kc) break;
+        }
+        if (tune.rows) break;
+      }
+      if (tune.acc_stages) break;
+    }
+  };
+  if (tune.pair == 1 && pair_ok) {
+    set_pair(1);
+    try_resident();
+  } else {
+    set_pair(0);
+    try_resident();
+    if (!found && pair_ok && tune.pair == 0) {
+      set_pair(1);
+      try_resident();
+      if (!found) set_pair(0);
     }
   }
   if (!found && tune.resident == 1) {
     set_error("conv: the filter bank (cin_p %d, n_pad %d) does not fit resident in shared memory", a.cin_p, e.n_pad);
     return MZ_ERR_UNSUPPORTED;
   }
-  // Otherwise stream the weights per patch: largest patch that keeps two TMEM stages and fits shared memory.
-  for (int acc_stages = tune.acc_stages ? tune.acc_stages : 2; acc_stages >= 1 && !found; --acc_stages) {
-    const int rmax = rows_cap(acc_stages);
-    for (int rows = rmax; rows >= 1 && !found; --rows) {
-      if (rows == 3) continue;  // instantiated for 1, 2 and 4 accumulator rows
-      for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {
-        for (int ew = ew_first; ew >= ew_last && !found; ew -= 4) {
-          p.epi_warps = ew;
-          for (int bs = tune.b_stages ? tune.b_stages : 4; bs >= 2 && !found; --bs) {
-            // deeper epilogue staging (more TMA stores / residual loads in flight) when shared memory allows
-            for (int staging = 2; staging >= 1 && !found; --staging) {
-              fill_geometry(p, a.cin_p, kc, rows, acc_stages, tune.halo_mode, tune.a_stages ? tune.a_stages : 2, bs,
-                            staging, false);
-              if (fits(p)) found = true;
-            }
-            if (tune.b_stages) break;
-          }
-        }
-        if (tune.kc) break;
-      }
-      if (tune.rows) break;
-    }
-    if (tune.acc_stages) break;
-  }
+  if (!found) try_stream();
   if (!found) {
     set_error("conv: no tcgen05 configuration fits (cin_p %d, n_pad %d, rows %d, acc_stages %d, kc %d, halo_mode %d)",
               a.cin_p, e.n_pad, tune.rows, tune.acc_stages, tune.kc, tune.halo_mode);
@@ -969,8 +998,8 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
         for (int i = 0; i < 24; ++i) m[i] += static_cast<double>(h[static_cast<size_t>(c) * 24 + i]) / grid;
       fprintf(stderr,
               "[mz prof] mode %d rows %d kc %d n %d rounds %d | producer: wait_a_empty %.0f wait_b_empty %.0f total %.0f | "
-              "mma: wait_acc_empty %.0f wait_a_full %.0f wait_b_full %.0f gaps %.0f total %.0f | epilogue: wait_acc_full %.0f total %.0f\n",
-              e.mode, p.rows, p.kc, e.n_pad, p.n_rounds, m[0], m[1], m[7], m[8], m[9], m[10], m[11], m[15], m[16], m[23]);
+              "mma: wait_acc_empty %.0f wait_a_full %.0f wait_b_full %.0f total %.0f | epilogue: wait_acc_full %.0f total %.0f\n",
+              e.mode, p.rows, p.kc, e.n_pad, p.n_rounds, m[0], m[1], m[7], m[8], m[9], m[10], m[15], m[16], m[23]);
     }
     return MZ_OK;
   };

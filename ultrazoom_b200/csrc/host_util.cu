@@ -103,6 +103,10 @@ int mz_padded_channels(int32_t c) {
   return p16 <= 64 ? p16 : ((c + 31) / 32) * 32;
 }
 
-int mz_zb_pitch(int32_t cp) { return cp == 48 ? 64 : cp; }
+int mz_zb_pitch(int32_t cp) {
+  // MZ_ZB_PITCH64=1 restores the 128-byte rows of an earlier layout for the 48-channel model (diagnostic)
+  static const bool wide = getenv("MZ_ZB_PITCH64") != nullptr;
+  return (cp == 48 && wide) ? 64 : cp;
+}
 
 }  // extern "C"

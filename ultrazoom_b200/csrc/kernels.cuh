@@ -68,7 +68,8 @@ struct ConvTcTune {
   int a_stages;    // activation ring depth
   int max_ctas;    // cap on the persistent grid (0 = SM count)
   int cluster;     // CTAs per cluster sharing the weight stream through TMA multicast: 1, 2 or 4 (0 = auto)
-  int pair;        // 1: CTA pairs issue M = 256 UMMAs (cta_group::2), each CTA holding half of the weight rows
+  int pair;        // CTA pairs issue M = 256 UMMAs (cta_group::2), each CTA holding half of the weight rows:
+                   // 0 = only when that makes the filter bank resident, 1 = always, 2 = never
   int resident;    // filter bank resident in shared memory: 0 = when it fits, 1 = require, 2 = never (stream per patch)
   int epi_warps;   // epilogue warps: 0 = auto (8), 4 or 8
   int dbg;         // timing experiments only (WRONG results): 1 skip weight loads, 2 skip activation loads,

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(128, 1) probe_umma_kernel(const __grid_constan
   const uint32_t b_smem = base + kProbeRows * 128;  // A region sized for kc = 64
   const uint32_t bar_full = b_smem + kProbeN * 128;
   const uint32_t bar_done = bar_full + 8;
-  const uint32_t tmem_slot = bar_done + 8;
+  const uint32_t tmem_slot = bar_done + 32;
   volatile uint32_t* tmem_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(128, 1) probe_umma_kernel(const __grid_constan
 struct RateParams {
   float* out;  // cycles per MMA, one per CTA
   int n, kc, iters, distinct_a, distinct_d, a_row_shift;
+  int gap_cycles, commit_in_gap;  // issuer idles gap_cycles (optionally after a tcgen05.commit) between bursts of 8 x iters_per_burst
+  int burst_iters;
   uint32_t tmem_cols;
 };
 
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(const RateParams p) 
   const uint32_t a_smem = base;
   const uint32_t b_smem = base + 8 * 16384;
   const uint32_t bar_done = b_smem + 32768;
-  const uint32_t tmem_slot = bar_done + 8;
+  const uint32_t tmem_slot = bar_done + 32;
   volatile uint32_t* tmem_gen = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   const int warp = threadIdx.x >> 5;
   for (uint32_t i = threadIdx.x; i < (8 * 16384 + 32768) / 4; i += blockDim.x)
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(const RateParams p) 
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     mbar_init(bar_done, 1);
+    mbar_init(bar_done + 16, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -129,12 +132,24 @@ __global__ void __launch_bounds__(128, 1) probe_rate_kernel(const RateParams p) 
     const uint32_t a_step = p.distinct_a > 1 ? (16384u >> 4) : 0u;
     const uint32_t d_step = p.distinct_d > 1 ? static_cast<uint32_t>(p.n) : 0u;
     const bool leader = elect_one();
+    const uint32_t dynmask = (p.iters & 1) ? 0xffffffffu : static_cast<uint32_t>(p.a_row_shift >> 8);  // runtime 0
     const long long t0 = clock64();
+    int until_gap = p.burst_iters;
     for (int it = 0; it < p.iters; ++it) {
+      const uint32_t dyn = static_cast<uint32_t>(it) & dynmask;
+      if (p.burst_iters > 0 && --until_gap < 0) {  // what the issuer of a real kernel does between two bursts
+        until_gap = p.burst_iters - 1;
+        if (p.commit_in_gap && leader) umma_commit(bar_done + 16);
+        const long long g0 = clock64();
+        while (clock64() - g0 < p.gap_cycles) {
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const uint64_t adesc = (static_cast<uint64_t>(hi) << 32) | (a_lo + (j & 1) * a_step + 2 * (j >> 1));
-        const uint64_t bdesc = (static_cast<uint64_t>(hi) << 32) | (b_lo + 2 * (j >> 1));
+        // dyn (a runtime zero unless iters is odd) keeps the descriptor words from being folded into loop-invariant
+        // registers: each UMMA is then preceded by the uniform adds that feed it, as in the convolution's issue loop
+        const uint64_t adesc = (static_cast<uint64_t>(hi) << 32) | (a_lo + (j & 1) * a_step + 2 * (j >> 1) + j * dyn);
+        const uint64_t bdesc = (static_cast<uint64_t>(hi) << 32) | (b_lo + 2 * (j >> 1) + (j >> 1) * dyn);
         if (leader) umma_acc(tmem_base + (j & 1) * d_step, adesc, bdesc, idesc);
       }
     }
@@ -235,6 +250,14 @@ int mz_probe_umma(int32_t kc, int32_t row_shift, int32_t base_offset_mode, float
   return rc;
 }
 
+static int g_gap_cycles = 0, g_commit_in_gap = 0, g_burst_iters = 0;
+int mz_probe_set_gap(int32_t burst_iters, int32_t gap_cycles, int32_t commit_in_gap) {
+  g_burst_iters = burst_iters;
+  g_gap_cycles = gap_cycles;
+  g_commit_in_gap = commit_in_gap;
+  return MZ_OK;
+}
+
 int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_t distinct_a, int32_t distinct_d,
                       int32_t a_row_shift, float* cycles_per_mma_out) {
   MZ_REQUIRE(a_row_shift >= 0 && a_row_shift <= 64, "probe: a_row_shift must be in [0, 64]");
@@ -254,9 +277,12 @@ int mz_probe_mma_rate(int32_t n, int32_t kc, int32_t iters, int32_t ctas, int32_
   p.distinct_a = distinct_a;
   p.distinct_d = distinct_d;
   p.a_row_shift = a_row_shift;
+  p.gap_cycles = g_gap_cycles;
+  p.commit_in_gap = g_commit_in_gap;
+  p.burst_iters = g_burst_iters;
   p.tmem_cols = 32;
   while (p.tmem_cols < static_cast<uint32_t>(n * distinct_d)) p.tmem_cols <<= 1;
-  const int smem = 1024 + 8 * 16384 + 32768 + 64;
+  const int smem = 1024 + 8 * 16384 + 32768 + 128;
   int rc = MZ_OK;
   cudaError_t e = cudaFuncSetAttribute(probe_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) {
