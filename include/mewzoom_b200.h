@@ -111,6 +111,15 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
 int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32_t c_rows,
                     float* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags);
 
+/* Frame-stream form of the same call: enqueue one batch on lane 0 or 1 (each lane has its own stream, staging
+ * buffers and workspace) and return at once; mz_upscale_host_wait(lane) blocks until everything enqueued on that
+ * lane (-1: both lanes) has finished and y_host is valid.  Alternating lanes double-buffers a stream of frames: the
+ * copies of frame i+1 and i-1 run under the kernels of frame i.  Host buffers should be pinned (cudaHostAlloc /
+ * torch pin_memory) -- pageable memory makes the copies synchronous -- and must stay untouched until the wait. */
+int mz_upscale_host_async(mz_model* m, int32_t lane, const float* x_host, const float* c_host, int32_t c_rows,
+                          float* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags);
+int mz_upscale_host_wait(mz_model* m, int32_t lane);
+
 /* Optional timing of the encoder's convolution stack (the 2L launches of the dominant kernel):
  * when enabled, mz_upscale records one CUDA event on `stream` before the first and one after the
  * last encoder convolution.  mz_model_conv_stack_ms waits for those events and returns the mean

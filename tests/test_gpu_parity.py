@@ -108,6 +108,20 @@ def test_control_vector_broadcast_and_api(dev):
     assert max_abs_err(ONNXModel(m)(x.to(dev), c.to(dev)).cpu(), a) == 0.0
     h = m.upscale_host(x, c)                                             # host-buffer entry point
     assert max_abs_err(h, a) == 0.0
+    # a batch of 5 is pipelined in five one-image chunks over the two lanes, per-image control vectors sliced per chunk
+    g5 = torch.Generator().manual_seed(5)
+    x5, c5 = torch.rand(5, 3, 24, 40, generator=g5), torch.rand(5, 3, generator=g5)
+    assert max_abs_err(m.upscale_host(x5, c5), m.upscale(x5.to(dev), c5.to(dev)).cpu()) == 0.0
+    # frame-stream form: frames alternate between the two lanes, each result valid after its lane's wait
+    xs = [torch.rand(1, 3, 24, 40, generator=g5).pin_memory() for _ in range(4)]
+    outs = [torch.empty(1, 3, 48, 80).pin_memory() for _ in range(4)]
+    for i, xi in enumerate(xs):
+        if i >= 2:
+            m.host_wait(i & 1)
+        m.upscale_host(xi, c, out=outs[i], lane=i & 1)
+    m.host_wait(-1)
+    for xi, oi in zip(xs, outs):
+        assert max_abs_err(oi, m.upscale(xi.to(dev), c.to(dev)).cpu()) == 0.0
     with pytest.raises(AssertionError):
         m.upscale(x.to(dev), torch.rand(3, 3, device=dev))
     with pytest.raises(AssertionError):

@@ -390,88 +390,100 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         cur_commit_acc = n_commit_acc;
         cur_first = n_first;
       }
-    } else
-    for (int round = 0; round < p.n_rounds; ++round) {
-      const uint32_t d_base = tmem_base + as * ROWS * acc_stride;
-      for (int c = 0; c < p.n_chunks; ++c) {
-        const uint32_t a_lo_stage = desc_lo0 + ((a_base + sa * p.a_stage_bytes) >> 4);
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const uint32_t b_lo_stage = desc_lo0 + ((b_base + sb * p.b_stage_bytes) >> 4);
-          const uint32_t a_lo_dy = a_lo_stage + dy * DY;
-          const uint32_t first = (c == 0 && dy == 0) ? 0u : 1u;  // 0: overwrite the accumulator
-          MZ_ISSUE_TAP(0)
-          MZ_ISSUE_TAP(1)
-          // ---- sample the barriers of the next step ----
-          const bool last_chunk = c == p.n_chunks - 1;
-          const bool last_step = dy == 2 && last_chunk && round == p.n_rounds - 1;
-          uint32_t nsb = sb + 1, npb = pb, nsa = sa, npa = pa, nas = as, npacc = pacc;
-          if (nsb == static_cast<uint32_t>(p.b_stages)) {
-            nsb = 0;
-            if (!p.res_b) npb ^= 1u;  // resident stages complete once (phase 0) and stay complete
-          }
-          bool b_ready = true, a_ready = true, acc_ready = true;
-          if (!last_step) {
-            b_ready = test_uniform(bar_b_full + 8 * nsb, npb);
-            if (dy == 2) {
-              if (++nsa == static_cast<uint32_t>(p.a_stages)) {
-                nsa = 0;
-                npa ^= 1u;
-              }
-              a_ready = test_uniform(bar_a_full + 8 * nsa, npa);
-              if (last_chunk && la_acc) {
-                if (++nas == static_cast<uint32_t>(p.acc_stages)) {
-                  nas = 0;
-                  npacc ^= 1u;
-                }
-                acc_ready = test_uniform(bar_acc_empty + 8 * nas, npacc ^ 1u);
-              }
-            }
-          }
-          MZ_ISSUE_TAP(2)
-          if (leader) {
-            if (PAIR) {  // release / signal in BOTH CTAs of the pair
-              if (!p.res_b) umma2_commit_mcast(bar_b_empty + 8 * sb, 3);
-              if (dy == 2) umma2_commit_mcast(bar_a_empty + 8 * sa, 3);
-              if (dy == 2 && last_chunk) umma2_commit_mcast(bar_acc_full + 8 * as, 3);
-            } else {
-              if (p.cluster > 1)
-                umma_commit_mcast(bar_b_empty + 8 * sb, cta_mask);
-              else if (!p.res_b)
-                umma_commit(bar_b_empty + 8 * sb);
-              if (dy == 2) umma_commit(bar_a_empty + 8 * sa);
-              if (dy == 2 && last_chunk) umma_commit(bar_acc_full + 8 * as);
-            }
-          }
-          // ---- now block on whatever was not ready when sampled ----
-          if (!last_step) {
-            if (dy == 2 && last_chunk) {
-              if (la_acc) {
-                if (!acc_ready) MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * nas, npacc ^ 1u));
-              } else {
-                uint32_t was = as + 1, wp = pacc;  // single TMEM stage: released by the epilogue of THIS patch
-                if (was == static_cast<uint32_t>(p.acc_stages)) {
-                  was = 0;
-                  wp ^= 1u;
-                }
-                MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * was, wp ^ 1u));
-              }
-            }
-            if (dy == 2 && !a_ready) MZ_TIMED(1, mbar_wait(bar_a_full + 8 * nsa, npa));
-            if (!b_ready) MZ_TIMED(2, mbar_wait(bar_b_full + 8 * nsb, npb));
-            tc_fence_after();
-          }
-          sb = nsb;
-          pb = npb;
+    } else {
+      // ---- streamed weights: one hand-off per filter row (weight stage), same minimal-gap structure ----
+      const uint32_t a_stage_u = static_cast<uint32_t>(p.a_stage_bytes) >> 4, b_stage_u = static_cast<uint32_t>(p.b_stage_bytes) >> 4;
+      const uint32_t a_lo0 = desc_lo0 + (a_base >> 4), b_lo0 = desc_lo0 + (b_base >> 4);
+      const uint32_t n_a_stages = static_cast<uint32_t>(p.a_stages), n_b_stages = static_cast<uint32_t>(p.b_stages);
+      const uint32_t n_acc_stages = static_cast<uint32_t>(p.acc_stages), acc_cols = ROWS * acc_stride;
+      const int n_chunks = p.n_chunks;
+      const int total_steps = p.n_rounds * n_chunks * 3;
+      uint32_t cur_a_lo_dy = a_lo0, cur_b_lo = b_lo0, cur_d = tmem_base;
+      uint32_t cur_commit_b = bar_b_empty, cur_commit_a = 0u, cur_commit_acc = 0u, cur_first = 0u;
+      int c = 0, dy = 0;
+      for (int step = 0; step < total_steps; ++step) {
+        const uint32_t d_base = cur_d, a_lo_dy = cur_a_lo_dy, b_lo_stage = cur_b_lo, first = cur_first;
+        MZ_ISSUE_TAP(0)
+        MZ_ISSUE_TAP(1)
+        // ---- bookkeeping of the NEXT step, one tap of tensor work still to be issued after it ----
+        uint32_t nsb = sb + 1, npb = pb, nsa = sa, npa = pa, nas = as, npacc = pacc;
+        if (nsb == n_b_stages) {
+          nsb = 0;
+          npb ^= 1u;
         }
-        if (++sa == static_cast<uint32_t>(p.a_stages)) {
-          sa = 0;
-          pa ^= 1u;
+        uint32_t n_a_lo_dy = cur_a_lo_dy + DY, n_d = cur_d, n_first = 1u;
+        int ndy = dy + 1, nc = c;
+        bool need_a = false, need_acc = false;
+        if (dy == 2) {
+          ndy = 0;
+          need_a = true;
+          if (++nsa == n_a_stages) {
+            nsa = 0;
+            npa ^= 1u;
+          }
+          n_a_lo_dy = a_lo0 + nsa * a_stage_u;
+          if (c == n_chunks - 1) {
+            nc = 0;
+            need_acc = true;
+            if (++nas == n_acc_stages) {
+              nas = 0;
+              npacc ^= 1u;
+            }
+            n_d = tmem_base + nas * acc_cols;
+            n_first = 0u;
+          } else {
+            nc = c + 1;
+          }
         }
-      }
-      if (++as == static_cast<uint32_t>(p.acc_stages)) {
-        as = 0;
-        pacc ^= 1u;
+        const uint32_t n_b_lo = b_lo0 + nsb * b_stage_u, n_commit_b = bar_b_empty + 8 * nsb;
+        const uint32_t n_commit_a = ndy == 2 ? bar_a_empty + 8 * nsa : 0u;
+        const uint32_t n_commit_acc = (ndy == 2 && nc == n_chunks - 1) ? bar_acc_full + 8 * nas : 0u;
+        bool ready = true;
+        if (step + 1 < total_steps) {
+          ready = test_uniform(bar_b_full + 8 * nsb, npb);
+          if (need_a) ready = test_uniform(bar_a_full + 8 * nsa, npa) && ready;
+          // (a single TMEM stage is released by the epilogue of THIS patch: always the slow path)
+          if (need_acc) ready = la_acc ? (test_uniform(bar_acc_empty + 8 * nas, npacc ^ 1u) && ready) : false;
+          tc_fence_after();
+        } else {
+          need_a = need_acc = false;
+        }
+        MZ_ISSUE_TAP(2)
+        if (leader) {
+          if (PAIR) {  // release / signal in BOTH CTAs of the pair
+            umma2_commit_mcast(cur_commit_b, 3);
+            if (cur_commit_a != 0u) umma2_commit_mcast(cur_commit_a, 3);
+            if (cur_commit_acc != 0u) umma2_commit_mcast(cur_commit_acc, 3);
+          } else {
+            if (p.cluster > 1)
+              umma_commit_mcast(cur_commit_b, cta_mask);
+            else
+              umma_commit(cur_commit_b);
+            if (cur_commit_a != 0u) umma_commit(cur_commit_a);
+            if (cur_commit_acc != 0u) umma_commit(cur_commit_acc);
+          }
+        }
+        if (!ready) {  // the producer or the epilogue is behind
+          if (need_acc) MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * nas, npacc ^ 1u));
+          if (need_a) MZ_TIMED(1, mbar_wait(bar_a_full + 8 * nsa, npa));
+          MZ_TIMED(2, mbar_wait(bar_b_full + 8 * nsb, npb));
+          tc_fence_after();
+        }
+        sb = nsb;
+        pb = npb;
+        sa = nsa;
+        pa = npa;
+        as = nas;
+        pacc = npacc;
+        dy = ndy;
+        c = nc;
+        cur_a_lo_dy = n_a_lo_dy;
+        cur_b_lo = n_b_lo;
+        cur_d = n_d;
+        cur_commit_b = n_commit_b;
+        cur_commit_a = n_commit_a;
+        cur_commit_acc = n_commit_acc;
+        cur_first = n_first;
       }
     }
 #undef MZ_ISSUE_TAP

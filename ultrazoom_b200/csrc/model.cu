@@ -27,14 +27,19 @@ struct mz_model {
   float* ctrl_b = nullptr;         // (L, 2hC)
   std::vector<uint8_t> have;       // per (kind, layer) upload flags
   ConvTcTune tune[3];
-  // buffers owned for the *_host entry point
-  void* ws = nullptr;
-  size_t ws_bytes = 0;
-  float* hx = nullptr;
-  float* hy = nullptr;
-  float* hc = nullptr;
-  size_t hx_bytes = 0, hy_bytes = 0, hc_bytes = 0;
-  cudaStream_t stream = nullptr;
+  // the *_host entry points: two lanes, each with its own stream, staging buffers and workspace, so that the
+  // host-to-device copy of one chunk / frame overlaps the kernels of the previous one and the device-to-host copy
+  // of the one before (the conv kernels fill the GPU on their own: two lanes never compute at the same time)
+  struct HostLane {
+    cudaStream_t stream = nullptr;
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    float* hx = nullptr;
+    float* hy = nullptr;
+    float* hc = nullptr;
+    size_t hx_bytes = 0, hy_bytes = 0, hc_bytes = 0;
+  };
+  HostLane lane[2];
   // optional conv-stack timing
   bool timing = false;
   int timing_calls = 0;  // mz_upscale calls recorded since timing was enabled (ring of kTimingSlots)
@@ -162,7 +167,8 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
     alloc(reinterpret_cast<void**>(&m->ctrl_w), sizeof(float) * m->L * 2 * m->hC * m->F);
     alloc(reinterpret_cast<void**>(&m->ctrl_b), sizeof(float) * m->L * 2 * m->hC);
   }
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2; ++i)
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->lane[i].stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     const int rc = cuda_fail(e, "model allocation", __FILE__, __LINE__);
     mz_model_destroy(m);
@@ -182,11 +188,13 @@ void mz_model_destroy(mz_model* m) {
   cudaFree(m->head);
   cudaFree(m->ctrl_w);
   cudaFree(m->ctrl_b);
-  cudaFree(m->ws);
-  cudaFree(m->hx);
-  cudaFree(m->hy);
-  cudaFree(m->hc);
-  if (m->stream) cudaStreamDestroy(m->stream);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(m->lane[i].ws);
+    cudaFree(m->lane[i].hx);
+    cudaFree(m->lane[i].hy);
+    cudaFree(m->lane[i].hc);
+    if (m->lane[i].stream) cudaStreamDestroy(m->lane[i].stream);
+  }
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   delete m;
 }
@@ -411,11 +419,10 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
   return simt ? launch_conv_simt(a, s) : launch_conv_tc(a, m->tune[2], m->cfg.device, s);
 }
 
-int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32_t c_rows, float* y_host, int32_t B,
-                    int32_t H, int32_t W, uint32_t flags) {
-  MZ_REQUIRE(m && x_host && y_host, "upscale_host: null pointer");
-  MZ_REQUIRE(B > 0 && H > 0 && W > 0, "upscale_host: empty input (B %d, H %d, W %d)", B, H, W);
-  DeviceGuard g(m->cfg.device);
+// one chunk (B images) on one lane: H2D, kernels, D2H -- all asynchronous on the lane's stream
+static int host_enqueue(mz_model* m, int li, const float* x_host, const float* c_host, int32_t c_rows, float* y_host,
+                        int32_t B, int32_t H, int32_t W, uint32_t flags) {
+  mz_model::HostLane& L = m->lane[li];
   const size_t xb = sizeof(float) * 3 * B * H * W;
   const size_t yb = xb * m->r * m->r;
   const size_t cb = c_host ? sizeof(float) * c_rows * (m->F > 0 ? m->F : 1) : 0;
@@ -424,6 +431,7 @@ int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32
   if (rc != MZ_OK) return rc;
   auto ensure = [&](void** p, size_t* have, size_t need) -> int {
     if (*have >= need) return MZ_OK;
+    MZ_CUDA(cudaStreamSynchronize(L.stream));  // nothing in flight may still use the old buffer
     if (*p) cudaFree(*p);
     *p = nullptr;
     *have = 0;
@@ -431,17 +439,63 @@ int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32
     *have = need;
     return MZ_OK;
   };
-  if ((rc = ensure(reinterpret_cast<void**>(&m->hx), &m->hx_bytes, xb)) != MZ_OK) return rc;
-  if ((rc = ensure(reinterpret_cast<void**>(&m->hy), &m->hy_bytes, yb)) != MZ_OK) return rc;
-  if (cb && (rc = ensure(reinterpret_cast<void**>(&m->hc), &m->hc_bytes, cb)) != MZ_OK) return rc;
-  if ((rc = ensure(&m->ws, &m->ws_bytes, wsb)) != MZ_OK) return rc;
-  MZ_CUDA(cudaMemcpyAsync(m->hx, x_host, xb, cudaMemcpyHostToDevice, m->stream));
-  if (cb) MZ_CUDA(cudaMemcpyAsync(m->hc, c_host, cb, cudaMemcpyHostToDevice, m->stream));
-  rc = mz_upscale(m, m->hx, cb ? m->hc : nullptr, c_rows, m->hy, B, H, W, m->ws, m->ws_bytes, flags, m->stream);
+  if ((rc = ensure(reinterpret_cast<void**>(&L.hx), &L.hx_bytes, xb)) != MZ_OK) return rc;
+  if ((rc = ensure(reinterpret_cast<void**>(&L.hy), &L.hy_bytes, yb)) != MZ_OK) return rc;
+  if (cb && (rc = ensure(reinterpret_cast<void**>(&L.hc), &L.hc_bytes, cb)) != MZ_OK) return rc;
+  if ((rc = ensure(&L.ws, &L.ws_bytes, wsb)) != MZ_OK) return rc;
+  MZ_CUDA(cudaMemcpyAsync(L.hx, x_host, xb, cudaMemcpyHostToDevice, L.stream));
+  if (cb) MZ_CUDA(cudaMemcpyAsync(L.hc, c_host, cb, cudaMemcpyHostToDevice, L.stream));
+  rc = mz_upscale(m, L.hx, cb ? L.hc : nullptr, c_rows, L.hy, B, H, W, L.ws, L.ws_bytes, flags, L.stream);
   if (rc != MZ_OK) return rc;
-  MZ_CUDA(cudaMemcpyAsync(y_host, m->hy, yb, cudaMemcpyDeviceToHost, m->stream));
-  MZ_CUDA(cudaStreamSynchronize(m->stream));
+  MZ_CUDA(cudaMemcpyAsync(y_host, L.hy, yb, cudaMemcpyDeviceToHost, L.stream));
   return MZ_OK;
+}
+
+int mz_upscale_host_async(mz_model* m, int32_t lane, const float* x_host, const float* c_host, int32_t c_rows,
+                          float* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags) {
+  MZ_REQUIRE(m && x_host && y_host, "upscale_host_async: null pointer");
+  MZ_REQUIRE(lane == 0 || lane == 1, "upscale_host_async: lane must be 0 or 1, %d given", lane);
+  MZ_REQUIRE(B > 0 && H > 0 && W > 0, "upscale_host_async: empty input (B %d, H %d, W %d)", B, H, W);
+  DeviceGuard g(m->cfg.device);
+  return host_enqueue(m, lane, x_host, c_host, c_rows, y_host, B, H, W, flags);
+}
+
+int mz_upscale_host_wait(mz_model* m, int32_t lane) {
+  MZ_REQUIRE(m, "upscale_host_wait: null model");
+  MZ_REQUIRE(lane >= -1 && lane <= 1, "upscale_host_wait: lane must be -1 (both), 0 or 1, %d given", lane);
+  DeviceGuard g(m->cfg.device);
+  for (int i = 0; i < 2; ++i)
+    if (lane < 0 || lane == i) MZ_CUDA(cudaStreamSynchronize(m->lane[i].stream));
+  return MZ_OK;
+}
+
+int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32_t c_rows, float* y_host, int32_t B,
+                    int32_t H, int32_t W, uint32_t flags) {
+  MZ_REQUIRE(m && x_host && y_host, "upscale_host: null pointer");
+  MZ_REQUIRE(B > 0 && H > 0 && W > 0, "upscale_host: empty input (B %d, H %d, W %d)", B, H, W);
+  if (m->F > 0) {
+    MZ_REQUIRE(c_host != nullptr, "Control vector c is required for control models.");
+    MZ_REQUIRE(c_rows == 1 || c_rows == B, "Batch size of c (%d) must match x (%d).", c_rows, B);
+  }
+  DeviceGuard g(m->cfg.device);
+  // A batch is cut into up to eight chunks that alternate between the two lanes: copies of chunk i+1 / i-1 run under
+  // the kernels of chunk i.  (Images are independent: chunking does not change any result.)
+  const int n_chunks = B >= 8 ? 8 : B;
+  const size_t x_img = static_cast<size_t>(3) * H * W, y_img = x_img * m->r * m->r;
+  const int F = m->F > 0 ? m->F : 1;
+  int b0 = 0, rc = MZ_OK;
+  for (int i = 0; i < n_chunks && rc == MZ_OK; ++i) {
+    const int nb = (B - b0 + (n_chunks - i) - 1) / (n_chunks - i);
+    const float* cc = c_host ? (c_rows == B ? c_host + static_cast<size_t>(b0) * F : c_host) : nullptr;
+    rc = host_enqueue(m, i & 1, x_host + b0 * x_img, cc, c_host ? (c_rows == B ? nb : 1) : 0, y_host + b0 * y_img, nb,
+                      H, W, flags);
+    b0 += nb;
+  }
+  for (int i = 0; i < 2; ++i) {
+    const cudaError_t e = cudaStreamSynchronize(m->lane[i].stream);
+    if (e != cudaSuccess && rc == MZ_OK) rc = cuda_fail(e, "upscale_host synchronize", __FILE__, __LINE__);
+  }
+  return rc;
 }
 
 }  // extern "C"

@@ -251,10 +251,16 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
 
     @torch.inference_mode()
     def upscale_host(self, x: Tensor, c: Optional[Tensor] = None, out: Optional[Tensor] = None,
-                     device: int = 0) -> Tensor:
-        """End-to-end call with HOST tensors: H2D copy, kernels, D2H copy (mz_upscale_host)."""
+                     device: int = 0, lane: Optional[int] = None) -> Tensor:
+        """End-to-end call with HOST tensors: H2D copy, kernels, D2H copy (mz_upscale_host).
+
+        ``lane=None``: synchronous; a batch is cut into chunks whose copies overlap the kernels of their neighbours.
+        ``lane=0|1``: frame-stream form (mz_upscale_host_async) -- the call only enqueues and returns ``out`` at once;
+        ``out`` is valid after ``host_wait(lane)``.  Alternating lanes double-buffers a stream of frames.  ``x``, ``c``
+        and ``out`` should be pinned and must not be touched until the wait."""
         c = self._check_inputs(x, c)
         assert not x.is_cuda, "upscale_host takes host tensors"
+        assert lane in (None, 0, 1), "lane must be None, 0 or 1"
         eng = self._engine(torch.device("cuda", device))
         x = x.to(torch.float32).contiguous()
         if c is not None:
@@ -264,11 +270,24 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         if out is None:
             out = torch.empty((B, 3, H * r, W * r), dtype=torch.float32)
         assert out.is_contiguous() and tuple(out.shape) == (B, 3, H * r, W * r) and out.dtype == torch.float32
-        _native.check(eng.lib.mz_upscale_host(
-            eng.handle, x.data_ptr(), c.data_ptr() if c is not None else None,
-            c.shape[0] if c is not None else 0, out.data_ptr(), B, H, W,
-            _native.FLAG_CLAMP01 | self._flags_extra))
+        flags = _native.FLAG_CLAMP01 | self._flags_extra
+        cp, cr = (c.data_ptr(), c.shape[0]) if c is not None else (None, 0)
+        if lane is None:
+            _native.check(eng.lib.mz_upscale_host(eng.handle, x.data_ptr(), cp, cr, out.data_ptr(), B, H, W, flags))
+        else:
+            self._host_keep = getattr(self, "_host_keep", {})
+            self._host_keep[(device, lane)] = (x, c, out)      # keep the (possibly converted) inputs alive until the wait
+            _native.check(eng.lib.mz_upscale_host_async(eng.handle, lane, x.data_ptr(), cp, cr, out.data_ptr(), B, H, W,
+                                                        flags))
         return out
+
+    def host_wait(self, lane: int = -1, device: int = 0) -> None:
+        """Block until the frames enqueued with ``upscale_host(..., lane=...)`` on that lane (-1: both) are done."""
+        eng = self._engine(torch.device("cuda", device))
+        _native.check(eng.lib.mz_upscale_host_wait(eng.handle, lane))
+        keep = getattr(self, "_host_keep", {})
+        for k in [k for k in keep if k[0] == device and (lane < 0 or k[1] == lane)]:
+            del keep[k]
 
 
 class ONNXModel(nn.Module):
