@@ -163,6 +163,14 @@ CONV_CASES = [
     (64, 128, (1, 9, 257), dict(resident=2)),
     (96, 192, (2, 30, 260), dict(pair=1, resident=1, max_ctas=4)),
     (96, 192, (1, 21, 300), dict(pair=1, resident=2)),
+    # filter rows fused along N (one UMMA per input row; the default where it applies) vs one UMMA per (row, tap)
+    (48, 96, (2, 13, 150), dict(fuse=1)),
+    (48, 96, (2, 13, 150), dict(fuse=2)),
+    (48, 96, (2, 41, 300), dict(fuse=1, max_ctas=3)),
+    (64, 128, (1, 9, 257), dict(fuse=1, max_ctas=2)),
+    (32, 48, (1, 7, 130), dict(fuse=1, rows=4)),
+    (32, 48, (2, 9, 100), dict(fuse=1, rows=2, max_ctas=2)),
+    (16, 64, (1, 6, 64), dict(fuse=1)),
     # four epilogue warps (one per TMEM lane quarter) instead of the default eight
     (48, 96, (2, 13, 150), dict(epi_warps=4)),
     (96, 192, (1, 21, 300), dict(epi_warps=4, resident=2)),
@@ -175,7 +183,7 @@ CONV_CASES = [
 @pytest.mark.parametrize("cin,cout,shape,tune", CONV_CASES)
 def test_conv1_film_silu(dev, cin, cout, shape, tune, halo_mode, dt):
     ops, native = _ops()
-    if halo_mode == 1 and tune.get("resident") == 1:
+    if halo_mode == 1 and (tune.get("resident") == 1 or tune.get("fuse") == 1):
         pytest.skip("the resident filter bank is a shared-halo (halo_mode 0) configuration")
     inp, w, film, _, acc = _conv_operands(cin, cout, shape, 7, ops, dt)
     ref = F.silu(acc * film[:, 0][:, None, None, :cout] + film[:, 1][:, None, None, :cout])
@@ -200,13 +208,15 @@ def test_conv1_film_silu(dev, cin, cout, shape, tune, halo_mode, dt):
     (192, 96, (1, 21, 300), dict(pair=1)), (192, 96, (2, 30, 260), dict(pair=1, max_ctas=4)), (128, 64, (1, 3, 129), dict(pair=1)),
     (96, 48, (2, 13, 150), dict(resident=1)), (96, 48, (2, 40, 300), dict(resident=1, max_ctas=3)), (96, 48, (2, 13, 150), dict(resident=2)),
     (128, 64, (1, 9, 257), dict(resident=1, max_ctas=2)), (192, 96, (1, 21, 300), dict(resident=2)),
+    (96, 48, (2, 13, 150), dict(fuse=1)), (96, 48, (2, 41, 300), dict(fuse=1, max_ctas=3)), (96, 48, (2, 13, 150), dict(fuse=2)),
+    (96, 48, (1, 7, 129), dict(fuse=1, rows=4, epi_warps=4)), (64, 64, (1, 9, 257), dict(fuse=1, max_ctas=2)), (64, 32, (2, 9, 100), dict(fuse=1, rows=2)),
     (96, 48, (2, 13, 150), dict(epi_warps=4)), (192, 96, (1, 21, 300), dict(epi_warps=4)), (96, 48, (2, 40, 300), dict(epi_warps=4, rows=4, max_ctas=3)),
     (96, 48, (2, 40, 300), dict(rows=4, resident=2, max_ctas=3)), (96, 48, (1, 7, 129), dict(rows=1)),
 ])
 @pytest.mark.parametrize("dt", DTYPES)
 def test_conv2_residual(dev, cin, cout, shape, tune, halo_mode, dt):
     ops, native = _ops()
-    if halo_mode == 1 and tune.get("resident") == 1:
+    if halo_mode == 1 and (tune.get("resident") == 1 or tune.get("fuse") == 1):
         pytest.skip("the resident filter bank is a shared-halo (halo_mode 0) configuration")
     inp, w, _, zf0, acc = _conv_operands(cin, cout, shape, 8, ops, dt)
     zref = zf0[..., :cout] + acc

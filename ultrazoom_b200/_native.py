@@ -54,6 +54,7 @@ class MzConvTune(C.Structure):
         ("pair", C.c_int32),
         ("resident", C.c_int32),
         ("epi_warps", C.c_int32),
+        ("fuse", C.c_int32),
     ]
 
 

@@ -21,6 +21,7 @@ ConvTcTune to_tune(const mz_conv_tune* t) {
     o.pair = t->pair;
     o.resident = t->resident;
     o.epi_warps = t->epi_warps;
+    o.fuse = t->fuse;
   }
   return o;
 }

@@ -53,6 +53,8 @@ struct TcParams {
   int cluster;       // CTAs per cluster sharing the weight stream by TMA multicast (1, 2 or 4)
   int pair;          // 1: CTA pairs issue M = 256 UMMAs (cta_group::2), weights split N/2 + N/2 between them
   int b_slice_rows;  // n_pad / cluster: weight rows each CTA loads and multicasts per stage
+  int fuse_g;        // FUSE kernels: vertical taps per UMMA window (2 | 3); 0 otherwise
+  uint32_t idesc_w[3];  // FUSE: instruction descriptors for windows of 1, 2, 3 stacked taps (N, 2N, 3N columns)
   int res_b;         // 1: the whole filter bank stays resident in shared memory (b_stages == 3 * n_chunks): it is
                      // loaded during the first patch and never again -- the persistent CTA then streams activations only
   long long* prof;   // optional per-CTA role timers (clock64 ticks), [grid][3 roles][8]; nullptr = off
@@ -94,8 +96,16 @@ __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
 // PAIR: the CTA pair of a cluster works as one 256-row UMMA (cta_group::2): the leader CTA issues M = 256 UMMAs whose
 // A operand is each CTA's own 128-pixel tile and whose B operand is split -- each CTA holds N/2 weight rows -- so
 // per CTA the weight stream (TMA writes AND tensor-core operand reads from shared memory) is halved.
-template <int MODE, int KT, int ROWS, bool PAIR>
+// VAR 0: plain.  VAR 1 (PAIR): see above.  VAR 2 (FUSE, resident filter bank only): filter rows are fused along N --
+// one UMMA multiplies an INPUT row's tile with the weights of up to three vertical taps stacked as [dy][N] rows and
+// accumulates into the adjacent accumulators of the output rows those taps feed (output row r lives at TMEM block
+// ROWS-1-r, so blocks of dy, dy+1, dy+2 are contiguous).  A patch of R rows then takes R+2 UMMAs per (dx, k-step)
+// instead of 3R: the 128 x 16 activation tile -- 4 KB of shared-memory operand fetch per UMMA, what bounds the small-N
+// shapes -- is fetched once per input row instead of once per (output row, tap).  Every UMMA accumulates; the epilogue
+// zeroes each accumulator column group right after reading it.
+template <int MODE, int KT, int ROWS, int VAR>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr bool PAIR = VAR == 1, FUSE = VAR == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -113,7 +123,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t bar_res = bar_acc_empty + 16;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen_base + sp.tmem_ptr);
 
-  const int warp = threadIdx.x >> 5;
+  // (broadcast from lane 0 so that the compiler knows the warp index -- and everything derived from it: role, TMEM lane
+  // quarter, staging addresses, TMA coordinates -- is warp-uniform and keeps it in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -150,6 +162,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (PAIR || p.cluster > 1) cluster_sync_all();  // peers' barriers must be initialised before anything is signalled to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  if (FUSE) {  // every UMMA accumulates: the accumulators start from zero (afterwards the epilogue re-zeroes them)
+    if (warp >= 4 && warp < 8) {
+      for (uint32_t col = 0; col < p.tmem_cols; col += 16)
+        tmem_zero16(tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + col);
+      tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
   const uint32_t cta_rank = (PAIR || p.cluster > 1) ? cluster_ctarank() : 0u;
   const uint16_t cta_mask = static_cast<uint16_t>((1u << p.cluster) - 1u);
 
@@ -212,7 +234,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           const uint32_t full_b = bar_b_full + 8 * sb;
           const uint32_t dstB = b_base + sb * p.b_stage_bytes;
-          if (PAIR) {
+          if (FUSE) {
+            if (lane == 0) {  // stage (c, dx): the three vertical taps of filter column dx, [sub][dy][N][kc]
+              const int dx = dy;
+              mbar_expect_tx(full_b, p.b_tx_bytes);
+              for (int sub = 0; sub < p.subs; ++sub)
+                for (int v = 0; v < 3; ++v)
+                  tma_load_3d(dstB + (sub * 3 + v) * tap_bytes, &p.tmB, full_b, (c * p.subs + sub) * p.kc, 0, v * 3 + dx);
+            }
+          } else if (PAIR) {
             if (lane == 0) {  // this CTA's half of the weight rows; stage layout [3 taps][N/2][kc]
               if (cta_rank == 0) mbar_expect_tx(full_b, 2 * p.b_tx_bytes);
               tma2_load_3d(dstB, &p.tmB, mapa_u32(full_b, 0), c * p.kc, cta_rank * p.b_slice_rows, dy * 3);
@@ -298,7 +328,105 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     MZ_TIMED(1, mbar_wait(bar_a_full + 8 * sa, pa));
     MZ_TIMED(2, mbar_wait(bar_b_full + 8 * sb, pb));
     tc_fence_after();
-    if (p.res_b) {
+    if (FUSE) {
+      // ---- resident filter bank, filter rows fused along N (see the kernel comment) ----
+      const uint32_t a_stage_u = static_cast<uint32_t>(p.a_stage_bytes) >> 4, b_stage_u = static_cast<uint32_t>(p.b_stage_bytes) >> 4;
+      const uint32_t a_lo0 = desc_lo0 + (a_base >> 4), b_lo0 = desc_lo0 + (b_base >> 4);
+      const uint32_t n_a_stages = static_cast<uint32_t>(p.a_stages), acc_cols = ROWS * acc_stride;
+      const uint32_t idw1 = p.idesc_w[0], idw2 = p.idesc_w[1], idw3 = p.idesc_w[2];
+      const bool g3 = p.fuse_g >= 3;
+      const int n_chunks = p.n_chunks;
+      const int total_steps = p.n_rounds * n_chunks;
+      uint32_t cur_a_lo = a_lo0, cur_b_lo = b_lo0, cur_d = tmem_base;
+      uint32_t cur_commit_a = bar_a_empty, cur_commit_acc = n_chunks == 1 ? bar_acc_full : 0u;
+      int c = 0;
+      bool first_round = true;
+      for (int step = 0; step < total_steps; ++step) {
+        const uint32_t d_base = cur_d;
+        uint32_t n_a_lo = 0, n_b_lo = 0, n_d = 0, n_commit_a = 0, n_commit_acc = 0;
+        uint32_t nsa = sa, npa = pa, nas = as, npacc = pacc;
+        bool ready = true, next_new_patch = false;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint32_t b_lo_dx = cur_b_lo + dx * b_stage_u;
+          if (first_round && step + dx > 0) {  // (stage 0 was waited for before the loop)
+            MZ_TIMED(2, mbar_wait(bar_b_full + 8 * (c * 3 + dx), 0));
+            tc_fence_after();
+          }
+          if (dx == 2) {
+            // ---- bookkeeping of the NEXT step, one filter column of tensor work still to be issued after it ----
+            const bool last_chunk = c == n_chunks - 1;
+            if (++nsa == n_a_stages) {
+              nsa = 0;
+              npa ^= 1u;
+            }
+            n_a_lo = a_lo0 + nsa * a_stage_u;
+            n_commit_a = bar_a_empty + 8 * nsa;
+            if (last_chunk) {
+              if (++nas == static_cast<uint32_t>(p.acc_stages)) {
+                nas = 0;
+                npacc ^= 1u;
+              }
+              n_b_lo = b_lo0;
+              next_new_patch = true;
+              c = 0;
+              first_round = false;
+            } else {
+              n_b_lo = cur_b_lo + 3 * b_stage_u;
+              ++c;
+            }
+            n_d = tmem_base + nas * acc_cols;
+            n_commit_acc = c == n_chunks - 1 ? bar_acc_full + 8 * nas : 0u;  // (c is already the next step's chunk)
+            if (step + 1 < total_steps) {
+              ready = test_uniform(bar_a_full + 8 * nsa, npa);
+              if (last_chunk) ready = test_uniform(bar_acc_empty + 8 * nas, npacc ^ 1u) && ready;
+              tc_fence_after();
+            }
+          }
+          if (issue) {
+#pragma unroll
+            for (int t = 0; t < KT; ++t) {
+#pragma unroll
+              for (int i = -1; i <= ROWS; ++i) {  // input row i feeds output rows i+1-dy, dy in [dy_lo, dy_hi]
+                const int dy_lo = (i + 2 - ROWS) > 0 ? (i + 2 - ROWS) : 0, dy_hi = (i + 1) < 2 ? (i + 1) : 2;
+                const int cnt = dy_hi - dy_lo + 1;
+                const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (cur_a_lo + (i + 1) * RP + dx * DX + t * a_kp);
+                const uint32_t b_lo = b_lo_dx + dy_lo * TB + t * b_kp;
+                const uint32_t d_lo = d_base + (ROWS - 2 - i + dy_lo) * acc_stride;  // block of output row i+1-dy_lo
+                if (cnt == 1) {
+                  umma_acc(d_lo, adesc, (static_cast<uint64_t>(desc_hi) << 32) | b_lo, idw1);
+                } else if (cnt == 2) {
+                  umma_acc(d_lo, adesc, (static_cast<uint64_t>(desc_hi) << 32) | b_lo, idw2);
+                } else if (g3) {
+                  umma_acc(d_lo, adesc, (static_cast<uint64_t>(desc_hi) << 32) | b_lo, idw3);
+                } else {  // three taps, windows of two: (dy0, dy1) then dy2
+                  umma_acc(d_lo, adesc, (static_cast<uint64_t>(desc_hi) << 32) | b_lo, idw2);
+                  umma_acc(d_lo + 2 * acc_stride, adesc, (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * TB), idw1);
+                }
+              }
+            }
+          }
+        }
+        if (leader) {
+          umma_commit(cur_commit_a);
+          if (cur_commit_acc != 0u) umma_commit(cur_commit_acc);
+        }
+        if (!ready) {  // rare: the producer or the epilogue is behind
+          if (next_new_patch) MZ_TIMED(0, mbar_wait(bar_acc_empty + 8 * nas, npacc ^ 1u));
+          MZ_TIMED(1, mbar_wait(bar_a_full + 8 * nsa, npa));
+          tc_fence_after();
+        }
+        sa = nsa;
+        pa = npa;
+        as = nas;
+        pacc = npacc;
+        cur_a_lo = n_a_lo;
+        cur_b_lo = n_b_lo;
+        cur_d = n_d;
+        cur_commit_a = n_commit_a;
+        cur_commit_acc = n_commit_acc;
+      }
+    } else if (p.res_b) {
       // ---- resident filter bank: one hand-off per K chunk, all nine taps issued back to back ----
       // Measured with mz_probe_set_gap (tools/gpu_diag.py gap): for the operand-fetch-bound UMMA shapes (N <= 128 at
       // M = 128) the tensor pipe has NO slack -- every cycle the issuing thread spends away from the next tcgen05.mma
@@ -582,8 +710,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_after();
       for (int r = (MODE == 0 ? 0 : half), k = 0; r < ROWS; r += (MODE == 0 ? 1 : nh), ++k) {
         const int y = y0 + r;
-        if (y >= p.epi.H || !live) break;  // warp-uniform
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (as * ROWS + r) * p.acc_stride;
+        // (FUSE keeps output row r in TMEM block ROWS-1-r so that the blocks of stacked vertical taps are adjacent)
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                               (as * ROWS + (FUSE ? ROWS - 1 - r : r)) * p.acc_stride;
+        if (y >= p.epi.H || !live) {  // warp-uniform: nothing to store for this row
+          if (!FUSE) break;
+          // the accumulators of a row that is not stored (below the image, surplus patch) still have to be re-zeroed
+          for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) {
+            if (MODE == 0 && nh == 2 &&
+                ((static_cast<uint32_t>(r) * nb16 + n0 / static_cast<uint32_t>(p.e16)) & 1u) != static_cast<uint32_t>(half))
+              continue;  // the other warp of this lane quarter owns that box
+            tmem_zero16(taddr + n0);
+          }
+          continue;
+        }
         if (MODE == 2) {
           float acc[48];
           uint32_t v[16];
@@ -618,6 +758,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             uint32_t v[16];
             tmem_ld16(taddr + n0, v);
             tmem_ld_wait();
+            if (FUSE) tmem_zero16(taddr + n0);
             const uint32_t bz = n0 >> sh32, cz = (n0 - (bz << sh32)) >> 2;  // fp32 box, first 16-byte chunk in its row
             const uint32_t zrow = st_z + bz * box32 + lane * row32;
             uint32_t o[8];
@@ -663,6 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               uint32_t v[16];
               tmem_ld16(taddr + n0, v);
               tmem_ld_wait();
+              if (FUSE) tmem_zero16(taddr + n0);
               float acc[16];
 #pragma unroll
               for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
@@ -690,6 +832,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
       }
+      if (FUSE) tmem_st_wait();  // the zeroes are in TMEM before the issuer may accumulate into this stage again
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -750,7 +893,7 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   p.n_chunks = cin_p / (kc * p.subs);
   p.rows = rows;
   p.acc_stages = acc_stages;
-  p.acc_stride = ((p.epi.n_pad + 31) / 32) * 32;
+  p.acc_stride = p.fuse_g ? p.epi.n_pad : ((p.epi.n_pad + 31) / 32) * 32;  // FUSE: adjacent blocks, no padding
   p.halo_mode = halo_mode;
   p.a_stages = a_stages;
   p.b_stages = res_b ? 3 * p.n_chunks : b_stages;
@@ -817,7 +960,6 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   // bank.  A bank that does not fit one CTA is split between the two CTAs of a pair (cta_group::2, M = 256 UMMAs:
   // each CTA holds N/2 weight rows).  Otherwise the weights are streamed per patch.
   // tune.pair: 0 = pair only when that makes the bank resident, 1 = always pair, 2 = never.
-  const int acc_stride = ((e.n_pad + 31) / 32) * 32;
   bool found = false;
   const int kc_first = tune.kc ? tune.kc : pick_kc(a.cin_p);
   const bool pair_ok = p.cluster == 1 && e.mode != 2 && tune.halo_mode == 0 && (e.n_pad / 2) % 8 == 0 &&
@@ -827,6 +969,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     p.b_slice_rows = on ? e.n_pad / 2 : e.n_pad / p.cluster;
   };
   auto rows_cap = [&](int acc_stages) {
+    const int acc_stride = p.fuse_g ? e.n_pad : ((e.n_pad + 31) / 32) * 32;
     int rmax = 512 / (acc_stages * acc_stride);
     if (rmax > 4) rmax = 4;
     if (rmax > e.H) rmax = e.H;
@@ -884,12 +1027,28 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
       if (tune.acc_stages) break;
     }
   };
+  // filter rows fused along N (VAR 2): resident, un-paired encoder convolutions whose stacked taps fit one UMMA
+  const int fuse_g = (256 / e.n_pad) >= 3 ? 3 : (256 / e.n_pad);
+  // Opt-in (tune.fuse = 1): it cuts the tensor-only time of the N = 48 convolution by 19 % (154 vs 190 us on a
+  // 4 x 960 x 540 batch) but not the whole kernel, which is bound by the L2 <-> SM traffic of its operands and epilogue.
+  const bool fuse_ok = e.mode != 2 && tune.fuse == 1 && fuse_g >= 2 && e.H >= 2 && (tune.rows == 0 || tune.rows >= 2) &&
+                       tune.pair != 1;
   if (tune.pair == 1 && pair_ok) {
     set_pair(1);
     try_resident();
   } else {
     set_pair(0);
-    try_resident();
+    if (fuse_ok) {
+      p.fuse_g = fuse_g;
+      try_resident();
+      if (found && p.rows < 2) found = false;
+      if (!found) p.fuse_g = 0;
+    }
+    if (!found && tune.fuse == 1) {
+      set_error("conv: the fused-row kernel does not apply (cin_p %d, n_pad %d)", a.cin_p, e.n_pad);
+      return MZ_ERR_UNSUPPORTED;
+    }
+    if (!found) try_resident();
     if (!found && pair_ok && tune.pair == 0) {
       set_pair(1);
       try_resident();
@@ -914,6 +1073,10 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   p.n_units = static_cast<int>(n_units);
   const int mma_m = p.pair ? 256 : 128;
   p.idesc = e.bf16 ? umma_idesc_bf16(mma_m, e.n_pad) : umma_idesc_f16(mma_m, e.n_pad);
+  for (int k = 1; k <= 3; ++k) {
+    const int nw = k * e.n_pad <= 256 ? k * e.n_pad : e.n_pad;
+    p.idesc_w[k - 1] = e.bf16 ? umma_idesc_bf16(128, nw) : umma_idesc_f16(128, nw);
+  }
   const CUtensorMapDataType tdt = e.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 
   const CUtensorMapSwizzle swz =
@@ -932,7 +1095,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     const uint64_t dims[3] = {static_cast<uint64_t>(a.cin_p), static_cast<uint64_t>(e.n_pad), 9};
     const uint64_t strides[2] = {static_cast<uint64_t>(a.cin_p) * 2, static_cast<uint64_t>(e.n_pad) * a.cin_p * 2};
     const uint32_t box[3] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.b_slice_rows),
-                             p.cluster > 1 ? 1u : 3u};  // pair: this CTA's N/2 rows of all three taps
+                             (p.cluster > 1 || p.fuse_g) ? 1u : 3u};  // pair: this CTA's N/2 rows of all three taps
     int rc = encode_tmap(&p.tmB, tdt, 3, const_cast<uint16_t*>(a.w), dims, strides, box, swz);
     if (rc != MZ_OK) return rc;
   }
@@ -973,9 +1136,9 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     if (verbose)
       fprintf(stderr,
               "[mz conv] mode %d cin_p %d n %d | rows %d kc %d subs %d chunks %d a_stages %d b_stages %d resident %d pair %d "
-              "cluster %d epi_warps %d o_ring %d res_rows %d e16 %d e32 %d acc_stages %d smem %u grid %d rounds %d\n",
+              "fuse %d cluster %d epi_warps %d o_ring %d res_rows %d e16 %d e32 %d acc_stages %d smem %u grid %d rounds %d\n",
               e.mode, a.cin_p, e.n_pad, p.rows, p.kc, p.subs, p.n_chunks, p.a_stages, p.b_stages, p.res_b, p.pair,
-              p.cluster, p.epi_warps, p.o_ring, p.res_rows, p.e16, p.e32, p.acc_stages, smem, grid, p.n_rounds);
+              p.fuse_g, p.cluster, p.epi_warps, p.o_ring, p.res_rows, p.e16, p.e32, p.acc_stages, smem, grid, p.n_rounds);
   }
   static long long* g_prof = nullptr;
   if (tune.dbg & 16) {
@@ -1017,27 +1180,43 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   };
   const int ks = p.subs > 1 ? p.subs : p.kc / 16;  // k-steps per stage and tap
   MZ_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "conv: the look-ahead issue loop needs at least two A and two B stages");
+  if (p.fuse_g) {
+#define MZ_FUSE_ROWS(M, K)                                                   \
+  if (p.rows == 2) return launch(conv_tc_kernel<M, K, 2, 2>);                \
+  if (p.rows == 4) return launch(conv_tc_kernel<M, K, 4, 2>);
+#define MZ_FUSE_KS(M)                   \
+  if (ks == 1) { MZ_FUSE_ROWS(M, 1) }   \
+  if (ks == 2) { MZ_FUSE_ROWS(M, 2) }   \
+  if (ks == 3) { MZ_FUSE_ROWS(M, 3) }   \
+  if (ks == 4) { MZ_FUSE_ROWS(M, 4) }
+    if (e.mode == 0) { MZ_FUSE_KS(0) }
+    if (e.mode == 1) { MZ_FUSE_KS(1) }
+#undef MZ_FUSE_KS
+#undef MZ_FUSE_ROWS
+    set_error("conv: no fused-row kernel for mode %d, %d k-steps, %d rows", e.mode, ks, p.rows);
+    return MZ_ERR_UNSUPPORTED;
+  }
   if (p.pair) {  // instantiated for the shapes the 64/96/128-channel encoders use
-    if (e.mode == 0 && ks == 1 && p.rows == 1) return launch(conv_tc_kernel<0, 1, 1, true>);
-    if (e.mode == 0 && ks == 1 && p.rows == 2) return launch(conv_tc_kernel<0, 1, 2, true>);
-    if (e.mode == 1 && ks == 1 && p.rows == 1) return launch(conv_tc_kernel<1, 1, 1, true>);
-    if (e.mode == 1 && ks == 1 && p.rows == 2) return launch(conv_tc_kernel<1, 1, 2, true>);
-    if (e.mode == 0 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<0, 2, 1, true>);
-    if (e.mode == 0 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<0, 2, 2, true>);
-    if (e.mode == 0 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<0, 4, 1, true>);
-    if (e.mode == 0 && ks == 4 && p.rows == 2) return launch(conv_tc_kernel<0, 4, 2, true>);
-    if (e.mode == 1 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<1, 2, 1, true>);
-    if (e.mode == 1 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<1, 2, 2, true>);
-    if (e.mode == 1 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<1, 4, 1, true>);
-    if (e.mode == 1 && ks == 4 && p.rows == 2) return launch(conv_tc_kernel<1, 4, 2, true>);
+    if (e.mode == 0 && ks == 1 && p.rows == 1) return launch(conv_tc_kernel<0, 1, 1, 1>);
+    if (e.mode == 0 && ks == 1 && p.rows == 2) return launch(conv_tc_kernel<0, 1, 2, 1>);
+    if (e.mode == 1 && ks == 1 && p.rows == 1) return launch(conv_tc_kernel<1, 1, 1, 1>);
+    if (e.mode == 1 && ks == 1 && p.rows == 2) return launch(conv_tc_kernel<1, 1, 2, 1>);
+    if (e.mode == 0 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<0, 2, 1, 1>);
+    if (e.mode == 0 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<0, 2, 2, 1>);
+    if (e.mode == 0 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<0, 4, 1, 1>);
+    if (e.mode == 0 && ks == 4 && p.rows == 2) return launch(conv_tc_kernel<0, 4, 2, 1>);
+    if (e.mode == 1 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<1, 2, 1, 1>);
+    if (e.mode == 1 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<1, 2, 2, 1>);
+    if (e.mode == 1 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<1, 4, 1, 1>);
+    if (e.mode == 1 && ks == 4 && p.rows == 2) return launch(conv_tc_kernel<1, 4, 2, 1>);
     set_error("conv: no CTA-pair kernel for mode %d, %d k-steps, %d rows", e.mode, ks, p.rows);
     return MZ_ERR_UNSUPPORTED;
   }
 #define MZ_DISPATCH_ROWS(M, K)                                     \
   switch (p.rows) {                                                \
-    case 1: return launch(conv_tc_kernel<M, K, 1, false>);         \
-    case 2: return launch(conv_tc_kernel<M, K, 2, false>);         \
-    default: return launch(conv_tc_kernel<M, K, 4, false>);        \
+    case 1: return launch(conv_tc_kernel<M, K, 1, 0>);         \
+    case 2: return launch(conv_tc_kernel<M, K, 2, 0>);         \
+    default: return launch(conv_tc_kernel<M, K, 4, 0>);        \
   }
 #define MZ_DISPATCH_KS(M)                                   \
   switch (ks) {                                             \
