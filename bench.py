@@ -250,7 +250,7 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item()) / steps
-        res = {"model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc, "ms_step": ms_step,
+        res = {"workload": workload, "model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc, "ms_step": ms_step,
                "conv_ms": conv_ms.value, "clocks": clocks, "value": world * out_px / (ms_step * 1e-3) / 1e6,
                "e2e": None}
         # ---- end to end through the public API with HOST buffers (H2D + kernels + D2H inside the timed region) ----
@@ -313,8 +313,15 @@ def main():
         tf = conv_flops / (conv_launch_ms * 1e-3) / 1e12
         gbs = conv_bytes / (conv_launch_ms * 1e-3) / 1e9
         total_flops = algorithmic_flops_per_lr_px(cfg) * npix
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):          # DRAM bytes per launch from the committed ncu capture of this workload
+            with open(tpath) as f:
+                tj = json.load(f).get(res["workload"])
+            if tj:
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
         common = {
-            "kernel": "conv_tc_kernel (3x3 implicit GEMM, tcgen05)", "traffic": None,
+            "kernel": "conv_tc_kernel (3x3 implicit GEMM, tcgen05)", "traffic": traffic, "traffic_source": traffic_src,
             "flops_per_launch": conv_flops, "bytes_per_launch": conv_bytes, "ms_per_launch": conv_launch_ms,
             "launches_per_step": 2 * L, "conv_share_of_step": res["conv_ms"] / res["ms_step"],
             "tensor": {"achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",

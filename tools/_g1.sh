@@ -1,8 +1,11 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_kernels.py -m gpu -q 2>&1 | tail -2
-{
-SWEEP_CFGS="[dict()]" timeout 300 python tools/sweep.py 48 540 960 4 2>&1
-SWEEP_CFGS="[dict()]" timeout 300 python tools/sweep.py 96 540 960 1 2>&1
-SWEEP_CFGS="[dict()]" timeout 300 python tools/sweep.py 54 720 1280 1 2>&1
-} > gpurun_out/sweep34.log 2>&1
-cat gpurun_out/sweep34.log
+for NW in cfg2 cfg4a; do
+  if [ $NW = cfg2 ]; then PER=43; else PER=83; fi
+  CMD="python bench.py --workload $NW --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-also"
+  $CMD > gpurun_out/plain_${NW}_r10.log 2>&1 && \
+  ncu --metrics gpu__time_duration.sum --clock-control none -s $((3*PER)) -c $PER --csv --log-file gpurun_out/launches_${NW}_r10.csv $CMD > gpurun_out/ncu1_${NW}_r10.log 2>&1
+  echo "ncu launches $NW rc=$?"
+  ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s $((2*PER-3+20)) -c 2 -f -o gpurun_out/prof_conv_${NW}_r10 $CMD > gpurun_out/ncu2_${NW}_r10.log 2>&1
+  echo "ncu full $NW rc=$?"
+done
+ls -la gpurun_out/*r10*
