@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--operands", default="float16", choices=["float16", "bfloat16"])
+    ap.add_argument("--residual-stream", default="auto", choices=["auto", "float32", "split"])
     ap.add_argument("--tune", default="", help="comma list k=v of mz_conv_tune fields, e.g. cluster=4,rows=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -218,7 +219,7 @@ def main():
         cfg = MODEL_CONFIGS[model_name]
         r = cfg["upscale_ratio"]
         torch.manual_seed(0)
-        model = MewZoom(**cfg, operand_dtype=args.operands).to(dev).eval()
+        model = MewZoom(**cfg, operand_dtype=args.operands, residual_stream=args.residual_stream).to(dev).eval()
         if tune_kw:
             model.set_conv_tune(-1, dev, **tune_kw)
         eng = model._engine(dev)
@@ -371,7 +372,9 @@ def main():
         "config": {"workload": desc, "model": model_name, "batch_per_gpu": B, "lr_h": H, "lr_w": W,
                    "parallelism": f"replica per GPU x{world}, batch-sharded, no collective",
                    "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
-                   "weights": "random init (seed 0)", "residual_stream": "fp32", "accumulate": "fp32", "mma_operands": args.operands,
+                   "weights": "random init (seed 0)",
+                   "residual_stream": ("fp32" if args.residual_stream != "split"
+                                       else "two 16-bit planes hi + lo (z to 2^-22)"), "accumulate": "fp32", "mma_operands": args.operands,
                    "tune": tune_kw},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,

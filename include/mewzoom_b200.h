@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define MZ_ABI_VERSION 1
+#define MZ_ABI_VERSION 2
 
 typedef enum mz_status {
   MZ_OK = 0,
@@ -55,10 +55,21 @@ typedef struct mz_config {
   int32_t device;             /* CUDA device ordinal                                 */
   int32_t operand_dtype;      /* MZ_DTYPE_F16 (default) or MZ_DTYPE_BF16: element type of  */
                               /* the tensor-core operands (activations + weights).  Both run */
-                              /* at the same tcgen05 rate; accumulation and the residual     */
-                              /* stream are fp32 either way.  fp16's 10-bit mantissa keeps   */
-                              /* max|err| vs the fp32 reference ~8x smaller.     */
+                              /* at the same tcgen05 rate; accumulation is fp32 either way.  */
+                              /* fp16's 10-bit mantissa keeps max|err| vs the fp32 reference */
+                              /* ~8x smaller.                                    */
+  int32_t residual_stream;    /* how the residual stream z lives in HBM between blocks:      */
+                              /* MZ_STREAM_AUTO (0): the library's choice -- currently fp32  */
+                              /* MZ_STREAM_FP32 (1): fp32 z + a 16-bit shadow (14C bytes/px  */
+                              /*   moved by conv2)                                           */
+                              /* MZ_STREAM_SPLIT (2): two 16-bit planes [hi | lo], hi =      */
+                              /*   round16(z) doubling as the next conv's operand, lo =      */
+                              /*   round16(z - hi): z to 2^-22 (fp16) at 12C bytes/px        */
 } mz_config;
+
+#define MZ_STREAM_AUTO 0
+#define MZ_STREAM_FP32 1
+#define MZ_STREAM_SPLIT 2
 
 #define MZ_DTYPE_F16 0
 #define MZ_DTYPE_BF16 1
@@ -159,6 +170,7 @@ int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, 
 /* FanOutProjection (model.py:212-242) fused with the NCHW->NHWC layout change:
  * zf (B,H,W,Cp) fp32 residual stream and zb (B,H,W,zb_pitch) 16-bit MMA operand (operand_dtype);
  * zb_pitch = 0 means Cp, a larger pitch is zero-filled (mz_zb_pitch gives the pitch mz_upscale uses).
+ * zf_dev == NULL selects the split stream: zb_dev is then z16 (B,H,W,2*Cp) = [hi | lo] per pixel.
  * w_dev is (Cp,3) fp32 and bias_dev (Cp,) fp32, zero-padded beyond the logical channel count. */
 int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev,
                  int32_t B, int32_t H, int32_t W, int32_t Cp, int32_t zb_pitch, int32_t operand_dtype, void* stream);
@@ -169,20 +181,24 @@ int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, 
  *   mode 0: out16 = SiLU(scale[b,n]*acc + shift[b,n])   (conv1 + control + SiLU); film_dev is
  *           (B,2,cout_p) fp32 -- scale row then shift row per image -- or NULL for scale 1, shift 0
  *   mode 1: zf += acc ; out16 = round16(zf)              (conv2 + ResidualConnection, model.py:789-792)
+ *   mode 3: the same on the split stream: out16_dev is z16 (B,H,W,2*cout_p) = [hi | lo], updated in place:
+ *           z = hi + lo + acc ; hi = round16(z) ; lo = round16(z - hi)
+ * in_pitch: channel pitch of the input in elements (0 = cin_p; 2*cin_p when the input is the hi half of a z16).
  * out_pitch: channel pitch of out16 in elements (0 = cout_p); channels beyond cout_p are left untouched.
  * use_tc = 1: tcgen05/TMEM/TMA kernel; 0: SIMT diagnostic kernel.  tune may be NULL. */
 int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev,
-               void* out16_dev, float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t cout_p,
-               int32_t out_pitch, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream);
+               void* out16_dev, float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t in_pitch,
+               int32_t cout_p, int32_t out_pitch, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune,
+               void* stream);
 
 /* SubpixelConv2d (model.py:885-930) + global skip (model.py:162) + optional clamp (:177):
  * y = [clamp](skip + PixelShuffle_r(conv3x3(z))).  skip_mode 0: none, 1: read y_dev in place
  * (precomputed bicubic), 2: recompute the bicubic from x_dev inside the epilogue.
  * wpacked_dev has cout_p = mz_padded_channels(3*r*r) rows per tap. */
 int mz_head_shuffle_add(const void* zb_dev, const void* wpacked_dev, const float* x_dev, float* y_dev,
-                        int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t r, int32_t skip_mode,
-                        int32_t clamp01, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune,
-                        void* stream);
+                        int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t in_pitch, int32_t r,
+                        int32_t skip_mode, int32_t clamp01, int32_t operand_dtype, int32_t use_tc,
+                        const mz_conv_tune* tune, void* stream);
 
 /* Repack OIHW fp32 (host) -> device fp16|bf16 [tap = ky*3+kx][cout_p][cin_p] (K-major rows; the TMA
  * applies the shared-memory swizzle).  With dst_dev == NULL only *bytes is written. */

@@ -28,14 +28,14 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _native.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_native.SIGNATURES) == names
-    assert lib.mz_abi_version() == 1
+    assert lib.mz_abi_version() == 2
 
 
 def test_padded_channels_and_error_plumbing():
     lib = _native.load()
     assert [lib.mz_padded_channels(c) for c in (48, 54, 96, 108, 192, 12, 27)] == [48, 64, 96, 128, 192, 16, 32]
     # invalid config -> MZ_ERR_INVALID with the reference's assertion wording (model.py:67-69)
-    cfg = _native.MzConfig(5, 48, 2, 20, 0, 0)
+    cfg = _native.MzConfig(5, 48, 2, 20, 0, 0, 0, 0)
     h = ctypes.c_void_p()
     rc = lib.mz_model_create(ctypes.byref(cfg), ctypes.byref(h))
     assert rc == _native.MZ_ERR_INVALID
@@ -48,7 +48,7 @@ def test_padded_channels_and_error_plumbing():
 def test_no_gpu_fails_loudly_no_fallback():
     lib = _native.load()
     assert lib.mz_device_count() == 0
-    cfg = _native.MzConfig(2, 48, 2, 20, 0, 0)
+    cfg = _native.MzConfig(2, 48, 2, 20, 0, 0, 0, 0)
     h = ctypes.c_void_p()
     rc = lib.mz_model_create(ctypes.byref(cfg), ctypes.byref(h))
     assert rc in (_native.MZ_ERR_CUDA, _native.MZ_ERR_INVALID, _native.MZ_ERR_UNSUPPORTED) and not h.value

@@ -28,6 +28,10 @@ DTYPE_F16, DTYPE_BF16 = 0, 1
 W_STEM_WEIGHT, W_STEM_BIAS, W_CONV1, W_CONV2, W_CTRL_WEIGHT, W_CTRL_BIAS, W_HEAD = range(7)
 
 
+STREAM_AUTO, STREAM_FP32, STREAM_SPLIT = 0, 1, 2
+STREAM_CODES = {"auto": STREAM_AUTO, "float32": STREAM_FP32, "split": STREAM_SPLIT}
+
+
 class MzConfig(C.Structure):
     _fields_ = [
         ("upscale_ratio", C.c_int32),
@@ -37,6 +41,7 @@ class MzConfig(C.Structure):
         ("control_features", C.c_int32),
         ("device", C.c_int32),
         ("operand_dtype", C.c_int32),
+        ("residual_stream", C.c_int32),
     ]
 
 
@@ -78,8 +83,8 @@ SIGNATURES = {
     "mz_upscale_host_wait": (C.c_int, [_P, _I]),
     "mz_bicubic_f32": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "mz_stem_pack": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "mz_conv3x3": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
-    "mz_head_shuffle_add": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
+    "mz_conv3x3": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
+    "mz_head_shuffle_add": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
     "mz_pack_conv_weight": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, C.POINTER(C.c_size_t)]),
     "mz_control_film": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mz_probe_umma": (C.c_int, [_I, _I, _I, C.POINTER(C.c_float)]),
@@ -113,8 +118,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError => the library is stale
             fn.restype = res
             fn.argtypes = args
-        if lib.mz_abi_version() != 1:
-            raise RuntimeError(f"ABI mismatch: library reports {lib.mz_abi_version()}, binding expects 1")
+        if lib.mz_abi_version() != 2:
+            raise RuntimeError(f"ABI mismatch: library reports {lib.mz_abi_version()}, binding expects 2")
         _lib = lib
         return lib
 

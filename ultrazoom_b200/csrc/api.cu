@@ -67,25 +67,27 @@ int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, 
 
 int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev, int32_t B,
                  int32_t H, int32_t W, int32_t Cp, int32_t zb_pitch, int32_t operand_dtype, void* stream) {
-  MZ_REQUIRE(x_dev && w_dev && bias_dev && zf_dev && zb_dev, "stem: null pointer");
+  MZ_REQUIRE(x_dev && w_dev && bias_dev && zb_dev, "stem: null pointer");  // zf_dev == NULL: split stream into zb_dev
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
   return launch_stem(x_dev, w_dev, bias_dev, zf_dev, static_cast<uint16_t*>(zb_dev), operand_dtype, B, H, W, Cp, zb_pitch,
                      static_cast<cudaStream_t>(stream));
 }
 
 int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev, void* out_bf16_dev,
-               float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t cout_p, int32_t out_pitch,
-               int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+               float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t in_pitch, int32_t cout_p,
+               int32_t out_pitch, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+  MZ_REQUIRE(in_pitch == 0 || (in_pitch >= cin_p && in_pitch % 8 == 0), "conv: in_pitch %d must be 0 or a multiple of 8 >= cin_p", in_pitch);
   MZ_REQUIRE(out_pitch == 0 || (out_pitch >= cout_p && out_pitch % 8 == 0), "conv: out_pitch %d must be 0 or a multiple of 8 >= cout_p", out_pitch);
   MZ_REQUIRE(in_dev && wpacked_dev && out_bf16_dev, "conv: null pointer");
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
-  MZ_REQUIRE(mode == 0 || mode == 1, "conv: mode must be 0 or 1, %d given", mode);
-  MZ_REQUIRE(mode == 0 || zf_dev, "conv: mode 1 needs the fp32 residual stream");
+  MZ_REQUIRE(mode == 0 || mode == 1 || mode == 3, "conv: mode must be 0, 1 or 3, %d given", mode);
+  MZ_REQUIRE(mode != 1 || zf_dev, "conv: mode 1 needs the fp32 residual stream");
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.in = static_cast<const uint16_t*>(in_dev);
   a.w = static_cast<const uint16_t*>(wpacked_dev);
   a.cin_p = cin_p;
+  a.in_pitch = in_pitch;
   a.epi.bf16 = operand_dtype == MZ_DTYPE_BF16;
   a.epi.mode = mode;
   a.epi.B = B;
@@ -101,8 +103,9 @@ int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const 
 }
 
 int mz_head_shuffle_add(const void* zb_dev, const void* wpacked_dev, const float* x_dev, float* y_dev, int32_t B,
-                        int32_t H, int32_t W, int32_t cin_p, int32_t r, int32_t skip_mode, int32_t clamp01,
-                        int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+                        int32_t H, int32_t W, int32_t cin_p, int32_t in_pitch, int32_t r, int32_t skip_mode,
+                        int32_t clamp01, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+  MZ_REQUIRE(in_pitch == 0 || (in_pitch >= cin_p && in_pitch % 8 == 0), "head: in_pitch %d must be 0 or a multiple of 8 >= cin_p", in_pitch);
   MZ_REQUIRE(zb_dev && wpacked_dev && y_dev, "head: null pointer");
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
   MZ_REQUIRE(r == 2 || r == 3 || r == 4, "Upscale ratio must be either 2, 3, or 4, %d given.", r);
@@ -113,6 +116,7 @@ int mz_head_shuffle_add(const void* zb_dev, const void* wpacked_dev, const float
   a.in = static_cast<const uint16_t*>(zb_dev);
   a.w = static_cast<const uint16_t*>(wpacked_dev);
   a.cin_p = cin_p;
+  a.in_pitch = in_pitch;
   a.epi.bf16 = operand_dtype == MZ_DTYPE_BF16;
   a.epi.mode = 2;
   a.epi.B = B;

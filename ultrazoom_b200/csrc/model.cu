@@ -18,6 +18,7 @@ using namespace mz;
 struct mz_model {
   mz_config cfg;
   int C, Cp, Cz, hC, hCp, L, r, F, headN, headNp, bf16;  // Cz: channel pitch of zb (>= Cp, zero padded)
+  bool split = false;  // residual stream as two 16-bit planes z16 = [hi | lo] (pitch 2 * Cp) instead of fp32 zf + zb
   float* stem_w = nullptr;  // (Cp,3)
   float* stem_b = nullptr;  // (Cp)
   uint16_t* conv1 = nullptr;  // L x [9][hCp][Cp]
@@ -72,9 +73,9 @@ WsPlan plan_ws(const mz_model* m, int B, int H, int W) {
   WsPlan p;
   size_t off = 0;
   p.zf = off;
-  off = align_up(off + npix * m->Cp * sizeof(float), 1024);
-  p.zb = off;
-  off = align_up(off + npix * m->Cz * sizeof(uint16_t), 1024);
+  if (!m->split) off = align_up(off + npix * m->Cp * sizeof(float), 1024);
+  p.zb = off;  // split stream: z16 = [hi | lo], 2 * Cp channels of 16 bits per pixel
+  off = align_up(off + npix * (m->split ? 2 * m->Cp : m->Cz) * sizeof(uint16_t), 1024);
   p.hid = off;
   off = align_up(off + npix * m->hCp * sizeof(uint16_t), 1024);
   p.film = off;
@@ -120,6 +121,8 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
              "control_features must be in [0, 64], %d given.", cfg->control_features);
   MZ_REQUIRE(cfg->operand_dtype == MZ_DTYPE_F16 || cfg->operand_dtype == MZ_DTYPE_BF16,
              "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given.", cfg->operand_dtype);
+  MZ_REQUIRE(cfg->residual_stream >= MZ_STREAM_AUTO && cfg->residual_stream <= MZ_STREAM_SPLIT,
+             "residual_stream must be MZ_STREAM_AUTO, MZ_STREAM_FP32 or MZ_STREAM_SPLIT, %d given.", cfg->residual_stream);
   const int hC = cfg->num_channels * cfg->hidden_ratio;
   MZ_REQUIRE(mz_padded_channels(hC) <= 256, "hidden width %d exceeds the 256-channel limit of one UMMA tile", hC);
 
@@ -146,6 +149,8 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   m->headN = 3 * m->r * m->r;
   m->headNp = mz_padded_channels(m->headN);
   m->bf16 = cfg->operand_dtype == MZ_DTYPE_BF16;
+  m->split = cfg->residual_stream == MZ_STREAM_SPLIT;  // (AUTO = fp32: measured equal or faster on all three models)
+  if (m->split) m->Cz = m->Cp;  // weights are packed against the logical pitch; the activation pitch is 2 * Cp
   m->have.assign(3 + 4 * m->L, 0);
   memset(m->tune, 0, sizeof(m->tune));
   const int hm = env_int("MZ_HALO_MODE", 0);  // 1 = diagnostic per-dx loads
@@ -348,7 +353,8 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     rc = launch_film(c_dev, c_rows, m->ctrl_w, m->ctrl_b, film, m->L, B, m->F, m->hC, m->hCp, s);
     if (rc != MZ_OK) return rc;
   }
-  rc = launch_stem(x_dev, m->stem_w, m->stem_b, zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s);
+  rc = launch_stem(x_dev, m->stem_w, m->stem_b, m->split ? nullptr : zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s);
+  const int zpitch = m->split ? 2 * m->Cp : 0;  // channel pitch of the convolutions that read the stream
   if (rc != MZ_OK) return rc;
 
   const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cz, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
@@ -360,6 +366,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     a.in = zb;
     a.w = m->conv1 + l * c1;
     a.cin_p = m->Cz;
+    a.in_pitch = zpitch;
     a.epi.mode = 0;
     a.epi.bf16 = m->bf16;
     a.epi.B = B;
@@ -375,7 +382,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     a.in = hid;
     a.w = m->conv2 + l * c2;
     a.cin_p = m->hCp;
-    a.epi.mode = 1;
+    a.epi.mode = m->split ? 3 : 1;
     a.epi.bf16 = m->bf16;
     a.epi.B = B;
     a.epi.H = H;
@@ -404,6 +411,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
   a.in = zb;
   a.w = m->head;
   a.cin_p = m->Cz;
+  a.in_pitch = zpitch;
   a.epi.mode = 2;
   a.epi.bf16 = m->bf16;
   a.epi.B = B;

@@ -141,9 +141,20 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
         const int n = g * 8 + i;
         o[i] = fmaf(__ldg(w + n * 3 + 2), r2, fmaf(__ldg(w + n * 3 + 1), r1, fmaf(__ldg(w + n * 3), r0, __ldg(bias + n))));
       }
-      float4* f = reinterpret_cast<float4*>(zf + static_cast<size_t>(pix) * Cp + g * 8);
-      f[0] = make_float4(o[0], o[1], o[2], o[3]);
-      f[1] = make_float4(o[4], o[5], o[6], o[7]);
+      if (zf != nullptr) {
+        float4* f = reinterpret_cast<float4*>(zf + static_cast<size_t>(pix) * Cp + g * 8);
+        f[0] = make_float4(o[0], o[1], o[2], o[3]);
+        f[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+    }
+    if (zf == nullptr) {  // split stream: z16 = [hi | lo], pitch 2 * Cp (Cz == Cp here)
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_op2(bf16, o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+      uint16_t* dst = zb + static_cast<size_t>(pix) * 2 * Cp + g * 8;
+      st_global_v4(dst, hi[0], hi[1], hi[2], hi[3]);
+      st_global_v4(dst + Cp, lo[0], lo[1], lo[2], lo[3]);
+      continue;
     }
     st_global_v4(zb + static_cast<size_t>(pix) * Cz + g * 8, pack_op2(bf16, o[0], o[1]), pack_op2(bf16, o[2], o[3]),
                  pack_op2(bf16, o[4], o[5]), pack_op2(bf16, o[6], o[7]));
@@ -154,7 +165,7 @@ int launch_stem(const float* x, const float* w, const float* bias, float* zf, ui
                 int W, int Cp, int zb_pitch, cudaStream_t s) {
   MZ_REQUIRE(Cp > 0 && Cp % 8 == 0, "stem: padded channel count must be a multiple of 8, %d given", Cp);
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "stem: empty input");
-  const int Cz = zb_pitch ? zb_pitch : Cp;
+  const int Cz = (zb_pitch && zf != nullptr) ? zb_pitch : Cp;
   MZ_REQUIRE(Cz >= Cp && Cz % 8 == 0, "stem: zb pitch %d must be a multiple of 8 and >= %d", Cz, Cp);
   const long long total = static_cast<long long>(B) * H * W * (Cz / 8);
   long long blocks = (total + 255) / 256;
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvArgs a) {
       for (int kx = 0; kx < 3; ++kx) {
         const int xx = x + kx - 1;
         if (xx < 0 || xx >= p.W) continue;
-        const uint16_t* src = a.in + ((static_cast<size_t>(b) * p.H + yy) * p.W + xx) * a.cin_p;
+        const uint16_t* src = a.in + ((static_cast<size_t>(b) * p.H + yy) * p.W + xx) * (a.in_pitch ? a.in_pitch : a.cin_p);
         const uint16_t* wt = a.w + (static_cast<size_t>(ky * 3 + kx) * p.n_pad + n0) * a.cin_p;
         for (int k = 0; k < a.cin_p; ++k) {
           const float v = op_to_float(p.bf16, src[k]);
@@ -259,7 +270,7 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvArgs a) {
       float h[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) h[i] = acc[i];
-      constexpr int M01 = MODE == 2 ? 0 : MODE;
+      constexpr int M01 = MODE == 2 ? 0 : MODE;  // (epilogue mode 0, 1 or 3)
       epi_store16<M01>(p, b, y, x, n0, h,
                        p.film != nullptr ? p.film + static_cast<size_t>(b) * 2 * p.n_pad : nullptr);
     }
@@ -278,6 +289,8 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
     conv_simt_kernel<0><<<gb, 128, 0, s>>>(a);
   else if (p.mode == 1)
     conv_simt_kernel<1><<<gb, 128, 0, s>>>(a);
+  else if (p.mode == 3)
+    conv_simt_kernel<3><<<gb, 128, 0, s>>>(a);
   else
     conv_simt_kernel<2><<<gb, 128, 0, s>>>(a);
   MZ_CUDA(cudaGetLastError());

@@ -85,7 +85,7 @@ class _Engine:
         self.device = device
         cfg = _native.MzConfig(owner.upscale_ratio, owner.num_channels, owner.hidden_ratio,
                                owner.num_encoder_layers, owner.control_features, device.index or 0,
-                               _native.dtype_code(owner.operand_dtype))
+                               _native.dtype_code(owner.operand_dtype), _native.STREAM_CODES[owner.residual_stream])
         handle = C.c_void_p()
         _native.check(self.lib.mz_model_create(C.byref(cfg), C.byref(handle)))
         self.handle = handle
@@ -145,12 +145,17 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         num_encoder_layers: int,
         control_features: int = 0,
         operand_dtype: str = "float16",
+        residual_stream: str = "auto",
     ):
         """``operand_dtype``: element type of the tensor-core operands ("float16" default, or "bfloat16").
-        Both run at the same tcgen05 rate with fp32 accumulation and an fp32 residual stream; fp16's 10-bit
-        mantissa keeps max|err| vs the fp32 reference ~8x smaller ("Numerics")."""
+        Both run at the same tcgen05 rate with fp32 accumulation; fp16's 10-bit mantissa keeps max|err| vs the fp32
+        reference ~8x smaller ("Numerics").
+        ``residual_stream``: how the residual stream lives in HBM between blocks -- "float32" (fp32 + a 16-bit shadow),
+        "split" (two 16-bit planes hi + lo: the same value to 2^-22 with 14 % less conv2 traffic; measured no faster,
+        kept as a tested option) or "auto" (the library's choice: float32)."""
         super().__init__()
         _native.dtype_code(operand_dtype)
+        assert residual_stream in _native.STREAM_CODES, f"residual_stream must be one of {sorted(_native.STREAM_CODES)}"
         assert upscale_ratio in self.AVAILABLE_UPSCALE_RATIOS, (
             f"Upscale ratio must be one of {self.AVAILABLE_UPSCALE_RATIOS}, but got {upscale_ratio}.")
         assert hidden_ratio in self.AVAILABLE_HIDDEN_RATIOS, (
@@ -169,6 +174,7 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         self.num_encoder_layers = num_encoder_layers
         self.control_features = control_features
         self.operand_dtype = str(operand_dtype).replace("torch.", "")
+        self.residual_stream = residual_stream
         self._engines: dict = {}
         self._flags_extra = 0
 

@@ -59,8 +59,9 @@ def pack_conv_weight(w: Tensor, device: torch.device, cout_p: Optional[int] = No
 
 
 def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None, dtype: torch.dtype = torch.float16,
-              zb_pitch: int = 0):
-    """FanOutProjection + NCHW->NHWC: returns (zf fp32 (B,H,W,Cp), zb fp16|bf16 (B,H,W,zb_pitch or Cp))."""
+              zb_pitch: int = 0, split: bool = False):
+    """FanOutProjection + NCHW->NHWC: returns (zf fp32 (B,H,W,Cp), zb fp16|bf16 (B,H,W,zb_pitch or Cp)), or with
+    ``split`` (None, z16 (B,H,W,2*Cp) = [hi | lo])."""
     _need_cuda(x)
     lib = _native.load()
     x = x.to(torch.float32).contiguous()
@@ -71,10 +72,11 @@ def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None,
     b = torch.zeros((cp,), dtype=torch.float32, device=x.device)
     w[:Cc] = weight.detach().reshape(Cc, 3).to(x.device, torch.float32)
     b[:Cc] = bias.detach().to(x.device, torch.float32)
-    zf = torch.empty((B, H, W, cp), dtype=torch.float32, device=x.device)
-    zb = torch.empty((B, H, W, zb_pitch or cp), dtype=dtype, device=x.device)
+    zf = None if split else torch.empty((B, H, W, cp), dtype=torch.float32, device=x.device)
+    zb = torch.empty((B, H, W, 2 * cp if split else (zb_pitch or cp)), dtype=dtype, device=x.device)
     with torch.cuda.device(x.device):
-        _native.check(lib.mz_stem_pack(x.data_ptr(), w.data_ptr(), b.data_ptr(), zf.data_ptr(), zb.data_ptr(),
+        _native.check(lib.mz_stem_pack(x.data_ptr(), w.data_ptr(), b.data_ptr(), zf.data_ptr() if zf is not None else None,
+                                       zb.data_ptr(),
                                        B, H, W, cp, zb_pitch, _native.dtype_code(dtype), _stream(x)))
     return zf, zb
 
@@ -96,25 +98,33 @@ def control_film(c: Tensor, weight: Tensor, bias: Tensor, B: int, hcp: Optional[
 
 
 def conv3x3(inp: Tensor, wpacked: Tensor, mode: int, film: Optional[Tensor] = None, zf: Optional[Tensor] = None,
-            use_tc: bool = True, tune: Optional[_native.MzConvTune] = None, out_pitch: int = 0) -> Tensor:
+            use_tc: bool = True, tune: Optional[_native.MzConvTune] = None, out_pitch: int = 0,
+            z16: Optional[Tensor] = None) -> Tensor:
     """3x3 conv on NHWC fp16|bf16 with the fused block epilogues; returns the 16-bit NHWC output (dtype of `inp`).
 
-    mode 0: SiLU(scale*acc+shift) with film (B,2,cout_p) or None; mode 1: zf += acc (in place), returns round16(zf)."""
+    mode 0: SiLU(scale*acc+shift) with film (B,2,cout_p) or None; mode 1: zf += acc (in place), returns round16(zf);
+    mode 3: the split stream z16 (B,H,W,2*cout_p) = [hi | lo] is updated in place and returned.
+    The input may be wider than the weights' cin_p (its first cin_p channels are used: the hi half of a z16)."""
     _need_cuda(inp, wpacked)
     assert inp.dtype in (torch.float16, torch.bfloat16) and wpacked.dtype == inp.dtype
     inp = inp.contiguous()
-    B, H, W, cin_p = inp.shape
-    _, cout_p, cin_w = wpacked.shape
-    assert cin_w == cin_p, "weight / activation channel mismatch"
-    alloc = torch.zeros if out_pitch > cout_p else torch.empty   # pad channels are never written by the kernel
-    out = alloc((B, H, W, out_pitch or cout_p), dtype=inp.dtype, device=inp.device)
+    B, H, W, in_pitch = inp.shape
+    _, cout_p, cin_p = wpacked.shape
+    assert in_pitch >= cin_p, "weight / activation channel mismatch"
+    if mode == 3:
+        assert z16 is not None and z16.is_contiguous() and tuple(z16.shape) == (B, H, W, 2 * cout_p) and z16.dtype == inp.dtype
+        out = z16
+    else:
+        alloc = torch.zeros if out_pitch > cout_p else torch.empty   # pad channels are never written by the kernel
+        out = alloc((B, H, W, out_pitch or cout_p), dtype=inp.dtype, device=inp.device)
     if mode == 1:
         assert zf is not None and zf.is_contiguous() and tuple(zf.shape) == (B, H, W, cout_p)
     with torch.cuda.device(inp.device):
         _native.check(_native.load().mz_conv3x3(
             inp.data_ptr(), wpacked.data_ptr(), mode, film.data_ptr() if film is not None else None,
-            out.data_ptr(), zf.data_ptr() if zf is not None else None, B, H, W, cin_p, cout_p,
-            out_pitch, _native.dtype_code(inp.dtype), 1 if use_tc else 0, C.byref(tune) if tune is not None else None, _stream(inp)))
+            out.data_ptr(), zf.data_ptr() if zf is not None else None, B, H, W, cin_p,
+            in_pitch if in_pitch != cin_p else 0, cout_p, out_pitch, _native.dtype_code(inp.dtype), 1 if use_tc else 0,
+            C.byref(tune) if tune is not None else None, _stream(inp)))
     return out
 
 
@@ -125,7 +135,9 @@ def head_shuffle_add(zb: Tensor, wpacked: Tensor, r: int, x: Optional[Tensor] = 
     _need_cuda(zb, wpacked)
     assert zb.dtype in (torch.float16, torch.bfloat16) and wpacked.dtype == zb.dtype
     zb = zb.contiguous()
-    B, H, W, cin_p = zb.shape
+    B, H, W, in_pitch = zb.shape
+    cin_p = wpacked.shape[2]
+    assert in_pitch >= cin_p, "weight / activation channel mismatch"
     if y is None:
         assert skip_mode != 1, "skip_mode 1 needs y preloaded with the bicubic image"
         y = torch.empty((B, 3, H * r, W * r), dtype=torch.float32, device=zb.device)
@@ -134,7 +146,7 @@ def head_shuffle_add(zb: Tensor, wpacked: Tensor, r: int, x: Optional[Tensor] = 
     with torch.cuda.device(zb.device):
         _native.check(_native.load().mz_head_shuffle_add(
             zb.data_ptr(), wpacked.data_ptr(), x.data_ptr() if x is not None else None, y.data_ptr(), B, H, W, cin_p,
-            r, skip_mode, 1 if clamp01 else 0, _native.dtype_code(zb.dtype), 1 if use_tc else 0, C.byref(tune) if tune is not None else None,
+            in_pitch if in_pitch != cin_p else 0, r, skip_mode, 1 if clamp01 else 0, _native.dtype_code(zb.dtype), 1 if use_tc else 0, C.byref(tune) if tune is not None else None,
             _stream(zb)))
     return y
 
