@@ -39,58 +39,72 @@ void make_bicubic_table(int r, BicubicTable* t) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// bicubic zoom: one thread -> VEC consecutive HR pixels of one HR row of one plane.
-// Reads hit L1/L2 (each LR pixel is reused r*r*16/… times); the kernel is bound by the HR write.
+// bicubic zoom.  One thread owns one LR column of a strip of kStrip LR rows and slides a 5-row window down it: each
+// new LR row costs five (coalesced, L1-resident) loads and R horizontal interpolations, then the R x R HR pixels of
+// the LR pixel leave as R row segments of R contiguous floats (a warp writes 32 * R contiguous floats per HR row).
+// ~2 loads per HR pixel at r = 2 (0.5 at r = 4) instead of 10 (5): the kernel is bound by the HR write.
+// Arithmetic order follows ATen's upsample_bicubic2d: horizontal taps first, then vertical.
 // ----------------------------------------------------------------------------------------------
+constexpr int kStrip = 8;
+
 template <int R>
-__global__ void __launch_bounds__(256) bicubic_kernel(const float* __restrict__ x, float* __restrict__ y, int planes,
-                                                      int H, int W, BicubicTable bt) {
-  // thread -> one LR column `lx` of one HR row: produces R consecutive HR pixels [lx*R, lx*R+R)
-  const int WR = W * R, HR = H * R;
-  const long long total = static_cast<long long>(planes) * HR * W;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int lx = static_cast<int>(idx % W);
-    const long long t = idx / W;
-    const int oy = static_cast<int>(t % HR);
-    const int pl = static_cast<int>(t / HR);
-    const float* plane = x + static_cast<size_t>(pl) * H * W;
-    const int py = oy % R;
-    const int by = oy / R + bt.off[py] - 1;
-    // the R phases need LR columns lx-2 .. lx+2
+__global__ void __launch_bounds__(128) bicubic_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W,
+                                                      int n_strips, BicubicTable bt) {
+  const int lx = blockIdx.x * 128 + threadIdx.x;
+  if (lx >= W) return;
+  const int pl = blockIdx.y / n_strips, strip = blockIdx.y - pl * n_strips;
+  const int ly0 = strip * kStrip, ly1 = min(ly0 + kStrip, H);
+  const float* plane = x + static_cast<size_t>(pl) * H * W;
+  const size_t WR = static_cast<size_t>(W) * R;
+  float* out = y + static_cast<size_t>(pl) * H * R * WR + static_cast<size_t>(lx) * R;
+  int xs[5];
+#pragma unroll
+  for (int m = 0; m < 5; ++m) xs[m] = min(max(lx - 2 + m, 0), W - 1);
+  // horizontally interpolated values of LR row yy (clamped) at the R phases of this column
+  auto hrow = [&](int yy, float (&h)[R]) {
+    const float* row = plane + static_cast<size_t>(min(max(yy, 0), H - 1)) * W;
     float v[5];
 #pragma unroll
-    for (int m = 0; m < 5; ++m) v[m] = 0.f;
+    for (int m = 0; m < 5; ++m) v[m] = __ldg(row + xs[m]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int yy = min(max(by + k, 0), H - 1);
-      const float* row = plane + static_cast<size_t>(yy) * W;
-      const float wy = bt.w[py][k];
-#pragma unroll
-      for (int m = 0; m < 5; ++m) {
-        const int xx = min(max(lx - 2 + m, 0), W - 1);
-        v[m] = fmaf(__ldg(row + xx), wy, v[m]);
-      }
-    }
-    float o[R];
-#pragma unroll
-    for (int p = 0; p < R; ++p) {
-      // taps start at lx + off[p] - 1  ->  v index (off[p] + 1) .. (off[p] + 4)
-      const int s = bt.off[p] + 1;
+    for (int j = 0; j < R; ++j) {
+      const int s = (2 * j + 1 < R) ? 0 : 1;  // first tap relative to lx-2 (phase offset -1 or 0)
       float a = 0.f;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) a = fmaf(s == 0 ? v[m] : v[m + 1], bt.w[p][m], a);
-      o[p] = a;
+      for (int m = 0; m < 4; ++m) a = fmaf(v[s + m], bt.w[j][m], a);
+      h[j] = a;
     }
-    float* dst = y + (static_cast<size_t>(pl) * HR + oy) * WR + static_cast<size_t>(lx) * R;
-    if (R == 4) {
-      *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-    } else if (R == 2) {
-      *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
-    } else {
+  };
+  float win[5][R];  // LR rows ly-2 .. ly+2
 #pragma unroll
-      for (int p = 0; p < R; ++p) dst[p] = o[p];
+  for (int k = 0; k < 4; ++k) hrow(ly0 - 2 + k, win[k]);
+  for (int ly = ly0; ly < ly1; ++ly) {
+    hrow(ly + 2, win[4]);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int s = (2 * i + 1 < R) ? 0 : 1;
+      float o[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a = fmaf(win[s + k][j], bt.w[i][k], a);
+        o[j] = a;
+      }
+      float* dst = out + (static_cast<size_t>(ly) * R + i) * WR;
+      if (R == 4) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[R > 2 ? 2 : 0], o[R - 1]);
+      } else if (R == 2) {
+        *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) dst[j] = o[j];
+      }
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int j = 0; j < R; ++j) win[k][j] = win[k + 1][j];
   }
 }
 
@@ -99,16 +113,16 @@ int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cu
   MZ_REQUIRE(planes > 0 && H > 0 && W > 0, "bicubic: empty input (planes %d, H %d, W %d)", planes, H, W);
   BicubicTable bt;
   make_bicubic_table(r, &bt);
-  const long long total = static_cast<long long>(planes) * H * r * W;
-  const int block = 256;
-  long long blocks = (total + block - 1) / block;
-  if (blocks > 148LL * 64) blocks = 148LL * 64;
+  const int n_strips = (H + kStrip - 1) / kStrip;
+  const long long gy = static_cast<long long>(planes) * n_strips;
+  MZ_REQUIRE(gy <= 65535, "bicubic: planes x row strips (%lld) exceeds the grid limit", gy);
+  const dim3 grid((W + 127) / 128, static_cast<unsigned>(gy));
   if (r == 2)
-    bicubic_kernel<2><<<static_cast<unsigned>(blocks), block, 0, s>>>(x, y, planes, H, W, bt);
+    bicubic_kernel<2><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, bt);
   else if (r == 3)
-    bicubic_kernel<3><<<static_cast<unsigned>(blocks), block, 0, s>>>(x, y, planes, H, W, bt);
+    bicubic_kernel<3><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, bt);
   else
-    bicubic_kernel<4><<<static_cast<unsigned>(blocks), block, 0, s>>>(x, y, planes, H, W, bt);
+    bicubic_kernel<4><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, bt);
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }
@@ -121,42 +135,45 @@ int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cu
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ zf,
                                                    uint16_t* __restrict__ zb, int bf16, int B, int H, int W, int Cp,
-                                                   int Cz) {
-  const int groups = Cz / 8;
-  const long long npix = static_cast<long long>(B) * H * W;
-  const long long total = npix * groups;
-  const size_t plane = static_cast<size_t>(H) * W;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(idx % groups);
-    const long long pix = idx / groups;
-    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (g * 8 < Cp) {  // channels beyond Cp exist only in the 16-bit shadow (zero padding up to its pitch)
-      const long long b = pix / static_cast<long long>(plane);
-      const size_t sp = static_cast<size_t>(pix - b * static_cast<long long>(plane));
-      const float* xb = x + static_cast<size_t>(b) * 3 * plane + sp;
-      const float r0 = __ldg(xb), r1 = __ldg(xb + plane), r2 = __ldg(xb + 2 * plane);
+                                                   int Cz, int ppb) {
+  // blockDim = (groups, pixels per pass): a thread keeps ITS eight channels' weights and bias in registers and walks
+  // the pixels of the block's range; the threads of a pixel write its channels as one contiguous run.
+  const int g = threadIdx.x;  // channel group: channels 8g .. 8g+7
+  const bool real = g * 8 < Cp;  // groups beyond Cp exist only in the 16-bit shadow (zero padding up to its pitch)
+  float wr[8][3], br[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int n = g * 8 + i;
-        o[i] = fmaf(__ldg(w + n * 3 + 2), r2, fmaf(__ldg(w + n * 3 + 1), r1, fmaf(__ldg(w + n * 3), r0, __ldg(bias + n))));
-      }
-      if (zf != nullptr) {
-        float4* f = reinterpret_cast<float4*>(zf + static_cast<size_t>(pix) * Cp + g * 8);
-        f[0] = make_float4(o[0], o[1], o[2], o[3]);
-        f[1] = make_float4(o[4], o[5], o[6], o[7]);
-      }
+  for (int i = 0; i < 8; ++i) {
+    const int n = g * 8 + i;
+    br[i] = real ? __ldg(bias + n) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) wr[i][c] = real ? __ldg(w + n * 3 + c) : 0.f;
+  }
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t npix = static_cast<size_t>(B) * plane;
+  const size_t p0 = static_cast<size_t>(blockIdx.x) * ppb;
+  const size_t p1 = p0 + ppb < npix ? p0 + ppb : npix;
+  for (size_t pix = p0 + threadIdx.y; pix < p1; pix += blockDim.y) {
+    const size_t b = pix / plane;
+    const float* xb = x + b * 3 * plane + (pix - b * plane);
+    const float r0 = __ldg(xb), r1 = __ldg(xb + plane), r2 = __ldg(xb + 2 * plane);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(wr[i][2], r2, fmaf(wr[i][1], r1, fmaf(wr[i][0], r0, br[i])));
+    if (real && zf != nullptr) {
+      float4* f = reinterpret_cast<float4*>(zf + pix * Cp + g * 8);
+      f[0] = make_float4(o[0], o[1], o[2], o[3]);
+      f[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
     if (zf == nullptr) {  // split stream: z16 = [hi | lo], pitch 2 * Cp (Cz == Cp here)
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) split_op2(bf16, o[2 * i], o[2 * i + 1], hi[i], lo[i]);
-      uint16_t* dst = zb + static_cast<size_t>(pix) * 2 * Cp + g * 8;
+      uint16_t* dst = zb + pix * 2 * Cp + g * 8;
       st_global_v4(dst, hi[0], hi[1], hi[2], hi[3]);
       st_global_v4(dst + Cp, lo[0], lo[1], lo[2], lo[3]);
       continue;
     }
-    st_global_v4(zb + static_cast<size_t>(pix) * Cz + g * 8, pack_op2(bf16, o[0], o[1]), pack_op2(bf16, o[2], o[3]),
+    st_global_v4(zb + pix * Cz + g * 8, pack_op2(bf16, o[0], o[1]), pack_op2(bf16, o[2], o[3]),
                  pack_op2(bf16, o[4], o[5]), pack_op2(bf16, o[6], o[7]));
   }
 }
@@ -167,10 +184,17 @@ int launch_stem(const float* x, const float* w, const float* bias, float* zf, ui
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "stem: empty input");
   const int Cz = (zb_pitch && zf != nullptr) ? zb_pitch : Cp;
   MZ_REQUIRE(Cz >= Cp && Cz % 8 == 0, "stem: zb pitch %d must be a multiple of 8 and >= %d", Cz, Cp);
-  const long long total = static_cast<long long>(B) * H * W * (Cz / 8);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 32) blocks = 148LL * 32;
-  stem_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(x, w, bias, zf, zb, bf16, B, H, W, Cp, Cz);
+  const int groups = Cz / 8;
+  MZ_REQUIRE(groups <= 256, "stem: zb pitch %d exceeds 2048 channels", Cz);
+  const int py = 256 / groups > 0 ? 256 / groups : 1;  // pixels per pass of a block
+  const long long npix = static_cast<long long>(B) * H * W;
+  // ~16 passes per block, but at least ~8 blocks per SM so that a small frame still fills the GPU
+  long long ppb = static_cast<long long>(py) * 16;
+  while (ppb > py && (npix + ppb - 1) / ppb < 148LL * 8) ppb -= py;
+  const long long blocks = (npix + ppb - 1) / ppb;
+  MZ_REQUIRE(blocks < (1LL << 31), "stem: too many pixels");
+  stem_kernel<<<static_cast<unsigned>(blocks), dim3(groups, py), 0, s>>>(x, w, bias, zf, zb, bf16, B, H, W, Cp, Cz,
+                                                                      static_cast<int>(ppb));
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }
