@@ -284,6 +284,13 @@ __device__ __forceinline__ void umma2_commit_mcast(uint32_t bar, uint16_t cta_ma
       : "memory");
 }
 
+// ---- programmatic dependent launch ----
+// launch_dependents: the next kernel of the stream (launched with programmatic stream serialisation) may start its
+// CTAs as soon as every CTA of this grid has executed it (or exited) and resources are free.  wait: blocks until the
+// preceding grid has completed and its memory is visible (returns at once when there is no programmatic dependency).
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM ----
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)

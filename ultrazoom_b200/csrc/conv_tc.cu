@@ -162,6 +162,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (PAIR || p.cluster > 1) cluster_sync_all();  // peers' barriers must be initialised before anything is signalled to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  // Programmatic dependent launch: the next convolution of the stream may place its CTAs on SMs as this grid's CTAs
+  // retire and run its prologue (barriers, TMEM, the resident filter bank) there; it touches activations only after
+  // its own griddepcontrol.wait, i.e. once this grid has completed.
+  griddep_launch_dependents();
   if (FUSE) {  // every UMMA accumulates: the accumulators start from zero (afterwards the epilogue re-zeroes them)
     if (warp >= 4 && warp < 8) {
       for (uint32_t col = 0; col < p.tmem_cols; col += 16)
@@ -190,6 +194,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t per_dx = (ROWS + 2) * kTileW * row_bytes;
     const uint32_t tap_bytes = p.epi.n_pad * row_bytes;  // one tap's [N][kc] tile inside a weight stage
     const uint32_t a_sub_bytes = static_cast<uint32_t>(p.a_kp) << 4;  // one 16-channel sub-tile of a fused stage
+    // fill weight stage `sbi` with the taps of (chunk c, filter row dy) [FUSE: filter column dy]
+    auto issue_b = [&](int c, int dy, uint32_t sbi) {
+      const uint32_t full_b = bar_b_full + 8 * sbi;
+      const uint32_t dstB = b_base + sbi * p.b_stage_bytes;
+      if (FUSE) {
+        if (lane == 0) {  // stage (c, dx): the three vertical taps of filter column dx, [sub][dy][N][kc]
+          const int dx = dy;
+          mbar_expect_tx(full_b, p.b_tx_bytes);
+          for (int sub = 0; sub < p.subs; ++sub)
+            for (int v = 0; v < 3; ++v)
+              tma_load_3d(dstB + (sub * 3 + v) * tap_bytes, &p.tmB, full_b, (c * p.subs + sub) * p.kc, 0, v * 3 + dx);
+        }
+      } else if (PAIR) {
+        if (lane == 0) {  // this CTA's half of the weight rows; stage layout [3 taps][N/2][kc]
+          if (cta_rank == 0) mbar_expect_tx(full_b, 2 * p.b_tx_bytes);
+          tma2_load_3d(dstB, &p.tmB, mapa_u32(full_b, 0), c * p.kc, cta_rank * p.b_slice_rows, dy * 3);
+        }
+      } else if (lane == 0 && (p.dbg & 1) && b_wrapped) {
+        mbar_arrive(full_b);
+      } else if (lane == 0) {
+        mbar_expect_tx(full_b, p.b_tx_bytes);
+        if (p.cluster > 1) {
+          for (int dx = 0; dx < 3; ++dx)
+            tma_load_3d_mcast(dstB + dx * tap_bytes + cta_rank * p.b_slice_rows * row_bytes, &p.tmB, full_b,
+                              c * p.kc, cta_rank * p.b_slice_rows, dy * 3 + dx, cta_mask);
+        } else {
+          for (int sub = 0; sub < p.subs; ++sub)  // stage layout [sub][3 taps][N][kc]
+            tma_load_3d(dstB + sub * 3 * tap_bytes, &p.tmB, full_b, (c * p.subs + sub) * p.kc, 0, dy * 3);
+        }
+      }
+    };
+    if (p.res_b) {
+      // The resident filter bank does not depend on the previous kernel: request all of it BEFORE waiting for that
+      // kernel to finish (programmatic dependent launch), so it is in shared memory when the first activations arrive.
+      for (int c = 0; c < p.n_chunks; ++c)
+        for (int dy = 0; dy < 3; ++dy) issue_b(c, dy, static_cast<uint32_t>(c * 3 + dy));
+    }
+    griddep_wait();  // activations (and everything else the previous kernels wrote) are valid from here on
     for (int round = 0; round < p.n_rounds; ++round) {
       // every CTA of a cluster walks the same number of rounds (the weight stream is shared); a CTA whose unit
       // index runs past the end recomputes the last unit and its epilogue stores nothing
@@ -225,41 +267,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           pa ^= 1u;
           a_wrapped = true;
         }
-        // one weight stage = the three horizontal taps of filter row dy: [3][N][kc]
-        for (int dy = 0; dy < 3; ++dy) {
-          if (p.res_b) {
-            if (round > 0) break;  // resident filter bank: stage (c, dy) was filled during the first patch
-          } else {
-            MZ_TIMED(1, mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u));
-          }
-          const uint32_t full_b = bar_b_full + 8 * sb;
-          const uint32_t dstB = b_base + sb * p.b_stage_bytes;
-          if (FUSE) {
-            if (lane == 0) {  // stage (c, dx): the three vertical taps of filter column dx, [sub][dy][N][kc]
-              const int dx = dy;
-              mbar_expect_tx(full_b, p.b_tx_bytes);
-              for (int sub = 0; sub < p.subs; ++sub)
-                for (int v = 0; v < 3; ++v)
-                  tma_load_3d(dstB + (sub * 3 + v) * tap_bytes, &p.tmB, full_b, (c * p.subs + sub) * p.kc, 0, v * 3 + dx);
-            }
-          } else if (PAIR) {
-            if (lane == 0) {  // this CTA's half of the weight rows; stage layout [3 taps][N/2][kc]
-              if (cta_rank == 0) mbar_expect_tx(full_b, 2 * p.b_tx_bytes);
-              tma2_load_3d(dstB, &p.tmB, mapa_u32(full_b, 0), c * p.kc, cta_rank * p.b_slice_rows, dy * 3);
-            }
-          } else if (lane == 0 && (p.dbg & 1) && b_wrapped) {
-            mbar_arrive(full_b);
-          } else if (lane == 0) {
-            mbar_expect_tx(full_b, p.b_tx_bytes);
-            if (p.cluster > 1) {
-              for (int dx = 0; dx < 3; ++dx)
-                tma_load_3d_mcast(dstB + dx * tap_bytes + cta_rank * p.b_slice_rows * row_bytes, &p.tmB, full_b,
-                                  c * p.kc, cta_rank * p.b_slice_rows, dy * 3 + dx, cta_mask);
-            } else {
-              for (int sub = 0; sub < p.subs; ++sub)  // stage layout [sub][3 taps][N][kc]
-                tma_load_3d(dstB + sub * 3 * tap_bytes, &p.tmB, full_b, (c * p.subs + sub) * p.kc, 0, dy * 3);
-            }
-          }
+        // one weight stage = the three horizontal taps of filter row dy: [3][N][kc] (a resident bank was requested
+        // before the loop)
+        for (int dy = 0; dy < 3 && !p.res_b; ++dy) {
+          MZ_TIMED(1, mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u));
+          issue_b(c, dy, sb);
           if (++sb == static_cast<uint32_t>(p.b_stages)) {
             sb = 0;
             pb ^= 1u;
@@ -626,6 +638,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // by TMA load before the accumulator is waited for, and the tiles of the NEXT patch are prefetched into L2 a whole
     // patch ahead.  (Per-thread 16-byte global accesses at a 384-byte lane stride cost 32 sectors per instruction
     // and made the epilogue, not the tensor pipe, the bottleneck.)
+    griddep_wait();  // FiLM table, residual stream, LR image: written by earlier kernels of the stream
     const int q = warp & 3;          // TMEM lane quarter this warp may read (== warp % 4)
     const int ew = warp - 4;         // staging slot / residual barrier of this warp
     const int half = ew >> 2;        // 0 | 1: which share of a patch this warp takes
@@ -1207,13 +1220,23 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = k;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (k > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = k;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    static const bool no_pdl = getenv("MZ_NO_PDL") != nullptr;
+    if (!no_pdl && !p.prof) {  // this grid may start while the previous kernel of the stream drains (see the kernel)
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = k > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     MZ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
     if (p.prof) {  // diagnostic: synchronise and print mean ticks per role (stderr)
       MZ_CUDA(cudaStreamSynchronize(s));
