@@ -1069,10 +1069,14 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
             p.epi_warps = ew;
             for (int bs = tune.b_stages ? tune.b_stages : 4; bs >= 2 && !found; --bs) {
               // deeper epilogue staging (more TMA stores / residual loads in flight) when shared memory allows
-              for (int staging = 2; staging >= 1 && !found; --staging) {
-                fill_geometry(p, a.cin_p, kc, rows, acc_stages, tune.halo_mode, tune.a_stages ? tune.a_stages : 2, bs,
-                              staging, false);
-                if (fits(p)) found = true;
+              // (measured on the 96-channel conv2: three activation stages beat deeper epilogue staging and a fifth
+              // weight stage; the pair's halved weight stages make room for them)
+              for (int as = tune.a_stages ? tune.a_stages : 3; as >= 2 && !found; --as) {
+                for (int staging = 2; staging >= 1 && !found; --staging) {
+                  fill_geometry(p, a.cin_p, kc, rows, acc_stages, tune.halo_mode, as, bs, staging, false);
+                  if (fits(p)) found = true;
+                }
+                if (tune.a_stages) break;
               }
               if (tune.b_stages) break;
             }
@@ -1115,6 +1119,14 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   if (!found && tune.resident == 1) {
     set_error("conv: the filter bank (cin_p %d, n_pad %d) does not fit resident in shared memory", a.cin_p, e.n_pad);
     return MZ_ERR_UNSUPPORTED;
+  }
+  if (!found && pair_ok && tune.pair == 0 && e.mode != 0 && a.cin_p >= 128) {
+    // streamed weights: the pair halves every CTA's weight stream and leaves room for a third activation stage
+    // (96-channel conv2: 181 vs 199 us)
+    set_pair(1);
+    try_stream();
+    if (found && (p.a_stages < 3 || p.kc < 32)) found = false;
+    if (!found) set_pair(0);
   }
   if (!found) try_stream();
   if (!found) {
