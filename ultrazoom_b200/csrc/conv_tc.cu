@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int i = threadIdx.x - 128; i < 2 * p.epi.n_pad; i += n_epi_threads) {
           float v = i < p.epi.n_pad ? 1.f : 0.f;
           if (p.epi.film != nullptr) v = __ldg(p.epi.film + static_cast<size_t>(b) * 2 * p.epi.n_pad + i);
-          film_s[i] = v;
+          film_s[i] = 0.5f * v;  // SiLU's v/2 folded into scale and shift (exact): see silu_h
         }
         named_bar_sync(1, n_epi_threads);
         film_b = b;
@@ -808,11 +808,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             rpar ^= 1u;
           }
           const uint32_t st_z = st_base + (all_rows ? k : 0) * row_stage, st_o = st_z + 32 * n_pad * 4;
-          for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + n0, v);
-            tmem_ld_wait();
-            if (FUSE) tmem_zero16(taddr + n0);
+          // sixteen channels: z += acc in the fp32 staging tile (in place), 16-bit shadow into the output tile
+          auto finish16 = [&](const uint32_t* v, uint32_t n0) {
             const uint32_t bz = n0 >> sh32, cz = (n0 - (bz << sh32)) >> 2;  // fp32 box, first 16-byte chunk in its row
             const uint32_t zrow = st_z + bz * box32 + lane * row32;
             uint32_t o[8];
@@ -832,6 +829,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t orow = st_o + bo * box16 + lane * row16;
             sts128(orow + swz_chunk(lane, co, row16) * 16, o[0], o[1], o[2], o[3]);
             sts128(orow + swz_chunk(lane, co + 1, row16) * 16, o[4], o[5], o[6], o[7]);
+          };
+          if ((n_pad & 31u) == 0) {  // one TMEM load + one wait per 32 columns
+            for (uint32_t n0 = 0; n0 < n_pad; n0 += 32) {
+              uint32_t v[32];
+              tmem_ld32(taddr + n0, v);
+              tmem_ld_wait();
+              if (FUSE) {
+                tmem_zero16(taddr + n0);
+                tmem_zero16(taddr + n0 + 16);
+              }
+              finish16(v, n0);
+              finish16(v + 16, n0 + 16);
+            }
+          } else {
+            for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) {
+              uint32_t v[16];
+              tmem_ld16(taddr + n0, v);
+              tmem_ld_wait();
+              if (FUSE) tmem_zero16(taddr + n0);
+              finish16(v, n0);
+            }
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -853,29 +871,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             __syncwarp();
             const uint32_t orow = buf + lane * row16;
-            for (uint32_t sub = 0; sub < static_cast<uint32_t>(p.e16); sub += 16) {
-              const uint32_t n0 = bx * p.e16 + sub;
-              uint32_t v[16];
-              tmem_ld16(taddr + n0, v);
-              tmem_ld_wait();
-              if (FUSE) tmem_zero16(taddr + n0);
-              float acc[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(v[i]);
+            // sixteen output channels: FiLM (pre-halved rows) + SiLU + 16-bit pack -> two swizzled 16-byte chunks
+            auto finish16 = [&](const uint32_t* v, uint32_t n0, uint32_t sub) {
               const float4* sc = reinterpret_cast<const float4*>(film_s + n0);
               const float4* sh = reinterpret_cast<const float4*>(film_s + n_pad + n0);
               uint32_t o[8];
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 const float4 g = sc[kk], h = sh[kk];
-                const float a0 = silu_f(fmaf(acc[4 * kk + 0], g.x, h.x)), a1 = silu_f(fmaf(acc[4 * kk + 1], g.y, h.y));
-                const float a2 = silu_f(fmaf(acc[4 * kk + 2], g.z, h.z)), a3 = silu_f(fmaf(acc[4 * kk + 3], g.w, h.w));
+                const float a0 = silu_h(fmaf(__uint_as_float(v[4 * kk + 0]), g.x, h.x));
+                const float a1 = silu_h(fmaf(__uint_as_float(v[4 * kk + 1]), g.y, h.y));
+                const float a2 = silu_h(fmaf(__uint_as_float(v[4 * kk + 2]), g.z, h.z));
+                const float a3 = silu_h(fmaf(__uint_as_float(v[4 * kk + 3]), g.w, h.w));
                 o[2 * kk] = pack_op2(p.epi.bf16, a0, a1);
                 o[2 * kk + 1] = pack_op2(p.epi.bf16, a2, a3);
               }
               const uint32_t co = sub >> 3;
               sts128(orow + swz_chunk(lane, co, row16) * 16, o[0], o[1], o[2], o[3]);
               sts128(orow + swz_chunk(lane, co + 1, row16) * 16, o[4], o[5], o[6], o[7]);
+            };
+            if (p.e16 >= 32) {  // one TMEM load + one wait per 32 columns
+              for (uint32_t sub = 0; sub < static_cast<uint32_t>(p.e16); sub += 32) {
+                const uint32_t n0 = bx * p.e16 + sub;
+                uint32_t v[32];
+                tmem_ld32(taddr + n0, v);
+                tmem_ld_wait();
+                if (FUSE) {
+                  tmem_zero16(taddr + n0);
+                  tmem_zero16(taddr + n0 + 16);
+                }
+                finish16(v, n0, sub);
+                finish16(v + 16, n0 + 16, sub + 16);
+              }
+            } else {
+              const uint32_t n0 = bx * p.e16;
+              uint32_t v[16];
+              tmem_ld16(taddr + n0, v);
+              tmem_ld_wait();
+              if (FUSE) tmem_zero16(taddr + n0);
+              finish16(v, n0, 0);
             }
             fence_proxy_async_smem();
             __syncwarp();
