@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--tune", default="", help="comma list k=v of mz_conv_tune fields, e.g. cluster=4,rows=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-sync", action="store_true", help="time the synchronous host call instead of the two-lane stream")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary MewZoom-4X-Ctrl measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -256,13 +257,14 @@ def main():
                "e2e": None}
         # ---- end to end through the public API with HOST buffers (H2D + kernels + D2H inside the timed region) ----
         if want_e2e:
-            # Every step copies its inputs from pinned host memory and its result back to pinned host memory.  A
-            # batch (B > 1) goes through the synchronous call, which pipelines chunks of the batch internally; a
-            # single-frame workload is a frame STREAM: frames alternate between the two lanes of the async form
-            # (submit frame i, then wait for frame i-1), each lane with its own pinned input / output buffers.
+            # Every step copies its inputs from pinned host memory and its result back to pinned host memory.  The
+            # workload is a STREAM of steps (frames or batches): steps alternate between the two lanes of the async
+            # form (submit step i, then wait for step i-2 on the same lane), each lane with its own pinned input /
+            # output buffers, so the copies of step i+1 / i-1 run under the kernels of step i.
+            # (--e2e-sync times the synchronous call instead, which pipelines chunks of one batch internally.)
             outs = [torch.empty((B, 3, H * r, W * r), dtype=torch.float32).pin_memory() for _ in range(2)]
             xs = [x_host, x_host.clone().pin_memory()]
-            stream_mode = B == 1
+            stream_mode = not args.e2e_sync
 
             def e2e_steps(n):
                 if not stream_mode:
@@ -290,7 +292,7 @@ def main():
             res["e2e"] = {"value": world * out_px * steps / dt / 1e6, "unit": "Mpx/s",
                           "h2d_bytes_per_step": x_host.numel() * 4 + (c_host.numel() * 4 if c_host is not None else 0),
                           "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": 1e3 * dt / steps,
-                          "api": ("MewZoom.upscale_host(lane=i%2) + host_wait -> mz_upscale_host_async (frame stream, two "
+                          "api": ("MewZoom.upscale_host(lane=i%2) + host_wait -> mz_upscale_host_async (stream of steps, two "
                                   "lanes, pinned host buffers)") if stream_mode else
                                  "MewZoom.upscale_host -> mz_upscale_host (pinned host buffers, batch pipelined in chunks)"}
         del model, eng, x, c

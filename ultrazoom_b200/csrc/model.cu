@@ -39,6 +39,8 @@ struct mz_model {
     float* hy = nullptr;
     float* hc = nullptr;
     size_t hx_bytes = 0, hy_bytes = 0, hc_bytes = 0;
+    cudaEvent_t kernels_done = nullptr;  // recorded after the lane's last kernel of a call
+    bool has_work = false;
   };
   HostLane lane[2];
   // optional conv-stack timing
@@ -172,8 +174,10 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
     alloc(reinterpret_cast<void**>(&m->ctrl_w), sizeof(float) * m->L * 2 * m->hC * m->F);
     alloc(reinterpret_cast<void**>(&m->ctrl_b), sizeof(float) * m->L * 2 * m->hC);
   }
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->lane[i].stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->lane[i].kernels_done, cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     const int rc = cuda_fail(e, "model allocation", __FILE__, __LINE__);
     mz_model_destroy(m);
@@ -198,6 +202,7 @@ void mz_model_destroy(mz_model* m) {
     cudaFree(m->lane[i].hx);
     cudaFree(m->lane[i].hy);
     cudaFree(m->lane[i].hc);
+    if (m->lane[i].kernels_done) cudaEventDestroy(m->lane[i].kernels_done);
     if (m->lane[i].stream) cudaStreamDestroy(m->lane[i].stream);
   }
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
@@ -453,8 +458,15 @@ static int host_enqueue(mz_model* m, int li, const float* x_host, const float* c
   if ((rc = ensure(&L.ws, &L.ws_bytes, wsb)) != MZ_OK) return rc;
   MZ_CUDA(cudaMemcpyAsync(L.hx, x_host, xb, cudaMemcpyHostToDevice, L.stream));
   if (cb) MZ_CUDA(cudaMemcpyAsync(L.hc, c_host, cb, cudaMemcpyHostToDevice, L.stream));
+  // The two lanes take turns on the SMs: this lane's kernels start when the other lane's have finished, so that one
+  // step's kernels run back to back (programmatic dependent launch, L2 prefetch) while the copies of its neighbours
+  // proceed on the copy engines -- instead of the kernels of two steps interleaving and both finishing late.
+  mz_model::HostLane& O = m->lane[li ^ 1];
+  if (O.has_work) MZ_CUDA(cudaStreamWaitEvent(L.stream, O.kernels_done, 0));
   rc = mz_upscale(m, L.hx, cb ? L.hc : nullptr, c_rows, L.hy, B, H, W, L.ws, L.ws_bytes, flags, L.stream);
   if (rc != MZ_OK) return rc;
+  MZ_CUDA(cudaEventRecord(L.kernels_done, L.stream));
+  L.has_work = true;
   MZ_CUDA(cudaMemcpyAsync(y_host, L.hy, yb, cudaMemcpyDeviceToHost, L.stream));
   return MZ_OK;
 }
