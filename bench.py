@@ -166,10 +166,33 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything but the one JSON line goes to stderr: libraries (NCCL's version banner with NCCL_DEBUG set, torch
+    warnings) write to file descriptor 1 behind Python's back."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -386,7 +409,7 @@ def main():
         ar = roofline_of(also_res, peaks)
         line["also"] = {"cfg4a": {"workload": also_res["desc"], "value": also_res["value"], "unit": "Mpx/s",
                                   "ms_per_frame": also_res["ms_step"], "roofline": ar}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
