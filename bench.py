@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--tune", default="", help="comma list k=v of mz_conv_tune fields, e.g. cluster=4,rows=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--io", default="float32", choices=["float32", "uint8"],
+                    help="image element type at the API (uint8: x = x8/255 in, floor(255 y + 0.5) out); the headline is float32")
     ap.add_argument("--e2e-sync", action="store_true", help="time the synchronous host call instead of the two-lane stream")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary MewZoom-4X-Ctrl measurement")
     args = ap.parse_args()
@@ -248,7 +250,11 @@ def main():
             model.set_conv_tune(-1, dev, **tune_kw)
         eng = model._engine(dev)
         g = torch.Generator().manual_seed(1234 + rank)
-        x_host = torch.rand(B, 3, H, W, generator=g).pin_memory()
+        x_host = torch.rand(B, 3, H, W, generator=g)
+        if args.io == "uint8":
+            x_host = (x_host * 255.0).round().to(torch.uint8)
+        x_host = x_host.pin_memory()
+        io_dt = x_host.dtype
         c_host = torch.tensor([[0.5, 0.2, 0.3]]).pin_memory() if cfg["control_features"] else None
         x = x_host.to(dev)
         c = c_host.to(dev) if c_host is not None else None
@@ -285,7 +291,7 @@ def main():
             # form (submit step i, then wait for step i-2 on the same lane), each lane with its own pinned input /
             # output buffers, so the copies of step i+1 / i-1 run under the kernels of step i.
             # (--e2e-sync times the synchronous call instead, which pipelines chunks of one batch internally.)
-            outs = [torch.empty((B, 3, H * r, W * r), dtype=torch.float32).pin_memory() for _ in range(2)]
+            outs = [torch.empty((B, 3, H * r, W * r), dtype=io_dt).pin_memory() for _ in range(2)]
             xs = [x_host, x_host.clone().pin_memory()]
             stream_mode = not args.e2e_sync
 
@@ -313,8 +319,8 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
             res["e2e"] = {"value": world * out_px * steps / dt / 1e6, "unit": "Mpx/s",
-                          "h2d_bytes_per_step": x_host.numel() * 4 + (c_host.numel() * 4 if c_host is not None else 0),
-                          "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": 1e3 * dt / steps,
+                          "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + (c_host.numel() * 4 if c_host is not None else 0),
+                          "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": 1e3 * dt / steps,
                           "api": ("MewZoom.upscale_host(lane=i%2) + host_wait -> mz_upscale_host_async (stream of steps, two "
                                   "lanes, pinned host buffers)") if stream_mode else
                                  "MewZoom.upscale_host -> mz_upscale_host (pinned host buffers, batch pipelined in chunks)"}
@@ -397,7 +403,7 @@ def main():
         "config": {"workload": desc, "model": model_name, "batch_per_gpu": B, "lr_h": H, "lr_w": W,
                    "parallelism": f"replica per GPU x{world}, batch-sharded, no collective",
                    "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
-                   "weights": "random init (seed 0)",
+                   "weights": "random init (seed 0)", "image_io": args.io,
                    "residual_stream": ("fp32" if args.residual_stream != "split"
                                        else "two 16-bit planes hi + lo (z to 2^-22)"), "accumulate": "fp32", "mma_operands": args.operands,
                    "tune": tune_kw},

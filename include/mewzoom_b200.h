@@ -43,6 +43,10 @@ typedef enum mz_status {
 /* flags for mz_upscale / mz_forward */
 #define MZ_FLAG_CLAMP01 1u        /* torch.clamp(z, 0, 1), model.py:177              */
 #define MZ_FLAG_SIMT_CONV 2u      /* diagnostic: SIMT direct conv instead of tcgen05  */
+#define MZ_FLAG_IO_U8 8u          /* x and y are 8-bit images (B,3,H,W) / (B,3,rH,rW): x = x8 / 255 (ToDtype(float32,   */
+                                  /* scale=True), test_compare.py:53-57), y8 = floor(255 clamp(y) + 0.5) (save_image,   */
+                                  /* test_compare.py:89).  Needs MZ_FLAG_CLAMP01.  4x less image traffic on PCIe / HBM.  */
+#define MZ_FLAG_U8_TRUNC 16u      /* with MZ_FLAG_IO_U8: y8 = floor(255 clamp(y)) (ToPILImage, README.md:81)             */
 #define MZ_FLAG_SKIP_FROM_BUFFER 4u /* head reads a precomputed bicubic image (mz_bicubic_f32 output in y) instead of recomputing it in its epilogue */
 
 /* Constructor kwargs of the 0.2.x-style MewZoom (README.md:254-258, model.py:52-69). */
@@ -106,29 +110,29 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
 int mz_workspace_bytes(const mz_model* m, int32_t B, int32_t H, int32_t W, size_t* bytes);
 
 /* ---- the hot path: replaces MewZoom.forward / MewZoom.upscale (model.py:149-179) ----
- * x_dev : (B,3,H,W) fp32 NCHW in [0,1]
+ * x_dev : (B,3,H,W) fp32 NCHW in [0,1]   (uint8 with MZ_FLAG_IO_U8)
  * c_dev : NULL for non-control models, else (B, control_features) fp32 (c_rows == B)
  *         or (1, control_features) (c_rows == 1, broadcast) -- validate.py:73-94
- * y_dev : (B,3,rH,rW) fp32 NCHW
+ * y_dev : (B,3,rH,rW) fp32 NCHW          (uint8 with MZ_FLAG_IO_U8)
  * flags : MZ_FLAG_CLAMP01 => upscale(), 0 => forward()
  */
-int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_rows, float* y_dev,
+int mz_upscale(mz_model* m, const void* x_dev, const float* c_dev, int32_t c_rows, void* y_dev,
                int32_t B, int32_t H, int32_t W, void* workspace_dev, size_t workspace_bytes,
                uint32_t flags, void* stream);
 
 /* Same call with HOST buffers: H2D copy of x (and c), the kernels, D2H copy of y, stream
  * synchronise.  Workspace and staging buffers are owned (and cached) by the model.  This is
  * the end-to-end entry point bench.py times as `e2e`. */
-int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32_t c_rows,
-                    float* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags);
+int mz_upscale_host(mz_model* m, const void* x_host, const float* c_host, int32_t c_rows,
+                    void* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags);
 
 /* Frame-stream form of the same call: enqueue one batch on lane 0 or 1 (each lane has its own stream, staging
  * buffers and workspace) and return at once; mz_upscale_host_wait(lane) blocks until everything enqueued on that
  * lane (-1: both lanes) has finished and y_host is valid.  Alternating lanes double-buffers a stream of frames: the
  * copies of frame i+1 and i-1 run under the kernels of frame i.  Host buffers should be pinned (cudaHostAlloc /
  * torch pin_memory) -- pageable memory makes the copies synchronous -- and must stay untouched until the wait. */
-int mz_upscale_host_async(mz_model* m, int32_t lane, const float* x_host, const float* c_host, int32_t c_rows,
-                          float* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags);
+int mz_upscale_host_async(mz_model* m, int32_t lane, const void* x_host, const float* c_host, int32_t c_rows,
+                          void* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags);
 int mz_upscale_host_wait(mz_model* m, int32_t lane);
 
 /* Optional timing of the encoder's convolution stack (the 2L launches of the dominant kernel):

@@ -114,6 +114,49 @@ def test_residual_stream_variants_agree(dev):
     assert max_abs_err(outs["float32"], outs["split"]) <= 8e-3
 
 
+def test_uint8_image_io(dev):
+    """8-bit images in and out (the callers' decode_image / ToDtype(scale=True) before and save_image / ToPILImage after
+    the reference's upscale, test_compare.py:53-57,89, README.md:81) against the oracle run on x8 / 255."""
+    o = make_oracle("MewZoom-2X-Ctrl", seed=2)
+    m = _model_from(dict(upscale_ratio=2, num_channels=48, hidden_ratio=2, num_encoder_layers=20, control_features=3),
+                    o.state_dict(), dev)
+    g = torch.Generator().manual_seed(8)
+    x8 = torch.randint(0, 256, (2, 3, 37, 150), generator=g, dtype=torch.uint8)
+    c = torch.rand(2, 3, generator=g)
+    with torch.inference_mode():
+        ref = o.upscale(x8.float() / 255.0, c)
+    y8 = m.upscale(x8.to(dev), c.to(dev)).cpu()
+    assert y8.dtype == torch.uint8 and tuple(y8.shape) == (2, 3, 74, 300)
+    want = torch.floor(ref * 255.0 + 0.5).clamp(0, 255).to(torch.uint8)          # save_image's rounding
+    diff = (y8.int() - want.int()).abs()
+    assert int(diff.max()) <= 1 and float((diff == 0).float().mean()) >= 0.9     # 4e-3 envelope = one 8-bit step
+    # against our own fp32 path the 8-bit result is the same rounding of (numerically almost) the same value
+    yf = m.upscale((x8.float() / 255.0).to(dev), c.to(dev)).cpu()
+    d2 = (y8.int() - torch.floor(yf * 255.0 + 0.5).int()).abs()
+    assert int(d2.max()) <= 1 and float((d2 == 0).float().mean()) >= 0.999
+    m.u8_truncate = True                                                          # ToPILImage's pic.mul(255).byte()
+    yt = m.upscale(x8.to(dev), c.to(dev)).cpu()
+    d3 = (yt.int() - torch.floor(yf * 255.0).clamp(0, 255).int()).abs()
+    assert int(d3.max()) <= 1 and float((d3 == 0).float().mean()) >= 0.999
+    m.u8_truncate = False
+    # host buffers (pinned, two lanes) and every ratio
+    h8 = m.upscale_host(x8, c)
+    assert torch.equal(h8, y8)
+    with pytest.raises(AssertionError):
+        m.forward(x8.to(dev), c.to(dev))
+    for name, r in (("MewZoom-3X-Ctrl", 3), ("MewZoom-4X-Ctrl", 4)):
+        o2 = make_oracle(name, seed=3)
+        m2 = _model_from(dict(upscale_ratio=o2.upscale_ratio, num_channels=o2.num_channels, hidden_ratio=o2.hidden_ratio,
+                              num_encoder_layers=o2.num_encoder_layers, control_features=3), o2.state_dict(), dev)
+        xs = torch.randint(0, 256, (1, 3, 20, 131), generator=g, dtype=torch.uint8)
+        cs = torch.rand(1, 3, generator=g)
+        with torch.inference_mode():
+            w2 = torch.floor(o2.upscale(xs.float() / 255.0, cs) * 255.0 + 0.5).clamp(0, 255).to(torch.uint8)
+        got = m2.upscale(xs.to(dev), cs.to(dev)).cpu()
+        d = (got.int() - w2.int()).abs()
+        assert int(d.max()) <= 2 and float((d <= 1).float().mean()) >= 0.999, (name, int(d.max()))
+
+
 def test_control_vector_broadcast_and_api(dev):
     from ultrazoom_b200 import ControlVector, ONNXModel
 

@@ -22,6 +22,8 @@ MZ_ERR_STATE = -5
 FLAG_CLAMP01 = 1
 FLAG_SIMT_CONV = 2
 FLAG_SKIP_FROM_BUFFER = 4
+FLAG_IO_U8 = 8
+FLAG_U8_TRUNC = 16
 
 DTYPE_F16, DTYPE_BF16 = 0, 1
 

@@ -69,7 +69,7 @@ int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, 
                  int32_t H, int32_t W, int32_t Cp, int32_t zb_pitch, int32_t operand_dtype, void* stream) {
   MZ_REQUIRE(x_dev && w_dev && bias_dev && zb_dev, "stem: null pointer");  // zf_dev == NULL: split stream into zb_dev
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
-  return launch_stem(x_dev, w_dev, bias_dev, zf_dev, static_cast<uint16_t*>(zb_dev), operand_dtype, B, H, W, Cp, zb_pitch,
+  return launch_stem(x_dev, nullptr, w_dev, bias_dev, zf_dev, static_cast<uint16_t*>(zb_dev), operand_dtype, B, H, W, Cp, zb_pitch,
                      static_cast<cudaStream_t>(stream));
 }
 

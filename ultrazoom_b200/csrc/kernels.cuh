@@ -46,6 +46,12 @@ struct EpiParams {
   // mode 2
   const float* x;  // LR image (B,3,H,W) fp32 -- only for skip_mode 2
   float* y;        // HR image (B,3,rH,rW) fp32
+  // 8-bit image I/O (MZ_FLAG_IO_U8): when set they replace x / y.  x8 holds round(255 * x), read back as x8 / 255
+  // (ToDtype(float32, scale=True), reference test_compare.py:53-57); y8 = floor(255 * clamp(v, 0, 1) + 0.5)
+  // (torchvision save_image, test_compare.py:89) or floor(255 * clamp(v, 0, 1)) with u8_trunc (ToPILImage, README.md:81)
+  const uint8_t* x8;
+  uint8_t* y8;
+  int u8_trunc;
   int r;
   int skip_mode;  // 0 none, 1 y already holds the bicubic image, 2 recompute bicubic from x
   int clamp01;
@@ -86,8 +92,9 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
 int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s);
 // zf != nullptr: fp32 stream zf + 16-bit shadow zb (pitch zb_pitch).  zf == nullptr: split stream, zb is z16 = [hi | lo]
 // with pitch 2 * Cp.
-int launch_stem(const float* x, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16, int B, int H,
-                int W, int Cp, int zb_pitch, cudaStream_t s);
+// x8 != nullptr: the image is 8-bit (B,3,H,W) and read as x8 / 255.
+int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16,
+                int B, int H, int W, int Cp, int zb_pitch, cudaStream_t s);
 int launch_film(const float* c, int c_rows, const float* w, const float* b, float* film, int L, int B, int F,
                 int hC, int hCp, cudaStream_t s);
 
@@ -174,8 +181,18 @@ __device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, in
   }
 }
 
-// Bicubic value of HR pixel (oy, ox) of one plane (H x W, fp32): 16 clamped taps, rows first.
-__device__ __forceinline__ float bicubic_at(const float* __restrict__ plane, int H, int W, const BicubicTable& bt,
+// LR pixel as float: fp32 planes as they are, 8-bit planes scaled by 1/255 (ToDtype(float32, scale=True))
+__device__ __forceinline__ float lr_px(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float lr_px(const uint8_t* p) { return static_cast<float>(__ldg(p)) * (1.0f / 255.0f); }
+// [0,1] -> 8 bits: floor(255 v + 0.5) (save_image) or floor(255 v) (ToPILImage); v is clamped here in any case
+__device__ __forceinline__ uint8_t to_u8(float v, int trunc) {
+  v = fminf(fmaxf(v, 0.f), 1.f);
+  return static_cast<uint8_t>(static_cast<int>(fmaf(v, 255.f, trunc ? 0.f : 0.5f)));
+}
+
+// Bicubic value of HR pixel (oy, ox) of one plane (H x W, fp32 | u8): 16 clamped taps, rows first.
+template <typename T>
+__device__ __forceinline__ float bicubic_at(const T* __restrict__ plane, int H, int W, const BicubicTable& bt,
                                             int oy, int ox) {
   const int r = bt.r;
   const int py = oy % r, px = ox % r;
@@ -184,12 +201,12 @@ __device__ __forceinline__ float bicubic_at(const float* __restrict__ plane, int
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int yy = min(max(by + k, 0), H - 1);
-    const float* row = plane + static_cast<size_t>(yy) * W;
+    const T* row = plane + static_cast<size_t>(yy) * W;
     float h = 0.f;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const int xx = min(max(bx + m, 0), W - 1);
-      h = fmaf(__ldg(row + xx), bt.w[px][m], h);
+      h = fmaf(lr_px(row + xx), bt.w[px][m], h);
     }
     acc = fmaf(h, bt.w[py][k], acc);
   }
@@ -208,15 +225,19 @@ __device__ __forceinline__ void epi_head(const EpiParams& p, int b, int y, int x
     if (n < 3 * rr) {
       const int c = n / rr, i = (n % rr) / r, j = n % r;
       const int oy = y * r + i, ox = x * r + j;
-      float* dst = p.y + ((static_cast<size_t>(b) * 3 + c) * HR + oy) * WR + ox;
+      const size_t di = ((static_cast<size_t>(b) * 3 + c) * HR + oy) * WR + ox;
       float v = acc[n];
       if (p.skip_mode == 1) {
-        v += *dst;
+        v += p.y[di];
       } else if (p.skip_mode == 2) {
-        v += bicubic_at(p.x + (static_cast<size_t>(b) * 3 + c) * p.H * p.W, p.H, p.W, p.bt, oy, ox);
+        const size_t pl = (static_cast<size_t>(b) * 3 + c) * p.H * p.W;
+        v += p.x8 != nullptr ? bicubic_at(p.x8 + pl, p.H, p.W, p.bt, oy, ox) : bicubic_at(p.x + pl, p.H, p.W, p.bt, oy, ox);
       }
       if (p.clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
-      *dst = v;
+      if (p.y8 != nullptr)
+        p.y8[di] = to_u8(v, p.u8_trunc);
+      else
+        p.y[di] = v;
     }
   }
 }
@@ -235,16 +256,20 @@ __device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int
     for (int i = 0; i < R; ++i)
 #pragma unroll
       for (int j = 0; j < R; ++j) out[i][j] = acc[c * R * R + i * R + j];
-    float* dst = p.y + ((static_cast<size_t>(b) * 3 + c) * HR + static_cast<size_t>(y) * R) * WR + static_cast<size_t>(x) * R;
+    const size_t d0 = ((static_cast<size_t>(b) * 3 + c) * HR + static_cast<size_t>(y) * R) * WR + static_cast<size_t>(x) * R;
+    float* dst = p.y + d0;
     if (p.skip_mode == 2) {
-      const float* plane = p.x + (static_cast<size_t>(b) * 3 + c) * H * W;
+      const size_t pl = (static_cast<size_t>(b) * 3 + c) * H * W;
       float hz[5][R];
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const float* row = plane + static_cast<size_t>(min(max(y - 2 + k, 0), H - 1)) * W;
+        const size_t ro = pl + static_cast<size_t>(min(max(y - 2 + k, 0), H - 1)) * W;
         float nb[5];
 #pragma unroll
-        for (int m = 0; m < 5; ++m) nb[m] = __ldg(row + min(max(x - 2 + m, 0), W - 1));
+        for (int m = 0; m < 5; ++m) {
+          const size_t xi = ro + min(max(x - 2 + m, 0), W - 1);
+          nb[m] = p.x8 != nullptr ? lr_px(p.x8 + xi) : lr_px(p.x + xi);
+        }
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const int s = (2 * j + 1 < R) ? 0 : 1;  // first tap relative to x-2 (phase offset -1 or 0)
@@ -265,6 +290,24 @@ __device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int
           out[i][j] += a;
         }
       }
+    }
+    if (p.y8 != nullptr) {  // 8-bit output: R bytes per HR row segment (a warp writes 32 * R contiguous bytes)
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        uint8_t* rowp = p.y8 + d0 + static_cast<size_t>(i) * WR;
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) w |= static_cast<uint32_t>(to_u8(out[i][j], p.u8_trunc)) << (8 * j);
+        if (R == 4) {
+          *reinterpret_cast<uint32_t*>(rowp) = w;
+        } else if (R == 2) {
+          *reinterpret_cast<uint16_t*>(rowp) = static_cast<uint16_t>(w);
+        } else {
+#pragma unroll
+          for (int j = 0; j < R; ++j) rowp[j] = static_cast<uint8_t>(w >> (8 * j));
+        }
+      }
+      continue;
     }
 #pragma unroll
     for (int i = 0; i < R; ++i) {

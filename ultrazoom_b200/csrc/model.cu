@@ -320,9 +320,16 @@ int mz_workspace_bytes(const mz_model* m, int32_t B, int32_t H, int32_t W, size_
   return MZ_OK;
 }
 
-int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_rows, float* y_dev, int32_t B, int32_t H,
+int mz_upscale(mz_model* m, const void* x_dev_v, const float* c_dev, int32_t c_rows, void* y_dev_v, int32_t B, int32_t H,
                int32_t W, void* workspace_dev, size_t workspace_bytes, uint32_t flags, void* stream) {
-  MZ_REQUIRE(m && x_dev && y_dev && workspace_dev, "upscale: null pointer");
+  MZ_REQUIRE(m && x_dev_v && y_dev_v && workspace_dev, "upscale: null pointer");
+  const bool io8 = (flags & MZ_FLAG_IO_U8) != 0;
+  MZ_REQUIRE(!io8 || ((flags & MZ_FLAG_CLAMP01) && !(flags & MZ_FLAG_SKIP_FROM_BUFFER)),
+             "upscale: 8-bit image I/O needs MZ_FLAG_CLAMP01 and recomputes the skip (no MZ_FLAG_SKIP_FROM_BUFFER)");
+  const float* x_dev = io8 ? nullptr : static_cast<const float*>(x_dev_v);
+  float* y_dev = io8 ? nullptr : static_cast<float*>(y_dev_v);
+  const uint8_t* x8 = io8 ? static_cast<const uint8_t*>(x_dev_v) : nullptr;
+  uint8_t* y8 = io8 ? static_cast<uint8_t*>(y_dev_v) : nullptr;
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "upscale: empty input (B %d, H %d, W %d)", B, H, W);
   if (m->F > 0) {
     MZ_REQUIRE(c_dev != nullptr, "Control vector c is required for control models.");
@@ -358,7 +365,7 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
     rc = launch_film(c_dev, c_rows, m->ctrl_w, m->ctrl_b, film, m->L, B, m->F, m->hC, m->hCp, s);
     if (rc != MZ_OK) return rc;
   }
-  rc = launch_stem(x_dev, m->stem_w, m->stem_b, m->split ? nullptr : zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s);
+  rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, m->split ? nullptr : zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s);
   const int zpitch = m->split ? 2 * m->Cp : 0;  // channel pitch of the convolutions that read the stream
   if (rc != MZ_OK) return rc;
 
@@ -425,6 +432,9 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
   a.epi.n_pad = m->headNp;
   a.epi.x = x_dev;
   a.epi.y = y_dev;
+  a.epi.x8 = x8;
+  a.epi.y8 = y8;
+  a.epi.u8_trunc = (flags & MZ_FLAG_U8_TRUNC) ? 1 : 0;
   a.epi.r = m->r;
   a.epi.skip_mode = skip_mode;
   a.epi.clamp01 = (flags & MZ_FLAG_CLAMP01) ? 1 : 0;
@@ -433,10 +443,10 @@ int mz_upscale(mz_model* m, const float* x_dev, const float* c_dev, int32_t c_ro
 }
 
 // one chunk (B images) on one lane: H2D, kernels, D2H -- all asynchronous on the lane's stream
-static int host_enqueue(mz_model* m, int li, const float* x_host, const float* c_host, int32_t c_rows, float* y_host,
+static int host_enqueue(mz_model* m, int li, const void* x_host, const float* c_host, int32_t c_rows, void* y_host,
                         int32_t B, int32_t H, int32_t W, uint32_t flags) {
   mz_model::HostLane& L = m->lane[li];
-  const size_t xb = sizeof(float) * 3 * B * H * W;
+  const size_t xb = ((flags & MZ_FLAG_IO_U8) ? 1 : sizeof(float)) * 3 * B * H * W;
   const size_t yb = xb * m->r * m->r;
   const size_t cb = c_host ? sizeof(float) * c_rows * (m->F > 0 ? m->F : 1) : 0;
   size_t wsb = 0;
@@ -471,8 +481,8 @@ static int host_enqueue(mz_model* m, int li, const float* x_host, const float* c
   return MZ_OK;
 }
 
-int mz_upscale_host_async(mz_model* m, int32_t lane, const float* x_host, const float* c_host, int32_t c_rows,
-                          float* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags) {
+int mz_upscale_host_async(mz_model* m, int32_t lane, const void* x_host, const float* c_host, int32_t c_rows,
+                          void* y_host, int32_t B, int32_t H, int32_t W, uint32_t flags) {
   MZ_REQUIRE(m && x_host && y_host, "upscale_host_async: null pointer");
   MZ_REQUIRE(lane == 0 || lane == 1, "upscale_host_async: lane must be 0 or 1, %d given", lane);
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "upscale_host_async: empty input (B %d, H %d, W %d)", B, H, W);
@@ -489,8 +499,11 @@ int mz_upscale_host_wait(mz_model* m, int32_t lane) {
   return MZ_OK;
 }
 
-int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32_t c_rows, float* y_host, int32_t B,
+int mz_upscale_host(mz_model* m, const void* x_host_v, const float* c_host, int32_t c_rows, void* y_host_v, int32_t B,
                     int32_t H, int32_t W, uint32_t flags) {
+  const size_t esz = (flags & MZ_FLAG_IO_U8) ? 1 : sizeof(float);
+  const uint8_t* x_host = static_cast<const uint8_t*>(x_host_v);
+  uint8_t* y_host = static_cast<uint8_t*>(y_host_v);
   MZ_REQUIRE(m && x_host && y_host, "upscale_host: null pointer");
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "upscale_host: empty input (B %d, H %d, W %d)", B, H, W);
   if (m->F > 0) {
@@ -501,7 +514,7 @@ int mz_upscale_host(mz_model* m, const float* x_host, const float* c_host, int32
   // A batch is cut into up to eight chunks that alternate between the two lanes: copies of chunk i+1 / i-1 run under
   // the kernels of chunk i.  (Images are independent: chunking does not change any result.)
   const int n_chunks = B >= 8 ? 8 : B;
-  const size_t x_img = static_cast<size_t>(3) * H * W, y_img = x_img * m->r * m->r;
+  const size_t x_img = static_cast<size_t>(3) * H * W * esz, y_img = x_img * m->r * m->r;  // bytes per image
   const int F = m->F > 0 ? m->F : 1;
   int b0 = 0, rc = MZ_OK;
   for (int i = 0; i < n_chunks && rc == MZ_OK; ++i) {

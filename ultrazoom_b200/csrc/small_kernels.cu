@@ -132,7 +132,8 @@ int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cu
 // channels >= C are written as zero (w/bias are zero-padded to Cp by the caller).
 // One thread -> 8 channels of one pixel (16-byte bf16 store, 2 x 16-byte fp32 stores).
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ x8,
+                                                   const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ zf,
                                                    uint16_t* __restrict__ zb, int bf16, int B, int H, int W, int Cp,
                                                    int Cz, int ppb) {
@@ -154,8 +155,17 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
   const size_t p1 = p0 + ppb < npix ? p0 + ppb : npix;
   for (size_t pix = p0 + threadIdx.y; pix < p1; pix += blockDim.y) {
     const size_t b = pix / plane;
-    const float* xb = x + b * 3 * plane + (pix - b * plane);
-    const float r0 = __ldg(xb), r1 = __ldg(xb + plane), r2 = __ldg(xb + 2 * plane);
+    const size_t xo = b * 3 * plane + (pix - b * plane);
+    float r0, r1, r2;
+    if (x8 != nullptr) {
+      // exact x8 / 255 (IEEE division, what ToDtype(float32, scale=True) computes): the network amplifies a 1-ulp
+      // difference of its input through 20..40 layers of 16-bit rounding to ~1e-3 at the output
+      r0 = __fdiv_rn(static_cast<float>(__ldg(x8 + xo)), 255.f);
+      r1 = __fdiv_rn(static_cast<float>(__ldg(x8 + xo + plane)), 255.f);
+      r2 = __fdiv_rn(static_cast<float>(__ldg(x8 + xo + 2 * plane)), 255.f);
+    } else {
+      r0 = __ldg(x + xo), r1 = __ldg(x + xo + plane), r2 = __ldg(x + xo + 2 * plane);
+    }
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = fmaf(wr[i][2], r2, fmaf(wr[i][1], r1, fmaf(wr[i][0], r0, br[i])));
@@ -178,8 +188,8 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
   }
 }
 
-int launch_stem(const float* x, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16, int B, int H,
-                int W, int Cp, int zb_pitch, cudaStream_t s) {
+int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16,
+                int B, int H, int W, int Cp, int zb_pitch, cudaStream_t s) {
   MZ_REQUIRE(Cp > 0 && Cp % 8 == 0, "stem: padded channel count must be a multiple of 8, %d given", Cp);
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "stem: empty input");
   const int Cz = (zb_pitch && zf != nullptr) ? zb_pitch : Cp;
@@ -193,7 +203,7 @@ int launch_stem(const float* x, const float* w, const float* bias, float* zf, ui
   while (ppb > py && (npix + ppb - 1) / ppb < 148LL * 8) ppb -= py;
   const long long blocks = (npix + ppb - 1) / ppb;
   MZ_REQUIRE(blocks < (1LL << 31), "stem: too many pixels");
-  stem_kernel<<<static_cast<unsigned>(blocks), dim3(groups, py), 0, s>>>(x, w, bias, zf, zb, bf16, B, H, W, Cp, Cz,
+  stem_kernel<<<static_cast<unsigned>(blocks), dim3(groups, py), 0, s>>>(x, x8, w, bias, zf, zb, bf16, B, H, W, Cp, Cz,
                                                                       static_cast<int>(ppb));
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;

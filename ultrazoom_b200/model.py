@@ -177,6 +177,7 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         self.residual_stream = residual_stream
         self._engines: dict = {}
         self._flags_extra = 0
+        self.u8_truncate = False
 
     # ---- reference model.py:94-115 ----
     @property
@@ -229,12 +230,16 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
                                "B200 (`x.cuda()`). There is no CPU fallback.")
         dev = x.device
         eng = self._engine(dev)
-        x = x.detach().to(torch.float32).contiguous()
+        io8 = x.dtype == torch.uint8       # 8-bit images in and out (upscale only): see upscale()
+        if io8:
+            assert flags & _native.FLAG_CLAMP01, "uint8 images are supported by upscale(), not forward()"
+            flags |= _native.FLAG_IO_U8 | (_native.FLAG_U8_TRUNC if self.u8_truncate else 0)
+        x = x.detach().contiguous() if io8 else x.detach().to(torch.float32).contiguous()
         if c is not None:
             c = c.detach().to(device=dev, dtype=torch.float32).contiguous()
         B, _, H, W = x.shape
         r = self.upscale_ratio
-        y = torch.empty((B, 3, H * r, W * r), dtype=torch.float32, device=dev)
+        y = torch.empty((B, 3, H * r, W * r), dtype=torch.uint8 if io8 else torch.float32, device=dev)
         ws = eng.workspace(B, H, W)
         ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
         ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
@@ -252,7 +257,12 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
 
     @torch.inference_mode()
     def upscale(self, x: Tensor, c: Optional[Tensor] = None) -> Tensor:
-        """``clamp(forward(x, c), 0, 1)`` (reference model.py:166-179); the clamp is fused in the head kernel."""
+        """``clamp(forward(x, c), 0, 1)`` (reference model.py:166-179); the clamp is fused in the head kernel.
+
+        A ``torch.uint8`` image (what ``decode_image`` returns, reference test_compare.py:53) is read as ``x / 255``
+        (``ToDtype(float32, scale=True)``, test_compare.py:55-57) and the result comes back as uint8,
+        ``floor(255 * y + 0.5)`` as ``save_image`` writes it (test_compare.py:89) -- or ``floor(255 * y)`` as
+        ``ToPILImage`` does (README.md:81) when ``model.u8_truncate`` is set: a quarter of the image traffic."""
         return self._run(x, c, _native.FLAG_CLAMP01)
 
     @torch.inference_mode()
@@ -268,15 +278,19 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         assert not x.is_cuda, "upscale_host takes host tensors"
         assert lane in (None, 0, 1), "lane must be None, 0 or 1"
         eng = self._engine(torch.device("cuda", device))
-        x = x.to(torch.float32).contiguous()
+        io8 = x.dtype == torch.uint8
+        x = x.contiguous() if io8 else x.to(torch.float32).contiguous()
         if c is not None:
             c = c.to(device="cpu", dtype=torch.float32).contiguous()
         B, _, H, W = x.shape
         r = self.upscale_ratio
+        odt = torch.uint8 if io8 else torch.float32
         if out is None:
-            out = torch.empty((B, 3, H * r, W * r), dtype=torch.float32)
-        assert out.is_contiguous() and tuple(out.shape) == (B, 3, H * r, W * r) and out.dtype == torch.float32
+            out = torch.empty((B, 3, H * r, W * r), dtype=odt)
+        assert out.is_contiguous() and tuple(out.shape) == (B, 3, H * r, W * r) and out.dtype == odt
         flags = _native.FLAG_CLAMP01 | self._flags_extra
+        if io8:
+            flags |= _native.FLAG_IO_U8 | (_native.FLAG_U8_TRUNC if self.u8_truncate else 0)
         cp, cr = (c.data_ptr(), c.shape[0]) if c is not None else (None, 0)
         if lane is None:
             _native.check(eng.lib.mz_upscale_host(eng.handle, x.data_ptr(), cp, cr, out.data_ptr(), B, H, W, flags))
