@@ -161,7 +161,7 @@ def run_reference(args):
         "impl": "reference", "metric": "output_mpx_per_s", "value": value, "unit": "Mpx/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "model": model_name, "batch": B, "lr_h": H, "lr_w": W},
+        "config": {"workload": desc, "batch": B, "lr_h": H, "lr_w": W},
         "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -388,7 +388,7 @@ def main():
     launches_per_step = 2 * L + 2 + (1 if cfg["control_features"] else 0)
     roofline = roofline_of(res, peaks)
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only
         threads = os.cpu_count() or 1
         sh, sw = H, W
         while sh * sw > 540 * 960:
@@ -400,7 +400,7 @@ def main():
         "metric": "output_mpx_per_s", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16" if args.operands == "float16" else "bf16", "data": "synthetic",
-        "config": {"workload": desc, "model": model_name, "batch_per_gpu": B, "lr_h": H, "lr_w": W,
+        "config": {"workload": desc, "batch_per_gpu": B, "lr_h": H, "lr_w": W,
                    "parallelism": f"replica per GPU x{world}, batch-sharded, no collective",
                    "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
                    "weights": "random init (seed 0)", "image_io": args.io,
