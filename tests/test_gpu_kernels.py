@@ -155,6 +155,7 @@ CONV_CASES = [
     (96, 192, (2, 30, 260), dict(pair=1, max_ctas=4)),
     (64, 64, (1, 5, 130), dict(pair=1)),
     (64, 128, (1, 1, 100), dict(pair=1)),
+    (48, 96, (2, 33, 300), dict(pair=1, max_ctas=4)),
     # filter bank resident in shared memory (the default when it fits) vs streamed per patch
     (48, 96, (2, 13, 150), dict(resident=1)),
     (48, 96, (2, 13, 150), dict(resident=2)),

@@ -1054,7 +1054,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   bool found = false;
   const int kc_first = tune.kc ? tune.kc : pick_kc(a.cin_p);
   const bool pair_ok = p.cluster == 1 && e.mode != 2 && tune.halo_mode == 0 && (e.n_pad / 2) % 8 == 0 &&
-                       a.cin_p % 32 == 0 && tune.pair != 2;
+                       a.cin_p % 16 == 0 && tune.pair != 2;
   auto set_pair = [&](int on) {
     p.pair = on;
     p.b_slice_rows = on ? e.n_pad / 2 : e.n_pad / p.cluster;
