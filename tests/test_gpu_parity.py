@@ -114,6 +114,32 @@ def test_residual_stream_variants_agree(dev):
     assert max_abs_err(outs["float32"], outs["split"]) <= 8e-3
 
 
+@pytest.mark.parametrize("name", ["MewZoom-2X-Ctrl", "MewZoom-3X-Ctrl", "MewZoom-4X-Ctrl"])
+def test_ragged_shapes_against_the_simt_twin(dev, name):
+    """Edge and ragged shapes (single row / column, widths around the 128-pixel tile, odd batches): the tcgen05 path,
+    whatever configuration the launcher picks (resident bank, CTA pairs, row count, dependent launch), agrees with
+    the SIMT direct convolution running the same 16-bit operands and epilogues."""
+    from ultrazoom_b200 import MODEL_CONFIGS, MewZoom, _native
+
+    torch.manual_seed(5)
+    cfg = dict(MODEL_CONFIGS[name])
+    cfg["num_encoder_layers"] = 3            # the kernels and their chaining are what is under test here
+    m = MewZoom(**cfg).to(dev).eval()
+    g = torch.Generator().manual_seed(6)
+    shapes = [(1, 1, 1), (1, 1, 130), (1, 2, 127), (3, 3, 129), (1, 5, 1), (2, 4, 256), (1, 7, 257), (1, 31, 64),
+              (5, 2, 33), (1, 65, 200)]
+    for B, H, W in shapes:
+        x, c = torch.rand(B, 3, H, W, generator=g).to(dev), torch.rand(B, 3, generator=g).to(dev)
+        m._flags_extra = 0
+        y = m.upscale(x, c)
+        m._flags_extra = _native.FLAG_SIMT_CONV
+        ys = m.upscale(x, c)
+        m._flags_extra = 0
+        assert tuple(y.shape) == (B, 3, H * cfg["upscale_ratio"], W * cfg["upscale_ratio"])
+        assert (y - ys).abs().max().item() <= 2e-3, (name, (B, H, W), (y - ys).abs().max().item())
+        assert torch.equal(y, m.upscale(x, c))
+
+
 def test_uint8_image_io(dev):
     """8-bit images in and out (the callers' decode_image / ToDtype(scale=True) before and save_image / ToPILImage after
     the reference's upscale, test_compare.py:53-57,89, README.md:81) against the oracle run on x8 / 255."""
