@@ -161,7 +161,7 @@ typedef struct mz_conv_tune {
                       /* 0 only when that makes the filter bank resident, 1 always, 2 never              */
   int32_t resident;   /* filter bank resident in shared memory: 0 when it fits, 1 require, 2 never       */
   int32_t epi_warps;  /* epilogue warps per CTA: 0 auto (8), 4 or 8                                      */
-  int32_t fuse;       /* vertical taps stacked along N, one UMMA per input row: 1 = on (opt-in)      */
+  int32_t fuse;       /* vertical taps stacked along N, one UMMA per input row: 0 auto, 1 force, 2 off */
 } mz_conv_tune;
 
 /* which = 0 conv1, 1 conv2, 2 head, -1 all.  Takes effect on the next mz_upscale. */

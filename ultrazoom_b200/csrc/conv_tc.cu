@@ -1124,10 +1124,10 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   };
   // filter rows fused along N (VAR 2): resident, un-paired encoder convolutions whose stacked taps fit one UMMA
   const int fuse_g = (256 / e.n_pad) >= 3 ? 3 : (256 / e.n_pad);
-  // Opt-in (tune.fuse = 1): it cuts the tensor-only time of the N = 48 convolution by 19 % (154 vs 190 us on a
-  // 4 x 960 x 540 batch) but not the whole kernel, which is bound by the L2 <-> SM traffic of its operands and epilogue.
-  const bool fuse_ok = e.mode != 2 && e.mode != 3 && tune.fuse == 1 && fuse_g >= 2 && e.H >= 2 && (tune.rows == 0 || tune.rows >= 2) &&
-                       tune.pair != 1;
+  // Automatic with three stacked taps (N <= 85: the 48-channel conv2, -19 % tensor-only time, -3.5 % on the whole 2X-Ctrl
+  // step); with two (N = 96 | 128) the 2N-wide windows measured slower than they save: opt-in (tune.fuse = 1) only.
+  const bool fuse_ok = e.mode != 2 && tune.fuse != 2 && (fuse_g >= 3 || (tune.fuse == 1 && fuse_g >= 2)) && e.H >= 2 &&
+                       (tune.rows == 0 || tune.rows >= 2) && tune.pair != 1;
   if (tune.pair == 1 && pair_ok) {
     set_pair(1);
     try_resident();
@@ -1311,6 +1311,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   if (ks == 4) { MZ_FUSE_ROWS(M, 4) }
     if (e.mode == 0) { MZ_FUSE_KS(0) }
     if (e.mode == 1) { MZ_FUSE_KS(1) }
+    if (e.mode == 3) { MZ_FUSE_KS(3) }
 #undef MZ_FUSE_KS
 #undef MZ_FUSE_ROWS
     set_error("conv: no fused-row kernel for mode %d, %d k-steps, %d rows", e.mode, ks, p.rows);

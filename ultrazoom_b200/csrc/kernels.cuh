@@ -82,7 +82,7 @@ struct ConvTcTune {
                    // 0 = only when that makes the filter bank resident, 1 = always, 2 = never
   int resident;    // filter bank resident in shared memory: 0 = when it fits, 1 = require, 2 = never (stream per patch)
   int epi_warps;   // epilogue warps: 0 = auto (8), 4 or 8
-  int fuse;        // filter rows fused along N (one UMMA per input row): 0 | 2 = off, 1 = on (opt-in experiment)
+  int fuse;        // filter rows fused along N (one UMMA per input row): 0 = when three taps stack (N <= 85), 1 = also with two, 2 = never
   int dbg;         // timing experiments only (WRONG results): 1 skip weight loads, 2 skip activation loads,
                    // 4 skip the epilogue body, 8 skip the MMAs
 };
