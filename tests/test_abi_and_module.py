@@ -116,3 +116,40 @@ def test_control_vector():
     with pytest.raises(AssertionError):
         ControlVector(gaussian_noise=-0.1)
     assert isinstance(ONNXModel(MewZoom(2, 16, 2, 1)), torch.nn.Module)
+
+
+def test_reference_checkpoint_recipes():
+    """The reference's loading recipe (test_compare.py:32-49: add_weight_norms -> load_state_dict of a compiled,
+    weight-normed state dict -> remove_parameterizations) works on this class, and from_checkpoint does it in one."""
+    torch.manual_seed(3)
+    cfg = dict(upscale_ratio=2, num_channels=16, hidden_ratio=2, num_encoder_layers=2, control_features=3)
+    trained = MewZoom(**cfg)
+    trained.add_weight_norms()
+    with torch.no_grad():
+        for p in trained.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    baked = {k: v.detach().clone() for k, v in
+             {"stem": trained.stem.conv.weight, "c1": trained.encoder[1].convnet.conv1.weight,
+              "head": trained.head.conv.weight}.items()}
+    ckpt = {"upscaler_args": cfg, "upscaler": {"_orig_mod." + k: v for k, v in trained.state_dict().items()}}
+    assert any("parametrizations.weight.original0" in k for k in ckpt["upscaler"])
+
+    # the reference's own sequence
+    m = MewZoom(**ckpt["upscaler_args"])
+    m.add_weight_norms()
+    sd = dict(ckpt["upscaler"])
+    for key in list(sd.keys()):
+        sd[key.replace("_orig_mod.", "")] = sd.pop(key)
+    m.load_state_dict(sd)
+    m.remove_parameterizations()
+    m.eval()
+    assert not any("parametrizations" in k for k in m.state_dict())
+    assert torch.allclose(m.stem.conv.weight, baked["stem"], atol=1e-6)
+    assert torch.allclose(m.encoder[1].convnet.conv1.weight, baked["c1"], atol=1e-6)
+
+    # one call
+    m2 = MewZoom.from_checkpoint(ckpt)
+    assert torch.allclose(m2.head.conv.weight, baked["head"], atol=1e-6)
+    assert torch.allclose(m2.encoder[1].convnet.conv1.weight, baked["c1"], atol=1e-6)
+    assert torch.equal(m2.encoder[0].control.linear.bias, trained.encoder[0].control.linear.bias)
+    assert sorted(m2.state_dict()) == sorted(MewZoom(**cfg).state_dict())

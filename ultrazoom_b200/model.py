@@ -192,6 +192,53 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         for p in self.parameters():
             p.requires_grad = False
 
+    # ---- reference model.py:117-139: checkpoints are written with weight-norm parametrizations in place ----
+    def add_weight_norms(self) -> None:
+        """Weight-normalise every convolution (stem, encoder, head), as the reference's training scripts do before
+        ``load_state_dict`` (test_compare.py:36).  The kernels always see the baked ``weight``."""
+        from torch.nn.utils.parametrizations import weight_norm
+        from torch.nn.utils.parametrize import is_parametrized
+
+        for module in self.modules():
+            if isinstance(module, nn.Conv2d) and not is_parametrized(module):
+                weight_norm(module)
+
+    def remove_parameterizations(self) -> None:
+        """Bake and remove all parametrizations (reference model.py:131-139, called before ``eval()``)."""
+        from torch.nn.utils.parametrize import is_parametrized, remove_parametrizations
+
+        for module in self.modules():
+            if is_parametrized(module):
+                for name in list(module.parametrizations.keys()):
+                    remove_parametrizations(module, name)
+
+    @staticmethod
+    def convert_reference_state_dict(state_dict: dict) -> dict:
+        """A reference training checkpoint's ``state_dict`` -> plain keys: strips the ``_orig_mod.`` prefixes of a
+        compiled model (test_compare.py:38-41) and bakes weight-norm pairs ``parametrizations.weight.original0/1``
+        (g, v) into ``weight = g * v / ||v||`` (norm over all dims but 0, as ``weight_norm(dim=0)`` defines it)."""
+        sd = {k.replace("_orig_mod.", ""): v for k, v in state_dict.items()}
+        out = {}
+        for k, v in sd.items():
+            if k.endswith(".parametrizations.weight.original0"):
+                prefix = k[: -len(".parametrizations.weight.original0")]
+                g, d = v.float(), sd[prefix + ".parametrizations.weight.original1"].float()
+                norm = d.flatten(1).norm(dim=1).reshape(-1, *([1] * (d.dim() - 1)))
+                out[prefix + ".weight"] = g * d / norm
+            elif ".parametrizations." not in k:
+                out[k] = v
+        return out
+
+    @classmethod
+    def from_checkpoint(cls, checkpoint, **kwargs) -> "MewZoom":
+        """Build a model from a reference training checkpoint -- a path or the loaded dict with ``upscaler_args`` and
+        ``upscaler`` (test_compare.py:32-49) -- ready for ``.to("cuda").eval()``."""
+        if not isinstance(checkpoint, dict):
+            checkpoint = torch.load(checkpoint, map_location="cpu", weights_only=True)
+        model = cls(**checkpoint["upscaler_args"], **kwargs)
+        model.load_state_dict(cls.convert_reference_state_dict(checkpoint["upscaler"]))
+        return model
+
     # ---- native plumbing ----
     def _engine(self, device: torch.device) -> _Engine:
         key = (device.type, device.index)
