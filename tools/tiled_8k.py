@@ -1,0 +1,80 @@
+"""BASELINE configs[4]: ONE 1920x1080 -> 7680x4320 MewZoom-4X-Ctrl frame, cut into halo-padded LR tiles, one tile per
+rank (one process per GPU, no collective on the data path; NCCL only for the timing barrier / max-reduce).
+
+    python tools/tiled_8k.py                                                   # 1 GPU, 1 tile (= the whole frame)
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/tiled_8k.py
+
+Every rank runs the whole network on its haloed tile (halo = 2L+1 = 81 LR pixels, exact) and keeps the HR core on its
+GPU.  Strong scaling: value = 33.2 output Mpx / max-over-ranks device time.  Rank 0 also checks its core against the
+same region of the un-tiled result.  Prints one JSON line."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ultrazoom_b200 import MODEL_CONFIGS, MewZoom  # noqa: E402
+from ultrazoom_b200.sharding import best_grid, frames_for_rank, halo_radius, plan_tiles, run_tile  # noqa: E402
+
+
+def main():
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    steps, warmup = 5, 3
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = MODEL_CONFIGS["MewZoom-4X-Ctrl"]
+    r, L, H, W = cfg["upscale_ratio"], cfg["num_encoder_layers"], 1080, 1920
+    torch.manual_seed(0)
+    model = MewZoom(**cfg).to(dev).eval()
+    g = torch.Generator().manual_seed(1234)           # every rank holds the same LR frame
+    x = torch.rand(1, 3, H, W, generator=g).to(dev)
+    c = torch.tensor([[0.5, 0.2, 0.3]], device=dev)
+    rows, cols = best_grid(H, W, world, halo_radius(L))
+    plan = plan_tiles(H, W, rows, cols, halo_radius(L))
+    mine = [plan[i] for i in frames_for_rank(len(plan), rank, world)]
+
+    def step():
+        return [run_tile(model.upscale, x, c, t, r) for t in mine]
+
+    for _ in range(warmup):
+        cores = step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        cores = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    err = None
+    if rank == 0:                                      # exactness of the tiling against the un-tiled frame
+        full = model.upscale(x, c)
+        t0 = mine[0]
+        err = float((full[:, :, t0.y0 * r:t0.y1 * r, t0.x0 * r:t0.x1 * r] - cores[0]).abs().max())
+        executed = sum((t.hy1 - t.hy0) * (t.hx1 - t.hx0) for t in plan) / (H * W)
+        print(json.dumps({
+            "metric": "output_mpx_per_s", "value": H * r * W * r / (ms * 1e-3) / 1e6, "unit": "Mpx/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "config": {"workload": "MewZoom-4X-Ctrl 96ch/40L, one 1920x1080->7680x4320 frame, halo-tiled "
+                                   f"{rows}x{cols} (BASELINE configs[4])", "halo_lr_px": halo_radius(L),
+                       "executed_over_algorithmic_work": executed},
+            "max_abs_diff_vs_untiled": err}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
