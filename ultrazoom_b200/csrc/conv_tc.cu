@@ -1012,7 +1012,84 @@ static bool fits(const TcParams& p) {
   return p.acc_stages * p.rows * p.acc_stride <= 512 && plan_smem(p).total + 1024 <= static_cast<uint32_t>(kMaxSmem);
 }
 
+// Everything a launch needs, prepared once per (operands, shape, tunables): the chosen geometry, the encoded tensor
+// maps and the kernel instantiation.  mz_upscale keeps one per convolution of the model, so a repeated call costs one
+// cudaLaunchKernelEx per convolution on the host instead of a configuration search and four cuTensorMapEncodeTiled.
+struct ConvLaunchImpl {
+  TcParams p;
+  const void* fn;
+  int grid, k;
+  uint32_t smem;
+  int mode, n_pad;
+};
+static_assert(sizeof(ConvLaunchImpl) <= sizeof(ConvLaunch::storage), "ConvLaunch::storage too small");
+
+static int run_prepared(ConvLaunchImpl& L, cudaStream_t s) {
+  TcParams& p = L.p;
+  static long long* g_prof = nullptr;
+  const bool prof = (p.dbg & 16) != 0;
+  if (prof) {
+    if (!g_prof) MZ_CUDA(cudaMalloc(&g_prof, sizeof(long long) * 4096 * 24));
+    MZ_CUDA(cudaMemsetAsync(g_prof, 0, sizeof(long long) * 4096 * 24, s));
+  }
+  TcParams q = p;  // what the kernel sees
+  q.prof = prof ? g_prof : nullptr;
+  q.dbg &= ~16;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (L.k > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = L.k;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  static const bool no_pdl = getenv("MZ_NO_PDL") != nullptr;
+  if (!no_pdl && !prof) {  // this grid may start while the previous kernel of the stream drains (see the kernel)
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  void* args[1] = {&q};
+  MZ_CUDA(cudaLaunchKernelExC(&cfg, L.fn, args));
+  if (prof) {  // diagnostic: synchronise and print mean ticks per role (stderr)
+    MZ_CUDA(cudaStreamSynchronize(s));
+    std::vector<long long> h(static_cast<size_t>(L.grid) * 24);
+    MZ_CUDA(cudaMemcpy(h.data(), g_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    double m[24] = {0};
+    for (int c = 0; c < L.grid; ++c)
+      for (int i = 0; i < 24; ++i) m[i] += static_cast<double>(h[static_cast<size_t>(c) * 24 + i]) / L.grid;
+    fprintf(stderr,
+            "[mz prof] mode %d rows %d kc %d n %d rounds %d | producer: wait_a_empty %.0f wait_b_empty %.0f total %.0f | "
+            "mma: wait_acc_empty %.0f wait_a_full %.0f wait_b_full %.0f total %.0f | epilogue: wait_acc_full %.0f total %.0f\n",
+            L.mode, p.rows, p.kc, L.n_pad, p.n_rounds, m[0], m[1], m[7], m[8], m[9], m[10], m[15], m[16], m[23]);
+  }
+  return MZ_OK;
+}
+
+int run_conv_tc(ConvLaunch& launch, cudaStream_t s) {
+  MZ_REQUIRE(launch.valid, "conv: launch was not prepared");
+  return run_prepared(*reinterpret_cast<ConvLaunchImpl*>(launch.storage), s);
+}
+
 int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaStream_t s) {
+  ConvLaunch L;
+  L.valid = false;
+  const int rc = prepare_conv_tc(a, tune, device, &L);
+  return rc != MZ_OK ? rc : run_conv_tc(L, s);
+}
+
+int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvLaunch* out) {
+  out->valid = false;
+  ConvLaunchImpl& L = *reinterpret_cast<ConvLaunchImpl*>(out->storage);
   const EpiParams& e = a.epi;
   MZ_REQUIRE(e.B > 0 && e.H > 0 && e.W > 0, "conv: empty input (B %d, H %d, W %d)", e.B, e.H, e.W);
   MZ_REQUIRE(a.cin_p > 0 && a.cin_p % 16 == 0, "conv: cin_p must be a positive multiple of 16, %d given", a.cin_p);
@@ -1031,7 +1108,7 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
   MZ_REQUIRE(tune.epi_warps == 0 || tune.epi_warps == 4 || tune.epi_warps == 8,
              "conv: epi_warps must be 0 (auto), 4 or 8, %d given", tune.epi_warps);
 
-  TcParams p;
+  TcParams& p = L.p;
   memset(&p, 0, sizeof(p));
   p.epi = e;
   p.epi_warps = tune.epi_warps ? tune.epi_warps : 8;
@@ -1250,52 +1327,15 @@ int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaSt
               e.mode, a.cin_p, e.n_pad, p.rows, p.kc, p.subs, p.n_chunks, p.a_stages, p.b_stages, p.res_b, p.pair,
               p.fuse_g, p.cluster, p.epi_warps, p.o_ring, p.res_rows, p.e16, p.e32, p.acc_stages, smem, grid, p.n_rounds);
   }
-  static long long* g_prof = nullptr;
-  if (tune.dbg & 16) {
-    if (!g_prof) MZ_CUDA(cudaMalloc(&g_prof, sizeof(long long) * 4096 * 24));
-    MZ_CUDA(cudaMemsetAsync(g_prof, 0, sizeof(long long) * 4096 * 24, s));
-    p.prof = g_prof;
-    p.dbg &= ~16;
-  }
-
-  auto launch = [&](auto kern) -> int {
+  auto launch = [&](auto kern) -> int {  // (records the instantiation; run_prepared launches it)
     MZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[2];
-    int na = 0;
-    if (k > 1) {
-      attr[na].id = cudaLaunchAttributeClusterDimension;
-      attr[na].val.clusterDim.x = k;
-      attr[na].val.clusterDim.y = 1;
-      attr[na].val.clusterDim.z = 1;
-      ++na;
-    }
-    static const bool no_pdl = getenv("MZ_NO_PDL") != nullptr;
-    if (!no_pdl && !p.prof) {  // this grid may start while the previous kernel of the stream drains (see the kernel)
-      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[na].val.programmaticStreamSerializationAllowed = 1;
-      ++na;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = na;
-    MZ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
-    if (p.prof) {  // diagnostic: synchronise and print mean ticks per role (stderr)
-      MZ_CUDA(cudaStreamSynchronize(s));
-      std::vector<long long> h(static_cast<size_t>(grid) * 24);
-      MZ_CUDA(cudaMemcpy(h.data(), p.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-      double m[24] = {0};
-      for (int c = 0; c < grid; ++c)
-        for (int i = 0; i < 24; ++i) m[i] += static_cast<double>(h[static_cast<size_t>(c) * 24 + i]) / grid;
-      fprintf(stderr,
-              "[mz prof] mode %d rows %d kc %d n %d rounds %d | producer: wait_a_empty %.0f wait_b_empty %.0f total %.0f | "
-              "mma: wait_acc_empty %.0f wait_a_full %.0f wait_b_full %.0f total %.0f | epilogue: wait_acc_full %.0f total %.0f\n",
-              e.mode, p.rows, p.kc, e.n_pad, p.n_rounds, m[0], m[1], m[7], m[8], m[9], m[10], m[15], m[16], m[23]);
-    }
+    L.fn = reinterpret_cast<const void*>(kern);
+    L.grid = grid;
+    L.k = k;
+    L.smem = smem;
+    L.mode = e.mode;
+    L.n_pad = e.n_pad;
+    out->valid = true;
     return MZ_OK;
   };
   const int ks = p.subs > 1 ? p.subs : p.kc / 16;  // k-steps per stage and tap

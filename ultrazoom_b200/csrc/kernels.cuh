@@ -89,6 +89,13 @@ struct ConvTcTune {
 
 int launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaStream_t s);
+// The same in two steps: prepare (geometry search, tensor-map encoding, kernel selection -- host work only) and run.
+struct alignas(64) ConvLaunch {
+  unsigned char storage[2048];
+  bool valid = false;
+};
+int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvLaunch* out);
+int run_conv_tc(ConvLaunch& launch, cudaStream_t s);
 int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s);
 // zf != nullptr: fp32 stream zf + 16-bit shadow zb (pitch zb_pitch).  zf == nullptr: split stream, zb is z16 = [hi | lo]
 // with pitch 2 * Cp.
