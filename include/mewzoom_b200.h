@@ -156,7 +156,9 @@ typedef struct mz_conv_tune {
   int32_t max_ctas;   /* cap on the persistent grid                                                  */
   int32_t cluster;    /* CTAs per cluster sharing the weight stream via TMA multicast: 1, 2 or 4       */
   int32_t dbg;        /* timing experiments ONLY (results are wrong): 1 skip weight loads, 2 skip        */
-                      /* activation loads, 4 skip the epilogue body, 8 skip the MMAs                     */
+                      /* activation loads, 4 skip the epilogue body, 8 skip the MMAs, 32 / 64 every UMMA */
+                      /* reads the same rows / k-step; 16 (results stay right) prints per-role clock64   */
+                      /* timers to stderr after a synchronising launch                                   */
   int32_t pair;       /* CTA pairs issue M = 256 UMMAs (cta_group::2), weights split between the two:    */
                       /* 0 only when that makes the filter bank resident, 1 always, 2 never              */
   int32_t resident;   /* filter bank resident in shared memory: 0 when it fits, 1 require, 2 never       */
