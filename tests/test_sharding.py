@@ -38,14 +38,33 @@ def test_plan_tiles_covers_image_and_clips_halo():
         plan_tiles(4, 4, 8, 1, 1)
 
 
-@pytest.mark.parametrize("rows,cols", [(1, 1), (2, 2), (3, 2)])
-def test_tiled_inference_is_exact(rows, cols):
+def test_columns_sized_for_the_128_pixel_kernel_tiles():
+    """align_w = 128: every haloed tile of the 1080p frame on a 2 x 4 grid is at most 640 pixels (5 kernel tiles) wide,
+    where the equal split makes the two middle columns 642 (6 tiles); the cores still partition the image."""
+    halo = halo_radius(40)
+    eq = plan_tiles(1080, 1920, 2, 4, halo)
+    al = plan_tiles(1080, 1920, 2, 4, halo, align_w=128)
+    assert max(-(-(t.hx1 - t.hx0) // 128) for t in eq) == 6
+    assert max(-(-(t.hx1 - t.hx0) // 128) for t in al) == 5
+    assert sum((t.y1 - t.y0) * (t.x1 - t.x0) for t in al) == 1080 * 1920
+    xs = sorted({(t.x0, t.x1) for t in al})
+    assert xs[0][0] == 0 and xs[-1][1] == 1920 and all(a[1] == b[0] for a, b in zip(xs, xs[1:]))
+    for n in (1, 2, 4, 8):
+        r_, c_ = best_grid(1080, 1920, n, halo, align_w=128)
+        assert r_ * c_ == n
+    # small images: one kernel tile per column is enough, the cores still partition the width
+    small = plan_tiles(8, 40, 1, 4, 3, align_w=128)
+    assert small[0].x0 == 0 and small[-1].x1 == 40 and all(a.x1 == b.x0 and a.x1 > a.x0 for a, b in zip(small, small[1:]))
+
+
+@pytest.mark.parametrize("rows,cols,align", [(1, 1, 1), (2, 2, 1), (3, 2, 1), (2, 3, 16)])
+def test_tiled_inference_is_exact(rows, cols, align):
     m = make_oracle(CFG, seed=5)
     g = torch.Generator().manual_seed(9)
     x = torch.rand(2, 3, 37, 29, generator=g)
     c = torch.rand(2, 3, generator=g)
     full = m.upscale(x, c)
-    tiled = upscale_tiled(m.upscale, x, c, 2, CFG["num_encoder_layers"], rows, cols)
+    tiled = upscale_tiled(m.upscale, x, c, 2, CFG["num_encoder_layers"], rows, cols, align_w=align)
     assert max_abs_err(full, tiled) <= 2e-6         # fp reassociation only (SURVEY.md Appendix B.4)
 
 

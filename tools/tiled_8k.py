@@ -35,8 +35,8 @@ def main():
     g = torch.Generator().manual_seed(1234)           # every rank holds the same LR frame
     x = torch.rand(1, 3, H, W, generator=g).to(dev)
     c = torch.tensor([[0.5, 0.2, 0.3]], device=dev)
-    rows, cols = best_grid(H, W, world, halo_radius(L))
-    plan = plan_tiles(H, W, rows, cols, halo_radius(L))
+    rows, cols = best_grid(H, W, world, halo_radius(L), align_w=128)   # columns sized for the kernel's 128-pixel tiles
+    plan = plan_tiles(H, W, rows, cols, halo_radius(L), align_w=128)
     mine = [plan[i] for i in frames_for_rank(len(plan), rank, world)]
 
     def step():

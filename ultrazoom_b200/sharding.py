@@ -55,19 +55,51 @@ def _splits(n: int, parts: int) -> List[Tuple[int, int]]:
     return out
 
 
-def plan_tiles(H: int, W: int, rows: int, cols: int, halo: int) -> List[Tile]:
+def _splits_aligned(n: int, parts: int, halo: int, align: int) -> List[Tuple[int, int]]:
+    """Split [0, n) into ``parts`` cores such that every HALOED extent (core + halo on each interior side) needs as
+    few ``align``-wide kernel tiles as possible and all parts need the same number: the convolution kernel works on
+    128-pixel-wide tiles, so a 642-pixel haloed tile costs six of them where 640 cost five."""
+    if parts == 1 or align <= 1:
+        return _splits(n, parts)
+    sides = [(1 if i > 0 else 0) + (1 if i < parts - 1 else 0) for i in range(parts)]
+    t = 1
+    while sum(max(t * align - halo * s, 0) for s in sides) < n:
+        t += 1
+    cap = [t * align - halo * s for s in sides]
+    if min(cap) <= 0:
+        return _splits(n, parts)
+    excess = sum(cap) - n
+    # hand the slack back evenly (never below one pixel per core); any core <= its cap keeps the tile count at t
+    core = list(cap)
+    i = 0
+    while excess > 0:
+        take = min(excess, max((core[i] - 1), 0), -(-excess // parts))
+        core[i] -= take
+        excess -= take
+        i = (i + 1) % parts
+    out, s0 = [], 0
+    for c in core:
+        out.append((s0, s0 + c))
+        s0 += c
+    assert s0 == n
+    return out
+
+
+def plan_tiles(H: int, W: int, rows: int, cols: int, halo: int, align_w: int = 1) -> List[Tile]:
+    """``align_w`` = 128 sizes the columns for the convolution kernel's 128-pixel tiles (see ``_splits_aligned``)."""
     assert rows > 0 and cols > 0 and rows <= H and cols <= W, f"bad grid {rows}x{cols} for a {H}x{W} image"
     assert halo >= 0
     tiles = []
     for iy, (y0, y1) in enumerate(_splits(H, rows)):
-        for ix, (x0, x1) in enumerate(_splits(W, cols)):
+        for ix, (x0, x1) in enumerate(_splits_aligned(W, cols, halo, align_w)):
             tiles.append(Tile(iy * cols + ix, y0, y1, x0, x1,
                               max(0, y0 - halo), min(H, y1 + halo), max(0, x0 - halo), min(W, x1 + halo)))
     return tiles
 
 
-def best_grid(H: int, W: int, n_tiles: int, halo: int) -> Tuple[int, int]:
-    """rows x cols = n_tiles grid with the least executed work (haloed area)."""
+def best_grid(H: int, W: int, n_tiles: int, halo: int, align_w: int = 1) -> Tuple[int, int]:
+    """rows x cols = n_tiles grid with the least executed work: the haloed area, or with ``align_w`` the slowest tile's
+    area with its width rounded up to whole kernel tiles (tiles run in parallel, one per GPU)."""
     best, best_cost = (1, n_tiles), None
     for rows in range(1, n_tiles + 1):
         if n_tiles % rows:
@@ -75,7 +107,11 @@ def best_grid(H: int, W: int, n_tiles: int, halo: int) -> Tuple[int, int]:
         cols = n_tiles // rows
         if rows > H or cols > W:
             continue
-        cost = sum((t.hy1 - t.hy0) * (t.hx1 - t.hx0) for t in plan_tiles(H, W, rows, cols, halo))
+        plan = plan_tiles(H, W, rows, cols, halo, align_w)
+        if align_w > 1:
+            cost = max((t.hy1 - t.hy0) * (-(-(t.hx1 - t.hx0) // align_w) * align_w) for t in plan)
+        else:
+            cost = sum((t.hy1 - t.hy0) * (t.hx1 - t.hx0) for t in plan)
         if best_cost is None or cost < best_cost:
             best, best_cost = (rows, cols), cost
     return best
@@ -95,12 +131,12 @@ def stitch(out: Tensor, tile_out: Tensor, t: Tile, r: int) -> None:
 
 def upscale_tiled(fn: Callable[[Tensor, Optional[Tensor]], Tensor], x: Tensor, c: Optional[Tensor], r: int,
                   num_encoder_layers: int, rows: int, cols: int, tiles: Optional[Sequence[int]] = None,
-                  out: Optional[Tensor] = None) -> Tensor:
+                  out: Optional[Tensor] = None, align_w: int = 1) -> Tensor:
     """Tiled inference, exact w.r.t. the full-image result.  ``tiles`` selects which tile indices THIS
     caller computes (e.g. ``frames_for_rank(rows*cols, rank, world)``); the others are left untouched in
     ``out`` so ranks can fill disjoint parts of a shared / gathered buffer."""
     B, _, H, W = x.shape
-    plan = plan_tiles(H, W, rows, cols, halo_radius(num_encoder_layers))
+    plan = plan_tiles(H, W, rows, cols, halo_radius(num_encoder_layers), align_w)
     if out is None:
         out = torch.zeros((B, 3, H * r, W * r), dtype=torch.float32, device=x.device)
     for t in plan:
