@@ -18,7 +18,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libmewzoom_b200.so")
-SOURCES = ["host_util.cu", "small_kernels.cu", "conv_tc.cu", "api.cu", "model.cu", "probe.cu"]
+# (source, extra defines, object name).  conv_tc.cu is compiled once per epilogue mode (its template instantiations
+# dominate the build time) and once for its host side; see the MZ_TC_PART comment in the file.
+SOURCES = [(f"{n}.cu", [], f"{n}.o") for n in ("host_util", "small_kernels", "api", "model", "probe")] + [
+    ("conv_tc.cu", [f"-DMZ_TC_PART={part}"], f"conv_tc_p{part}.o") for part in range(5)
+]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -54,19 +58,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = _nvcc()
 
-    def compile_one(src: str) -> str:
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+    def compile_one(unit) -> str:
+        src, defines, objname = unit
+        obj = os.path.join(OBJDIR, objname)
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+            raise RuntimeError(f"nvcc failed for {unit[0]} {unit[1]}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             sys.stderr.write(r.stderr)
         return obj
 
-    with cf.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+    with cf.ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static"], capture_output=True, text=True)
     if r.returncode != 0:

@@ -729,15 +729,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
                                (as * ROWS + (FUSE ? ROWS - 1 - r : r)) * p.acc_stride;
         if (y >= p.epi.H || !live) {  // warp-uniform: nothing to store for this row
-          if (!FUSE) break;
-          // the accumulators of a row that is not stored (below the image, surplus patch) still have to be re-zeroed
-          for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) {
-            if (MODE == 0 && nh == 2 &&
-                ((static_cast<uint32_t>(r) * nb16 + n0 / static_cast<uint32_t>(p.e16)) & 1u) != static_cast<uint32_t>(half))
-              continue;  // the other warp of this lane quarter owns that box
-            tmem_zero16(taddr + n0);
+          if constexpr (!FUSE) {
+            break;
+          } else {
+            // the accumulators of a row that is not stored (below the image, surplus patch) still have to be re-zeroed
+            for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) {
+              if (MODE == 0 && nh == 2 &&
+                  ((static_cast<uint32_t>(r) * nb16 + n0 / static_cast<uint32_t>(p.e16)) & 1u) != static_cast<uint32_t>(half))
+                continue;  // the other warp of this lane quarter owns that box
+              tmem_zero16(taddr + n0);
+            }
+            continue;
           }
-          continue;
         }
         if (MODE == 2) {
           float acc[48];
@@ -958,6 +961,60 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
+// ---- kernel lookup -------------------------------------------------------------------------------------------------
+// One lookup function per epilogue mode, so that the build can compile the instantiations of each mode in its own
+// translation unit: build.py compiles this file five times, with -DMZ_TC_PART=<mode> for the kernels of modes 0..3 and
+// -DMZ_TC_PART=4 for the host side.  Without the define (a plain `nvcc -c conv_tc.cu`) everything lands in one object.
+//   var 0: one CTA per patch, 1: CTA pair (cta_group::2), 2: fused rows.  Returns nullptr for a shape that has no kernel.
+const void* tc_kernel_mode0(int ks, int rows, int var);
+const void* tc_kernel_mode1(int ks, int rows, int var);
+const void* tc_kernel_mode2(int ks, int rows, int var);
+const void* tc_kernel_mode3(int ks, int rows, int var);
+
+template <int M, int K>
+static const void* tc_kernel_rows(int rows, int var) {
+  if (var == 0) {
+    if (rows == 1) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 1, 0>);
+    if (rows == 2) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 2, 0>);
+    if (rows == 4) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 4, 0>);
+  }
+  if constexpr (M != 2) {  // the head has neither a pair nor a fused-row form
+    if constexpr (K != 3) {  // pairs: the shapes the 64/96/128-channel encoders use
+      if (var == 1 && rows == 1) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 1, 1>);
+      if (var == 1 && rows == 2) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 2, 1>);
+    }
+    if (var == 2 && rows == 2) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 2, 2>);
+    if (var == 2 && rows == 4) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 4, 2>);
+  }
+  return nullptr;
+}
+
+template <int M>
+static const void* tc_kernel_lookup(int ks, int rows, int var) {
+  switch (ks) {
+    case 1: return tc_kernel_rows<M, 1>(rows, var);
+    case 2: return tc_kernel_rows<M, 2>(rows, var);
+    case 3: return tc_kernel_rows<M, 3>(rows, var);
+    case 4: return tc_kernel_rows<M, 4>(rows, var);
+    default: return nullptr;
+  }
+}
+
+#if !defined(MZ_TC_PART) || MZ_TC_PART == 0
+const void* tc_kernel_mode0(int ks, int rows, int var) { return tc_kernel_lookup<0>(ks, rows, var); }
+#endif
+#if !defined(MZ_TC_PART) || MZ_TC_PART == 1
+const void* tc_kernel_mode1(int ks, int rows, int var) { return tc_kernel_lookup<1>(ks, rows, var); }
+#endif
+#if !defined(MZ_TC_PART) || MZ_TC_PART == 2
+const void* tc_kernel_mode2(int ks, int rows, int var) { return tc_kernel_lookup<2>(ks, rows, var); }
+#endif
+#if !defined(MZ_TC_PART) || MZ_TC_PART == 3
+const void* tc_kernel_mode3(int ks, int rows, int var) { return tc_kernel_lookup<3>(ks, rows, var); }
+#endif
+
+#if !defined(MZ_TC_PART) || MZ_TC_PART == 4  // ---- host side ----------------------------------------------------------
+
 static int pick_kc(int cin_p) { return cin_p % 64 == 0 ? 64 : (cin_p % 32 == 0 ? 32 : 16); }
 
 static uint32_t pow2_cols(uint32_t c) {
@@ -1327,77 +1384,30 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
               e.mode, a.cin_p, e.n_pad, p.rows, p.kc, p.subs, p.n_chunks, p.a_stages, p.b_stages, p.res_b, p.pair,
               p.fuse_g, p.cluster, p.epi_warps, p.o_ring, p.res_rows, p.e16, p.e32, p.acc_stages, smem, grid, p.n_rounds);
   }
-  auto launch = [&](auto kern) -> int {  // (records the instantiation; run_prepared launches it)
-    MZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    L.fn = reinterpret_cast<const void*>(kern);
-    L.grid = grid;
-    L.k = k;
-    L.smem = smem;
-    L.mode = e.mode;
-    L.n_pad = e.n_pad;
-    out->valid = true;
-    return MZ_OK;
-  };
   const int ks = p.subs > 1 ? p.subs : p.kc / 16;  // k-steps per stage and tap
   MZ_REQUIRE(p.a_stages >= 2 && p.b_stages >= 2, "conv: the look-ahead issue loop needs at least two A and two B stages");
-  if (p.fuse_g) {
-#define MZ_FUSE_ROWS(M, K)                                                   \
-  if (p.rows == 2) return launch(conv_tc_kernel<M, K, 2, 2>);                \
-  if (p.rows == 4) return launch(conv_tc_kernel<M, K, 4, 2>);
-#define MZ_FUSE_KS(M)                   \
-  if (ks == 1) { MZ_FUSE_ROWS(M, 1) }   \
-  if (ks == 2) { MZ_FUSE_ROWS(M, 2) }   \
-  if (ks == 3) { MZ_FUSE_ROWS(M, 3) }   \
-  if (ks == 4) { MZ_FUSE_ROWS(M, 4) }
-    if (e.mode == 0) { MZ_FUSE_KS(0) }
-    if (e.mode == 1) { MZ_FUSE_KS(1) }
-    if (e.mode == 3) { MZ_FUSE_KS(3) }
-#undef MZ_FUSE_KS
-#undef MZ_FUSE_ROWS
-    set_error("conv: no fused-row kernel for mode %d, %d k-steps, %d rows", e.mode, ks, p.rows);
+  const int var = p.fuse_g ? 2 : (p.pair ? 1 : 0);
+  const void* fn = e.mode == 0   ? tc_kernel_mode0(ks, p.rows, var)
+                   : e.mode == 1 ? tc_kernel_mode1(ks, p.rows, var)
+                   : e.mode == 3 ? tc_kernel_mode3(ks, p.rows, var)
+                                 : tc_kernel_mode2(ks, p.rows, var);
+  if (!fn) {
+    set_error("conv: no %s kernel for mode %d, %d k-steps, %d rows", var == 2 ? "fused-row" : (var == 1 ? "CTA-pair" : "tcgen05"),
+              e.mode, ks, p.rows);
     return MZ_ERR_UNSUPPORTED;
   }
-  if (p.pair) {  // instantiated for the shapes the 64/96/128-channel encoders use
-    if (e.mode == 0 && ks == 1 && p.rows == 1) return launch(conv_tc_kernel<0, 1, 1, 1>);
-    if (e.mode == 0 && ks == 1 && p.rows == 2) return launch(conv_tc_kernel<0, 1, 2, 1>);
-    if (e.mode == 1 && ks == 1 && p.rows == 1) return launch(conv_tc_kernel<1, 1, 1, 1>);
-    if (e.mode == 1 && ks == 1 && p.rows == 2) return launch(conv_tc_kernel<1, 1, 2, 1>);
-    if (e.mode == 0 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<0, 2, 1, 1>);
-    if (e.mode == 0 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<0, 2, 2, 1>);
-    if (e.mode == 0 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<0, 4, 1, 1>);
-    if (e.mode == 0 && ks == 4 && p.rows == 2) return launch(conv_tc_kernel<0, 4, 2, 1>);
-    if (e.mode == 1 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<1, 2, 1, 1>);
-    if (e.mode == 1 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<1, 2, 2, 1>);
-    if (e.mode == 1 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<1, 4, 1, 1>);
-    if (e.mode == 1 && ks == 4 && p.rows == 2) return launch(conv_tc_kernel<1, 4, 2, 1>);
-    if (e.mode == 3 && ks == 1 && p.rows == 1) return launch(conv_tc_kernel<3, 1, 1, 1>);
-    if (e.mode == 3 && ks == 1 && p.rows == 2) return launch(conv_tc_kernel<3, 1, 2, 1>);
-    if (e.mode == 3 && ks == 2 && p.rows == 1) return launch(conv_tc_kernel<3, 2, 1, 1>);
-    if (e.mode == 3 && ks == 2 && p.rows == 2) return launch(conv_tc_kernel<3, 2, 2, 1>);
-    if (e.mode == 3 && ks == 4 && p.rows == 1) return launch(conv_tc_kernel<3, 4, 1, 1>);
-    if (e.mode == 3 && ks == 4 && p.rows == 2) return launch(conv_tc_kernel<3, 4, 2, 1>);
-    set_error("conv: no CTA-pair kernel for mode %d, %d k-steps, %d rows", e.mode, ks, p.rows);
-    return MZ_ERR_UNSUPPORTED;
-  }
-#define MZ_DISPATCH_ROWS(M, K)                                     \
-  switch (p.rows) {                                                \
-    case 1: return launch(conv_tc_kernel<M, K, 1, 0>);         \
-    case 2: return launch(conv_tc_kernel<M, K, 2, 0>);         \
-    default: return launch(conv_tc_kernel<M, K, 4, 0>);        \
-  }
-#define MZ_DISPATCH_KS(M)                                   \
-  switch (ks) {                                             \
-    case 4: MZ_DISPATCH_ROWS(M, 4)                          \
-    case 3: MZ_DISPATCH_ROWS(M, 3)                          \
-    case 2: MZ_DISPATCH_ROWS(M, 2)                          \
-    default: MZ_DISPATCH_ROWS(M, 1)                         \
-  }
-  if (e.mode == 0) MZ_DISPATCH_KS(0)
-  if (e.mode == 1) MZ_DISPATCH_KS(1)
-  if (e.mode == 3) MZ_DISPATCH_KS(3)
-  MZ_DISPATCH_KS(2)
-#undef MZ_DISPATCH_KS
-#undef MZ_DISPATCH_ROWS
+  // (records the instantiation; run_prepared launches it)
+  MZ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+  L.fn = fn;
+  L.grid = grid;
+  L.k = k;
+  L.smem = smem;
+  L.mode = e.mode;
+  L.n_pad = e.n_pad;
+  out->valid = true;
+  return MZ_OK;
 }
+
+#endif  // host side
 
 }  // namespace mz
