@@ -245,3 +245,37 @@ def test_size_independent_properties_at_full_size(dev):
     crop = x[:1, :, :64 + R, :64 + R].cpu()
     ref = o.upscale(crop, c[:1].cpu())[:, :, :128, :128]
     assert max_abs_err(y[:1, :, :128, :128].cpu(), ref) <= 4e-3
+
+
+@pytest.mark.parametrize("name,shape", [("MewZoom-2X-Ctrl", (2, 3, 40, 56)), ("MewZoom-4X-Ctrl", (1, 3, 33, 130)),
+                                        ("MewZoom-3X", (1, 3, 24, 40))])
+def test_cuda_graph_replay_matches_the_eager_call(dev, name, shape):
+    """MewZoom.capture: the whole call recorded into a CUDA graph (cluster launches, dependent-launch edges) and replayed
+    on NEW inputs copied into its buffers is bit-identical to the ordinary call, float and uint8 images, and still
+    within the oracle's tolerance."""
+    from ultrazoom_b200 import MODEL_CONFIGS
+
+    o = make_oracle(name, seed=11)
+    m = _model_from(MODEL_CONFIGS[name], o.state_dict(), dev)
+    g = torch.Generator().manual_seed(12)
+    ctrl = MODEL_CONFIGS[name]["control_features"] > 0
+    x0, x1 = torch.rand(shape, generator=g), torch.rand(shape, generator=g)
+    c0 = torch.rand(shape[0], 3, generator=g) if ctrl else None
+    c1 = torch.rand(shape[0], 3, generator=g) if ctrl else None
+    to = lambda t: None if t is None else t.to(dev)  # noqa: E731
+    graph = m.capture(to(x0), to(c0))
+    assert torch.equal(graph.replay(), m.upscale(to(x0), to(c0)))
+    y1 = graph(to(x1), to(c1)).clone()
+    assert torch.equal(y1, m.upscale(to(x1), to(c1)))
+    tol, min_psnr = TOL[name.replace("-Ctrl", "")]
+    ref = o.upscale(x1, c1)
+    assert max_abs_err(y1.cpu(), ref) <= tol and psnr(y1.cpu(), ref) >= min_psnr
+    for _ in range(3):                                                   # replays are repeatable
+        assert torch.equal(graph.replay(), y1)
+    fwd = m.capture(to(x0), to(c0), clamp=False)                         # un-clamped forward
+    assert torch.equal(fwd(to(x1), to(c1)), m.forward(to(x1), to(c1)))
+    x8 = (x1 * 255).to(torch.uint8).to(dev)                              # 8-bit images in and out
+    g8 = m.capture(x8, to(c1))
+    assert g8.y.dtype == torch.uint8 and torch.equal(g8.replay(), m.upscale(x8, to(c1)))
+    with pytest.raises(AssertionError):
+        graph(to(x1)[:, :, :-1], to(c1))

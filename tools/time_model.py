@@ -30,3 +30,19 @@ e1.record()
 t_host = (time.perf_counter() - t0) / n
 torch.cuda.synchronize()
 print(f"{name} {B}x{H}x{W}: device {e0.elapsed_time(e1) / n * 1e3:.1f} us per call, host enqueue {t_host * 1e6:.1f} us per call")
+
+# the same call replayed from a CUDA graph (MewZoom.capture): no host work per kernel
+g = m.capture(x, c)
+for _ in range(5):
+    g.replay()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+e0.record()
+for _ in range(n):
+    g.replay()
+e1.record()
+t_host = (time.perf_counter() - t0) / n
+torch.cuda.synchronize()
+same = torch.equal(g.replay(), m.upscale(x, c))
+print(f"{name} {B}x{H}x{W}: graph replay {e0.elapsed_time(e1) / n * 1e3:.1f} us per call, host enqueue {t_host * 1e6:.1f} us per call, "
+      f"bit-identical to the eager call: {same}")

@@ -312,6 +312,14 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         ``ToPILImage`` does (README.md:81) when ``model.u8_truncate`` is set: a quarter of the image traffic."""
         return self._run(x, c, _native.FLAG_CLAMP01)
 
+    def capture(self, x: Tensor, c: Optional[Tensor] = None, clamp: bool = True) -> "GraphedUpscale":
+        """Record one ``upscale`` (``clamp=False``: ``forward``) call at the shape of ``x`` into a CUDA graph.
+
+        A frame of a few hundred pixels a side is launch-bound (2L + 3 kernels, most of them cluster launches of
+        15-20 us of host time each); replaying the recorded graph removes the host from that loop.  The dependent-launch
+        edges between the kernels are kept by the capture.  See ``GraphedUpscale``."""
+        return GraphedUpscale(self, x, c, _native.FLAG_CLAMP01 if clamp else 0)
+
     @torch.inference_mode()
     def upscale_host(self, x: Tensor, c: Optional[Tensor] = None, out: Optional[Tensor] = None,
                      device: int = 0, lane: Optional[int] = None) -> Tensor:
@@ -355,6 +363,46 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         keep = getattr(self, "_host_keep", {})
         for k in [k for k in keep if k[0] == device and (lane < 0 or k[1] == lane)]:
             del keep[k]
+
+
+class GraphedUpscale:
+    """``MewZoom.capture``: a CUDA graph of the whole call with fixed input and output buffers.
+
+    ``g = model.capture(x, c); y = g(x2, c2)`` copies ``x2``/``c2`` (same shapes and dtypes as at capture) into the
+    graph's input buffers, replays it on the current stream and returns the graph's output tensor ``g.y`` -- the same
+    tensor on every call, so consume or clone it before the next replay.  ``g.replay()`` skips the copies (fill
+    ``g.x`` / ``g.c`` yourself).  The graph reads the engine's packed weights in place: parameters changed after the
+    capture are picked up by the next ordinary call (which re-packs them), not by a replay on its own."""
+
+    def __init__(self, model: MewZoom, x: Tensor, c: Optional[Tensor], flags: int):
+        c = model._check_inputs(x, c)
+        if not x.is_cuda:
+            raise RuntimeError("MewZoom.capture needs a CUDA input (there is no CPU fallback).")
+        self.model = model
+        self.x = (x.detach() if x.dtype == torch.uint8 else x.detach().to(torch.float32)).contiguous().clone()
+        self.c = None if c is None else c.detach().to(device=x.device, dtype=torch.float32).contiguous().clone()
+        with torch.inference_mode():
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):        # warm-up: packs the weights, sizes the workspace, prepares the launches
+                model._run(self.x, self.c, flags)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.y = model._run(self.x, self.c, flags)
+
+    def replay(self) -> Tensor:
+        self.graph.replay()
+        return self.y
+
+    def __call__(self, x: Tensor, c: Optional[Tensor] = None) -> Tensor:
+        assert tuple(x.shape) == tuple(self.x.shape) and (x.dtype == torch.uint8) == (self.x.dtype == torch.uint8), (
+            f"Graph was captured for input {tuple(self.x.shape)} {self.x.dtype}, got {tuple(x.shape)} {x.dtype}.")
+        self.x.copy_(x, non_blocking=True)
+        if self.c is not None:
+            assert c is not None, "Control vector c is required for control models."
+            self.c.copy_(c.reshape(-1, self.c.shape[1]).expand_as(self.c), non_blocking=True)
+        return self.replay()
 
 
 class ONNXModel(nn.Module):
