@@ -52,7 +52,7 @@ typedef enum mz_status {
 /* Constructor kwargs of the 0.2.x-style MewZoom (README.md:254-258, model.py:52-69). */
 typedef struct mz_config {
   int32_t upscale_ratio;      /* 2, 3 or 4   (SubpixelConv2d, model.py:894-898)      */
-  int32_t num_channels;       /* C           (README.md:37-42)                       */
+  int32_t num_channels;       /* C <= 512    (README.md:37-42); C * hidden_ratio <= 1024 */
   int32_t hidden_ratio;       /* 1, 2 or 4   (InvertedBottleneck, model.py:738)      */
   int32_t num_encoder_layers; /* L                                                   */
   int32_t control_features;   /* 0 or 3      (ControlVector, README.md:118-122)      */

@@ -279,3 +279,38 @@ def test_cuda_graph_replay_matches_the_eager_call(dev, name, shape):
     assert g8.y.dtype == torch.uint8 and torch.equal(g8.replay(), m.upscale(x8, to(c1)))
     with pytest.raises(AssertionError):
         graph(to(x1)[:, :, :-1], to(c1))
+
+
+@pytest.mark.parametrize("cfg,tol", [
+    (dict(upscale_ratio=2, num_channels=96, hidden_ratio=4, num_encoder_layers=3, control_features=3), 4e-3),   # 384 = 2 x 192
+    (dict(upscale_ratio=3, num_channels=80, hidden_ratio=4, num_encoder_layers=2, control_features=0), 4e-3),   # 320 = 2 x 160
+    (dict(upscale_ratio=2, num_channels=128, hidden_ratio=4, num_encoder_layers=2, control_features=3), 6e-3),  # 512 = 2 x 256
+    (dict(upscale_ratio=4, num_channels=48, hidden_ratio=1, num_encoder_layers=3, control_features=3), 4e-3),   # hidden_ratio 1
+    # above 128 channels conv2 is sliced as well (each launch adds into its channel slice of the residual stream)
+    (dict(upscale_ratio=2, num_channels=160, hidden_ratio=2, num_encoder_layers=2, control_features=3), 6e-3),  # 2 x 80 / 2 x 160
+    (dict(upscale_ratio=2, num_channels=256, hidden_ratio=1, num_encoder_layers=2, control_features=0), 6e-3),  # 2 x 128 / 256
+    (dict(upscale_ratio=3, num_channels=384, hidden_ratio=2, num_encoder_layers=2, control_features=3), 8e-3),  # 3 x 128 / 3 x 256
+])
+def test_hidden_widths_beyond_one_umma_tile(dev, cfg, tol):
+    """InvertedBottleneck allows hidden_ratio 1, 2 and 4 and any channel count (reference model.py:737-738; the 0.3.0
+    U-Net runs it at 192 and 384 channels).  A hidden width above the 256 columns of one UMMA tile runs conv1 as slices
+    of output channels (each with its own filter bank and FiLM rows), more than 128 channels slice conv2 the same way;
+    the result matches the oracle like any other model, the SIMT twin, and is deterministic."""
+    from ultrazoom_b200 import _native
+
+    o = make_oracle(cfg, seed=21)
+    m = _model_from(cfg, o.state_dict(), dev)
+    g = torch.Generator().manual_seed(22)
+    x = torch.rand(2, 3, 37, 150, generator=g)
+    c = torch.rand(2, 3, generator=g) if cfg["control_features"] else None
+    ref = o.upscale(x, c)
+    assert residual_rms(o, x, c) >= 0.05
+    cd = None if c is None else c.to(dev)
+    y = m.upscale(x.to(dev), cd)
+    assert max_abs_err(y.cpu(), ref) <= tol, max_abs_err(y.cpu(), ref)
+    assert psnr(y.cpu(), ref) >= 60.0
+    assert torch.equal(y, m.upscale(x.to(dev), cd))
+    m._flags_extra = _native.FLAG_SIMT_CONV
+    ys = m.upscale(x.to(dev), cd)
+    m._flags_extra = 0
+    assert (y - ys).abs().max().item() <= 2e-3

@@ -152,7 +152,7 @@ int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t 
 int mz_control_film(const float* c_dev, int32_t c_rows, const float* w_dev, const float* b_dev, float* film_dev,
                     int32_t L, int32_t B, int32_t F, int32_t hC, int32_t hCp, void* stream) {
   MZ_REQUIRE(c_dev && w_dev && b_dev && film_dev, "film: null pointer");
-  return launch_film(c_dev, c_rows, w_dev, b_dev, film_dev, L, B, F, hC, hCp, static_cast<cudaStream_t>(stream));
+  return launch_film(c_dev, c_rows, w_dev, b_dev, film_dev, L, B, F, hC, hCp, hCp, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1357,8 +1357,8 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
     int rc = encode_tmap(&p.tmO, tdt, 4, e.out_bf16, dims, st16, box16, swz_of(p.e16 * 2));
     if (rc != MZ_OK) return rc;
     if (e.mode == 1) {
-      const uint64_t st32[3] = {static_cast<uint64_t>(e.n_pad) * 4, static_cast<uint64_t>(e.W) * e.n_pad * 4,
-                                static_cast<uint64_t>(e.H) * e.W * e.n_pad * 4};
+      const uint64_t zp = e.zf_pitch ? e.zf_pitch : e.n_pad;
+      const uint64_t st32[3] = {zp * 4, static_cast<uint64_t>(e.W) * zp * 4, static_cast<uint64_t>(e.H) * e.W * zp * 4};
       const uint32_t box32[4] = {static_cast<uint32_t>(p.e32), 32u, 1u, 1u};
       rc = encode_tmap(&p.tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e.zf, dims, st32, box32, swz_of(p.e32 * 4));
       if (rc != MZ_OK) return rc;

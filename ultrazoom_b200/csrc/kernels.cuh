@@ -43,6 +43,7 @@ struct EpiParams {
   int out_pitch;            // channel pitch of out_bf16 in elements (0 = n_pad); > n_pad when the consumer wants
                             // zero-padded channels (48-channel zb is kept at pitch 64: 128-byte TMA rows)
   float* zf;                // mode 1: fp32 residual stream, updated in place
+  int zf_pitch;             // channel pitch of zf in elements (0 = n_pad); > n_pad when this launch owns a channel slice
   // mode 2
   const float* x;  // LR image (B,3,H,W) fp32 -- only for skip_mode 2
   float* y;        // HR image (B,3,rH,rW) fp32
@@ -102,8 +103,9 @@ int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cu
 // x8 != nullptr: the image is 8-bit (B,3,H,W) and read as x8 / 255.
 int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16,
                 int B, int H, int W, int Cp, int zb_pitch, cudaStream_t s);
+// film: [L][hCp / ns][B][2][ns] -- one [B][2][ns] table (scale row, shift row) per conv1 launch; ns == hCp normally
 int launch_film(const float* c, int c_rows, const float* w, const float* b, float* film, int L, int B, int F,
-                int hC, int hCp, cudaStream_t s);
+                int hC, int hCp, int ns, cudaStream_t s);
 
 ConvTcTune to_tune(const mz_conv_tune* t);
 int current_device();
@@ -124,7 +126,7 @@ __device__ __forceinline__ void st_global_v4(void* p, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ void epi_residual16(const EpiParams& p, int b, int y, int x, int n0, const float (&acc)[16],
                                                const float4* zin) {
   const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
-  float4* zf = reinterpret_cast<float4*>(p.zf + pix * p.n_pad + n0);
+  float4* zf = reinterpret_cast<float4*>(p.zf + pix * (p.zf_pitch ? p.zf_pitch : p.n_pad) + n0);
   uint32_t o[8];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -180,7 +182,7 @@ __device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, in
       zl[q] = lo;
     }
   } else {
-    const float4* zf = reinterpret_cast<const float4*>(p.zf + pix * p.n_pad + n0);
+    const float4* zf = reinterpret_cast<const float4*>(p.zf + pix * (p.zf_pitch ? p.zf_pitch : p.n_pad) + n0);
     float4 zin[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) zin[q] = zf[q];

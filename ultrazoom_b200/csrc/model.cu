@@ -18,11 +18,17 @@ using namespace mz;
 struct mz_model {
   mz_config cfg;
   int C, Cp, Cz, hC, hCp, L, r, F, headN, headNp, bf16;  // Cz: channel pitch of zb (>= Cp, zero padded)
+  // A hidden width above the 256 columns of one UMMA tile runs conv1 as S launches of ns output channels each
+  // (hCp = S * ns): slice s has its own packed filter bank and FiLM rows and writes channels [s * ns, (s + 1) * ns) of
+  // the hidden tensor.  Likewise conv2 above 128 output channels (its epilogue stages whole fp32 + 16-bit row tiles):
+  // S2 launches of ns2 channels each (Cp = S2 * ns2), each adding into its channel slice of the residual stream.
+  // S = S2 = 1 for every named model.
+  int S = 1, ns = 0, S2 = 1, ns2 = 0;
   bool split = false;  // residual stream as two 16-bit planes z16 = [hi | lo] (pitch 2 * Cp) instead of fp32 zf + zb
   float* stem_w = nullptr;  // (Cp,3)
   float* stem_b = nullptr;  // (Cp)
-  uint16_t* conv1 = nullptr;  // L x [9][hCp][Cp]
-  uint16_t* conv2 = nullptr;  // L x [9][Cp][hCp]
+  uint16_t* conv1 = nullptr;  // L x S x [9][ns][Cz]
+  uint16_t* conv2 = nullptr;  // L x S2 x [9][ns2][hCp]
   uint16_t* head = nullptr;   // [9][headNp][Cp]
   float* ctrl_w = nullptr;         // (L, 2hC, F)
   float* ctrl_b = nullptr;         // (L, 2hC)
@@ -43,7 +49,8 @@ struct mz_model {
     bool has_work = false;
   };
   HostLane lane[2];
-  // prepared launches, one per convolution of the model (conv1 l -> 2l, conv2 l -> 2l + 1, head -> 2L), reused while the
+  // prepared launches, one per convolution of the model (layer l: conv1 slices at l (S + S2) + s, conv2 slices after
+  // them; head -> L (S + S2)), reused while the
   // operands, shape and tunables of that convolution stay the same (`keys` holds what they were prepared for)
   struct ConvKey {
     ConvArgs a;
@@ -158,7 +165,8 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   MZ_REQUIRE(cfg->residual_stream >= MZ_STREAM_AUTO && cfg->residual_stream <= MZ_STREAM_SPLIT,
              "residual_stream must be MZ_STREAM_AUTO, MZ_STREAM_FP32 or MZ_STREAM_SPLIT, %d given.", cfg->residual_stream);
   const int hC = cfg->num_channels * cfg->hidden_ratio;
-  MZ_REQUIRE(mz_padded_channels(hC) <= 256, "hidden width %d exceeds the 256-channel limit of one UMMA tile", hC);
+  MZ_REQUIRE(cfg->num_channels <= 512 && hC <= 1024, "num_channels %d / hidden width %d exceed 512 / 1024 channels",
+             cfg->num_channels, hC);
 
   int ndev = 0;
   MZ_CUDA(cudaGetDeviceCount(&ndev));
@@ -174,9 +182,15 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   m->cfg = *cfg;
   m->C = cfg->num_channels;
   m->Cp = mz_padded_channels(m->C);
+  m->S2 = (m->Cp + 127) / 128;
+  m->ns2 = (m->Cp + 16 * m->S2 - 1) / (16 * m->S2) * 16;
+  m->Cp = m->S2 * m->ns2;
   m->Cz = mz_zb_pitch(m->Cp);
   m->hC = hC;
   m->hCp = mz_padded_channels(hC);
+  m->S = (m->hCp + 255) / 256;
+  m->ns = (m->hCp + 16 * m->S - 1) / (16 * m->S) * 16;
+  m->hCp = m->S * m->ns;
   m->L = cfg->num_encoder_layers;
   m->r = cfg->upscale_ratio;
   m->F = cfg->control_features;
@@ -185,10 +199,16 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   m->bf16 = cfg->operand_dtype == MZ_DTYPE_BF16;
   m->split = cfg->residual_stream == MZ_STREAM_SPLIT;  // (AUTO = fp32: measured equal or faster on all three models)
   if (m->split) m->Cz = m->Cp;  // weights are packed against the logical pitch; the activation pitch is 2 * Cp
+  if (m->split && m->S2 > 1) {
+    set_error("residual_stream split is not available above 128 channels (%d given)", m->C);
+    delete m;
+    return MZ_ERR_UNSUPPORTED;
+  }
   m->have.assign(3 + 4 * m->L, 0);
-  m->prepared.resize(2 * (2 * m->L + 1));
-  m->keys.resize(2 * (2 * m->L + 1));
-  m->victim.assign(2 * m->L + 1, 0);
+  const int n_convs = (m->S + m->S2) * m->L + 1;
+  m->prepared.resize(2 * n_convs);
+  m->keys.resize(2 * n_convs);
+  m->victim.assign(n_convs, 0);
   for (auto& k : m->keys) memset(&k, 0xff, sizeof(k));
   memset(m->tune, 0, sizeof(m->tune));
   const int hm = env_int("MZ_HALO_MODE", 0);  // 1 = diagnostic per-dx loads
@@ -269,17 +289,25 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
     case MZ_W_CONV1: {
       MZ_REQUIRE(numel == static_cast<size_t>(m->hC) * m->C * 9, "conv1 weight: expected %d elements, got %zu",
                  m->hC * m->C * 9, numel);
-      pack_conv_weight_host(host_data, m->hC, m->C, m->hCp, m->Cz, m->bf16, packed);
-      MZ_CUDA(cudaMemcpy(m->conv1 + static_cast<size_t>(layer) * packed.size(), packed.data(),
-                         packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      for (int sl = 0; sl < m->S; ++sl) {  // one packed bank per slice of ns output channels
+        const int n0 = sl * m->ns, rows = n0 < m->hC ? (m->hC - n0 < m->ns ? m->hC - n0 : m->ns) : 0;
+        pack_conv_weight_host(host_data + static_cast<size_t>(n0 < m->hC ? n0 : 0) * m->C * 9, rows, m->C, m->ns, m->Cz,
+                              m->bf16, packed);
+        MZ_CUDA(cudaMemcpy(m->conv1 + (static_cast<size_t>(layer) * m->S + sl) * packed.size(), packed.data(),
+                           packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      }
       break;
     }
     case MZ_W_CONV2: {
       MZ_REQUIRE(numel == static_cast<size_t>(m->hC) * m->C * 9, "conv2 weight: expected %d elements, got %zu",
                  m->hC * m->C * 9, numel);
-      pack_conv_weight_host(host_data, m->C, m->hC, m->Cp, m->hCp, m->bf16, packed);
-      MZ_CUDA(cudaMemcpy(m->conv2 + static_cast<size_t>(layer) * packed.size(), packed.data(),
-                         packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      for (int sl = 0; sl < m->S2; ++sl) {  // one packed bank per slice of ns2 output channels
+        const int n0 = sl * m->ns2, rows = n0 < m->C ? (m->C - n0 < m->ns2 ? m->C - n0 : m->ns2) : 0;
+        pack_conv_weight_host(host_data + static_cast<size_t>(n0 < m->C ? n0 : 0) * m->hC * 9, rows, m->hC, m->ns2, m->hCp,
+                              m->bf16, packed);
+        MZ_CUDA(cudaMemcpy(m->conv2 + (static_cast<size_t>(layer) * m->S2 + sl) * packed.size(), packed.data(),
+                           packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      }
       break;
     }
     case MZ_W_HEAD: {
@@ -398,49 +426,57 @@ int mz_upscale(mz_model* m, const void* x_dev_v, const float* c_dev, int32_t c_r
   int rc;
 
   if (m->F > 0) {
-    rc = launch_film(c_dev, c_rows, m->ctrl_w, m->ctrl_b, film, m->L, B, m->F, m->hC, m->hCp, s);
+    rc = launch_film(c_dev, c_rows, m->ctrl_w, m->ctrl_b, film, m->L, B, m->F, m->hC, m->hCp, m->ns, s);
     if (rc != MZ_OK) return rc;
   }
   rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, m->split ? nullptr : zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s);
   const int zpitch = m->split ? 2 * m->Cp : 0;  // channel pitch of the convolutions that read the stream
   if (rc != MZ_OK) return rc;
 
-  const size_t c1 = static_cast<size_t>(9) * m->hCp * m->Cz, c2 = static_cast<size_t>(9) * m->Cp * m->hCp;
   const int slot = m->timing_calls % kTimingSlots;
   if (m->timing) MZ_CUDA(cudaEventRecord(m->ev[2 * slot], s));
+  // one slice of conv1's / conv2's filter bank
+  const size_t c1s = static_cast<size_t>(9) * m->ns * m->Cz, c2s = static_cast<size_t>(9) * m->ns2 * m->hCp;
+  const int S = m->S, S2 = m->S2;
   for (int l = 0; l < m->L; ++l) {
     ConvArgs a;
-    memset(&a, 0, sizeof(a));
-    a.in = zb;
-    a.w = m->conv1 + l * c1;
-    a.cin_p = m->Cz;
-    a.in_pitch = zpitch;
-    a.epi.mode = 0;
-    a.epi.bf16 = m->bf16;
-    a.epi.B = B;
-    a.epi.H = H;
-    a.epi.W = W;
-    a.epi.n_pad = m->hCp;
-    a.epi.film = m->F > 0 ? film + static_cast<size_t>(l) * B * 2 * m->hCp : nullptr;
-    a.epi.out_bf16 = hid;
-    rc = simt ? launch_conv_simt(a, s) : run_conv(m, 2 * l, a, m->tune[0], s);
-    if (rc != MZ_OK) return rc;
+    for (int sl = 0; sl < S; ++sl) {
+      memset(&a, 0, sizeof(a));
+      a.in = zb;
+      a.w = m->conv1 + (static_cast<size_t>(l) * S + sl) * c1s;
+      a.cin_p = m->Cz;
+      a.in_pitch = zpitch;
+      a.epi.mode = 0;
+      a.epi.bf16 = m->bf16;
+      a.epi.B = B;
+      a.epi.H = H;
+      a.epi.W = W;
+      a.epi.n_pad = m->ns;
+      a.epi.film = m->F > 0 ? film + (static_cast<size_t>(l) * S + sl) * B * 2 * m->ns : nullptr;
+      a.epi.out_bf16 = hid + static_cast<size_t>(sl) * m->ns;
+      a.epi.out_pitch = S > 1 ? m->hCp : 0;
+      rc = simt ? launch_conv_simt(a, s) : run_conv(m, l * (S + S2) + sl, a, m->tune[0], s);
+      if (rc != MZ_OK) return rc;
+    }
 
-    memset(&a, 0, sizeof(a));
-    a.in = hid;
-    a.w = m->conv2 + l * c2;
-    a.cin_p = m->hCp;
-    a.epi.mode = m->split ? 3 : 1;
-    a.epi.bf16 = m->bf16;
-    a.epi.B = B;
-    a.epi.H = H;
-    a.epi.W = W;
-    a.epi.n_pad = m->Cp;
-    a.epi.out_bf16 = zb;
-    a.epi.out_pitch = m->Cz;
-    a.epi.zf = zf;
-    rc = simt ? launch_conv_simt(a, s) : run_conv(m, 2 * l + 1, a, m->tune[1], s);
-    if (rc != MZ_OK) return rc;
+    for (int sl = 0; sl < S2; ++sl) {
+      memset(&a, 0, sizeof(a));
+      a.in = hid;
+      a.w = m->conv2 + (static_cast<size_t>(l) * S2 + sl) * c2s;
+      a.cin_p = m->hCp;
+      a.epi.mode = m->split ? 3 : 1;
+      a.epi.bf16 = m->bf16;
+      a.epi.B = B;
+      a.epi.H = H;
+      a.epi.W = W;
+      a.epi.n_pad = m->ns2;
+      a.epi.out_bf16 = zb + static_cast<size_t>(sl) * m->ns2;
+      a.epi.out_pitch = m->Cz;
+      a.epi.zf = zf + static_cast<size_t>(sl) * m->ns2;
+      a.epi.zf_pitch = S2 > 1 ? m->Cp : 0;
+      rc = simt ? launch_conv_simt(a, s) : run_conv(m, l * (S + S2) + S + sl, a, m->tune[1], s);
+      if (rc != MZ_OK) return rc;
+    }
   }
 
   if (m->timing) {
@@ -475,7 +511,7 @@ int mz_upscale(mz_model* m, const void* x_dev_v, const float* c_dev, int32_t c_r
   a.epi.skip_mode = skip_mode;
   a.epi.clamp01 = (flags & MZ_FLAG_CLAMP01) ? 1 : 0;
   make_bicubic_table(m->r, &a.epi.bt);
-  return simt ? launch_conv_simt(a, s) : run_conv(m, 2 * m->L, a, m->tune[2], s);
+  return simt ? launch_conv_simt(a, s) : run_conv(m, m->L * (S + S2), a, m->tune[2], s);
 }
 
 // one chunk (B images) on one lane: H2D, kernels, D2H -- all asynchronous on the lane's stream

@@ -215,7 +215,7 @@ int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* 
 // ----------------------------------------------------------------------------------------------
 __global__ void film_kernel(const float* __restrict__ c, int c_rows, const float* __restrict__ w,
                             const float* __restrict__ bias, float* __restrict__ film, int L, int B, int F, int hC,
-                            int hCp) {
+                            int hCp, int ns) {
   const long long total = static_cast<long long>(L) * B * hCp;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -237,20 +237,23 @@ __global__ void film_kernel(const float* __restrict__ c, int c_rows, const float
       scale = 1.f + g;
       shift = be;
     }
-    float* dst = film + (static_cast<size_t>(l) * B + b) * 2 * hCp;
-    dst[n] = scale;
-    dst[hCp + n] = shift;
+    // [l][slice][b][scale row | shift row][ns]: one [B][2][ns] table per conv1 launch (ns == hCp: one slice)
+    const int sl = n / ns, j = n - sl * ns;
+    float* dst = film + ((static_cast<size_t>(l) * (hCp / ns) + sl) * B + b) * 2 * ns;
+    dst[j] = scale;
+    dst[ns + j] = shift;
   }
 }
 
 int launch_film(const float* c, int c_rows, const float* w, const float* b, float* film, int L, int B, int F, int hC,
-                int hCp, cudaStream_t s) {
+                int hCp, int ns, cudaStream_t s) {
   MZ_REQUIRE(c_rows == 1 || c_rows == B, "Batch size of c (%d) must match x (%d).", c_rows, B);
   MZ_REQUIRE(L > 0 && B > 0 && F > 0 && hC > 0 && hCp >= hC, "film: bad shape");
+  MZ_REQUIRE(ns > 0 && hCp % ns == 0, "film: slice width %d does not divide the padded width %d", ns, hCp);
   const long long total = static_cast<long long>(L) * B * hCp;
   long long blocks = (total + 255) / 256;
   if (blocks > 1024) blocks = 1024;
-  film_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(c, c_rows, w, b, film, L, B, F, hC, hCp);
+  film_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(c, c_rows, w, b, film, L, B, F, hC, hCp, ns);
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }
