@@ -15,7 +15,7 @@ done
 if [ "${REF:-0}" = "1" ]; then python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_$TAG.json 2> gpurun_out/bench_ref_$TAG.err; cat gpurun_out/bench_ref_$TAG.json; fi
 if [ "${NCU:-0}" = "1" ]; then
   NW=${NCU_WL:-cfg4a}
-  CMD="python bench.py --workload $NW --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
+  CMD="python bench.py --workload $NW --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-also"
   $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -s ${NCU_SKIP:-249} -c ${NCU_COUNT:-83} --csv --log-file gpurun_out/launches_${NW}_$TAG.csv $CMD > gpurun_out/ncu1_$TAG.log 2>&1
   echo "ncu launches rc=$?"
