@@ -217,6 +217,13 @@ int mz_control_film(const float* c_dev, int32_t c_rows, const float* w_dev /*L,2
                     const float* b_dev /*L,2hC*/, float* film_dev /*L,B,2,hCp*/, int32_t L, int32_t B,
                     int32_t F, int32_t hC, int32_t hCp, void* stream);
 
+/* Spatial sharding (partitioning 2): put a tile's HR core -- `height` rows of `width_bytes` bytes at
+ * pitch `spitch` -- into the assembled frame at pitch `dpitch`, asynchronously on `stream`.  `dst` may live on another
+ * GPU (a peer mapping opened from the owner's IPC handle) or in pinned host memory: a one-sided cudaMemcpy2DAsync, no
+ * collective.  One call per colour plane of the tile. */
+int mz_put_plane_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
+                       void* stream);
+
 /* Hardware probes used by tests and DESIGN.md (not on the hot path).
  * mz_probe_umma: one 128 x 64 x kc UMMA whose A descriptor starts `row_shift` rows into a
  * TMA-swizzled tile; base_offset_mode 0 leaves the descriptor's base_offset 0, 1 sets it to

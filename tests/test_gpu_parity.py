@@ -314,3 +314,34 @@ def test_hidden_widths_beyond_one_umma_tile(dev, cfg, tol):
     ys = m.upscale(x.to(dev), cd)
     m._flags_extra = 0
     assert (y - ys).abs().max().item() <= 2e-3
+
+
+def test_put_core_assembles_the_frame(dev):
+    """Spatial sharding, stitch step: each tile's HR core is put into the assembled frame with 2-D
+    copies (mz_put_plane_async) -- into a device buffer (a peer GPU's in the multi-GPU run, tools/tiled_8k.py) or into
+    pinned host memory; the assembled frame equals the un-tiled result bit for bit."""
+    from ultrazoom_b200 import MODEL_CONFIGS, MewZoom
+    from ultrazoom_b200.sharding import halo_radius, plan_tiles, put_core, run_tile
+
+    torch.manual_seed(31)
+    cfg = dict(MODEL_CONFIGS["MewZoom-2X-Ctrl"])
+    cfg["num_encoder_layers"] = 4
+    m = MewZoom(**cfg).to(dev).eval()
+    g = torch.Generator().manual_seed(32)
+    x, c = torch.rand(2, 3, 70, 300, generator=g).to(dev), torch.rand(2, 3, generator=g).to(dev)
+    full = m.upscale(x, c)
+    plan = plan_tiles(70, 300, 2, 2, halo_radius(4), align_w=128)
+    on_gpu = torch.zeros_like(full)
+    on_host = torch.zeros(full.shape, dtype=full.dtype).pin_memory()
+    for t in plan:
+        core = run_tile(m.upscale, x, c, t, 2)
+        put_core(on_gpu, core, t, 2)
+        put_core(on_host, core, t, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(on_gpu, full) and torch.equal(on_host, full.cpu())
+    x8 = (x * 255).to(torch.uint8)                                       # 8-bit frames stitch the same way
+    full8, frame8 = m.upscale(x8, c), torch.zeros(2, 3, 140, 600, dtype=torch.uint8, device=dev)
+    for t in plan:
+        put_core(frame8, run_tile(m.upscale, x8, c, t, 2), t, 2)
+    torch.cuda.synchronize()
+    assert torch.equal(frame8, full8)

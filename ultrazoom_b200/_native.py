@@ -83,6 +83,7 @@ SIGNATURES = {
     "mz_upscale_host": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, C.c_uint32]),
     "mz_upscale_host_async": (C.c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, C.c_uint32]),
     "mz_upscale_host_wait": (C.c_int, [_P, _I]),
+    "mz_put_plane_async": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.c_size_t, C.c_size_t, _P]),
     "mz_bicubic_f32": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "mz_stem_pack": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mz_conv3x3": (C.c_int, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),

@@ -149,6 +149,45 @@ int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t 
   return MZ_OK;
 }
 
+int mz_put_plane_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
+                       void* stream) {
+  MZ_REQUIRE(dst && src, "put_plane: null pointer");
+  MZ_REQUIRE(width_bytes > 0 && height > 0 && dpitch >= width_bytes && spitch >= width_bytes,
+             "put_plane: bad geometry (width %zu bytes, height %zu, pitches %zu / %zu)", width_bytes, height, dpitch, spitch);
+  // a put into another GPU's memory goes over NVLink only with peer access enabled between the two devices in THIS
+  // process (a mapping opened from an IPC handle does not imply it); without it the runtime stages through the host
+  cudaPointerAttributes as, ad;
+  if (cudaPointerGetAttributes(&as, src) == cudaSuccess && cudaPointerGetAttributes(&ad, dst) == cudaSuccess &&
+      as.type == cudaMemoryTypeDevice && ad.type == cudaMemoryTypeDevice && as.device != ad.device) {
+    static bool enabled[64][64];
+    const int a = as.device, b = ad.device;
+    if (a >= 0 && a < 64 && b >= 0 && b < 64 && !enabled[a][b]) {
+      int prev = 0;
+      MZ_CUDA(cudaGetDevice(&prev));
+      const int pair[2][2] = {{a, b}, {b, a}};
+      for (const auto& pr : pair) {
+        int can = 0;
+        MZ_CUDA(cudaDeviceCanAccessPeer(&can, pr[0], pr[1]));
+        if (!can) continue;
+        MZ_CUDA(cudaSetDevice(pr[0]));
+        const cudaError_t e = cudaDeviceEnablePeerAccess(pr[1], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          cudaSetDevice(prev);
+          MZ_CUDA(e);
+        }
+        cudaGetLastError();  // (clears cudaErrorPeerAccessAlreadyEnabled)
+      }
+      MZ_CUDA(cudaSetDevice(prev));
+      enabled[a][b] = enabled[b][a] = true;
+    }
+  } else {
+    cudaGetLastError();  // (an unregistered host pointer makes cudaPointerGetAttributes fail on old drivers)
+  }
+  MZ_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height, cudaMemcpyDefault,
+                            static_cast<cudaStream_t>(stream)));
+  return MZ_OK;
+}
+
 int mz_control_film(const float* c_dev, int32_t c_rows, const float* w_dev, const float* b_dev, float* film_dev,
                     int32_t L, int32_t B, int32_t F, int32_t hC, int32_t hCp, void* stream) {
   MZ_REQUIRE(c_dev && w_dev && b_dev && film_dev, "film: null pointer");

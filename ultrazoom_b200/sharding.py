@@ -144,3 +144,47 @@ def upscale_tiled(fn: Callable[[Tensor, Optional[Tensor]], Tensor], x: Tensor, c
             continue
         stitch(out, run_tile(fn, x, c, t, r), t, r)
     return out
+
+
+# ---- assembling the frame on one GPU: one-sided puts over NVLink, no collective --------------------
+def share_frame(frame: Optional[Tensor], owner: int, rank: int, group=None) -> Tensor:
+    """Make the owner's HR frame addressable from every rank of this node.
+
+    The owner passes its CUDA tensor; its allocation is exported as a CUDA IPC handle, handed to the other ranks ONCE
+    over the control plane (``broadcast_object_list``) and mapped there with lazy peer access, so ``put_core`` can write
+    into it directly through NVLink / NVSwitch.  Returns the tensor on every rank (the owner's own, a peer view
+    elsewhere).  Call it outside the timed loop; keep the returned tensor alive while puts are in flight."""
+    import torch.distributed as dist
+
+    meta = [None]
+    if rank == owner:
+        assert frame is not None and frame.is_cuda and frame.is_contiguous()
+        meta[0] = (tuple(frame.shape), frame.dtype, frame.storage_offset(), frame.untyped_storage()._share_cuda_())
+    dist.broadcast_object_list(meta, src=owner, group=group)
+    if rank == owner:
+        return frame
+    shape, dtype, offset, handle = meta[0]
+    storage = torch.UntypedStorage._new_shared_cuda(*handle)
+    view = torch.empty(0, dtype=dtype, device=storage.device)
+    view.set_(storage, offset, shape)
+    return view
+
+
+def put_core(frame: Tensor, tile_out: Tensor, t: Tile, r: int) -> None:
+    """Write the HR core of tile ``t`` (``run_tile``'s result on this rank's GPU) into ``frame`` -- which may live on
+    another GPU (``share_frame``) or in pinned host memory -- as 2-D copies on the current stream (mz_put_plane_async),
+    one per image plane.  Nothing synchronises: order a later reader with an event or the timing barrier."""
+    from . import _native
+
+    lib = _native.load()
+    B, C, h, w = tile_out.shape
+    assert (h, w) == ((t.y1 - t.y0) * r, (t.x1 - t.x0) * r) and frame.shape[:2] == tile_out.shape[:2]
+    assert tile_out.stride(3) == 1 and frame.stride(3) == 1 and frame.dtype == tile_out.dtype
+    es = tile_out.element_size()
+    stream = torch.cuda.current_stream(tile_out.device).cuda_stream
+    for b in range(B):
+        for ch in range(C):
+            dst = frame[b, ch, t.y0 * r:t.y1 * r, t.x0 * r:t.x1 * r]
+            src = tile_out[b, ch]
+            _native.check(lib.mz_put_plane_async(dst.data_ptr(), dst.stride(0) * es, src.data_ptr(), src.stride(0) * es,
+                                                 w * es, h, stream))
