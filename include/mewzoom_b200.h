@@ -120,6 +120,21 @@ int mz_upscale(mz_model* m, const void* x_dev, const float* c_dev, int32_t c_row
                int32_t B, int32_t H, int32_t W, void* workspace_dev, size_t workspace_bytes,
                uint32_t flags, void* stream);
 
+/* The same call with a WINDOWED output, for halo-tiled inference (partitioning 2): of the (H, W) input
+ * tile only the LR pixels win_y0 <= y < win_y1, win_x0 <= x < win_x1 (the tile's core) are written, and they go
+ * straight into an assembled frame: y_dev is where HR pixel (win_y0 * r, win_x0 * r) of plane 0 of image 0 lands,
+ * HR rows are y_row_pitch elements apart and the three colour planes (and then the images) y_plane_pitch elements.
+ * y_dev may be another GPU's memory with peer access enabled (mz_enable_peer_access): the head kernel's stores then ARE
+ * the transfer over NVLink -- no tile output buffer, no copy, no collective.  The bicubic skip is always recomputed. */
+int mz_upscale_window(mz_model* m, const void* x_dev, const float* c_dev, int32_t c_rows, void* y_dev,
+                      int64_t y_row_pitch, int64_t y_plane_pitch, int32_t B, int32_t H, int32_t W, int32_t win_y0,
+                      int32_t win_y1, int32_t win_x0, int32_t win_x1, void* workspace_dev, size_t workspace_bytes,
+                      uint32_t flags, void* stream);
+
+/* Enable peer access between two visible devices in this process, both directions (idempotent).  Needed before kernels
+ * or copies of device `a` touch memory of device `b` that was mapped from a CUDA IPC handle. */
+int mz_enable_peer_access(int32_t a, int32_t b);
+
 /* Same call with HOST buffers: H2D copy of x (and c), the kernels, D2H copy of y, stream
  * synchronise.  Workspace and staging buffers are owned (and cached) by the model.  This is
  * the end-to-end entry point bench.py times as `e2e`. */
@@ -223,6 +238,15 @@ int mz_control_film(const float* c_dev, int32_t c_rows, const float* w_dev /*L,2
  * collective.  One call per colour plane of the tile. */
 int mz_put_plane_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
                        void* stream);
+
+/* The assembled frame of a multi-process (one process per GPU) tiled run.  The owner allocates it and gets a 64-byte
+ * CUDA IPC handle to hand to the other processes of the node (control plane: any byte transport); each of them opens
+ * it WITH ITS OWN GPU CURRENT, which maps the owner's memory for that GPU's kernels and copy engines over NVLink
+ * (cudaIpcMemLazyEnablePeerAccess) -- a mapping opened under another device is reachable by copies only.
+ * close: owner != 0 frees the allocation, otherwise the mapping is released. */
+int mz_ipc_frame_create(size_t bytes, void** dev_ptr, void* handle64);
+int mz_ipc_frame_open(const void* handle64, void** dev_ptr);
+int mz_ipc_frame_close(void* dev_ptr, int32_t owner);
 
 /* Hardware probes used by tests and DESIGN.md (not on the hot path).
  * mz_probe_umma: one 128 x 64 x kc UMMA whose A descriptor starts `row_shift` rows into a

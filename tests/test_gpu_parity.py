@@ -339,9 +339,56 @@ def test_put_core_assembles_the_frame(dev):
         put_core(on_host, core, t, 2)
     torch.cuda.synchronize()
     assert torch.equal(on_gpu, full) and torch.equal(on_host, full.cpu())
+    from ultrazoom_b200.sharding import run_tile_into, share_frame
+
+    shared = share_frame(tuple(full.shape), torch.float32, 0, 0, dev)    # the IPC-exportable frame (owner side here)
+    assert torch.count_nonzero(shared.tensor).item() == 0
+    for t in plan[:2]:
+        put_core(shared.tensor, run_tile(m.upscale, x, c, t, 2), t, 2)
+    for t in plan[2:]:
+        run_tile_into(m, x, c, t, 2, shared.tensor)
+    torch.cuda.synchronize()
+    assert torch.equal(shared.tensor, full)
+    shared.close()
     x8 = (x * 255).to(torch.uint8)                                       # 8-bit frames stitch the same way
     full8, frame8 = m.upscale(x8, c), torch.zeros(2, 3, 140, 600, dtype=torch.uint8, device=dev)
     for t in plan:
         put_core(frame8, run_tile(m.upscale, x8, c, t, 2), t, 2)
     torch.cuda.synchronize()
     assert torch.equal(frame8, full8)
+
+
+@pytest.mark.parametrize("name", ["MewZoom-2X-Ctrl", "MewZoom-3X-Ctrl", "MewZoom-4X-Ctrl"])
+def test_windowed_output_assembles_the_frame(dev, name):
+    """mz_upscale_window: the head kernel of each haloed tile stores only the tile's core, straight into the assembled
+    frame (the multi-GPU run points it at a peer GPU's buffer: tools/tiled_8k.py).  The frame equals the un-tiled
+    result bit for bit, float and 8-bit images, tcgen05 and SIMT kernels; nothing outside a window is touched."""
+    from ultrazoom_b200 import MODEL_CONFIGS, MewZoom, _native
+    from ultrazoom_b200.sharding import halo_radius, plan_tiles, run_tile_into
+
+    torch.manual_seed(41)
+    cfg = dict(MODEL_CONFIGS[name])
+    cfg["num_encoder_layers"] = 3
+    r = cfg["upscale_ratio"]
+    m = MewZoom(**cfg).to(dev).eval()
+    g = torch.Generator().manual_seed(42)
+    x, c = torch.rand(2, 3, 45, 290, generator=g).to(dev), torch.rand(2, 3, generator=g).to(dev)
+    plan = plan_tiles(45, 290, 2, 2, halo_radius(3), align_w=128)
+    for simt in (0, _native.FLAG_SIMT_CONV):
+        m._flags_extra = simt
+        full = m.upscale(x, c)
+        frame = torch.full_like(full, -1.0)
+        for t in plan[:-1]:
+            run_tile_into(m, x, c, t, r, frame)
+        last = plan[-1]
+        assert torch.all(frame[:, :, last.y0 * r:last.y1 * r, last.x0 * r:last.x1 * r] == -1.0)   # untouched so far
+        run_tile_into(m, x, c, last, r, frame)
+        assert torch.equal(frame, full), (name, simt, (frame - full).abs().max().item())
+    m._flags_extra = 0
+    x8 = (x * 255).to(torch.uint8)
+    full8, frame8 = m.upscale(x8, c), torch.zeros(2, 3, 45 * r, 290 * r, dtype=torch.uint8, device=dev)
+    for t in plan:
+        run_tile_into(m, x8, c, t, r, frame8)
+    assert torch.equal(frame8, full8)
+    with pytest.raises(AssertionError):                                  # a window that does not fit the frame
+        m.upscale_into(x, c, frame, (0, 45, 0, 290), (r, 0))

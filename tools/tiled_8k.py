@@ -6,7 +6,9 @@ rank (one process per GPU, no collective on the data path; NCCL only for the tim
 
 Every rank runs the whole network on its haloed tile (halo = 2L+1 = 81 LR pixels, exact) and puts the HR core of the
 tile into the frame assembled on rank 0's GPU: a one-sided 2-D copy over NVLink into rank 0's buffer, mapped once
-through a CUDA IPC handle (sharding.share_frame / put_core); `--no-stitch` leaves the cores on their GPUs.  Strong
+through a CUDA IPC handle (sharding.share_frame): by default the head kernel of the tile stores its core straight into
+that buffer (run_tile_into -> mz_upscale_window: the stores are the transfer), `--copy-put` writes the tile locally and
+copies the core (put_core), `--no-stitch` leaves the cores on their GPUs.  Strong
 scaling: value = 33.2 output Mpx / max-over-ranks device time, puts included.  Rank 0 checks the assembled frame
 against the un-tiled result.  Prints one JSON line."""
 import json
@@ -20,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ultrazoom_b200 import MODEL_CONFIGS, MewZoom  # noqa: E402
 from ultrazoom_b200.sharding import (best_grid, frames_for_rank, halo_radius, plan_tiles, put_core, run_tile,  # noqa: E402
-                                     share_frame)
+                                     run_tile_into, share_frame)
 
 
 def main():
@@ -45,11 +47,16 @@ def main():
     stitched = "--no-stitch" not in sys.argv
     frame = None
     if stitched:                                       # the assembled 8K frame lives on rank 0's GPU
-        frame = torch.zeros(1, 3, H * r, W * r, device=dev) if rank == 0 else None
-        if world > 1:
-            frame = share_frame(frame, 0, rank)
+        shared = share_frame((1, 3, H * r, W * r), torch.float32, 0, rank, dev)
+        frame = shared.tensor
+
+    copy_put = "--copy-put" in sys.argv
 
     def step():
+        if stitched and not copy_put:
+            for t in mine:
+                run_tile_into(model, x, c, t, r, frame)
+            return None
         cores = [run_tile(model.upscale, x, c, t, r) for t in mine]
         if stitched:
             for t, core in zip(mine, cores):
@@ -88,8 +95,14 @@ def main():
             "config": {"workload": "MewZoom-4X-Ctrl 96ch/40L, one 1920x1080->7680x4320 frame, halo-tiled "
                                    f"{rows}x{cols} (BASELINE configs[4])", "halo_lr_px": halo_radius(L),
                        "executed_over_algorithmic_work": executed,
-                       "stitch": "one-sided 2-D puts into rank 0's frame (CUDA IPC peer mapping)" if stitched else "none"},
+                       "stitch": ("none" if not stitched else "2-D copies of the cores into rank 0's frame (CUDA IPC peer mapping)"
+                                  if copy_put else "head kernel stores the core into rank 0's frame (CUDA IPC peer mapping)")},
             "max_abs_diff_vs_untiled": err}), flush=True)
+    if world > 1:
+        dist.barrier()
+    if stitched:
+        frame = None
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -80,6 +80,12 @@ SIGNATURES = {
     "mz_model_conv_stack_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "mz_workspace_bytes": (C.c_int, [_P, _I, _I, _I, C.POINTER(C.c_size_t)]),
     "mz_upscale": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _P, C.c_size_t, C.c_uint32, _P]),
+    "mz_upscale_window": (C.c_int, [_P, _P, _P, _I, _P, C.c_int64, C.c_int64, _I, _I, _I, _I, _I, _I, _I, _P, C.c_size_t,
+                                    C.c_uint32, _P]),
+    "mz_enable_peer_access": (C.c_int, [_I, _I]),
+    "mz_ipc_frame_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), _P]),
+    "mz_ipc_frame_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "mz_ipc_frame_close": (C.c_int, [_P, _I]),
     "mz_upscale_host": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, C.c_uint32]),
     "mz_upscale_host_async": (C.c_int, [_P, _I, _P, _P, _I, _P, _I, _I, _I, C.c_uint32]),
     "mz_upscale_host_wait": (C.c_int, [_P, _I]),

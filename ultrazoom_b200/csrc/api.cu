@@ -1,6 +1,8 @@
 // api.cu -- extern "C" per-kernel entry points declared in include/mewzoom_b200.h.
 #include <vector>
 
+#include <string.h>
+
 #include "kernels.cuh"
 
 namespace mz {
@@ -149,6 +151,34 @@ int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t 
   return MZ_OK;
 }
 
+int mz_enable_peer_access(int32_t a, int32_t b) {
+  static bool enabled[64][64];
+  MZ_REQUIRE(a >= 0 && a < 64 && b >= 0 && b < 64, "enable_peer_access: device index out of range (%d, %d)", a, b);
+  if (a == b || enabled[a][b]) return MZ_OK;
+  int prev = 0;
+  MZ_CUDA(cudaGetDevice(&prev));
+  const int pair[2][2] = {{a, b}, {b, a}};
+  for (const auto& pr : pair) {
+    int can = 0;
+    MZ_CUDA(cudaDeviceCanAccessPeer(&can, pr[0], pr[1]));
+    if (!can) {
+      cudaSetDevice(prev);
+      set_error("enable_peer_access: device %d cannot access device %d", pr[0], pr[1]);
+      return MZ_ERR_UNSUPPORTED;
+    }
+    MZ_CUDA(cudaSetDevice(pr[0]));
+    const cudaError_t e = cudaDeviceEnablePeerAccess(pr[1], 0);
+    cudaGetLastError();  // (clears cudaErrorPeerAccessAlreadyEnabled)
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+      cudaSetDevice(prev);
+      MZ_CUDA(e);
+    }
+  }
+  MZ_CUDA(cudaSetDevice(prev));
+  enabled[a][b] = enabled[b][a] = true;
+  return MZ_OK;
+}
+
 int mz_put_plane_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t height,
                        void* stream) {
   MZ_REQUIRE(dst && src, "put_plane: null pointer");
@@ -159,32 +189,48 @@ int mz_put_plane_async(void* dst, size_t dpitch, const void* src, size_t spitch,
   cudaPointerAttributes as, ad;
   if (cudaPointerGetAttributes(&as, src) == cudaSuccess && cudaPointerGetAttributes(&ad, dst) == cudaSuccess &&
       as.type == cudaMemoryTypeDevice && ad.type == cudaMemoryTypeDevice && as.device != ad.device) {
-    static bool enabled[64][64];
-    const int a = as.device, b = ad.device;
-    if (a >= 0 && a < 64 && b >= 0 && b < 64 && !enabled[a][b]) {
-      int prev = 0;
-      MZ_CUDA(cudaGetDevice(&prev));
-      const int pair[2][2] = {{a, b}, {b, a}};
-      for (const auto& pr : pair) {
-        int can = 0;
-        MZ_CUDA(cudaDeviceCanAccessPeer(&can, pr[0], pr[1]));
-        if (!can) continue;
-        MZ_CUDA(cudaSetDevice(pr[0]));
-        const cudaError_t e = cudaDeviceEnablePeerAccess(pr[1], 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
-          cudaSetDevice(prev);
-          MZ_CUDA(e);
-        }
-        cudaGetLastError();  // (clears cudaErrorPeerAccessAlreadyEnabled)
-      }
-      MZ_CUDA(cudaSetDevice(prev));
-      enabled[a][b] = enabled[b][a] = true;
-    }
+    (void)mz_enable_peer_access(as.device, ad.device);  // (without a peer path the copy still works, through the host)
   } else {
     cudaGetLastError();  // (an unregistered host pointer makes cudaPointerGetAttributes fail on old drivers)
   }
   MZ_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height, cudaMemcpyDefault,
                             static_cast<cudaStream_t>(stream)));
+  return MZ_OK;
+}
+
+int mz_ipc_frame_create(size_t bytes, void** dev_ptr, void* handle64) {
+  MZ_REQUIRE(bytes > 0 && dev_ptr && handle64, "ipc_frame_create: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI passes IPC handles as 64 bytes");
+  *dev_ptr = nullptr;
+  void* p = nullptr;
+  MZ_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    MZ_CUDA(e);
+  }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return MZ_OK;
+}
+
+int mz_ipc_frame_open(const void* handle64, void** dev_ptr) {
+  MZ_REQUIRE(handle64 && dev_ptr, "ipc_frame_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  *dev_ptr = nullptr;
+  MZ_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MZ_OK;
+}
+
+int mz_ipc_frame_close(void* dev_ptr, int32_t owner) {
+  if (!dev_ptr) return MZ_OK;
+  if (owner)
+    MZ_CUDA(cudaFree(dev_ptr));
+  else
+    MZ_CUDA(cudaIpcCloseMemHandle(dev_ptr));
   return MZ_OK;
 }
 

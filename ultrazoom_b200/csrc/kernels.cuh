@@ -56,8 +56,22 @@ struct EpiParams {
   int r;
   int skip_mode;  // 0 none, 1 y already holds the bicubic image, 2 recompute bicubic from x
   int clamp01;
+  // Windowed output (mz_upscale_window; all zero = the whole image, densely): only LR pixels wy0 <= y < wy1,
+  // wx0 <= x < wx1 are stored, pixel (wy0, wx0) of plane 0 of image 0 at y / y8 itself, HR rows y_row elements and
+  // colour planes y_plane elements apart -- a tile's core written straight into an assembled (possibly remote) frame.
+  int wy0, wy1, wx0, wx1;
+  long long y_row, y_plane;
   BicubicTable bt;
 };
+
+// address of HR pixel (oy, ox) of colour plane (b, c) in the output of mode 2, or -1 outside the window
+__host__ __device__ inline long long head_out_index(const EpiParams& p, int b, int c, int y, int x, int i, int j) {
+  const long long WR = static_cast<long long>(p.W) * p.r, HR = static_cast<long long>(p.H) * p.r;
+  if (p.wy1 > 0 && (y < p.wy0 || y >= p.wy1 || x < p.wx0 || x >= p.wx1)) return -1;
+  const long long row = p.y_row ? p.y_row : WR, plane = p.y_plane ? p.y_plane : HR * WR;
+  return (static_cast<long long>(b) * 3 + c) * plane + (static_cast<long long>(y - p.wy0) * p.r + i) * row +
+         static_cast<long long>(x - p.wx0) * p.r + j;
+}
 
 // One 3x3 convolution launch (both kernels).
 struct ConvArgs {
@@ -228,13 +242,13 @@ __device__ __forceinline__ float bicubic_at(const T* __restrict__ plane, int H, 
 template <int NMAX>
 __device__ __forceinline__ void epi_head(const EpiParams& p, int b, int y, int x, const float (&acc)[NMAX]) {
   const int r = p.r, rr = r * r;
-  const int HR = p.H * r, WR = p.W * r;
 #pragma unroll
   for (int n = 0; n < NMAX; ++n) {
     if (n < 3 * rr) {
       const int c = n / rr, i = (n % rr) / r, j = n % r;
       const int oy = y * r + i, ox = x * r + j;
-      const size_t di = ((static_cast<size_t>(b) * 3 + c) * HR + oy) * WR + ox;
+      const long long di = head_out_index(p, b, c, y, x, i, j);
+      if (di < 0) continue;
       float v = acc[n];
       if (p.skip_mode == 1) {
         v += p.y[di];
@@ -257,7 +271,10 @@ __device__ __forceinline__ void epi_head(const EpiParams& p, int b, int y, int x
 template <int R>
 __device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int x, const float (&acc)[48]) {
   const int H = p.H, W = p.W;
-  const size_t HR = static_cast<size_t>(H) * R, WR = static_cast<size_t>(W) * R;
+  const long long first = head_out_index(p, b, 0, y, x, 0, 0);
+  if (first < 0) return;  // outside the output window
+  const size_t row_pitch = p.y_row ? static_cast<size_t>(p.y_row) : static_cast<size_t>(W) * R;
+  const size_t plane_pitch = p.y_plane ? static_cast<size_t>(p.y_plane) : static_cast<size_t>(H) * R * W * R;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float out[R][R];
@@ -265,7 +282,7 @@ __device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int
     for (int i = 0; i < R; ++i)
 #pragma unroll
       for (int j = 0; j < R; ++j) out[i][j] = acc[c * R * R + i * R + j];
-    const size_t d0 = ((static_cast<size_t>(b) * 3 + c) * HR + static_cast<size_t>(y) * R) * WR + static_cast<size_t>(x) * R;
+    const size_t d0 = static_cast<size_t>(first) + c * plane_pitch;
     float* dst = p.y + d0;
     if (p.skip_mode == 2) {
       const size_t pl = (static_cast<size_t>(b) * 3 + c) * H * W;
@@ -303,7 +320,7 @@ __device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int
     if (p.y8 != nullptr) {  // 8-bit output: R bytes per HR row segment (a warp writes 32 * R contiguous bytes)
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        uint8_t* rowp = p.y8 + d0 + static_cast<size_t>(i) * WR;
+        uint8_t* rowp = p.y8 + d0 + static_cast<size_t>(i) * row_pitch;
         uint32_t w = 0;
 #pragma unroll
         for (int j = 0; j < R; ++j) w |= static_cast<uint32_t>(to_u8(out[i][j], p.u8_trunc)) << (8 * j);
@@ -320,7 +337,7 @@ __device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int
     }
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      float* rowp = dst + static_cast<size_t>(i) * WR;
+      float* rowp = dst + static_cast<size_t>(i) * row_pitch;
       if (p.skip_mode == 1) {
 #pragma unroll
         for (int j = 0; j < R; ++j) out[i][j] += rowp[j];

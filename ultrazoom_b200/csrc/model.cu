@@ -384,8 +384,17 @@ int mz_workspace_bytes(const mz_model* m, int32_t B, int32_t H, int32_t W, size_
   return MZ_OK;
 }
 
-int mz_upscale(mz_model* m, const void* x_dev_v, const float* c_dev, int32_t c_rows, void* y_dev_v, int32_t B, int32_t H,
-               int32_t W, void* workspace_dev, size_t workspace_bytes, uint32_t flags, void* stream) {
+}  // extern "C"
+
+// output window of mz_upscale_window (nullptr: the whole image, densely)
+struct OutWindow {
+  int y0, y1, x0, x1;
+  long long row_pitch, plane_pitch;
+};
+
+static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, int32_t c_rows, void* y_dev_v, int32_t B,
+                        int32_t H, int32_t W, void* workspace_dev, size_t workspace_bytes, uint32_t flags, void* stream,
+                        const OutWindow* win) {
   MZ_REQUIRE(m && x_dev_v && y_dev_v && workspace_dev, "upscale: null pointer");
   const bool io8 = (flags & MZ_FLAG_IO_U8) != 0;
   MZ_REQUIRE(!io8 || ((flags & MZ_FLAG_CLAMP01) && !(flags & MZ_FLAG_SKIP_FROM_BUFFER)),
@@ -510,8 +519,43 @@ int mz_upscale(mz_model* m, const void* x_dev_v, const float* c_dev, int32_t c_r
   a.epi.r = m->r;
   a.epi.skip_mode = skip_mode;
   a.epi.clamp01 = (flags & MZ_FLAG_CLAMP01) ? 1 : 0;
+  if (win) {
+    a.epi.wy0 = win->y0;
+    a.epi.wy1 = win->y1;
+    a.epi.wx0 = win->x0;
+    a.epi.wx1 = win->x1;
+    a.epi.y_row = win->row_pitch;
+    a.epi.y_plane = win->plane_pitch;
+  }
   make_bicubic_table(m->r, &a.epi.bt);
   return simt ? launch_conv_simt(a, s) : run_conv(m, m->L * (S + S2), a, m->tune[2], s);
+}
+
+extern "C" {
+
+int mz_upscale(mz_model* m, const void* x_dev, const float* c_dev, int32_t c_rows, void* y_dev, int32_t B, int32_t H,
+               int32_t W, void* workspace_dev, size_t workspace_bytes, uint32_t flags, void* stream) {
+  return upscale_impl(m, x_dev, c_dev, c_rows, y_dev, B, H, W, workspace_dev, workspace_bytes, flags, stream, nullptr);
+}
+
+int mz_upscale_window(mz_model* m, const void* x_dev, const float* c_dev, int32_t c_rows, void* y_dev, int64_t y_row_pitch,
+                      int64_t y_plane_pitch, int32_t B, int32_t H, int32_t W, int32_t win_y0, int32_t win_y1,
+                      int32_t win_x0, int32_t win_x1, void* workspace_dev, size_t workspace_bytes, uint32_t flags,
+                      void* stream) {
+  MZ_REQUIRE(m, "upscale_window: null model");
+  MZ_REQUIRE(0 <= win_y0 && win_y0 < win_y1 && win_y1 <= H && 0 <= win_x0 && win_x0 < win_x1 && win_x1 <= W,
+             "upscale_window: window [%d, %d) x [%d, %d) is not inside the %d x %d input", win_y0, win_y1, win_x0, win_x1,
+             H, W);
+  const int64_t r = m->r;
+  MZ_REQUIRE(y_row_pitch >= (win_x1 - win_x0) * r && y_plane_pitch >= y_row_pitch * (win_y1 - win_y0) * r,
+             "upscale_window: pitches (%lld, %lld) are smaller than the window", static_cast<long long>(y_row_pitch),
+             static_cast<long long>(y_plane_pitch));
+  MZ_REQUIRE(!(flags & MZ_FLAG_SKIP_FROM_BUFFER), "upscale_window: the bicubic skip is recomputed (no MZ_FLAG_SKIP_FROM_BUFFER)");
+  const int es = (flags & MZ_FLAG_IO_U8) ? 1 : 4, vec = m->r == 3 ? es : es * m->r;  // bytes of one vector store
+  MZ_REQUIRE(reinterpret_cast<uintptr_t>(y_dev) % vec == 0 && (y_row_pitch * es) % vec == 0 && (y_plane_pitch * es) % vec == 0,
+             "upscale_window: y and its pitches must be aligned to %d bytes", vec);
+  const OutWindow w{win_y0, win_y1, win_x0, win_x1, y_row_pitch, y_plane_pitch};
+  return upscale_impl(m, x_dev, c_dev, c_rows, y_dev, B, H, W, workspace_dev, workspace_bytes, flags, stream, &w);
 }
 
 // one chunk (B images) on one lane: H2D, kernels, D2H -- all asynchronous on the lane's stream

@@ -312,6 +312,43 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         ``ToPILImage`` does (README.md:81) when ``model.u8_truncate`` is set: a quarter of the image traffic."""
         return self._run(x, c, _native.FLAG_CLAMP01)
 
+    @torch.inference_mode()
+    def upscale_into(self, x: Tensor, c: Optional[Tensor], frame: Tensor, window: tuple, at: tuple) -> None:
+        """Halo-tiled inference without a tile output: ``upscale`` the LR tile ``x`` and write only its core -- the LR
+        pixels ``window = (y0, y1, x0, x1)`` of the tile -- straight into ``frame`` (B,3,rH',rW'), whose HR pixel
+        ``at = (fy, fx)`` receives the core's first pixel (mz_upscale_window).  ``frame`` may live on another GPU
+        (``sharding.share_frame``): the head kernel's stores are then the transfer over NVLink."""
+        c = self._check_inputs(x, c)
+        if not x.is_cuda:
+            raise RuntimeError("ultrazoom_b200.MewZoom runs on sm_100a CUDA kernels only (no CPU fallback).")
+        dev = x.device
+        eng = self._engine(dev)
+        io8 = x.dtype == torch.uint8
+        flags = _native.FLAG_CLAMP01 | self._flags_extra
+        if io8:
+            flags |= _native.FLAG_IO_U8 | (_native.FLAG_U8_TRUNC if self.u8_truncate else 0)
+        x = x.detach().contiguous() if io8 else x.detach().to(torch.float32).contiguous()
+        if c is not None:
+            c = c.detach().to(device=dev, dtype=torch.float32).contiguous()
+        B, _, H, W = x.shape
+        r = self.upscale_ratio
+        y0, y1, x0, x1 = window
+        fy, fx = at
+        assert frame.is_cuda and frame.dim() == 4 and frame.shape[0] == B and frame.shape[1] == 3, "frame must be (B,3,H',W')"
+        assert frame.dtype == (torch.uint8 if io8 else torch.float32) and frame.stride(3) == 1
+        assert frame.stride(0) == 3 * frame.stride(1), "frame planes must be evenly spaced"
+        assert 0 <= fy and fy + (y1 - y0) * r <= frame.shape[2] and 0 <= fx and fx + (x1 - x0) * r <= frame.shape[3], (
+            "the window does not fit into the frame at that position")
+        if frame.device != dev:
+            _native.check(eng.lib.mz_enable_peer_access(dev.index or 0, frame.device.index or 0))
+        ws = eng.workspace(B, H, W)
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        dst = frame[0, 0, fy, fx].data_ptr() if frame.numel() else 0
+        _native.check(eng.lib.mz_upscale_window(
+            eng.handle, x.data_ptr(), c.data_ptr() if c is not None else None, c.shape[0] if c is not None else 0,
+            dst, frame.stride(2), frame.stride(1), B, H, W, y0, y1, x0, x1, ws_ptr,
+            ws.numel() - (ws_ptr - ws.data_ptr()), flags, torch.cuda.current_stream(dev).cuda_stream))
+
     def capture(self, x: Tensor, c: Optional[Tensor] = None, clamp: bool = True) -> "GraphedUpscale":
         """Record one ``upscale`` (``clamp=False``: ``forward``) call at the shape of ``x`` into a CUDA graph.
 

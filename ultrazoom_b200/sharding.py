@@ -147,27 +147,54 @@ def upscale_tiled(fn: Callable[[Tensor, Optional[Tensor]], Tensor], x: Tensor, c
 
 
 # ---- assembling the frame on one GPU: one-sided puts over NVLink, no collective --------------------
-def share_frame(frame: Optional[Tensor], owner: int, rank: int, group=None) -> Tensor:
-    """Make the owner's HR frame addressable from every rank of this node.
+class SharedFrame:
+    """The assembled HR frame of a one-process-per-GPU tiled run: allocated by the owner rank, mapped by every other rank
+    of the node through a CUDA IPC handle opened with that rank's own GPU current (mz_ipc_frame_*), so that both the
+    head kernel's stores (``run_tile_into``) and 2-D copies (``put_core``) reach it over NVLink.  ``.tensor`` is the
+    (B,3,H,W) view on each rank; keep the object alive while anything is in flight, ``close()`` when done."""
 
-    The owner passes its CUDA tensor; its allocation is exported as a CUDA IPC handle, handed to the other ranks ONCE
-    over the control plane (``broadcast_object_list``) and mapped there with lazy peer access, so ``put_core`` can write
-    into it directly through NVLink / NVSwitch.  Returns the tensor on every rank (the owner's own, a peer view
-    elsewhere).  Call it outside the timed loop; keep the returned tensor alive while puts are in flight."""
-    import torch.distributed as dist
+    def __init__(self, shape, dtype: torch.dtype, owner: int, rank: int, device: torch.device, group=None):
+        import ctypes as C
 
-    meta = [None]
-    if rank == owner:
-        assert frame is not None and frame.is_cuda and frame.is_contiguous()
-        meta[0] = (tuple(frame.shape), frame.dtype, frame.storage_offset(), frame.untyped_storage()._share_cuda_())
-    dist.broadcast_object_list(meta, src=owner, group=group)
-    if rank == owner:
-        return frame
-    shape, dtype, offset, handle = meta[0]
-    storage = torch.UntypedStorage._new_shared_cuda(*handle)
-    view = torch.empty(0, dtype=dtype, device=storage.device)
-    view.set_(storage, offset, shape)
-    return view
+        import torch.distributed as dist
+
+        from . import _native
+
+        self.lib, self.owner = _native.load(), rank == owner
+        self.ptr = C.c_void_p()
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(device):
+            if self.owner:
+                nbytes = numel * torch.empty(0, dtype=dtype).element_size()
+                _native.check(self.lib.mz_ipc_frame_create(nbytes, C.byref(self.ptr), handle))
+            box = [handle.raw if self.owner else None]
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                dist.broadcast_object_list(box, src=owner, group=group)   # control plane: 64 bytes, once
+            if not self.owner:
+                _native.check(self.lib.mz_ipc_frame_open(box[0], C.byref(self.ptr)))
+        typestr = {torch.float32: "<f4", torch.uint8: "|u1"}[dtype]
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": tuple(int(d) for d in shape), "typestr": typestr,
+                                        "data": (self.ptr.value, False), "version": 2}
+
+        self.tensor = torch.as_tensor(_Mem())      # zero-copy view of the mapping (on the device CUDA reports for it)
+
+    def close(self) -> None:
+        if self.ptr:
+            from . import _native
+
+            self.tensor = None
+            _native.check(self.lib.mz_ipc_frame_close(self.ptr, 1 if self.owner else 0))
+            self.ptr = None
+
+
+def share_frame(shape, dtype: torch.dtype, owner: int, rank: int, device: torch.device, group=None) -> SharedFrame:
+    """Collective over the control plane (once, outside the timed loop): see ``SharedFrame``."""
+    return SharedFrame(shape, dtype, owner, rank, device, group)
 
 
 def put_core(frame: Tensor, tile_out: Tensor, t: Tile, r: int) -> None:
@@ -188,3 +215,10 @@ def put_core(frame: Tensor, tile_out: Tensor, t: Tile, r: int) -> None:
             src = tile_out[b, ch]
             _native.check(lib.mz_put_plane_async(dst.data_ptr(), dst.stride(0) * es, src.data_ptr(), src.stride(0) * es,
                                                  w * es, h, stream))
+
+
+def run_tile_into(model, x: Tensor, c: Optional[Tensor], t: Tile, r: int, frame: Tensor) -> None:
+    """``run_tile`` + ``put_core`` in one pass: the head kernel of the tile writes the core straight into ``frame``
+    (``MewZoom.upscale_into`` -> mz_upscale_window); with a peer ``frame`` its stores are the NVLink transfer."""
+    model.upscale_into(x[:, :, t.hy0:t.hy1, t.hx0:t.hx1], c, frame,
+                       (t.y0 - t.hy0, t.y1 - t.hy0, t.x0 - t.hx0, t.x1 - t.hx0), (t.y0 * r, t.x0 * r))
