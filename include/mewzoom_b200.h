@@ -16,6 +16,9 @@
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
  *     Nothing here synchronises the device or allocates on the hot call
  *     (mz_upscale), except the *_host convenience entry points.
+ *   - threads: an mz_model is not re-entrant -- calls on ONE model are serialised by the caller (its
+ *     prepared-launch cache and host lanes are unsynchronised); different models (one per GPU, or several
+ *     per GPU) may be driven from different host threads concurrently.
  *   - there is no CPU fallback: without an sm_100 device every compute entry
  *     point fails with MZ_ERR_CUDA / MZ_ERR_UNSUPPORTED.
  */

@@ -1,4 +1,5 @@
 // api.cu -- extern "C" per-kernel entry points declared in include/mewzoom_b200.h.
+#include <mutex>
 #include <vector>
 
 #include <string.h>
@@ -153,8 +154,11 @@ int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t 
 
 int mz_enable_peer_access(int32_t a, int32_t b) {
   static bool enabled[64][64];
+  static std::mutex mu;
   MZ_REQUIRE(a >= 0 && a < 64 && b >= 0 && b < 64, "enable_peer_access: device index out of range (%d, %d)", a, b);
-  if (a == b || enabled[a][b]) return MZ_OK;
+  if (a == b) return MZ_OK;
+  std::lock_guard<std::mutex> lock(mu);
+  if (enabled[a][b]) return MZ_OK;
   int prev = 0;
   MZ_CUDA(cudaGetDevice(&prev));
   const int pair[2][2] = {{a, b}, {b, a}};
