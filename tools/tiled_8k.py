@@ -8,7 +8,7 @@ Every rank runs the whole network on its haloed tile (halo = 2L+1 = 81 LR pixels
 tile into the frame assembled on rank 0's GPU: a one-sided 2-D copy over NVLink into rank 0's buffer, mapped once
 through a CUDA IPC handle (sharding.share_frame): by default the head kernel of the tile stores its core straight into
 that buffer (run_tile_into -> mz_upscale_window: the stores are the transfer), `--copy-put` writes the tile locally and
-copies the core (put_core), `--no-stitch` leaves the cores on their GPUs.  Strong
+copies the core (put_core), `--no-stitch` leaves the cores on their GPUs; `--io-uint8` runs 8-bit frames.  Strong
 scaling: value = 33.2 output Mpx / max-over-ranks device time, puts included.  Rank 0 checks the assembled frame
 against the un-tiled result.  Prints one JSON line."""
 import json
@@ -39,6 +39,9 @@ def main():
     model = MewZoom(**cfg).to(dev).eval()
     g = torch.Generator().manual_seed(1234)           # every rank holds the same LR frame
     x = torch.rand(1, 3, H, W, generator=g).to(dev)
+    io8 = "--io-uint8" in sys.argv                     # 8-bit frame in and out: a quarter of the bytes put over NVLink
+    if io8:
+        x = (x * 255).to(torch.uint8)
     c = torch.tensor([[0.5, 0.2, 0.3]], device=dev)
     rows, cols = best_grid(H, W, world, halo_radius(L), align_w=128)   # columns sized for the kernel's 128-pixel tiles
     plan = plan_tiles(H, W, rows, cols, halo_radius(L), align_w=128)
@@ -47,7 +50,7 @@ def main():
     stitched = "--no-stitch" not in sys.argv
     frame = None
     if stitched:                                       # the assembled 8K frame lives on rank 0's GPU
-        shared = share_frame((1, 3, H * r, W * r), torch.float32, 0, rank, dev)
+        shared = share_frame((1, 3, H * r, W * r), torch.uint8 if io8 else torch.float32, 0, rank, dev)
         frame = shared.tensor
 
     copy_put = "--copy-put" in sys.argv
@@ -85,15 +88,15 @@ def main():
         full = model.upscale(x, c)
         t0 = mine[0]
         if stitched:                                   # every rank's puts landed before the barrier above returned
-            err = float((full - frame).abs().max())
+            err = float((full.float() - frame.float()).abs().max())
         else:
-            err = float((full[:, :, t0.y0 * r:t0.y1 * r, t0.x0 * r:t0.x1 * r] - cores[0]).abs().max())
+            err = float((full[:, :, t0.y0 * r:t0.y1 * r, t0.x0 * r:t0.x1 * r].float() - cores[0].float()).abs().max())
         executed = sum((t.hy1 - t.hy0) * (t.hx1 - t.hx0) for t in plan) / (H * W)
         print(json.dumps({
             "metric": "output_mpx_per_s", "value": H * r * W * r / (ms * 1e-3) / 1e6, "unit": "Mpx/s", "n_gpus": world,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "config": {"workload": "MewZoom-4X-Ctrl 96ch/40L, one 1920x1080->7680x4320 frame, halo-tiled "
-                                   f"{rows}x{cols} (BASELINE configs[4])", "halo_lr_px": halo_radius(L),
+                                   f"{rows}x{cols} (BASELINE configs[4])", "halo_lr_px": halo_radius(L), "image_io": "uint8" if io8 else "float32",
                        "executed_over_algorithmic_work": executed,
                        "stitch": ("none" if not stitched else "2-D copies of the cores into rank 0's frame (CUDA IPC peer mapping)"
                                   if copy_put else "head kernel stores the core into rank 0's frame (CUDA IPC peer mapping)")},
