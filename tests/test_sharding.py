@@ -124,3 +124,33 @@ def test_world_size_two_gloo():
             err, count = ret[r]
             assert err <= 2e-6
             assert count == [1.0] * 7
+
+
+@pytest.mark.parametrize("H,W,rows,cols,halo,r,align", [(45, 290, 2, 2, 7, 2, 128), (1080, 1920, 2, 4, 81, 4, 128),
+                                                       (33, 70, 3, 2, 5, 3, 1)])
+def test_run_tile_into_windows_tile_the_frame_exactly_once(H, W, rows, cols, halo, r, align):
+    """Host logic of the fused stitch (MewZoom.upscale_into): for every tile the window handed to the kernel is the
+    tile's core in tile-local coordinates and lands at the core's HR position; together the windows cover the frame
+    exactly once.  A stand-in model records what it is asked to do and "upscales" by nearest-neighbour replication."""
+    from ultrazoom_b200.sharding import plan_tiles, run_tile_into
+
+    class Recorder:
+        def __init__(self):
+            self.calls = []
+
+        def upscale_into(self, x, c, frame, window, at):
+            y0, y1, x0, x1 = window
+            fy, fx = at
+            assert 0 <= y0 < y1 <= x.shape[2] and 0 <= x0 < x1 <= x.shape[3]
+            core = x[:, :, y0:y1, x0:x1].repeat_interleave(r, 2).repeat_interleave(r, 3)
+            frame[:, :, fy:fy + core.shape[2], fx:fx + core.shape[3]] += core
+            self.calls.append((window, at))
+
+    x = torch.rand(1, 3, H, W, generator=torch.Generator().manual_seed(0)) + 1.0
+    frame = torch.zeros(1, 3, H * r, W * r)
+    rec = Recorder()
+    plan = plan_tiles(H, W, rows, cols, halo, align)
+    for t in plan:
+        run_tile_into(rec, x, None, t, r, frame)
+    assert len(rec.calls) == len(plan)
+    assert torch.equal(frame, x.repeat_interleave(r, 2).repeat_interleave(r, 3))   # every HR pixel written exactly once
