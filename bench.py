@@ -1,12 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- output Mpx/s of MewZoom.upscale on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4a|cfg4b|cfg4c] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4a|cfg4b|cfg4c|cfg5] [--impl reference]
 
 One "step" = one pass of the hot path (FiLM table, stem, 2L fused 3x3 convolutions, head) over one batch of
 synthetic frames.  Default workload = BASELINE.json configs[1]: MewZoom-2X-Ctrl (48 ch / 20 layers), batch 16 of
 960x540 -> 1920x1080.  With N > 1 (torchrun, one rank per GPU) every rank processes its own batch (weak scaling,
 no data-path collective); time = max over ranks, value = all ranks' output pixels / time.
+`--workload cfg5` (BASELINE configs[4]) is the STRONG-scaling case: ONE 1920x1080 -> 7680x4320 MewZoom-4X-Ctrl frame cut
+into N halo-padded tiles, one per rank, each rank's head kernel storing its core straight into the frame on rank 0's GPU
+(CUDA IPC mapping, NVLink); value = 33.2 Mpx / max-over-ranks time.  The default (cfg2) line carries it -- and the
+4X-Ctrl / 3X-Ctrl frames -- under "also", so that the driver's 1 -> 8 GPU runs record the spatial split as well.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU implementation of the path: the
 reference is pure PyTorch, its 0.2.x model class is absent from the snapshot, so this is the oracle restatement
@@ -33,8 +37,25 @@ WORKLOADS = {
     "cfg4a": ("MewZoom-4X-Ctrl", 1, 540, 960, "MewZoom-4X-Ctrl 96ch/40L, 1 frame 960x540->3840x2160 (BASELINE configs[3], 4K output)"),
     "cfg4b": ("MewZoom-4X-Ctrl", 1, 1080, 1920, "MewZoom-4X-Ctrl 96ch/40L, 1 frame 1920x1080->7680x4320 (BASELINE configs[3], 1080p input)"),
     "cfg4c": ("MewZoom-2X-Ctrl", 1, 1080, 1920, "MewZoom-2X-Ctrl 48ch/20L, 1 frame 1920x1080->3840x2160 (literal 1080p->4K)"),
+    "cfg5": ("MewZoom-4X-Ctrl", 1, 1080, 1920, "MewZoom-4X-Ctrl 96ch/40L, ONE 1920x1080->7680x4320 frame halo-tiled across the GPUs (BASELINE configs[4])"),
     "tiny": ("MewZoom-2X-Ctrl", 1, 64, 128, "MewZoom-2X-Ctrl 48ch/20L, 1 frame 128x64 (debug)"),
 }
+
+
+def config_of(workload: str, world: int, args) -> dict:
+    """The `config` object of the JSON line -- the same keys and values in both arms (`--impl reference` times the
+    CPU path on THIS configuration), so that the driver can tell the two lines describe one workload."""
+    model_name, B, H, W, desc = WORKLOADS[workload]
+    tiled = workload == "cfg5"
+    return {"workload": desc, "batch_per_gpu": B, "lr_h": H, "lr_w": W,
+            "parallelism": (f"one halo-padded tile per GPU x{world} (halo 2L+1 = 81 LR px), cores stored into rank 0's "
+                            "frame over NVLink, no collective") if tiled else
+                           f"replica per GPU x{world}, batch-sharded, no collective",
+            "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
+            "weights": "random init (seed 0)", "image_io": args.io,
+            "residual_stream": ("fp32" if args.residual_stream != "split" else "two 16-bit planes hi + lo (z to 2^-22)"),
+            "accumulate": "fp32", "mma_operands": args.operands,
+            "tune": {k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)}}
 
 
 def algorithmic_flops_per_lr_px(cfg) -> float:
@@ -160,8 +181,9 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "output_mpx_per_s", "value": value, "unit": "Mpx/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "batch": B, "lr_h": H, "lr_w": W},
+        "higher_is_better": True, "scaling": "strong" if args.workload == "cfg5" else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": config_of(args.workload, args.gpus, args),
         "cpu_baseline": {"value": value, "unit": "Mpx/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -207,7 +229,8 @@ def main():
     ap.add_argument("--io", default="float32", choices=["float32", "uint8"],
                     help="image element type at the API (uint8: x = x8/255 in, floor(255 y + 0.5) out); the headline is float32")
     ap.add_argument("--e2e-sync", action="store_true", help="time the synchronous host call instead of the two-lane stream")
-    ap.add_argument("--no-also", action="store_true", help="skip the secondary MewZoom-4X-Ctrl measurement")
+    ap.add_argument("--no-also", action="store_true",
+                    help="skip the secondary records (4X-Ctrl frame, 3X-Ctrl frame, halo-tiled 8K frame)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least three warm-up steps
@@ -241,6 +264,8 @@ def main():
     def measure(workload: str, steps: int, warmup: int, want_e2e: bool, sample_clocks: bool):
         """W untimed + exactly K timed steps (CUDA events on the launching stream, barrier + synchronize on both
         sides, max over ranks) of one workload; optionally the end-to-end leg with host buffers."""
+        if workload == "cfg5":
+            return measure_tiled(steps, warmup, want_e2e, sample_clocks)
         model_name, B, H, W, desc = WORKLOADS[workload]
         cfg = MODEL_CONFIGS[model_name]
         r = cfg["upscale_ratio"]
@@ -277,13 +302,14 @@ def main():
         conv_ms = C.c_float()
         _native.check(eng.lib.mz_model_conv_stack_ms(eng.handle, C.byref(conv_ms)))
         _native.check(eng.lib.mz_model_enable_timing(eng.handle, 0))
+        assert not model.saturated(dev), "fp16 operand saturation during the timed region"
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item()) / steps
         res = {"workload": workload, "model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc, "ms_step": ms_step,
                "conv_ms": conv_ms.value, "clocks": clocks, "value": world * out_px / (ms_step * 1e-3) / 1e6,
-               "e2e": None}
+               "e2e": None, "scaling": "weak", "steps": steps}
         # ---- end to end through the public API with HOST buffers (H2D + kernels + D2H inside the timed region) ----
         if want_e2e:
             # Every step copies its inputs from pinned host memory and its result back to pinned host memory.  The
@@ -328,23 +354,140 @@ def main():
         torch.cuda.empty_cache()
         return res
 
+    def measure_tiled(steps: int, warmup: int, want_e2e: bool, sample_clocks: bool):
+        """cfg5 (BASELINE configs[4]), strong scaling: ONE 1080p -> 8K MewZoom-4X-Ctrl frame, `world` halo-padded tiles
+        (sharding.best_grid / plan_tiles, columns sized for the kernel's 128-pixel tiles), one per rank.  Every rank
+        runs the whole network on its tile and its head kernel stores the tile's core straight into the frame that
+        lives on rank 0's GPU (CUDA IPC mapping opened with the rank's own GPU current: the stores ARE the NVLink
+        transfer).  No collective on the data path; NCCL carries the timing barrier and the max-reduce only.
+        value = 33.2 output Mpx / max-over-ranks device time.  Rank 0 checks the assembled frame against the
+        un-tiled result (bit-exact) outside the timed region."""
+        from ultrazoom_b200.sharding import best_grid, frames_for_rank, halo_radius, plan_tiles, run_tile_into, share_frame
+
+        model_name, B, H, W, desc = WORKLOADS["cfg5"]
+        cfg = MODEL_CONFIGS[model_name]
+        r, L = cfg["upscale_ratio"], cfg["num_encoder_layers"]
+        torch.manual_seed(0)
+        model = MewZoom(**cfg, operand_dtype=args.operands, residual_stream=args.residual_stream).to(dev).eval()
+        if tune_kw:
+            model.set_conv_tune(-1, dev, **tune_kw)
+        eng = model._engine(dev)
+        g = torch.Generator().manual_seed(1234)             # every rank holds the same LR frame
+        x_host = torch.rand(B, 3, H, W, generator=g)
+        if args.io == "uint8":
+            x_host = (x_host * 255.0).round().to(torch.uint8)
+        x_host = x_host.pin_memory()
+        c_host = torch.tensor([[0.5, 0.2, 0.3]]).pin_memory()
+        x, c = x_host.to(dev), c_host.to(dev)
+        R = halo_radius(L)
+        rows, cols = best_grid(H, W, world, R, align_w=128)
+        plan = plan_tiles(H, W, rows, cols, R, align_w=128)
+        mine = [plan[i] for i in frames_for_rank(len(plan), rank, world)]
+        shared = share_frame((B, 3, H * r, W * r), x_host.dtype, 0, rank, dev)
+        frame = shared.tensor
+        out_px = B * H * r * W * r
+
+        def step():
+            for t in mine:
+                run_tile_into(model, x, c, t, r, frame)
+
+        for _ in range(warmup):
+            step()
+        barrier()
+        _native.check(eng.lib.mz_model_enable_timing(eng.handle, 1))
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+        conv_ms = C.c_float()
+        _native.check(eng.lib.mz_model_conv_stack_ms(eng.handle, C.byref(conv_ms)))
+        _native.check(eng.lib.mz_model_enable_timing(eng.handle, 0))
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / steps
+        executed = sum((t_.hy1 - t_.hy0) * (t_.hx1 - t_.hx0) for t_ in plan) / (H * W)
+        err = None
+        if rank == 0:                                       # every rank's stores landed before the barrier returned
+            full = model.upscale(x, c)
+            err = float((full.float() - frame.float()).abs().max())
+            del full
+        res = {"workload": "cfg5", "model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc,
+               "ms_step": ms_step, "conv_ms": conv_ms.value, "clocks": clocks, "value": out_px / (ms_step * 1e-3) / 1e6,
+               "e2e": None, "scaling": "strong", "steps": steps, "npix_executed": int(sum((t_.hy1 - t_.hy0) * (t_.hx1 - t_.hx0) for t_ in mine)),
+               "tiling": {"grid": f"{rows}x{cols}", "halo_lr_px": R, "executed_over_algorithmic_work": executed,
+                          "max_abs_diff_vs_untiled": err,
+                          "stitch": "head kernel stores the core into rank 0's frame (CUDA IPC peer mapping, NVLink)"}}
+        if want_e2e:
+            # end to end: every rank copies ITS haloed tile from pinned host memory, runs it into rank 0's frame, and
+            # rank 0 copies the assembled frame to pinned host memory; wall clock with a barrier on both sides.
+            tiles_host = [x_host[:, :, t_.hy0:t_.hy1, t_.hx0:t_.hx1].contiguous().pin_memory() for t_ in mine]
+            out_host = torch.empty((B, 3, H * r, W * r), dtype=x_host.dtype).pin_memory() if rank == 0 else None
+
+            def e2e_step():
+                for t_, th in zip(mine, tiles_host):
+                    xt = th.to(dev, non_blocking=True)
+                    cc = c_host.to(dev, non_blocking=True)
+                    model.upscale_into(xt, cc, frame, (t_.y0 - t_.hy0, t_.y1 - t_.hy0, t_.x0 - t_.hx0, t_.x1 - t_.hx0),
+                                       (t_.y0 * r, t_.x0 * r))
+                barrier()                                   # all cores are in the frame
+                if rank == 0:
+                    out_host.copy_(frame, non_blocking=True)
+                    torch.cuda.synchronize()
+
+            e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_step()
+            barrier()
+            dt = time.perf_counter() - t0
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            res["e2e"] = {"value": out_px * steps / dt / 1e6, "unit": "Mpx/s",
+                          "h2d_bytes_per_step": int(sum(th.numel() * th.element_size() for th in tiles_host)) + 12,
+                          "d2h_bytes_per_step": out_px * 3 * x_host.element_size(), "ms_per_step": 1e3 * dt / steps,
+                          "api": "MewZoom.upscale_into per tile (pinned host tile -> device), assembled frame -> pinned host on rank 0"}
+        barrier()
+        frame = None
+        shared.close()
+        del model, eng, x, c
+        torch.cuda.empty_cache()
+        return res
+
     def roofline_of(res, peaks):
         """Roofline of the dominant kernel (one encoder convolution launch; conv1 and conv2 alternate, so per-launch
-        figures are their mean).  Algorithmic work per launch, unpadded:
+        figures are their mean), per SURVEY.md 8(d).  Algorithmic work per launch, unpadded:
           flops = 2 * 9 * C * hC per LR pixel (conv1 == conv2)
-          bytes = mean of conv1 (read zb 2C, write hidden 2hC) and conv2 (read hidden 2hC + zf 4C, write zf 4C + zb 2C)
-        The bound is whichever of flops/peak_tensor and bytes/peak_hbm is the longer time."""
-        cfg, npix = res["cfg"], res["B"] * res["H"] * res["W"]
+          bytes = 6C per LR pixel (16-bit in + out of a convolution: SURVEY 8(d) "conv-stack minimum traffic")
+        and, beside it, the bytes THIS design moves per launch (fp32 residual stream + 16-bit shadow):
+          mean of conv1 (read zb 2C, write hidden 2hC) and conv2 (read hidden 2hC + zf 4C, write zf 4C + zb 2C).
+        The bound is whichever of flops / peak_tensor and algorithmic bytes / peak_hbm is the longer time; the
+        tensor fraction is given against both the sustained and the burst 16-bit dense peak."""
+        cfg = res["cfg"]
+        npix = res.get("npix_executed") or res["B"] * res["H"] * res["W"]    # (cfg5: the haloed tile this rank ran)
+        npix_alg = res["B"] * res["H"] * res["W"] / (world if res["workload"] == "cfg5" else 1)
         L, C_ = cfg["num_encoder_layers"], cfg["num_channels"]
         hC = C_ * cfg["hidden_ratio"]
         conv_launch_ms = res["conv_ms"] / (2 * L)
-        conv_flops = conv_flops_per_launch(cfg, npix)
-        conv_bytes = 0.5 * ((2 * C_ + 2 * hC) + (2 * hC + 4 * C_ + 4 * C_ + 2 * C_)) * npix
+        conv_flops = conv_flops_per_launch(cfg, npix_alg)
+        alg_bytes = 6.0 * C_ * npix_alg
+        design_bytes = 0.5 * ((2 * C_ + 2 * hC) + (2 * hC + 4 * C_ + 4 * C_ + 2 * C_)) * npix
         t_tensor = conv_flops / (peaks["bf16_sustained"] * 1e12)
-        t_hbm = conv_bytes / (peaks["hbm"] * 1e9)
+        t_hbm = alg_bytes / (peaks["hbm"] * 1e9)
         tf = conv_flops / (conv_launch_ms * 1e-3) / 1e12
-        gbs = conv_bytes / (conv_launch_ms * 1e-3) / 1e9
-        total_flops = algorithmic_flops_per_lr_px(cfg) * npix
+        gbs_alg = alg_bytes / (conv_launch_ms * 1e-3) / 1e9
+        gbs_design = design_bytes / (conv_launch_ms * 1e-3) / 1e9
+        total_flops = algorithmic_flops_per_lr_px(cfg) * res["B"] * res["H"] * res["W"]
         traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):          # DRAM bytes per launch from the committed ncu capture of this workload
@@ -352,28 +495,37 @@ def main():
                 tj = json.load(f).get(res["workload"])
             if tj:
                 traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
+        n_gpus = world if res["workload"] == "cfg5" else 1
         common = {
             "kernel": "conv_tc_kernel (3x3 implicit GEMM, tcgen05)", "traffic": traffic, "traffic_source": traffic_src,
-            "flops_per_launch": conv_flops, "bytes_per_launch": conv_bytes, "ms_per_launch": conv_launch_ms,
+            "flops_per_launch": conv_flops, "bytes_per_launch": alg_bytes, "design_bytes_per_launch": design_bytes,
+            "ms_per_launch": conv_launch_ms,
             "launches_per_step": 2 * L, "conv_share_of_step": res["conv_ms"] / res["ms_step"],
             "tensor": {"achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                        "frac": tf / peaks["bf16_sustained"], "frac_of_burst_peak": tf / peaks["bf16_burst"]},
-            "hbm": {"achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"]},
-            "whole_step_tflops": total_flops / (res["ms_step"] * 1e-3) / 1e12,
+            "hbm": {"achieved": gbs_alg, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs_alg / peaks["hbm"],
+                    "basis": "algorithmic bytes 6C per LR px per launch (SURVEY 8(d))"},
+            "hbm_design": {"achieved": gbs_design, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs_design / peaks["hbm"],
+                           "basis": "bytes this design moves: fp32 residual stream + 16-bit shadow + hidden round trip"},
+            "whole_step_tflops_per_gpu": total_flops / n_gpus / (res["ms_step"] * 1e-3) / 1e12,
+            "whole_step_frac_of_burst_peak": total_flops / n_gpus / (res["ms_step"] * 1e-3) / 1e12 / peaks["bf16_burst"],
             "peak_source": peaks["source"] + "; tensor = sustained 16-bit dense (kernel timed inside a long step)",
         }
         if t_hbm > t_tensor:
-            return {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                    **common}
+            return {"bound": "hbm", "achieved": gbs_alg, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": gbs_alg / peaks["hbm"], **common}
         return {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": tf / peaks["bf16_sustained"], **common}
 
     main_res = measure(args.workload, args.steps, args.warmup, not args.no_e2e, True)
-    # The north_star's efficiency target is stated on MewZoom-4X-Ctrl: measure that frame too (same protocol) so the
-    # one JSON line carries both the configs[1] headline and the 4X-Ctrl roofline fraction.
-    also_res = None
+    # The north_star's efficiency target is stated on MewZoom-4X-Ctrl and its hard multi-GPU case is the spatial split:
+    # the default line carries those as first-class records (own clocks; 4X-Ctrl with its own e2e) under "also".
+    also = {}
     if args.workload == "cfg2" and not args.no_also:
-        also_res = measure("cfg4a", max(3, args.steps), args.warmup, False, False)
+        k = max(3, args.steps)
+        also["cfg4a"] = measure("cfg4a", k, args.warmup, not args.no_e2e, True)
+        also["cfg3"] = measure("cfg3", k, args.warmup, False, True)
+        also["cfg5"] = measure("cfg5", max(3, min(args.steps, 5)), args.warmup, False, True)
 
     if rank != 0:
         if world > 1:
@@ -398,23 +550,24 @@ def main():
                         "sample": f"1 frame {sw}x{sh} of the workload, fp32 oracle, {dt:.1f} s"}
     line = {
         "metric": "output_mpx_per_s", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": res["scaling"],
         "vs_baseline": None, "dtype": "f16" if args.operands == "float16" else "bf16", "data": "synthetic",
-        "config": {"workload": desc, "batch_per_gpu": B, "lr_h": H, "lr_w": W,
-                   "parallelism": f"replica per GPU x{world}, batch-sharded, no collective",
-                   "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
-                   "weights": "random init (seed 0)", "image_io": args.io,
-                   "residual_stream": ("fp32" if args.residual_stream != "split"
-                                       else "two 16-bit planes hi + lo (z to 2^-22)"), "accumulate": "fp32", "mma_operands": args.operands,
-                   "tune": tune_kw},
+        "config": config_of(args.workload, world, args),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         "ms_per_frame": ms_step / B,
     }
-    if also_res is not None:
-        ar = roofline_of(also_res, peaks)
-        line["also"] = {"cfg4a": {"workload": also_res["desc"], "value": also_res["value"], "unit": "Mpx/s",
-                                  "ms_per_frame": also_res["ms_step"], "roofline": ar}}
+    if "tiling" in res:
+        line["tiling"] = res["tiling"]
+    if also:
+        line["also"] = {}
+        for name, ar in also.items():
+            rec = {"workload": ar["desc"], "value": ar["value"], "unit": "Mpx/s", "scaling": ar["scaling"],
+                   "steps": ar["steps"], "ms_per_frame": ar["ms_step"], "roofline": roofline_of(ar, peaks),
+                   "clocks": ar["clocks"], "e2e": ar["e2e"], "config": config_of(name, world, args)}
+            if "tiling" in ar:
+                rec["tiling"] = ar["tiling"]
+            line["also"][name] = rec
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -19,6 +19,9 @@
  *   - threads: an mz_model is not re-entrant -- calls on ONE model are serialised by the caller (its
  *     prepared-launch cache and host lanes are unsynchronised); different models (one per GPU, or several
  *     per GPU) may be driven from different host threads concurrently.
+ *   - streams: the kernels of one mz_upscale share the caller's workspace and run in order on `stream`; two calls
+ *     on ONE model (or on one workspace) must not overlap on the device -- before enqueueing on another stream,
+ *     make it wait for the previous call (an event).  The Python mirror does so.
  *   - there is no CPU fallback: without an sm_100 device every compute entry
  *     point fails with MZ_ERR_CUDA / MZ_ERR_UNSUPPORTED.
  */
@@ -32,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MZ_ABI_VERSION 2
+#define MZ_ABI_VERSION 3
 
 typedef enum mz_status {
   MZ_OK = 0,
@@ -108,6 +111,20 @@ void mz_model_destroy(mz_model* m);
  * 16-bit K-major per-tap layout the tcgen05 kernels read.  `layer` is ignored for
  * stem/head kinds.  `numel` must match the shape implied by the config. */
 int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* host_data, size_t numel);
+
+/* The same from a DEVICE tensor (fp32, PyTorch layout) on `stream`: the repack runs as a kernel, so a model whose
+ * parameters already live on the GPU (MewZoom.to("cuda"), model.py:47 of test_compare.py) is packed without a round
+ * trip through host memory.  An fp16-operand weight beyond +-65504 cannot be reported synchronously here: it raises
+ * the flag mz_model_saturated reads. */
+int mz_model_set_weight_dev(mz_model* m, int32_t kind, int32_t layer, const float* dev_data, size_t numel, void* stream);
+
+/* fp16 range guard.  With MZ_DTYPE_F16 operands every 16-bit rounding in the path saturates (cvt.rn.satfinite) instead
+ * of producing inf; a kernel that rounds a magnitude above 65504 -- an activation of the stem, of a hidden tensor or
+ * of the residual stream, or a device-packed weight -- also sets a host-mapped flag.  *saturated = 1 if any kernel
+ * that has COMPLETED so far did (the call does not synchronise; synchronise the stream first for a definite answer
+ * about a particular mz_upscale).  reset != 0 clears the flag.  A saturated result is wrong: re-run the frame on a
+ * model created with MZ_DTYPE_BF16 (same range as fp32).  mz_model_set_weight rejects out-of-range weights at once. */
+int mz_model_saturated(mz_model* m, int32_t reset, int32_t* saturated);
 
 /* Bytes of device scratch mz_upscale needs for a (B,3,H,W) input. */
 int mz_workspace_bytes(const mz_model* m, int32_t B, int32_t H, int32_t W, size_t* bytes);

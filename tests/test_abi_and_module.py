@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _native.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_native.SIGNATURES) == names
-    assert lib.mz_abi_version() == 2
+    assert lib.mz_abi_version() == _native.ABI_VERSION == 3
 
 
 def test_padded_channels_and_error_plumbing():
@@ -153,3 +153,40 @@ def test_reference_checkpoint_recipes():
     assert torch.allclose(m2.encoder[1].convnet.conv1.weight, baked["c1"], atol=1e-6)
     assert torch.equal(m2.encoder[0].control.linear.bias, trained.encoder[0].control.linear.bias)
     assert sorted(m2.state_dict()) == sorted(MewZoom(**cfg).state_dict())
+
+
+def test_reference_import_paths_work_verbatim():
+    """Reference README.md:69,102-103: `from ultrazoom.model import MewZoom`, `from ultrazoom.control import
+    ControlVector` resolve to the B200-native classes (the `ultrazoom/` shim package)."""
+    from ultrazoom.control import ControlVector as RefCV
+    from ultrazoom.model import MewZoom as RefMewZoom
+    from ultrazoom.model import ONNXModel as RefONNX
+
+    assert RefMewZoom is MewZoom and RefCV is ControlVector and RefONNX is ONNXModel
+    c = RefCV(gaussian_blur=0.5, gaussian_noise=0.2, jpeg_compression=0.3).to_tensor()       # README.md:118-122
+    assert c.dtype == torch.float32 and c.tolist() == pytest.approx([0.5, 0.2, 0.3])
+
+
+def test_parameter_cache_follows_replaced_parameters():
+    """The flat parameter list the engine polls is cached; parametrizations and direct assignment replace Parameter
+    objects and must be noticed (identity check), `.to()` / `load_state_dict` keep them."""
+    m = MewZoom(2, 16, 2, 2, control_features=3)
+    p0 = m._flat_params()
+    assert len(p0) == len(list(m.parameters())) and all(a is b for a, b in zip(p0, m.parameters()))
+    assert m._flat_params() is not p0 and all(a is b for a, b in zip(m._flat_params(), p0))
+    m.add_weight_norms()
+    p1 = m._flat_params()
+    assert len(p1) == len(list(m.parameters())) > len(p0)
+    m.remove_parameterizations()
+    assert len(m._flat_params()) == len(p0)
+    m.head.conv.weight = torch.nn.Parameter(torch.zeros_like(m.head.conv.weight))
+    assert any(p is m.head.conv.weight for p in m._flat_params())
+    assert MewZoom(2, 16, 2, 2, operand_dtype="auto").operand_dtype == "auto"
+    with pytest.raises(AssertionError):
+        MewZoom(2, 16, 2, 2, operand_dtype="float64")
+
+
+def test_build_is_idempotent_under_the_lock():
+    from ultrazoom_b200 import build as b
+
+    assert b.build_locked() == b.LIB and os.path.exists(b.LIB)

@@ -12,6 +12,8 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmewzoom_b200.so")
 
+ABI_VERSION = 3
+
 MZ_OK = 0
 MZ_ERR_INVALID = -1
 MZ_ERR_CUDA = -2
@@ -75,6 +77,8 @@ SIGNATURES = {
     "mz_model_create": (C.c_int, [C.POINTER(MzConfig), C.POINTER(_P)]),
     "mz_model_destroy": (None, [_P]),
     "mz_model_set_weight": (C.c_int, [_P, _I, _I, _P, C.c_size_t]),
+    "mz_model_set_weight_dev": (C.c_int, [_P, _I, _I, _P, C.c_size_t, _P]),
+    "mz_model_saturated": (C.c_int, [_P, _I, C.POINTER(_I)]),
     "mz_model_set_tune": (C.c_int, [_P, _I, C.POINTER(MzConvTune)]),
     "mz_model_enable_timing": (C.c_int, [_P, _I]),
     "mz_model_conv_stack_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
@@ -113,12 +117,20 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            if not build_if_missing:
-                raise RuntimeError(f"{LIB_PATH} is missing; run `python -m ultrazoom_b200.build`")
+        if build_if_missing:
+            # build() is a digest comparison when the library is current: a stale .so after an edit under csrc/ is
+            # rebuilt instead of loaded silently.  One process per GPU (torchrun): an inter-process lock keeps the
+            # ranks from running nvcc into the same objects at once.  Without nvcc (a deployment box) a library that
+            # is already there is loaded as it is.
             from . import build as _build
 
-            _build.build()
+            try:
+                _build.build_locked()
+            except RuntimeError:
+                if not os.path.exists(LIB_PATH):
+                    raise
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing; run `python -m ultrazoom_b200.build`")
         try:
             lib = C.CDLL(LIB_PATH)
         except OSError as e:  # pragma: no cover - depends on the box
@@ -127,8 +139,8 @@ def load(build_if_missing: bool = True) -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError => the library is stale
             fn.restype = res
             fn.argtypes = args
-        if lib.mz_abi_version() != 2:
-            raise RuntimeError(f"ABI mismatch: library reports {lib.mz_abi_version()}, binding expects 2")
+        if lib.mz_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"ABI mismatch: library reports {lib.mz_abi_version()}, binding expects {ABI_VERSION}")
         _lib = lib
         return lib
 

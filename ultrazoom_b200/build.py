@@ -81,5 +81,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_locked(force: bool = False, verbose: bool = False) -> str:
+    """build() under an inter-process file lock (one process per GPU: every rank calls this at import)."""
+    import fcntl
+
+    os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return build(force=force, verbose=verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -2,6 +2,7 @@
 #include <mutex>
 #include <vector>
 
+#include <math.h>
 #include <string.h>
 
 #include "kernels.cuh"
@@ -36,13 +37,15 @@ int current_device() {
 }
 
 // OIHW fp32 -> [tap][cout_p][cin_p] fp16 | bf16 bits (zero padded), host side.
-void pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, int bf16,
+bool pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, int bf16,
                            std::vector<uint16_t>& out) {
   out.assign(static_cast<size_t>(9) * cout_p * cin_p, 0);
+  bool in_range = true;
   for (int o = 0; o < cout; ++o)
     for (int i = 0; i < cin; ++i)
       for (int t = 0; t < 9; ++t) {
         const float v = w[(static_cast<size_t>(o) * cin + i) * 9 + t];
+        if (!bf16 && !(fabsf(v) <= MZ_F16_MAX)) in_range = false;
         uint16_t bits;
         if (bf16) {
           const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -53,6 +56,7 @@ void pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int ci
         }
         out[(static_cast<size_t>(t) * cout_p + o) * cin_p + i] = bits;
       }
+  return in_range;
 }
 
 bool dtype_ok(int d) { return d == MZ_DTYPE_F16 || d == MZ_DTYPE_BF16; }
@@ -147,7 +151,8 @@ int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t 
   if (!dst_dev) return MZ_OK;
   MZ_REQUIRE(w_host, "pack: null weight pointer");
   std::vector<uint16_t> tmp;
-  pack_conv_weight_host(w_host, cout, cin, cout_p, cin_p, operand_dtype == MZ_DTYPE_BF16, tmp);
+  MZ_REQUIRE(pack_conv_weight_host(w_host, cout, cin, cout_p, cin_p, operand_dtype == MZ_DTYPE_BF16, tmp),
+             "pack: a weight exceeds the fp16 operand range (|w| > 65504 or not finite); use MZ_DTYPE_BF16");
   MZ_CUDA(cudaMemcpy(dst_dev, tmp.data(), n, cudaMemcpyHostToDevice));
   return MZ_OK;
 }

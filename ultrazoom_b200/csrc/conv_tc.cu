@@ -645,6 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int nh = p.epi_warps >> 2;  // warps per lane quarter (1 | 2)
     float* film_s = reinterpret_cast<float*>(gen_base + sp.film);
     int film_b = -1;
+    float amax = 0.f;  // fp16 range guard: largest magnitude this thread rounded into a 16-bit operand (EpiParams::sat)
     uint32_t as = 0, pacc = 0, rpar = 0, ring = 0;
     const uint32_t n_pad = p.epi.n_pad;
     // residual tiles: mode 1 fp32 (n_pad channels), mode 3 the 16-bit pair [hi | lo] (2 * n_pad channels)
@@ -791,8 +792,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float2 h = unpack_op2(p.epi.bf16, hw[j]), l = unpack_op2(p.epi.bf16, lw[j]);
-                split_op2(p.epi.bf16, h.x + l.x + __uint_as_float(v[8 * kk + 2 * j]),
-                          h.y + l.y + __uint_as_float(v[8 * kk + 2 * j + 1]), ho[j], lo[j]);
+                const float z0 = h.x + l.x + __uint_as_float(v[8 * kk + 2 * j]);
+                const float z1 = h.y + l.y + __uint_as_float(v[8 * kk + 2 * j + 1]);
+                amax = fmaxf(amax, fmaxf(fabsf(z0), fabsf(z1)));
+                split_op2(p.epi.bf16, z0, z1, ho[j], lo[j]);
               }
               sts128(ha, ho[0], ho[1], ho[2], ho[3]);
               sts128(la, lo[0], lo[1], lo[2], lo[3]);
@@ -825,6 +828,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               z.z += __uint_as_float(v[4 * kk + 2]);
               z.w += __uint_as_float(v[4 * kk + 3]);
               sts128(addr, __float_as_uint(z.x), __float_as_uint(z.y), __float_as_uint(z.z), __float_as_uint(z.w));
+              amax = fmaxf(fmaxf(amax, fmaxf(fabsf(z.x), fabsf(z.y))), fmaxf(fabsf(z.z), fabsf(z.w)));
               o[2 * kk] = pack_op2(p.epi.bf16, z.x, z.y);
               o[2 * kk + 1] = pack_op2(p.epi.bf16, z.z, z.w);
             }
@@ -886,6 +890,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const float a1 = silu_h(fmaf(__uint_as_float(v[4 * kk + 1]), g.y, h.y));
                 const float a2 = silu_h(fmaf(__uint_as_float(v[4 * kk + 2]), g.z, h.z));
                 const float a3 = silu_h(fmaf(__uint_as_float(v[4 * kk + 3]), g.w, h.w));
+                amax = fmaxf(fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1))), fmaxf(fabsf(a2), fabsf(a3)));
                 o[2 * kk] = pack_op2(p.epi.bf16, a0, a1);
                 o[2 * kk + 1] = pack_op2(p.epi.bf16, a2, a3);
               }
@@ -938,6 +943,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     if (lane == 0) bulk_wait_all();  // every TMA store of this warp has landed before the CTA exits
+    // (an infinite value is caught too; fmaxf drops NaNs, which the 16-bit conversion keeps as NaN anyway)
+    if (MODE != 2 && !p.epi.bf16 && p.epi.sat != nullptr && !(amax <= MZ_F16_MAX)) *p.epi.sat = 1u;
   }
 
   if (prof_on && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
@@ -1135,6 +1142,23 @@ static int run_prepared(ConvLaunchImpl& L, cudaStream_t s) {
 int run_conv_tc(ConvLaunch& launch, cudaStream_t s) {
   MZ_REQUIRE(launch.valid, "conv: launch was not prepared");
   return run_prepared(*reinterpret_cast<ConvLaunchImpl*>(launch.storage), s);
+}
+
+void patch_conv_epi(ConvLaunch& launch, const EpiParams& e) {
+  EpiParams& d = reinterpret_cast<ConvLaunchImpl*>(launch.storage)->p.epi;
+  d.x = e.x;
+  d.y = e.y;
+  d.x8 = e.x8;
+  d.y8 = e.y8;
+  d.u8_trunc = e.u8_trunc;
+  d.skip_mode = e.skip_mode;
+  d.clamp01 = e.clamp01;
+  d.wy0 = e.wy0;
+  d.wy1 = e.wy1;
+  d.wx0 = e.wx0;
+  d.wx1 = e.wx1;
+  d.y_row = e.y_row;
+  d.y_plane = e.y_plane;
 }
 
 int launch_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, cudaStream_t s) {

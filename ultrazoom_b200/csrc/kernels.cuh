@@ -61,8 +61,15 @@ struct EpiParams {
   // colour planes y_plane elements apart -- a tile's core written straight into an assembled (possibly remote) frame.
   int wy0, wy1, wx0, wx1;
   long long y_row, y_plane;
+  // fp16 range guard: a kernel that is about to round a value beyond +-65504 into a 16-bit fp16 operand (where
+  // cvt.rn.satfinite would clip it silently) writes 1 here.  Points at a host-mapped word owned by the mz_model
+  // (mz_model_saturated); nullptr = not tracked (per-kernel entry points).
+  unsigned int* sat;
   BicubicTable bt;
 };
+
+// largest finite fp16: a pre-rounding magnitude above it saturates the operand
+#define MZ_F16_MAX 65504.0f
 
 // address of HR pixel (oy, ox) of colour plane (b, c) in the output of mode 2, or -1 outside the window
 __host__ __device__ inline long long head_out_index(const EpiParams& p, int b, int c, int y, int x, int i, int j) {
@@ -111,12 +118,14 @@ struct alignas(64) ConvLaunch {
 };
 int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvLaunch* out);
 int run_conv_tc(ConvLaunch& launch, cudaStream_t s);
+// head (mode 2) only: replace the image pointers, output window and image-epilogue flags of a prepared launch
+void patch_conv_epi(ConvLaunch& launch, const EpiParams& e);
 int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s);
 // zf != nullptr: fp32 stream zf + 16-bit shadow zb (pitch zb_pitch).  zf == nullptr: split stream, zb is z16 = [hi | lo]
 // with pitch 2 * Cp.
 // x8 != nullptr: the image is 8-bit (B,3,H,W) and read as x8 / 255.
 int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16,
-                int B, int H, int W, int Cp, int zb_pitch, cudaStream_t s);
+                int B, int H, int W, int Cp, int zb_pitch, cudaStream_t s, unsigned int* sat = nullptr);
 // film: [L][hCp / ns][B][2][ns] -- one [B][2][ns] table (scale row, shift row) per conv1 launch; ns == hCp normally
 int launch_film(const float* c, int c_rows, const float* w, const float* b, float* film, int L, int B, int F,
                 int hC, int hCp, int ns, cudaStream_t s);
@@ -124,9 +133,13 @@ int launch_film(const float* c, int c_rows, const float* w, const float* b, floa
 ConvTcTune to_tune(const mz_conv_tune* t);
 int current_device();
 bool dtype_ok(int d);
-// OIHW fp32 -> [tap = ky*3+kx][cout_p][cin_p] fp16 | bf16, zero padded (host).
-void pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, int bf16,
+// OIHW fp32 -> [tap = ky*3+kx][cout_p][cin_p] fp16 | bf16, zero padded (host).  Returns false when a weight does not
+// fit the fp16 operand range (|w| > 65504 or not finite) -- it would be clipped silently.
+bool pack_conv_weight_host(const float* w, int cout, int cin, int cout_p, int cin_p, int bf16,
                            std::vector<uint16_t>& out);
+// The same on the device (w_dev fp32 OIHW -> out_dev); an out-of-range fp16 weight sets *sat (may be nullptr).
+int launch_pack_conv_weight(const float* w_dev, uint16_t* out_dev, int cout, int cin, int cout_p, int cin_p, int bf16,
+                            unsigned int* sat, cudaStream_t s);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
@@ -142,6 +155,7 @@ __device__ __forceinline__ void epi_residual16(const EpiParams& p, int b, int y,
   const size_t pix = (static_cast<size_t>(b) * p.H + y) * p.W + x;
   float4* zf = reinterpret_cast<float4*>(p.zf + pix * (p.zf_pitch ? p.zf_pitch : p.n_pad) + n0);
   uint32_t o[8];
+  float amax = 0.f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float4 z = zin[q];
@@ -150,9 +164,11 @@ __device__ __forceinline__ void epi_residual16(const EpiParams& p, int b, int y,
     z.z += acc[4 * q + 2];
     z.w += acc[4 * q + 3];
     zf[q] = z;
+    amax = fmaxf(fmaxf(amax, fmaxf(fabsf(z.x), fabsf(z.y))), fmaxf(fabsf(z.z), fabsf(z.w)));
     o[2 * q] = pack_op2(p.bf16, z.x, z.y);
     o[2 * q + 1] = pack_op2(p.bf16, z.z, z.w);
   }
+  if (!p.bf16 && p.sat != nullptr && !(amax <= MZ_F16_MAX)) *p.sat = 1u;
   uint16_t* dst = p.out_bf16 + pix * (p.out_pitch ? p.out_pitch : p.n_pad) + n0;
   st_global_v4(dst, o[0], o[1], o[2], o[3]);
   st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
@@ -179,8 +195,14 @@ __device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, in
       }
     }
     uint32_t o[8];
+    float amax = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) o[q] = pack_op2(p.bf16, silu_f(acc[2 * q]), silu_f(acc[2 * q + 1]));
+    for (int q = 0; q < 8; ++q) {
+      const float s0 = silu_f(acc[2 * q]), s1 = silu_f(acc[2 * q + 1]);
+      amax = fmaxf(amax, fmaxf(fabsf(s0), fabsf(s1)));
+      o[q] = pack_op2(p.bf16, s0, s1);
+    }
+    if (!p.bf16 && p.sat != nullptr && !(amax <= MZ_F16_MAX)) *p.sat = 1u;
     uint16_t* dst = p.out_bf16 + pix * (p.out_pitch ? p.out_pitch : p.n_pad) + n0;
     st_global_v4(dst, o[0], o[1], o[2], o[3]);
     st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);

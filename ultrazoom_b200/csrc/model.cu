@@ -32,6 +32,12 @@ struct mz_model {
   uint16_t* head = nullptr;   // [9][headNp][Cp]
   float* ctrl_w = nullptr;         // (L, 2hC, F)
   float* ctrl_b = nullptr;         // (L, 2hC)
+  // fp16 range guard (EpiParams::sat): one host-mapped word the kernels set when a value beyond +-65504 is about to be
+  // rounded into an fp16 operand; read without synchronising by mz_model_saturated
+  unsigned int* sat_host = nullptr;
+  unsigned int* sat_dev = nullptr;
+  float* pack_tmp = nullptr;  // device staging for mz_model_set_weight_dev (largest fp32 tensor of the model)
+  size_t pack_tmp_elems = 0;
   std::vector<uint8_t> have;       // per (kind, layer) upload flags
   ConvTcTune tune[3];
   // the *_host entry points: two lanes, each with its own stream, staging buffers and workspace, so that the
@@ -128,11 +134,24 @@ static int run_conv(mz_model* m, int slot, const ConvArgs& a, const ConvTcTune& 
   memset(&key, 0, sizeof(key));
   key.a = a;
   key.t = t;
+  if (a.epi.mode == 2) {
+    // The head reads the LR image and writes the HR image through plain pointers (no tensor map): they, the output
+    // window and the flags of the image epilogue are not part of what was prepared -- a fresh output tensor per call
+    // must not cost a geometry search and two tensor-map encodes.  They are patched into the prepared launch below.
+    key.a.epi.x = nullptr;
+    key.a.epi.y = nullptr;
+    key.a.epi.x8 = nullptr;
+    key.a.epi.y8 = nullptr;
+    key.a.epi.u8_trunc = key.a.epi.skip_mode = key.a.epi.clamp01 = 0;
+    key.a.epi.wy0 = key.a.epi.wy1 = key.a.epi.wx0 = key.a.epi.wx1 = 0;
+    key.a.epi.y_row = key.a.epi.y_plane = 0;
+  }
   // two ways per convolution: the two host lanes (and a caller ping-ponging two buffer sets) alternate operands
   for (int way = 0; way < 2; ++way) {
     const int i = 2 * slot + way;
     if (m->prepared[i].valid && memcmp(&key, &m->keys[i], sizeof(key)) == 0) {
       m->victim[slot] = static_cast<uint8_t>(way ^ 1);
+      if (a.epi.mode == 2) patch_conv_epi(m->prepared[i], a.epi);
       return run_conv_tc(m->prepared[i], s);
     }
   }
@@ -226,6 +245,11 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   alloc(reinterpret_cast<void**>(&m->conv1), sizeof(uint16_t) * c1 * m->L);
   alloc(reinterpret_cast<void**>(&m->conv2), sizeof(uint16_t) * c2 * m->L);
   alloc(reinterpret_cast<void**>(&m->head), sizeof(uint16_t) * 9 * m->headNp * m->Cz);
+  if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&m->sat_host), sizeof(unsigned int), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *m->sat_host = 0u;
+    e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&m->sat_dev), m->sat_host, 0);
+  }
   if (m->F > 0) {
     alloc(reinterpret_cast<void**>(&m->ctrl_w), sizeof(float) * m->L * 2 * m->hC * m->F);
     alloc(reinterpret_cast<void**>(&m->ctrl_b), sizeof(float) * m->L * 2 * m->hC);
@@ -253,6 +277,8 @@ void mz_model_destroy(mz_model* m) {
   cudaFree(m->head);
   cudaFree(m->ctrl_w);
   cudaFree(m->ctrl_b);
+  cudaFree(m->pack_tmp);
+  if (m->sat_host) cudaFreeHost(m->sat_host);
   for (int i = 0; i < 2; ++i) {
     cudaFree(m->lane[i].ws);
     cudaFree(m->lane[i].hx);
@@ -264,6 +290,10 @@ void mz_model_destroy(mz_model* m) {
   for (cudaEvent_t e : m->ev) cudaEventDestroy(e);
   delete m;
 }
+
+static const char* const kRangeMsg =
+    "set_weight: a %s weight of layer %d exceeds the fp16 operand range (|w| > 65504 or not finite): it would be clipped "
+    "silently -- build the model with operand_dtype bfloat16";
 
 int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* host_data, size_t numel) {
   MZ_REQUIRE(m && host_data, "set_weight: null pointer");
@@ -291,8 +321,8 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
                  m->hC * m->C * 9, numel);
       for (int sl = 0; sl < m->S; ++sl) {  // one packed bank per slice of ns output channels
         const int n0 = sl * m->ns, rows = n0 < m->hC ? (m->hC - n0 < m->ns ? m->hC - n0 : m->ns) : 0;
-        pack_conv_weight_host(host_data + static_cast<size_t>(n0 < m->hC ? n0 : 0) * m->C * 9, rows, m->C, m->ns, m->Cz,
-                              m->bf16, packed);
+        MZ_REQUIRE(pack_conv_weight_host(host_data + static_cast<size_t>(n0 < m->hC ? n0 : 0) * m->C * 9, rows, m->C, m->ns,
+                                         m->Cz, m->bf16, packed), kRangeMsg, "conv1", layer);
         MZ_CUDA(cudaMemcpy(m->conv1 + (static_cast<size_t>(layer) * m->S + sl) * packed.size(), packed.data(),
                            packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
       }
@@ -303,8 +333,8 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
                  m->hC * m->C * 9, numel);
       for (int sl = 0; sl < m->S2; ++sl) {  // one packed bank per slice of ns2 output channels
         const int n0 = sl * m->ns2, rows = n0 < m->C ? (m->C - n0 < m->ns2 ? m->C - n0 : m->ns2) : 0;
-        pack_conv_weight_host(host_data + static_cast<size_t>(n0 < m->C ? n0 : 0) * m->hC * 9, rows, m->hC, m->ns2, m->hCp,
-                              m->bf16, packed);
+        MZ_REQUIRE(pack_conv_weight_host(host_data + static_cast<size_t>(n0 < m->C ? n0 : 0) * m->hC * 9, rows, m->hC, m->ns2,
+                                         m->hCp, m->bf16, packed), kRangeMsg, "conv2", layer);
         MZ_CUDA(cudaMemcpy(m->conv2 + (static_cast<size_t>(layer) * m->S2 + sl) * packed.size(), packed.data(),
                            packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
       }
@@ -313,7 +343,7 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
     case MZ_W_HEAD: {
       MZ_REQUIRE(numel == static_cast<size_t>(m->headN) * m->C * 9, "head weight: expected %d elements, got %zu",
                  m->headN * m->C * 9, numel);
-      pack_conv_weight_host(host_data, m->headN, m->C, m->headNp, m->Cz, m->bf16, packed);
+      MZ_REQUIRE(pack_conv_weight_host(host_data, m->headN, m->C, m->headNp, m->Cz, m->bf16, packed), kRangeMsg, "head", 0);
       MZ_CUDA(cudaMemcpy(m->head, packed.data(), packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
       break;
     }
@@ -334,6 +364,82 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
       return MZ_ERR_INVALID;
   }
   m->have[flag_index(m, kind, layer)] = 1;
+  return MZ_OK;
+}
+
+int mz_model_set_weight_dev(mz_model* m, int32_t kind, int32_t layer, const float* dev_data, size_t numel, void* stream) {
+  MZ_REQUIRE(m && dev_data, "set_weight_dev: null pointer");
+  const bool per_layer =
+      kind == MZ_W_CONV1 || kind == MZ_W_CONV2 || kind == MZ_W_CTRL_WEIGHT || kind == MZ_W_CTRL_BIAS;
+  MZ_REQUIRE(!per_layer || (layer >= 0 && layer < m->L), "set_weight: layer %d out of range [0, %d)", layer, m->L);
+  MZ_REQUIRE((kind != MZ_W_CTRL_WEIGHT && kind != MZ_W_CTRL_BIAS) || m->F > 0,
+             "set_weight: this model has no control modules");
+  DeviceGuard g(m->cfg.device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = MZ_OK;
+  switch (kind) {
+    case MZ_W_STEM_WEIGHT:
+      MZ_REQUIRE(numel == static_cast<size_t>(m->C) * 3, "stem weight: expected %d elements, got %zu", m->C * 3, numel);
+      MZ_CUDA(cudaMemcpyAsync(m->stem_w, dev_data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, s));
+      break;
+    case MZ_W_STEM_BIAS:
+      MZ_REQUIRE(numel == static_cast<size_t>(m->C), "stem bias: expected %d elements, got %zu", m->C, numel);
+      MZ_CUDA(cudaMemcpyAsync(m->stem_b, dev_data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, s));
+      break;
+    case MZ_W_CONV1: {
+      MZ_REQUIRE(numel == static_cast<size_t>(m->hC) * m->C * 9, "conv1 weight: expected %d elements, got %zu",
+                 m->hC * m->C * 9, numel);
+      const size_t bank = static_cast<size_t>(9) * m->ns * m->Cz;
+      for (int sl = 0; sl < m->S && rc == MZ_OK; ++sl) {
+        const int n0 = sl * m->ns, rows = n0 < m->hC ? (m->hC - n0 < m->ns ? m->hC - n0 : m->ns) : 0;
+        rc = launch_pack_conv_weight(dev_data + static_cast<size_t>(n0 < m->hC ? n0 : 0) * m->C * 9,
+                                     m->conv1 + (static_cast<size_t>(layer) * m->S + sl) * bank, rows, m->C, m->ns, m->Cz,
+                                     m->bf16, m->sat_dev, s);
+      }
+      break;
+    }
+    case MZ_W_CONV2: {
+      MZ_REQUIRE(numel == static_cast<size_t>(m->hC) * m->C * 9, "conv2 weight: expected %d elements, got %zu",
+                 m->hC * m->C * 9, numel);
+      const size_t bank = static_cast<size_t>(9) * m->ns2 * m->hCp;
+      for (int sl = 0; sl < m->S2 && rc == MZ_OK; ++sl) {
+        const int n0 = sl * m->ns2, rows = n0 < m->C ? (m->C - n0 < m->ns2 ? m->C - n0 : m->ns2) : 0;
+        rc = launch_pack_conv_weight(dev_data + static_cast<size_t>(n0 < m->C ? n0 : 0) * m->hC * 9,
+                                     m->conv2 + (static_cast<size_t>(layer) * m->S2 + sl) * bank, rows, m->hC, m->ns2,
+                                     m->hCp, m->bf16, m->sat_dev, s);
+      }
+      break;
+    }
+    case MZ_W_HEAD:
+      MZ_REQUIRE(numel == static_cast<size_t>(m->headN) * m->C * 9, "head weight: expected %d elements, got %zu",
+                 m->headN * m->C * 9, numel);
+      rc = launch_pack_conv_weight(dev_data, m->head, m->headN, m->C, m->headNp, m->Cz, m->bf16, m->sat_dev, s);
+      break;
+    case MZ_W_CTRL_WEIGHT: {
+      const size_t n = static_cast<size_t>(2) * m->hC * m->F;
+      MZ_REQUIRE(numel == n, "control weight: expected %zu elements, got %zu", n, numel);
+      MZ_CUDA(cudaMemcpyAsync(m->ctrl_w + layer * n, dev_data, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+      break;
+    }
+    case MZ_W_CTRL_BIAS: {
+      const size_t n = static_cast<size_t>(2) * m->hC;
+      MZ_REQUIRE(numel == n, "control bias: expected %zu elements, got %zu", n, numel);
+      MZ_CUDA(cudaMemcpyAsync(m->ctrl_b + layer * n, dev_data, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+      break;
+    }
+    default:
+      set_error("set_weight: unknown weight kind %d", kind);
+      return MZ_ERR_INVALID;
+  }
+  if (rc != MZ_OK) return rc;
+  m->have[flag_index(m, kind, layer)] = 1;
+  return MZ_OK;
+}
+
+int mz_model_saturated(mz_model* m, int32_t reset, int32_t* saturated) {
+  MZ_REQUIRE(m && saturated, "saturated: null pointer");
+  *saturated = (m->sat_host && *static_cast<volatile unsigned int*>(m->sat_host)) ? 1 : 0;
+  if (reset && m->sat_host) *static_cast<volatile unsigned int*>(m->sat_host) = 0u;
   return MZ_OK;
 }
 
@@ -438,7 +544,8 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
     rc = launch_film(c_dev, c_rows, m->ctrl_w, m->ctrl_b, film, m->L, B, m->F, m->hC, m->hCp, m->ns, s);
     if (rc != MZ_OK) return rc;
   }
-  rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, m->split ? nullptr : zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s);
+  rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, m->split ? nullptr : zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s,
+                   m->sat_dev);
   const int zpitch = m->split ? 2 * m->Cp : 0;  // channel pitch of the convolutions that read the stream
   if (rc != MZ_OK) return rc;
 
@@ -464,6 +571,7 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
       a.epi.film = m->F > 0 ? film + (static_cast<size_t>(l) * S + sl) * B * 2 * m->ns : nullptr;
       a.epi.out_bf16 = hid + static_cast<size_t>(sl) * m->ns;
       a.epi.out_pitch = S > 1 ? m->hCp : 0;
+      a.epi.sat = m->sat_dev;
       rc = simt ? launch_conv_simt(a, s) : run_conv(m, l * (S + S2) + sl, a, m->tune[0], s);
       if (rc != MZ_OK) return rc;
     }
@@ -483,6 +591,7 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
       a.epi.out_pitch = m->Cz;
       a.epi.zf = zf + static_cast<size_t>(sl) * m->ns2;
       a.epi.zf_pitch = S2 > 1 ? m->Cp : 0;
+      a.epi.sat = m->sat_dev;
       rc = simt ? launch_conv_simt(a, s) : run_conv(m, l * (S + S2) + S + sl, a, m->tune[1], s);
       if (rc != MZ_OK) return rc;
     }

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
                                                    const float* __restrict__ w,
                                                    const float* __restrict__ bias, float* __restrict__ zf,
                                                    uint16_t* __restrict__ zb, int bf16, int B, int H, int W, int Cp,
-                                                   int Cz, int ppb) {
+                                                   int Cz, int ppb, unsigned int* sat) {
   // blockDim = (groups, pixels per pass): a thread keeps ITS eight channels' weights and bias in registers and walks
   // the pixels of the block's range; the threads of a pixel write its channels as one contiguous run.
   const int g = threadIdx.x;  // channel group: channels 8g .. 8g+7
@@ -169,6 +169,12 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = fmaf(wr[i][2], r2, fmaf(wr[i][1], r1, fmaf(wr[i][0], r0, br[i])));
+    if (!bf16 && sat != nullptr) {  // fp16 range guard (see EpiParams::sat)
+      float amax = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(o[i]));
+      if (!(amax <= MZ_F16_MAX)) *sat = 1u;
+    }
     if (real && zf != nullptr) {
       float4* f = reinterpret_cast<float4*>(zf + pix * Cp + g * 8);
       f[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
 }
 
 int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16,
-                int B, int H, int W, int Cp, int zb_pitch, cudaStream_t s) {
+                int B, int H, int W, int Cp, int zb_pitch, cudaStream_t s, unsigned int* sat) {
   MZ_REQUIRE(Cp > 0 && Cp % 8 == 0, "stem: padded channel count must be a multiple of 8, %d given", Cp);
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "stem: empty input");
   const int Cz = (zb_pitch && zf != nullptr) ? zb_pitch : Cp;
@@ -204,7 +210,38 @@ int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* 
   const long long blocks = (npix + ppb - 1) / ppb;
   MZ_REQUIRE(blocks < (1LL << 31), "stem: too many pixels");
   stem_kernel<<<static_cast<unsigned>(blocks), dim3(groups, py), 0, s>>>(x, x8, w, bias, zf, zb, bf16, B, H, W, Cp, Cz,
-                                                                      static_cast<int>(ppb));
+                                                                      static_cast<int>(ppb), sat);
+  MZ_CUDA(cudaGetLastError());
+  return MZ_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// weight repack on the device: OIHW fp32 -> [tap][cout_p][cin_p] fp16 | bf16, zero padded (what
+// pack_conv_weight_host does on the CPU; used by mz_model_set_weight_dev so that a model living on
+// the GPU is packed without a round trip through host memory).
+// ----------------------------------------------------------------------------------------------
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int cout, int cin,
+                                        int cout_p, int cin_p, int bf16, unsigned int* sat) {
+  const long long total = 9LL * cout_p * cin_p;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % cin_p);
+    const long long r = idx / cin_p;
+    const int o = static_cast<int>(r % cout_p), t = static_cast<int>(r / cout_p);
+    float v = 0.f;
+    if (o < cout && i < cin) v = __ldg(w + (static_cast<size_t>(o) * cin + i) * 9 + t);
+    if (!bf16 && sat != nullptr && !(fabsf(v) <= MZ_F16_MAX)) *sat = 1u;
+    out[idx] = bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+  }
+}
+
+int launch_pack_conv_weight(const float* w_dev, uint16_t* out_dev, int cout, int cin, int cout_p, int cin_p, int bf16,
+                            unsigned int* sat, cudaStream_t s) {
+  MZ_REQUIRE(cout >= 0 && cin > 0 && cout_p >= cout && cin_p >= cin, "pack: bad shape (%d,%d)->(%d,%d)", cout, cin, cout_p, cin_p);
+  const long long total = 9LL * cout_p * cin_p;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  pack_conv_weight_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(w_dev, out_dev, cout, cin, cout_p, cin_p, bf16, sat);
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }

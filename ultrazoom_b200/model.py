@@ -76,21 +76,30 @@ class SubpixelConv2d(nn.Module):
 
 
 class _Engine:
-    """One native mz_model on one device + cached workspace."""
+    """One native mz_model on one device (for one operand dtype) + its cached workspace.
 
-    def __init__(self, owner: "MewZoom", device: torch.device):
+    One workspace and one prepared-launch cache serve every call, so calls are serialised on the device: a call
+    enqueued on a different CUDA stream than the previous one first waits for that call's kernels (an event), and the
+    workspace is marked as used on every stream that touched it, so the caching allocator cannot hand it out while
+    kernels still run (stream-level concurrency)."""
+
+    def __init__(self, owner: "MewZoom", device: torch.device, operand_dtype: str):
         self.lib = _native.load()
         if self.lib.mz_device_count() == 0:
             raise RuntimeError("no sm_100 (B200) device visible; ultrazoom_b200 has no CPU or non-Blackwell fallback")
         self.device = device
+        self.operand_dtype = operand_dtype
         cfg = _native.MzConfig(owner.upscale_ratio, owner.num_channels, owner.hidden_ratio,
                                owner.num_encoder_layers, owner.control_features, device.index or 0,
-                               _native.dtype_code(owner.operand_dtype), _native.STREAM_CODES[owner.residual_stream])
+                               _native.dtype_code(operand_dtype), _native.STREAM_CODES[owner.residual_stream])
         handle = C.c_void_p()
         _native.check(self.lib.mz_model_create(C.byref(cfg), C.byref(handle)))
         self.handle = handle
         self.versions = None
         self.ws: Optional[Tensor] = None
+        self.ws_stream = None          # the stream the workspace was allocated on
+        self.last_stream = None        # cuda_stream of the previous call on this engine
+        self.last_event: Optional[torch.cuda.Event] = None
 
     def __del__(self):
         try:
@@ -101,33 +110,71 @@ class _Engine:
             pass
 
     def sync_weights(self, owner: "MewZoom") -> None:
-        versions = tuple((p.data_ptr(), p._version) for p in owner.parameters())
+        params = owner._flat_params()
+        versions = tuple([(p.data_ptr(), p._version) for p in params])
         if versions == self.versions:
             return
         lib, h = self.lib, self.handle
+        stream = torch.cuda.current_stream(self.device)
+        on_device = False
 
         def put(kind: int, layer: int, t: Tensor) -> None:
-            a = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
-            _native.check(lib.mz_model_set_weight(h, kind, layer, a.data_ptr(), a.numel()))
+            nonlocal on_device
+            if t.is_cuda and t.device == self.device:
+                # packed by a kernel on the current stream (mz_model_set_weight_dev): no round trip through the host
+                a = t.detach().to(torch.float32).contiguous()
+                _native.check(lib.mz_model_set_weight_dev(h, kind, layer, a.data_ptr(), a.numel(), stream.cuda_stream))
+                on_device = True
+            else:
+                a = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+                _native.check(lib.mz_model_set_weight(h, kind, layer, a.data_ptr(), a.numel()))
 
-        put(_native.W_STEM_WEIGHT, 0, owner.stem.conv.weight)
-        put(_native.W_STEM_BIAS, 0, owner.stem.conv.bias)
-        for l, blk in enumerate(owner.encoder):
-            put(_native.W_CONV1, l, blk.convnet.conv1.weight)
-            put(_native.W_CONV2, l, blk.convnet.conv2.weight)
-            if owner.control_features > 0:
-                put(_native.W_CTRL_WEIGHT, l, blk.control.linear.weight)
-                put(_native.W_CTRL_BIAS, l, blk.control.linear.bias)
-        put(_native.W_HEAD, 0, owner.head.conv.weight)
+        with torch.cuda.device(self.device):
+            put(_native.W_STEM_WEIGHT, 0, owner.stem.conv.weight)
+            put(_native.W_STEM_BIAS, 0, owner.stem.conv.bias)
+            for l, blk in enumerate(owner.encoder):
+                put(_native.W_CONV1, l, blk.convnet.conv1.weight)
+                put(_native.W_CONV2, l, blk.convnet.conv2.weight)
+                if owner.control_features > 0:
+                    put(_native.W_CTRL_WEIGHT, l, blk.control.linear.weight)
+                    put(_native.W_CTRL_BIAS, l, blk.control.linear.bias)
+            put(_native.W_HEAD, 0, owner.head.conv.weight)
+            if on_device and self.operand_dtype == "float16" and not torch.cuda.is_current_stream_capturing():
+                stream.synchronize()        # once per weight change: the device-side pack reports range errors by flag
+                if self.saturated(reset=True):
+                    raise AssertionError("a convolution weight exceeds the fp16 operand range (|w| > 65504 or not finite); "
+                                         "build the model with operand_dtype='bfloat16' (or 'auto')")
         self.versions = versions
 
-    def workspace(self, B: int, H: int, W: int) -> Tensor:
+    def saturated(self, reset: bool = False) -> bool:
+        """Has any COMPLETED kernel of this engine rounded a value beyond the fp16 range (mz_model_saturated)?"""
+        flag = C.c_int32()
+        _native.check(self.lib.mz_model_saturated(self.handle, 1 if reset else 0, C.byref(flag)))
+        return bool(flag.value)
+
+    def workspace(self, B: int, H: int, W: int, stream: "torch.cuda.Stream") -> Tensor:
         need = C.c_size_t()
         _native.check(self.lib.mz_workspace_bytes(self.handle, B, H, W, C.byref(need)))
         if self.ws is None or self.ws.numel() < need.value:
-            self.ws = None
+            self.ws = None     # (kernels still using the old buffer were recorded on it with record_stream)
             self.ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=self.device)
+            self.ws_stream = stream.cuda_stream
+        elif stream.cuda_stream != self.ws_stream and not torch.cuda.is_current_stream_capturing():
+            self.ws.record_stream(stream)
         return self.ws
+
+    def begin(self, stream: "torch.cuda.Stream") -> None:
+        """Order this call after the previous one when that ran on another stream (they share the workspace)."""
+        if self.last_stream is not None and self.last_stream != stream.cuda_stream and self.last_event is not None:
+            stream.wait_event(self.last_event)
+
+    def end(self, stream: "torch.cuda.Stream") -> None:
+        if torch.cuda.is_current_stream_capturing():
+            return
+        if self.last_event is None:
+            self.last_event = torch.cuda.Event()
+        self.last_event.record(stream)
+        self.last_stream = stream.cuda_stream
 
 
 class MewZoom(nn.Module, PyTorchModelHubMixin):
@@ -147,14 +194,18 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         operand_dtype: str = "float16",
         residual_stream: str = "auto",
     ):
-        """``operand_dtype``: element type of the tensor-core operands ("float16" default, or "bfloat16").
+        """``operand_dtype``: element type of the tensor-core operands ("float16" default, "bfloat16", or "auto").
         Both run at the same tcgen05 rate with fp32 accumulation; fp16's 10-bit mantissa keeps max|err| vs the fp32
-        reference ~8x smaller ("Numerics").
+        reference ~8x smaller ("Numerics"), but its range ends at 65504: every kernel that rounds a larger
+        magnitude into an fp16 operand raises a flag (``saturated()``); with "float16" the next call then raises
+        instead of returning clipped images, with "auto" every call is checked (one stream synchronisation) and a
+        saturated one is re-run -- like all later ones -- with bfloat16 operands.
         ``residual_stream``: how the residual stream lives in HBM between blocks -- "float32" (fp32 + a 16-bit shadow),
         "split" (two 16-bit planes hi + lo: the same value to 2^-22 with 14 % less conv2 traffic; measured no faster,
         kept as a tested option) or "auto" (the library's choice: float32)."""
         super().__init__()
-        _native.dtype_code(operand_dtype)
+        if str(operand_dtype) != "auto":
+            _native.dtype_code(operand_dtype)
         assert residual_stream in _native.STREAM_CODES, f"residual_stream must be one of {sorted(_native.STREAM_CODES)}"
         assert upscale_ratio in self.AVAILABLE_UPSCALE_RATIOS, (
             f"Upscale ratio must be one of {self.AVAILABLE_UPSCALE_RATIOS}, but got {upscale_ratio}.")
@@ -178,6 +229,8 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         self._engines: dict = {}
         self._flags_extra = 0
         self.u8_truncate = False
+        self._auto_dtype = "float16"      # operand_dtype="auto": what the next call runs with
+        self._param_cache = None
 
     # ---- reference model.py:94-115 ----
     @property
@@ -202,6 +255,7 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         for module in self.modules():
             if isinstance(module, nn.Conv2d) and not is_parametrized(module):
                 weight_norm(module)
+        self._invalidate_params()
 
     def remove_parameterizations(self) -> None:
         """Bake and remove all parametrizations (reference model.py:131-139, called before ``eval()``)."""
@@ -211,6 +265,7 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
             if is_parametrized(module):
                 for name in list(module.parametrizations.keys()):
                     remove_parametrizations(module, name)
+        self._invalidate_params()
 
     @staticmethod
     def convert_reference_state_dict(state_dict: dict) -> dict:
@@ -240,14 +295,54 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         return model
 
     # ---- native plumbing ----
-    def _engine(self, device: torch.device) -> _Engine:
-        key = (device.type, device.index)
+    def _flat_params(self) -> list:
+        """The parameters as a flat list, cached: ``Module.parameters()`` walks the module tree on every call, which is
+        most of the host time of a small frame.  Each entry remembers the ``_parameters`` dict and key it came from, so
+        a replaced Parameter object (parametrizations, direct assignment) is noticed by an identity check."""
+        cache = self._param_cache
+        if cache is not None and all(d.get(n) is p for d, n, p in cache):
+            return [p for _, _, p in cache]
+        cache = [(m._parameters, n, p) for m in self.modules() for n, p in m._parameters.items() if p is not None]
+        self._param_cache = cache
+        return [p for _, _, p in cache]
+
+    def _invalidate_params(self) -> None:
+        self._param_cache = None
+        for eng in self._engines.values():
+            eng.versions = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._invalidate_params()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._invalidate_params()
+        return out
+
+    def _operand_dtype_now(self) -> str:
+        return self._auto_dtype if self.operand_dtype == "auto" else self.operand_dtype
+
+    def _engine(self, device: torch.device, operand_dtype: Optional[str] = None) -> _Engine:
+        dt = operand_dtype or self._operand_dtype_now()
+        dt = "bfloat16" if _native.dtype_code(dt) == _native.DTYPE_BF16 else "float16"
+        key = (device.type, device.index, dt)
         eng = self._engines.get(key)
         if eng is None:
-            eng = _Engine(self, device)
+            eng = _Engine(self, device, dt)
             self._engines[key] = eng
         eng.sync_weights(self)
         return eng
+
+    def saturated(self, device: Optional[torch.device] = None, sync: bool = True, reset: bool = False) -> bool:
+        """fp16 range guard: did a kernel round a magnitude beyond 65504 into an fp16 operand (the result of that call
+        is then clipped, i.e. wrong)?  ``sync`` waits for the device first."""
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        if sync:
+            torch.cuda.synchronize(dev)
+        eng = self._engines.get((dev.type, dev.index, "float16"))
+        return eng.saturated(reset) if eng is not None else False
 
     def set_conv_tune(self, which: int = -1, device: Optional[torch.device] = None, **kw) -> None:
         """Override the tcgen05 kernel's tunables (see mz_conv_tune); for benches and tests."""
@@ -270,13 +365,12 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         assert c.shape[0] in (1, x.shape[0]), "Batch size of c must match x."
         return c
 
-    def _run(self, x: Tensor, c: Optional[Tensor], flags: int) -> Tensor:
+    def _run(self, x: Tensor, c: Optional[Tensor], flags: int, ws: Optional[Tensor] = None) -> Tensor:
         c = self._check_inputs(x, c)
         if not x.is_cuda:
             raise RuntimeError("ultrazoom_b200.MewZoom runs on sm_100a CUDA kernels only; move the input to a "
                                "B200 (`x.cuda()`). There is no CPU fallback.")
         dev = x.device
-        eng = self._engine(dev)
         io8 = x.dtype == torch.uint8       # 8-bit images in and out (upscale only): see upscale()
         if io8:
             assert flags & _native.FLAG_CLAMP01, "uint8 images are supported by upscale(), not forward()"
@@ -286,16 +380,36 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
             c = c.detach().to(device=dev, dtype=torch.float32).contiguous()
         B, _, H, W = x.shape
         r = self.upscale_ratio
-        y = torch.empty((B, 3, H * r, W * r), dtype=torch.uint8 if io8 else torch.float32, device=dev)
-        ws = eng.workspace(B, H, W)
-        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
-        ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        _native.check(eng.lib.mz_upscale(
-            eng.handle, x.data_ptr(), c.data_ptr() if c is not None else None,
-            c.shape[0] if c is not None else 0, y.data_ptr(), B, H, W, ws_ptr, ws_bytes,
-            flags | self._flags_extra, stream))
-        return y
+        capturing = torch.cuda.is_current_stream_capturing()
+        auto = self.operand_dtype == "auto" and not capturing
+        while True:
+            eng = self._engine(dev)
+            f16 = eng.operand_dtype == "float16"
+            if f16 and not capturing and eng.saturated(reset=auto):
+                if not auto:
+                    raise RuntimeError(
+                        "an earlier call on this model rounded a value beyond the fp16 range (65504) into a tensor-core "
+                        "operand: its result was clipped.  Use operand_dtype='bfloat16' or 'auto' for this checkpoint "
+                        "(model.saturated(reset=True) clears the flag).")
+                self._auto_dtype = "bfloat16"
+                continue
+            y = torch.empty((B, 3, H * r, W * r), dtype=torch.uint8 if io8 else torch.float32, device=dev)
+            stream = torch.cuda.current_stream(dev)
+            eng.begin(stream)
+            w = ws if ws is not None else eng.workspace(B, H, W, stream)
+            ws_ptr = (w.data_ptr() + 1023) // 1024 * 1024
+            ws_bytes = w.numel() - (ws_ptr - w.data_ptr())
+            _native.check(eng.lib.mz_upscale(
+                eng.handle, x.data_ptr(), c.data_ptr() if c is not None else None,
+                c.shape[0] if c is not None else 0, y.data_ptr(), B, H, W, ws_ptr, ws_bytes,
+                flags | self._flags_extra, stream.cuda_stream))
+            eng.end(stream)
+            if auto and f16:
+                stream.synchronize()       # "auto": a saturated fp16 call is repeated with bfloat16 operands
+                if eng.saturated(reset=True):
+                    self._auto_dtype = "bfloat16"
+                    continue
+            return y
 
     # ---- reference model.py:149-179 ----
     def forward(self, x: Tensor, c: Optional[Tensor] = None) -> Tensor:
@@ -341,13 +455,16 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
             "the window does not fit into the frame at that position")
         if frame.device != dev:
             _native.check(eng.lib.mz_enable_peer_access(dev.index or 0, frame.device.index or 0))
-        ws = eng.workspace(B, H, W)
+        stream = torch.cuda.current_stream(dev)
+        eng.begin(stream)
+        ws = eng.workspace(B, H, W, stream)
         ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
         dst = frame[0, 0, fy, fx].data_ptr() if frame.numel() else 0
         _native.check(eng.lib.mz_upscale_window(
             eng.handle, x.data_ptr(), c.data_ptr() if c is not None else None, c.shape[0] if c is not None else 0,
             dst, frame.stride(2), frame.stride(1), B, H, W, y0, y1, x0, x1, ws_ptr,
-            ws.numel() - (ws_ptr - ws.data_ptr()), flags, torch.cuda.current_stream(dev).cuda_stream))
+            ws.numel() - (ws_ptr - ws.data_ptr()), flags, stream.cuda_stream))
+        eng.end(stream)
 
     def capture(self, x: Tensor, c: Optional[Tensor] = None, clamp: bool = True) -> "GraphedUpscale":
         """Record one ``upscale`` (``clamp=False``: ``forward``) call at the shape of ``x`` into a CUDA graph.
@@ -418,15 +535,23 @@ class GraphedUpscale:
         self.model = model
         self.x = (x.detach() if x.dtype == torch.uint8 else x.detach().to(torch.float32)).contiguous().clone()
         self.c = None if c is None else c.detach().to(device=x.device, dtype=torch.float32).contiguous().clone()
+        # The graph bakes in raw pointers: it owns everything they point at -- its input / output tensors, a PRIVATE
+        # workspace (the engine's cached one is dropped and re-allocated when a later call needs a larger one) and the
+        # engine itself (packed weights, FiLM parameters).
+        self.engine = model._engine(x.device)
+        need = C.c_size_t()
+        B, _, H, W = self.x.shape
+        _native.check(self.engine.lib.mz_workspace_bytes(self.engine.handle, B, H, W, C.byref(need)))
+        self.ws = torch.empty(need.value + 1024, dtype=torch.uint8, device=x.device)
         with torch.inference_mode():
             side = torch.cuda.Stream(device=x.device)
             side.wait_stream(torch.cuda.current_stream(x.device))
-            with torch.cuda.stream(side):        # warm-up: packs the weights, sizes the workspace, prepares the launches
-                model._run(self.x, self.c, flags)
+            with torch.cuda.stream(side):        # warm-up: packs the weights, prepares the launches
+                model._run(self.x, self.c, flags, ws=self.ws)
             torch.cuda.current_stream(x.device).wait_stream(side)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.y = model._run(self.x, self.c, flags)
+                self.y = model._run(self.x, self.c, flags, ws=self.ws)
 
     def replay(self) -> Tensor:
         self.graph.replay()
