@@ -199,10 +199,28 @@ typedef struct mz_conv_tune {
   int32_t resident;   /* filter bank resident in shared memory: 0 when it fits, 1 require, 2 never       */
   int32_t epi_warps;  /* epilogue warps per CTA: 0 auto (8), 4 or 8                                      */
   int32_t fuse;       /* vertical taps stacked along N, one UMMA per input row: 0 auto, 1 force, 2 off */
+  int32_t block;      /* (which = 0 only) the whole encoder block as ONE kernel -- conv1 -> control -> SiLU -> conv2 ->    */
+                      /* residual with the hidden tensor kept in shared memory: 0 when the model qualifies (48 channels,  */
+                      /* hidden 96, fp32 stream), 1 require, 2 never (two kernels per block)                             */
+  int32_t seg_rows;   /* fused block: output rows per segment, 0 auto                                                    */
 } mz_conv_tune;
 
 /* which = 0 conv1, 1 conv2, 2 head, -1 all.  Takes effect on the next mz_upscale. */
 int mz_model_set_tune(mz_model* m, int32_t which, const mz_conv_tune* tune);
+
+/* 1 if mz_upscale runs this model's encoder blocks as ONE kernel each (hidden tensor never written to HBM), else 0. */
+int mz_model_fused_block(const mz_model* m);
+
+/* One encoder block as one kernel (EncoderBlock.forward, model.py:507-511 = InvertedBottleneck :773-778 + skip :789-792,
+ * with the control module between conv1 and SiLU), for 48 channels / hidden 96:
+ *   zf += conv2(SiLU(scale * conv1(zb_in) + shift)) ; zb_out = round16(zf)
+ * zb_in / zb_out: (B,H,W,48) 16-bit NHWC, DIFFERENT buffers (the input is read with a halo); zf: (B,H,W,48) fp32, in
+ * place; w1_packed [9][96][48] and w2_packed [9][48][96] from mz_pack_conv_weight; film_dev (B,2,96) or NULL.
+ * seg_rows / max_ctas: 0 = auto (tests use them to force several segments / rounds on small images).
+ * This entry point synchronises `stream` (it stacks conv2's bank into a temporary); mz_upscale keeps stacked banks. */
+int mz_block_fused(const void* zb_in_dev, void* zb_out_dev, float* zf_dev, const void* w1_packed_dev,
+                   const void* w2_packed_dev, const float* film_dev, int32_t B, int32_t H, int32_t W,
+                   int32_t operand_dtype, int32_t seg_rows, int32_t max_ctas, void* stream);
 
 /* Upsample(scale_factor=r, mode="bicubic") -- model.py:71,156.  NCHW fp32, `planes` = B*3 planes. */
 int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, int32_t W, int32_t r,

@@ -64,6 +64,8 @@ class MzConvTune(C.Structure):
         ("resident", C.c_int32),
         ("epi_warps", C.c_int32),
         ("fuse", C.c_int32),
+        ("block", C.c_int32),
+        ("seg_rows", C.c_int32),
     ]
 
 
@@ -83,6 +85,8 @@ SIGNATURES = {
     "mz_model_enable_timing": (C.c_int, [_P, _I]),
     "mz_model_conv_stack_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "mz_workspace_bytes": (C.c_int, [_P, _I, _I, _I, C.POINTER(C.c_size_t)]),
+    "mz_model_fused_block": (C.c_int, [_P]),
+    "mz_block_fused": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mz_upscale": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _P, C.c_size_t, C.c_uint32, _P]),
     "mz_upscale_window": (C.c_int, [_P, _P, _P, _I, _P, C.c_int64, C.c_int64, _I, _I, _I, _I, _I, _I, _I, _P, C.c_size_t,
                                     C.c_uint32, _P]),

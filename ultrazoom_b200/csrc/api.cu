@@ -26,6 +26,8 @@ ConvTcTune to_tune(const mz_conv_tune* t) {
     o.resident = t->resident;
     o.epi_warps = t->epi_warps;
     o.fuse = t->fuse;
+    o.block = t->block;
+    o.seg_rows = t->seg_rows;
   }
   return o;
 }
@@ -138,6 +140,40 @@ int mz_head_shuffle_add(const void* zb_dev, const void* wpacked_dev, const float
   make_bicubic_table(r, &a.epi.bt);
   if (use_tc) return launch_conv_tc(a, to_tune(tune), current_device(), static_cast<cudaStream_t>(stream));
   return launch_conv_simt(a, static_cast<cudaStream_t>(stream));
+}
+
+int mz_block_fused(const void* zb_in_dev, void* zb_out_dev, float* zf_dev, const void* w1_packed_dev,
+                   const void* w2_packed_dev, const float* film_dev, int32_t B, int32_t H, int32_t W, int32_t operand_dtype,
+                   int32_t seg_rows, int32_t max_ctas, void* stream) {
+  MZ_REQUIRE(zb_in_dev && zb_out_dev && zf_dev && w1_packed_dev && w2_packed_dev, "block_fused: null pointer");
+  MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint16_t* stacked = nullptr;
+  MZ_CUDA(cudaMalloc(&stacked, sizeof(uint16_t) * 9 * 48 * 96));
+  int rc = stack_conv2_bank(static_cast<const uint16_t*>(w2_packed_dev), stacked, s);
+  if (rc == MZ_OK) {
+    FusedBlockArgs a;
+    memset(&a, 0, sizeof(a));
+    a.zb_in = static_cast<const uint16_t*>(zb_in_dev);
+    a.zb_out = static_cast<uint16_t*>(zb_out_dev);
+    a.zf = zf_dev;
+    a.w1 = static_cast<const uint16_t*>(w1_packed_dev);
+    a.w2s = stacked;
+    a.film = film_dev;
+    a.B = B;
+    a.H = H;
+    a.W = W;
+    a.bf16 = operand_dtype == MZ_DTYPE_BF16;
+    a.seg_rows = seg_rows;
+    a.max_ctas = max_ctas;
+    ConvLaunch L;
+    rc = prepare_block_fused(a, current_device(), &L);
+    if (rc == MZ_OK) rc = run_block_fused(L, s);
+  }
+  const cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(stacked);
+  if (rc == MZ_OK && e != cudaSuccess) return cuda_fail(e, "block_fused synchronize", __FILE__, __LINE__);
+  return rc;
 }
 
 int mz_pack_conv_weight(const float* w_host, int32_t cout, int32_t cin, int32_t cout_p, int32_t cin_p,

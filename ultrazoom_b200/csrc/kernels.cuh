@@ -105,6 +105,9 @@ struct ConvTcTune {
   int resident;    // filter bank resident in shared memory: 0 = when it fits, 1 = require, 2 = never (stream per patch)
   int epi_warps;   // epilogue warps: 0 = auto (8), 4 or 8
   int fuse;        // filter rows fused along N (one UMMA per input row): 0 = when three taps stack (N <= 85), 1 = also with two, 2 = never
+  int block;       // whole encoder block (conv1 -> FiLM -> SiLU -> conv2 -> residual) as ONE kernel (block_fused.cu):
+                   // 0 = when the model qualifies (48 channels, hidden 96), 1 = require, 2 = never (two kernels per block)
+  int seg_rows;    // fused block: output rows per segment (0 = auto)
   int dbg;         // timing experiments only (WRONG results): 1 skip weight loads, 2 skip activation loads,
                    // 4 skip the epilogue body, 8 skip the MMAs
 };
@@ -120,6 +123,24 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
 int run_conv_tc(ConvLaunch& launch, cudaStream_t s);
 // head (mode 2) only: replace the image pointers, output window and image-epilogue flags of a prepared launch
 void patch_conv_epi(ConvLaunch& launch, const EpiParams& e);
+// ---- one encoder block as one kernel (block_fused.cu): zf += conv2(SiLU(FiLM(conv1(zb_in)))), zb_out = round16(zf) ----
+struct FusedBlockArgs {
+  const uint16_t* zb_in;  // (B,H,W,48) 16-bit: read with a halo, so the output goes to a second buffer
+  uint16_t* zb_out;       // (B,H,W,48) 16-bit
+  float* zf;              // (B,H,W,48) fp32 residual stream, updated in place
+  const uint16_t* w1;     // conv1 bank [9][96][48]
+  const uint16_t* w2s;    // conv2 bank, vertical taps stacked per filter column: [3 dx][144][96] (stack_conv2_bank)
+  const float* film;      // [B][2][96] or nullptr
+  unsigned int* sat;      // fp16 range guard (EpiParams::sat) or nullptr
+  int B, H, W, bf16;
+  int seg_rows;           // output rows per segment (0 = auto)
+  int max_ctas;           // cap on the persistent grid (0 = SM count)
+};
+bool fused_block_applies(int Cp, int hCp, int zb_pitch);
+int stack_conv2_bank(const uint16_t* packed, uint16_t* stacked, cudaStream_t s);
+int prepare_block_fused(const FusedBlockArgs& a, int device, ConvLaunch* out);
+int run_block_fused(ConvLaunch& launch, cudaStream_t s);
+
 int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s);
 // zf != nullptr: fp32 stream zf + 16-bit shadow zb (pitch zb_pitch).  zf == nullptr: split stream, zb is z16 = [hi | lo]
 // with pitch 2 * Cp.

@@ -30,6 +30,16 @@ struct mz_model {
   uint16_t* conv1 = nullptr;  // L x S x [9][ns][Cz]
   uint16_t* conv2 = nullptr;  // L x S2 x [9][ns2][hCp]
   uint16_t* head = nullptr;   // [9][headNp][Cp]
+  // fused encoder block (block_fused.cu; 48-channel models): conv2's banks with the vertical taps stacked per filter
+  // column, L x [3 dx][144][96]; the 16-bit stream then ping-pongs between zb and the (otherwise unused) hidden buffer
+  uint16_t* conv2s = nullptr;
+  bool fused_ok = false;
+  struct FusedKey {
+    FusedBlockArgs a;
+  };
+  std::vector<ConvLaunch> fprepared;  // two ways per layer, like `prepared`
+  std::vector<FusedKey> fkeys;
+  std::vector<uint8_t> fvictim;
   float* ctrl_w = nullptr;         // (L, 2hC, F)
   float* ctrl_b = nullptr;         // (L, 2hC)
   // fp16 range guard (EpiParams::sat): one host-mapped word the kernels set when a value beyond +-65504 is about to be
@@ -164,7 +174,35 @@ static int run_conv(mz_model* m, int slot, const ConvArgs& a, const ConvTcTune& 
   return run_conv_tc(m->prepared[i], s);
 }
 
+// launch fused block `layer` through its prepared-launch cache
+static int run_fused(mz_model* m, int layer, const FusedBlockArgs& a, cudaStream_t s) {
+  mz_model::FusedKey key;
+  memset(&key, 0, sizeof(key));
+  key.a = a;
+  for (int way = 0; way < 2; ++way) {
+    const int i = 2 * layer + way;
+    if (m->fprepared[i].valid && memcmp(&key, &m->fkeys[i], sizeof(key)) == 0) {
+      m->fvictim[layer] = static_cast<uint8_t>(way ^ 1);
+      return run_block_fused(m->fprepared[i], s);
+    }
+  }
+  const int i = 2 * layer + m->fvictim[layer];
+  m->fvictim[layer] ^= 1;
+  m->fprepared[i].valid = false;
+  const int rc = prepare_block_fused(a, m->cfg.device, &m->fprepared[i]);
+  if (rc != MZ_OK) return rc;
+  m->fkeys[i] = key;
+  return run_block_fused(m->fprepared[i], s);
+}
+
+static bool fused_wanted(const mz_model* m) {
+  static const bool env_off = getenv("MZ_NO_FUSED_BLOCK") != nullptr;
+  return m->fused_ok && !env_off && m->tune[0].block != 2;
+}
+
 extern "C" {
+
+int mz_model_fused_block(const mz_model* m) { return (m && fused_wanted(m)) ? 1 : 0; }
 
 int mz_model_create(const mz_config* cfg, mz_model** out) {
   MZ_REQUIRE(cfg && out, "model_create: null pointer");
@@ -245,6 +283,14 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   alloc(reinterpret_cast<void**>(&m->conv1), sizeof(uint16_t) * c1 * m->L);
   alloc(reinterpret_cast<void**>(&m->conv2), sizeof(uint16_t) * c2 * m->L);
   alloc(reinterpret_cast<void**>(&m->head), sizeof(uint16_t) * 9 * m->headNp * m->Cz);
+  m->fused_ok = !m->split && m->S == 1 && m->S2 == 1 && fused_block_applies(m->Cp, m->hCp, m->Cz);
+  if (m->fused_ok) {
+    alloc(reinterpret_cast<void**>(&m->conv2s), sizeof(uint16_t) * c2 * m->L);
+    m->fprepared.resize(2 * m->L);
+    m->fkeys.resize(2 * m->L);
+    m->fvictim.assign(m->L, 0);
+    for (auto& k : m->fkeys) memset(&k, 0xff, sizeof(k));
+  }
   if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&m->sat_host), sizeof(unsigned int), cudaHostAllocMapped);
   if (e == cudaSuccess) {
     *m->sat_host = 0u;
@@ -275,6 +321,7 @@ void mz_model_destroy(mz_model* m) {
   cudaFree(m->conv1);
   cudaFree(m->conv2);
   cudaFree(m->head);
+  cudaFree(m->conv2s);
   cudaFree(m->ctrl_w);
   cudaFree(m->ctrl_b);
   cudaFree(m->pack_tmp);
@@ -337,6 +384,12 @@ int mz_model_set_weight(mz_model* m, int32_t kind, int32_t layer, const float* h
                                          m->hCp, m->bf16, packed), kRangeMsg, "conv2", layer);
         MZ_CUDA(cudaMemcpy(m->conv2 + (static_cast<size_t>(layer) * m->S2 + sl) * packed.size(), packed.data(),
                            packed.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      }
+      if (m->fused_ok) {  // the fused block's view of the same bank
+        const size_t bank = static_cast<size_t>(9) * m->Cp * m->hCp;
+        const int rc = stack_conv2_bank(m->conv2 + layer * bank, m->conv2s + layer * bank, nullptr);
+        if (rc != MZ_OK) return rc;
+        MZ_CUDA(cudaStreamSynchronize(nullptr));  // (callers' streams need not be ordered with the legacy stream)
       }
       break;
     }
@@ -408,6 +461,7 @@ int mz_model_set_weight_dev(mz_model* m, int32_t kind, int32_t layer, const floa
                                      m->conv2 + (static_cast<size_t>(layer) * m->S2 + sl) * bank, rows, m->hC, m->ns2,
                                      m->hCp, m->bf16, m->sat_dev, s);
       }
+      if (rc == MZ_OK && m->fused_ok) rc = stack_conv2_bank(m->conv2 + layer * bank, m->conv2s + layer * bank, s);
       break;
     }
     case MZ_W_HEAD:
@@ -554,7 +608,38 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
   // one slice of conv1's / conv2's filter bank
   const size_t c1s = static_cast<size_t>(9) * m->ns * m->Cz, c2s = static_cast<size_t>(9) * m->ns2 * m->hCp;
   const int S = m->S, S2 = m->S2;
-  for (int l = 0; l < m->L; ++l) {
+  // Fused blocks (48-channel models): one kernel per block, the hidden tensor stays on the SM; the 16-bit stream
+  // ping-pongs between zb and the hidden buffer (a block reads its input with a halo, so it cannot write in place).
+  const bool fused = !simt && fused_wanted(m);
+  if (m->tune[0].block == 1 && !fused) {
+    set_error("upscale: the fused encoder block was required (tune.block = 1) but does not apply to this model / call");
+    return MZ_ERR_UNSUPPORTED;
+  }
+  uint16_t* zcur = zb;
+  uint16_t* znxt = hid;
+  for (int l = 0; l < m->L && fused; ++l) {
+    FusedBlockArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.zb_in = zcur;
+    fa.zb_out = znxt;
+    fa.zf = zf;
+    fa.w1 = m->conv1 + static_cast<size_t>(l) * c1s;
+    fa.w2s = m->conv2s + static_cast<size_t>(l) * c2s;
+    fa.film = m->F > 0 ? film + static_cast<size_t>(l) * B * 2 * m->ns : nullptr;
+    fa.sat = m->sat_dev;
+    fa.B = B;
+    fa.H = H;
+    fa.W = W;
+    fa.bf16 = m->bf16;
+    fa.seg_rows = m->tune[0].seg_rows;
+    fa.max_ctas = m->tune[0].max_ctas;
+    rc = run_fused(m, l, fa, s);
+    if (rc != MZ_OK) return rc;
+    uint16_t* t = zcur;
+    zcur = znxt;
+    znxt = t;
+  }
+  for (int l = 0; l < m->L && !fused; ++l) {
     ConvArgs a;
     for (int sl = 0; sl < S; ++sl) {
       memset(&a, 0, sizeof(a));
@@ -610,7 +695,7 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
   }
   ConvArgs a;
   memset(&a, 0, sizeof(a));
-  a.in = zb;
+  a.in = zcur;
   a.w = m->head;
   a.cin_p = m->Cz;
   a.in_pitch = zpitch;

@@ -165,6 +165,9 @@ class _Engine:
 
     def begin(self, stream: "torch.cuda.Stream") -> None:
         """Order this call after the previous one when that ran on another stream (they share the workspace)."""
+        if torch.cuda.is_current_stream_capturing():
+            return      # (a capturing stream may not wait for an event recorded outside the capture; torch synchronises
+                        # the device before a capture begins, so everything earlier has finished)
         if self.last_stream is not None and self.last_stream != stream.cuda_stream and self.last_event is not None:
             stream.wait_event(self.last_event)
 

@@ -128,6 +128,25 @@ def conv3x3(inp: Tensor, wpacked: Tensor, mode: int, film: Optional[Tensor] = No
     return out
 
 
+def block_fused(zb: Tensor, w1_packed: Tensor, w2_packed: Tensor, film: Optional[Tensor], zf: Tensor, seg_rows: int = 0,
+                max_ctas: int = 0) -> Tensor:
+    """One encoder block as one kernel (mz_block_fused): zf += conv2(SiLU(scale * conv1(zb) + shift)) in place, returns
+    the new 16-bit stream round16(zf).  zb (B,H,W,48) 16-bit, w1_packed (9,96,48), w2_packed (9,48,96), film (B,2,96)."""
+    _need_cuda(zb, w1_packed, w2_packed, zf)
+    assert zb.dtype in (torch.float16, torch.bfloat16) and w1_packed.dtype == zb.dtype and w2_packed.dtype == zb.dtype
+    zb = zb.contiguous()
+    B, H, W, Cc = zb.shape
+    assert Cc == 48 and tuple(w1_packed.shape) == (9, 96, 48) and tuple(w2_packed.shape) == (9, 48, 96), "48 / 96 channels only"
+    assert zf.is_contiguous() and tuple(zf.shape) == (B, H, W, 48) and zf.dtype == torch.float32
+    out = torch.empty_like(zb)
+    with torch.cuda.device(zb.device):
+        _native.check(_native.load().mz_block_fused(
+            zb.data_ptr(), out.data_ptr(), zf.data_ptr(), w1_packed.data_ptr(), w2_packed.data_ptr(),
+            film.data_ptr() if film is not None else None, B, H, W, _native.dtype_code(zb.dtype), seg_rows, max_ctas,
+            _stream(zb)))
+    return out
+
+
 def head_shuffle_add(zb: Tensor, wpacked: Tensor, r: int, x: Optional[Tensor] = None, y: Optional[Tensor] = None,
                      skip_mode: int = 2, clamp01: bool = False, use_tc: bool = True,
                      tune: Optional[_native.MzConvTune] = None) -> Tensor:
