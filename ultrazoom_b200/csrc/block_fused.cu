@@ -22,7 +22,8 @@
 //                  -> TMA store; zeroes the accumulator block for its next use.
 //     The ring has NB = 4 blocks plus 2 overflow blocks, so that the stacked window never wraps (a split window would
 //     need differently split filter banks in the two CTAs): rows whose block index is 0 or 1 collect the contributions
-//     of the previous lap in the overflow blocks, and epilogue-2 adds the two parts.
+//     of the previous lap in the overflow blocks, and epilogue-2 adds the two parts.  The block of an output row is
+//     its image row mod 4, so the result does not depend on batch size, segment height or grid size bit for bit.
 //   * zb is read with a halo from neighbouring strips and segments, so the block writes its 16-bit output to a SECOND
 //     buffer (ping-pong between blocks); the fp32 stream is updated in place (no halo there).
 //
@@ -54,7 +55,7 @@ constexpr uint32_t oHid = oZb + kZbStages * kZbRow;                   // 135,168
 constexpr uint32_t oStage = (oHid + kHidBufs * kHidBuf + 256 + 1023) & ~1023u;   // (+256: the dx = 2 tap reads two rows past a tile)
 constexpr uint32_t oFilm = oStage + 4 * kStageWarp;
 constexpr uint32_t oBars = oFilm + 2 * kHC * 4;
-constexpr uint32_t kNumBars = 1 + 2 * kZbStages + 2 * kAcc1Stages + 2 * kHidBufs + 2 * kNB + 4;
+constexpr uint32_t kNumBars = 1 + 2 * kZbStages + 2 * kAcc1Stages + 2 * kHidBufs + 2 * kNB + 12;
 constexpr uint32_t oTmemPtr = oBars + kNumBars * 8;
 constexpr uint32_t kSmemBytes = oTmemPtr + 16 + 1024;                 // + alignment slack
 static_assert(kSmemBytes <= 232448, "fused block: shared memory plan exceeds 227 KB");
@@ -75,7 +76,21 @@ struct FbParams {
   int T;               // output rows per segment
   int n_sp, n_seg, n_units;   // strip pairs per row, segments per image, units = B * n_sp * n_seg
   uint32_t idesc1, idesc2;
+  int dbg;            // timing experiments only (WRONG results): 1 epilogue-2 drains without residual / stores, 2 epilogue-1 skips
+                      // the FiLM + SiLU math, 4 no conv1 UMMAs, 8 no conv2 UMMAs
+  long long* prof;    // optional role timers (clock64 ticks), [cluster][16]; nullptr = off
 };
+
+#define FB_TIMED(slot, stmt)                         \
+  do {                                               \
+    if (prof_on) {                                   \
+      const long long _t = clock64();                \
+      stmt;                                          \
+      tick[slot] += clock64() - _t;                  \
+    } else {                                         \
+      stmt;                                          \
+    }                                                \
+  } while (0)
 
 __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __grid_constant__ FbParams p) {
   using namespace fb;
@@ -95,7 +110,7 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
   const uint32_t bar_hid_empty = bar_hid_full + 8 * kHidBufs;         // [2] local : conv2 no longer reads the buffer
   const uint32_t bar_acc2_full = bar_hid_empty + 8 * kHidBufs;        // [4] local : an output row's accumulator is complete
   const uint32_t bar_acc2_empty = bar_acc2_full + 8 * kNB;            // [4] leader: epilogue-2 of both CTAs has read + zeroed it
-  const uint32_t bar_res = bar_acc2_empty + 8 * kNB;                  // [4] local : residual tile of an epilogue-2 warp
+  const uint32_t bar_res = bar_acc2_empty + 8 * kNB;                  // [4][3] local: residual slice j of an epilogue-2 warp
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen_base + oTmemPtr);
 
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -124,7 +139,7 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
       mbar_init(bar_acc2_full + 8 * i, 1);
       mbar_init(bar_acc2_empty + 8 * i, 8);   // four epilogue-2 warps of each CTA
     }
-    for (int i = 0; i < 4; ++i) mbar_init(bar_res + 8 * i, 1);
+    for (int i = 0; i < 12; ++i) mbar_init(bar_res + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -150,6 +165,9 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
   const int n_clusters = static_cast<int>(gridDim.x >> 1), cluster_id = static_cast<int>(blockIdx.x >> 1);
   const int units_per_img = p.n_sp * p.n_seg;
   const int T = p.T, steps = T + 2, rows_per_unit = T + 4;
+  const bool prof_on = p.prof != nullptr;
+  long long tick[7] = {0, 0, 0, 0, 0, 0, 0};
+  const long long t_role0 = prof_on ? clock64() : 0;
 
   // unit -> (image, first output row, first output pixel of THIS CTA's strip)
   auto unit_geom = [&](int unit, int& b, int& y0, int& x0) {
@@ -180,7 +198,7 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
       unit_geom(unit, b, y0, x0);
       for (int rho = 0; rho < rows_per_unit; ++rho, ++cnt) {
         const uint32_t st = cnt % kZbStages, par = (cnt / kZbStages) & 1u;
-        mbar_wait(bar_zb_empty + 8 * st, par ^ 1u);
+        FB_TIMED(0, mbar_wait(bar_zb_empty + 8 * st, par ^ 1u));
         if (lane == 0) {
           if (cta_rank == 0) mbar_expect_tx(bar_zb_full + 8 * st, 2 * kZbRowTx);
           const uint32_t full = mapa_u32(bar_zb_full + 8 * st, 0);
@@ -205,18 +223,36 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
     uint32_t pos = 0;     // conv2 ring position of output row rho' = 0 of the current unit
     uint32_t opened = 0;  // ring positions < opened have been claimed from epilogue-2
     for (int unit = cluster_id; unit < p.n_units; unit += n_clusters) {
+      {
+        // Ring block of an output row = image row mod 4, whatever the batch, segment or round: rows in blocks 0 / 1 sum
+        // two partial accumulators (overflow blocks), so tying the block to the image row makes the fp32 association --
+        // hence every bit of the result -- independent of how the work was cut.  Skipped positions are handed to
+        // epilogue-2 as junk rows.
+        int b, y0, x0;
+        unit_geom(unit, b, y0, x0);
+        const uint32_t lead = (static_cast<uint32_t>(y0 + 2) - pos) & 3u;
+        for (uint32_t s2 = 0; s2 < lead; ++s2, ++pos) {
+          while (opened <= pos) {
+            FB_TIMED(3, mbar_wait(bar_acc2_empty + 8 * (opened % kNB), ((opened / kNB) & 1u) ^ 1u));
+            ++opened;
+          }
+          if (leader) umma2_commit_mcast(bar_acc2_full + 8 * (pos % kNB), 3);
+          __syncwarp();
+        }
+      }
       for (int i = 0; i <= steps; ++i) {
         if (i < steps) {
           // ---- conv1(i): hidden row i from zb rows rho = i, i+1, i+2 ----
           for (int k = (i == 0 ? 0 : 2); k < 3; ++k) {
             const uint32_t c = zcnt + i + k;
-            mbar_wait(bar_zb_full + 8 * (c % kZbStages), (c / kZbStages) & 1u);
+            FB_TIMED(0, mbar_wait(bar_zb_full + 8 * (c % kZbStages), (c / kZbStages) & 1u));
           }
           const uint32_t st1 = a1 % kAcc1Stages;
-          mbar_wait(bar_acc1_empty + 8 * st1, ((a1 / kAcc1Stages) & 1u) ^ 1u);
+          FB_TIMED(1, mbar_wait(bar_acc1_empty + 8 * st1, ((a1 / kAcc1Stages) & 1u) ^ 1u));
           tc_fence_after();
           const uint32_t d1 = tmem_base + kAcc1Col + st1 * kHC;
           if (leader) {
+            if (!(p.dbg & 4))
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
               const uint32_t arow = base + oZb + ((zcnt + i + dy) % kZbStages) * kZbRow;
@@ -247,14 +283,15 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
           // ---- conv2(j): hidden row j adds to output rows rho' = j, j+1, j+2 (ring positions pos + j ...) ----
           const int j = i - 1;
           const uint32_t hb = hcnt % kHidBufs;
-          mbar_wait(bar_hid_full + 8 * hb, (hcnt / kHidBufs) & 1u);
+          FB_TIMED(2, mbar_wait(bar_hid_full + 8 * hb, (hcnt / kHidBufs) & 1u));
           while (opened <= pos + j + 2) {  // claim the blocks this window opens (drained + zeroed by epilogue-2)
-            mbar_wait(bar_acc2_empty + 8 * (opened % kNB), ((opened / kNB) & 1u) ^ 1u);
+            FB_TIMED(3, mbar_wait(bar_acc2_empty + 8 * (opened % kNB), ((opened / kNB) & 1u) ^ 1u));
             ++opened;
           }
           tc_fence_after();
           const uint32_t d2 = tmem_base + kRingCol + ((pos + j) % kNB) * kC;
           if (leader) {
+            if (!(p.dbg & 8))
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
 #pragma unroll
@@ -309,8 +346,8 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
         const uint32_t st1 = a1 % kAcc1Stages, hb = a1 % kHidBufs;
         const int hy = y0 - 1 + i;
         const bool keep = px_ok && hy >= 0 && hy < p.H;  // conv2 zero-pads the HIDDEN tensor: outside the image it is 0, not SiLU(shift)
-        mbar_wait(bar_acc1_full + 8 * st1, (a1 / kAcc1Stages) & 1u);
-        mbar_wait(bar_hid_empty + 8 * hb, ((a1 / kHidBufs) & 1u) ^ 1u);
+        FB_TIMED(0, mbar_wait(bar_acc1_full + 8 * st1, (a1 / kAcc1Stages) & 1u));
+        FB_TIMED(1, mbar_wait(bar_hid_empty + 8 * hb, ((a1 / kHidBufs) & 1u) ^ 1u));
         __syncwarp();
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kAcc1Col + st1 * kHC;
@@ -318,8 +355,8 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
 #pragma unroll
         for (int c = 0; c < 3; ++c) {  // 32 channels = one 64-byte row of chunk tile c
           uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
-          tmem_ld_wait();
+          FB_TIMED(2, { tmem_ld32(taddr + c * 32, v); tmem_ld_wait(); });
+          const long long t_math = prof_on ? clock64() : 0;
           const float4* sc = reinterpret_cast<const float4*>(film_s + c * 32);
           const float4* sh = reinterpret_cast<const float4*>(film_s + kHC + c * 32);
           uint32_t o[16];
@@ -331,6 +368,7 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
             float a2 = silu_h(fmaf(__uint_as_float(v[4 * kk + 2]), g.z, h.z));
             float a3 = silu_h(fmaf(__uint_as_float(v[4 * kk + 3]), g.w, h.w));
             if (!keep) a0 = a1v = a2 = a3 = 0.f;
+            if (p.dbg & 2) a0 = a1v = a2 = a3 = __uint_as_float(v[4 * kk]);
             amax = fmaxf(fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1v))), fmaxf(fabsf(a2), fabsf(a3)));
             o[2 * kk] = pack_op2(p.bf16, a0, a1v);
             o[2 * kk + 1] = pack_op2(p.bf16, a2, a3);
@@ -339,104 +377,144 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
             sts128(crow + swz_chunk(px_row, ch, 64) * 16, o[4 * ch], o[4 * ch + 1], o[4 * ch + 2], o[4 * ch + 3]);
+          if (prof_on) tick[3] += clock64() - t_math;
         }
-        tc_fence_before();
-        fence_proxy_async_smem();  // the UMMAs (async proxy) read what these threads wrote
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_cluster(mapa_u32(bar_acc1_empty + 8 * st1, 0));
-          mbar_arrive_cluster(mapa_u32(bar_hid_full + 8 * hb, 0));
-        }
+        FB_TIMED(4, {
+          tc_fence_before();
+          fence_proxy_async_smem();  // the UMMAs (async proxy) read what these threads wrote
+          __syncwarp();
+        });
+        FB_TIMED(5, {
+          if (lane == 0) {
+            mbar_arrive_remote(mapa_u32(bar_acc1_empty + 8 * st1, 0));
+            mbar_arrive_remote(mapa_u32(bar_hid_full + 8 * hb, 0));
+          }
+        });
       }
     }
     if (!p.bf16 && p.sat != nullptr && !(amax <= MZ_F16_MAX)) *p.sat = 1u;
   } else if (warp >= 8) {
     // =============================== epilogue-2: finished output row -> + residual -> zf, zb -> TMA store ===============================
+    // Per row: read the accumulator block (plus its overflow part) into registers, zero it and hand it back to the
+    // issuer AT ONCE; then the row is finished in three 16-channel slices, each with its own staging slot (fp32 box +
+    // 16-bit box) and residual barrier: slice j of the NEXT row is requested as soon as slice j's stores of this row
+    // have been read (one slice later: bulk_wait_read<1>), so residual loads run a row ahead and neither their latency
+    // nor the store read-out is on the row's critical path.
     griddep_wait();  // the residual stream is written by earlier kernels of the stream
     const int q = warp & 3;
     const uint32_t st_z = base + oStage + q * kStageWarp, st_o = st_z + kStageZ;
-    const uint32_t my_res = bar_res + 8 * q;
+    const uint32_t my_res = bar_res + 8 * (q * 3);  // one barrier per slice slot
     const CUtensorMap* tmZ = &p.tmZ[q == 3 ? 1 : 0];  // the last warp's box is 30 pixels: a strip is 126 wide
     const CUtensorMap* tmO = &p.tmO[q == 3 ? 1 : 0];
-    const uint32_t res_bytes = (q == 3 ? 30u : 32u) * kC * 4;
+    const uint32_t slice_bytes = (q == 3 ? 30u : 32u) * 16 * 4;
     float amax = 0.f;
     const bool lane_live = !(q == 3 && lane >= 30);  // the last two pixel rows of a 128-pixel tile belong to the next strip
     uint32_t pos = 0, rpar = 0;
+    bool preloaded = false;    // slices 0 and 1 of the current row's residual were requested during the previous row ...
+    bool pending_last = false;  // ... and slice 2 still has to be (its slot was being stored from until now)
     for (int unit = cluster_id; unit < p.n_units; unit += n_clusters) {
       int b, y0, x0;
       unit_geom(unit, b, y0, x0);
       const int xw = x0 + q * 32;  // first output pixel of this warp
-      for (int rho = 0; rho < rows_per_unit; ++rho, ++pos) {
+      const int lead = static_cast<int>((static_cast<uint32_t>(y0 + 2) - pos) & 3u);  // junk positions: see the issuer
+      for (int rho = -lead; rho < rows_per_unit; ++rho, ++pos) {
         const int y = y0 - 2 + rho;
-        const bool store = rho >= 2 && rho < T + 2 && y < p.H && xw < p.W;  // (warp-uniform)
+        const bool store = rho >= 2 && rho < T + 2 && y < p.H && xw < p.W && !(p.dbg & 1);  // (warp-uniform)
         const uint32_t k = pos % kNB, par = (pos / kNB) & 1u;
         if (store && lane == 0) {
-          bulk_wait_read<0>();  // the stores of the previous row have finished reading the staging tiles
-          mbar_expect_tx(my_res, res_bytes);
-          for (int bx = 0; bx < 3; ++bx) tma_load_4d(st_z + bx * 2048, tmZ, my_res, bx * 16, xw, y, b);
-          if (rho + 1 < T + 2 && y + 1 < p.H)  // L2 prefetch of the next row's residual tile
-            for (int bx = 0; bx < 3; ++bx) tma_prefetch_4d(tmZ, bx * 16, xw, y + 1, b);
+          if (!preloaded) {  // first stored row of a segment: nothing was requested ahead
+            FB_TIMED(2, bulk_wait_read<0>());
+            for (int j = 0; j < 3; ++j) {
+              mbar_expect_tx(my_res + 8 * j, slice_bytes);
+              tma_load_4d(st_z + j * 2048, tmZ, my_res + 8 * j, j * 16, xw, y, b);
+            }
+          } else if (pending_last) {
+            FB_TIMED(2, bulk_wait_read<0>());
+            mbar_expect_tx(my_res + 16, slice_bytes);
+            tma_load_4d(st_z + 2 * 2048, tmZ, my_res + 16, 32, xw, y, b);
+          }
         }
-        mbar_wait(bar_acc2_full + 8 * k, par);
+        FB_TIMED(0, mbar_wait(bar_acc2_full + 8 * k, par));
         __syncwarp();
         tc_fence_after();
+        const long long t_body = prof_on ? clock64() : 0;
         const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kRingCol;
         const uint32_t t_main = lane_base + k * kC, t_ovf = lane_base + (kNB + k) * kC;
         const bool has_ovf = k < 2;  // rows in blocks 0 / 1 collected the previous lap's contributions in the overflow blocks
+        uint32_t v[48];
         if (store) {
-          mbar_wait(my_res, rpar);
-          rpar ^= 1u;
-#pragma unroll
-          for (int n0 = 0; n0 < kC; n0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(t_main + n0, v);
+          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+          uint32_t(&v1)[16] = *reinterpret_cast<uint32_t(*)[16]>(&v[32]);
+          tmem_ld32(t_main, v0);
+          tmem_ld16(t_main + 32, v1);
+          if (has_ovf) {
+            uint32_t w0[32], w1[16];
+            tmem_ld32(t_ovf, w0);
+            tmem_ld16(t_ovf + 32, w1);
             tmem_ld_wait();
-            tmem_zero16(t_main + n0);
-            if (has_ovf) {
-              uint32_t w[16];
-              tmem_ld16(t_ovf + n0, w);
-              tmem_ld_wait();
-              tmem_zero16(t_ovf + n0);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
-            }
-            const uint32_t zrow = st_z + (n0 >> 4) * 2048 + lane * 64;
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w0[e]));
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[32 + e] = __float_as_uint(__uint_as_float(v[32 + e]) + __uint_as_float(w1[e]));
+          } else {
+            tmem_ld_wait();
+          }
+        }
+#pragma unroll
+        for (int n0 = 0; n0 < kC; n0 += 16) {
+          tmem_zero16(t_main + n0);
+          if (has_ovf) tmem_zero16(t_ovf + n0);
+        }
+        tmem_st_wait();  // the zeroes are in TMEM before the issuer may accumulate into the block again
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(mapa_u32(bar_acc2_empty + 8 * k, 0));
+        if (prof_on) tick[3] += clock64() - t_body;
+        if (store) {
+          const bool next_store = rho + 1 < T + 2 && y + 1 < p.H;  // the next position stores too (same strip, next row)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            FB_TIMED(1, mbar_wait(my_res + 8 * j, rpar));
+            const uint32_t zrow = st_z + j * 2048 + lane * 64;
             uint32_t o[8];
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint32_t addr = zrow + swz_chunk(lane, kk, 64) * 16;
               float4 z = lds128f(addr);
-              z.x += __uint_as_float(v[4 * kk + 0]);
-              z.y += __uint_as_float(v[4 * kk + 1]);
-              z.z += __uint_as_float(v[4 * kk + 2]);
-              z.w += __uint_as_float(v[4 * kk + 3]);
+              z.x += __uint_as_float(v[16 * j + 4 * kk + 0]);
+              z.y += __uint_as_float(v[16 * j + 4 * kk + 1]);
+              z.z += __uint_as_float(v[16 * j + 4 * kk + 2]);
+              z.w += __uint_as_float(v[16 * j + 4 * kk + 3]);
               sts128(addr, __float_as_uint(z.x), __float_as_uint(z.y), __float_as_uint(z.z), __float_as_uint(z.w));
               if (lane_live) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(z.x), fabsf(z.y))), fmaxf(fabsf(z.z), fabsf(z.w)));
               o[2 * kk] = pack_op2(p.bf16, z.x, z.y);
               o[2 * kk + 1] = pack_op2(p.bf16, z.z, z.w);
             }
-            const uint32_t orow = st_o + (n0 >> 4) * 1024 + lane * 32;
+            const uint32_t orow = st_o + j * 1024 + lane * 32;
             sts128(orow + swz_chunk(lane, 0, 32) * 16, o[0], o[1], o[2], o[3]);
             sts128(orow + swz_chunk(lane, 1, 32) * 16, o[4], o[5], o[6], o[7]);
+            FB_TIMED(4, {
+              fence_proxy_async_smem();
+              __syncwarp();
+            });
+            const long long t_tail = prof_on ? clock64() : 0;
+            if (lane == 0) {
+              tma_store_4d(tmZ, st_z + j * 2048, j * 16, xw, y, b);
+              tma_store_4d(tmO, st_o + j * 1024, j * 16, xw, y, b);
+              bulk_commit();
+              if (j >= 1 && next_store) {  // slot j-1: its stores (one group back) have been read -> next row's slice
+                bulk_wait_read<1>();
+                mbar_expect_tx(my_res + 8 * (j - 1), slice_bytes);
+                tma_load_4d(st_z + (j - 1) * 2048, tmZ, my_res + 8 * (j - 1), (j - 1) * 16, xw, y + 1, b);
+              }
+            }
+            if (prof_on) tick[5] += clock64() - t_tail;
           }
-        } else {  // a junk row (above / below the segment, outside the image): only re-zero its accumulators
-#pragma unroll
-          for (int n0 = 0; n0 < kC; n0 += 16) {
-            tmem_zero16(t_main + n0);
-            if (has_ovf) tmem_zero16(t_ovf + n0);
-          }
-        }
-        tmem_st_wait();  // the zeroes are in TMEM before the issuer may accumulate into the block again
-        tc_fence_before();
-        if (store) fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive_cluster(mapa_u32(bar_acc2_empty + 8 * k, 0));
-          if (store) {
-            for (int bx = 0; bx < 3; ++bx) tma_store_4d(tmZ, st_z + bx * 2048, bx * 16, xw, y, b);
-            for (int bx = 0; bx < 3; ++bx) tma_store_4d(tmO, st_o + bx * 1024, bx * 16, xw, y, b);
-            bulk_commit();
-          }
+          rpar ^= 1u;
+          preloaded = next_store;
+          pending_last = next_store;
+        } else {
+          preloaded = pending_last = false;
         }
       }
     }
@@ -444,6 +522,12 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
     if (!p.bf16 && p.sat != nullptr && !(amax <= MZ_F16_MAX)) *p.sat = 1u;
   }
 
+  if (prof_on && lane == 0 && cta_rank == 0 && (warp == 0 || warp == 1 || warp == 4 || warp == 8)) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : (warp == 4 ? 2 : 3));
+    long long* dst = p.prof + (static_cast<size_t>(cluster_id) * 4 + role) * 8;
+    for (int i = 0; i < 7; ++i) dst[i] = tick[i];
+    dst[7] = clock64() - t_role0;
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // no CTA may exit while its peer can still signal into it or read its operands
@@ -548,6 +632,10 @@ int prepare_block_fused(const FusedBlockArgs& a, int device, ConvLaunch* out) {
     const uint32_t box[3] = {32u, 72u, 1u};
     if ((rc = encode_tmap(&p.tmW2, tdt, 3, const_cast<uint16_t*>(a.w2s), dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B)) != MZ_OK) return rc;
   }
+  {
+    const char* d = getenv("MZ_FB_DBG");
+    p.dbg = d ? atoi(d) : 0;
+  }
   MZ_CUDA(cudaFuncSetAttribute(block_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fb::kSmemBytes)));
   {
     static const bool verbose = getenv("MZ_VERBOSE") != nullptr;
@@ -584,8 +672,35 @@ int run_block_fused(ConvLaunch& launch, cudaStream_t s) {
   cfg.attrs = attr;
   cfg.numAttrs = na;
   FbParams q = L.p;
+  static const bool prof = getenv("MZ_FB_PROF") != nullptr;
+  static long long* g_prof = nullptr;
+  static int prof_left = 3;  // print the first few launches only
+  const bool do_prof = prof && prof_left > 0;
+  if (do_prof) {
+    if (!g_prof) MZ_CUDA(cudaMalloc(&g_prof, sizeof(long long) * 128 * 32));
+    MZ_CUDA(cudaMemsetAsync(g_prof, 0, sizeof(long long) * 128 * 32, s));
+    q.prof = g_prof;
+    cfg.numAttrs = 1;  // (no dependent launch while timing)
+  }
   void* args[1] = {&q};
   MZ_CUDA(cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(block_fused_kernel), args));
+  if (do_prof) {
+    --prof_left;
+    MZ_CUDA(cudaStreamSynchronize(s));
+    const int nc = L.grid / 2;
+    std::vector<long long> h(static_cast<size_t>(nc) * 32);
+    MZ_CUDA(cudaMemcpy(h.data(), g_prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    double m[32] = {0};
+    for (int c = 0; c < nc; ++c)
+      for (int i = 0; i < 32; ++i) m[i] += static_cast<double>(h[static_cast<size_t>(c) * 32 + i]) / nc;
+    fprintf(stderr,
+            "[mz fused prof] T %d units %d clusters %d | producer: wait_zb_empty %.0f total %.0f | issuer: wait_zb_full %.0f "
+            "wait_acc1_empty %.0f wait_hid_full %.0f wait_acc2_empty %.0f total %.0f | epi1: wait_acc1_full %.0f wait_hid_empty "
+            "%.0f tmem_ld %.0f math+sts %.0f fences %.0f arrives %.0f total %.0f | epi2: wait_acc2_full %.0f wait_residual %.0f "
+            "wait_store_read %.0f body(incl. residual wait) %.0f st_wait+fences %.0f arrive+stores %.0f total %.0f\n",
+            L.p.T, L.p.n_units, nc, m[0], m[7], m[8], m[9], m[10], m[11], m[15], m[16], m[17], m[18], m[19], m[20], m[21], m[23],
+            m[24], m[25], m[26], m[27], m[28], m[29], m[31]);
+  }
   return MZ_OK;
 }
 

@@ -226,6 +226,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same with the default semantics (.release at CTA scope) on a shared::cluster address -- what CUTLASS's
+// ClusterBarrier::arrive emits.  The cluster-scope release above costs ~1200 cycles per arrive (measured with the role
+// timers of block_fused.cu: it drains the thread's outstanding memory operations cluster-wide); what the waiter
+// needs ordered here lives in the ARRIVING CTA's own shared memory / TMEM and is consumed by that CTA's tensor core on a
+// command that is issued hundreds of cycles after the arrive is observed (generic -> async proxy ordering is the
+// explicit fence.proxy.async before the arrive).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA loads of a CTA pair: data lands in the executing CTA, bytes complete on a barrier that may live in the peer
 __device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
                                              int c2, int c3) {

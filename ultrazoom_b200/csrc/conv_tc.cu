@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) {
         if (PAIR)
-          mbar_arrive_cluster(mapa_u32(bar_acc_empty + 8 * as, 0));  // the leader's issuer waits for both CTAs
+          mbar_arrive_remote(mapa_u32(bar_acc_empty + 8 * as, 0));  // the leader's issuer waits for both CTAs
         else
           mbar_arrive(bar_acc_empty + 8 * as);
       }

@@ -85,15 +85,22 @@ def _splits_aligned(n: int, parts: int, halo: int, align: int) -> List[Tuple[int
     return out
 
 
-def plan_tiles(H: int, W: int, rows: int, cols: int, halo: int, align_w: int = 1) -> List[Tile]:
-    """``align_w`` = 128 sizes the columns for the convolution kernel's 128-pixel tiles (see ``_splits_aligned``)."""
+ROW_ALIGN = 4   # the fused-block kernel ties its accumulator ring (4 blocks) to the image row: see plan_tiles
+
+
+def plan_tiles(H: int, W: int, rows: int, cols: int, halo: int, align_w: int = 1, align_rows: int = ROW_ALIGN) -> List[Tile]:
+    """``align_w`` = 128 sizes the columns for the convolution kernel's 128-pixel tiles (see ``_splits_aligned``).
+    ``align_rows``: the first row of a haloed tile is moved up to a multiple of it (a few more halo rows are harmless).
+    The fused encoder block sums the accumulators of rows 0 / 1 mod 4 in two parts; with tile origins on multiples of 4
+    a row keeps its association inside a tile, so tiled inference stays BIT-identical to the un-tiled frame."""
     assert rows > 0 and cols > 0 and rows <= H and cols <= W, f"bad grid {rows}x{cols} for a {H}x{W} image"
-    assert halo >= 0
+    assert halo >= 0 and align_rows >= 1
     tiles = []
     for iy, (y0, y1) in enumerate(_splits(H, rows)):
         for ix, (x0, x1) in enumerate(_splits_aligned(W, cols, halo, align_w)):
-            tiles.append(Tile(iy * cols + ix, y0, y1, x0, x1,
-                              max(0, y0 - halo), min(H, y1 + halo), max(0, x0 - halo), min(W, x1 + halo)))
+            hy0 = max(0, y0 - halo)
+            hy0 -= hy0 % align_rows
+            tiles.append(Tile(iy * cols + ix, y0, y1, x0, x1, hy0, min(H, y1 + halo), max(0, x0 - halo), min(W, x1 + halo)))
     return tiles
 
 
