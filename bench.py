@@ -303,13 +303,14 @@ def main():
         _native.check(eng.lib.mz_model_conv_stack_ms(eng.handle, C.byref(conv_ms)))
         _native.check(eng.lib.mz_model_enable_timing(eng.handle, 0))
         assert not model.saturated(dev), "fp16 operand saturation during the timed region"
+        fused = bool(eng.lib.mz_model_fused_block(eng.handle))
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item()) / steps
         res = {"workload": workload, "model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc, "ms_step": ms_step,
                "conv_ms": conv_ms.value, "clocks": clocks, "value": world * out_px / (ms_step * 1e-3) / 1e6,
-               "e2e": None, "scaling": "weak", "steps": steps}
+               "e2e": None, "scaling": "weak", "steps": steps, "fused": fused}
         # ---- end to end through the public API with HOST buffers (H2D + kernels + D2H inside the timed region) ----
         if want_e2e:
             # Every step copies its inputs from pinned host memory and its result back to pinned host memory.  The
@@ -421,7 +422,7 @@ def main():
             del full
         res = {"workload": "cfg5", "model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc,
                "ms_step": ms_step, "conv_ms": conv_ms.value, "clocks": clocks, "value": out_px / (ms_step * 1e-3) / 1e6,
-               "e2e": None, "scaling": "strong", "steps": steps, "npix_executed": int(sum((t_.hy1 - t_.hy0) * (t_.hx1 - t_.hx0) for t_ in mine)),
+               "e2e": None, "scaling": "strong", "steps": steps, "fused": bool(eng.lib.mz_model_fused_block(eng.handle)), "npix_executed": int(sum((t_.hy1 - t_.hy0) * (t_.hx1 - t_.hx0) for t_ in mine)),
                "tiling": {"grid": f"{rows}x{cols}", "halo_lr_px": R, "executed_over_algorithmic_work": executed,
                           "max_abs_diff_vs_untiled": err,
                           "stitch": "head kernel stores the core into rank 0's frame (CUDA IPC peer mapping, NVLink)"}}
@@ -478,10 +479,18 @@ def main():
         npix_alg = res["B"] * res["H"] * res["W"] / (world if res["workload"] == "cfg5" else 1)
         L, C_ = cfg["num_encoder_layers"], cfg["num_channels"]
         hC = C_ * cfg["hidden_ratio"]
-        conv_launch_ms = res["conv_ms"] / (2 * L)
-        conv_flops = conv_flops_per_launch(cfg, npix_alg)
-        alg_bytes = 6.0 * C_ * npix_alg
-        design_bytes = 0.5 * ((2 * C_ + 2 * hC) + (2 * hC + 4 * C_ + 4 * C_ + 2 * C_)) * npix
+        # Dominant kernel: two launches per encoder block (conv1, conv2), or ONE when the block runs fused
+        # (block_fused_kernel: both convolutions, hidden tensor on-chip) -- per-launch work and bytes double, the
+        # fractions are the same ratios either way.
+        per = 1 if res.get("fused") else 2
+        n_launch = per * L
+        conv_launch_ms = res["conv_ms"] / n_launch
+        conv_flops = conv_flops_per_launch(cfg, npix_alg) * (2 // per)
+        alg_bytes = 6.0 * C_ * npix_alg * (2 // per)
+        if res.get("fused"):   # read zb 2C + zf 4C, write zf 4C + zb 2C: the hidden tensor never leaves the SM
+            design_bytes = 12.0 * C_ * npix
+        else:
+            design_bytes = 0.5 * ((2 * C_ + 2 * hC) + (2 * hC + 4 * C_ + 4 * C_ + 2 * C_)) * npix
         t_tensor = conv_flops / (peaks["bf16_sustained"] * 1e12)
         t_hbm = alg_bytes / (peaks["hbm"] * 1e9)
         tf = conv_flops / (conv_launch_ms * 1e-3) / 1e12
@@ -492,21 +501,25 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):          # DRAM bytes per launch from the committed ncu capture of this workload
             with open(tpath) as f:
-                tj = json.load(f).get(res["workload"])
+                tj = json.load(f).get(res["workload"] + ("_fused" if res.get("fused") else ""))
             if tj:
                 traffic, traffic_src = tj["traffic_bytes_per_launch"], tj["source"]
         n_gpus = world if res["workload"] == "cfg5" else 1
         common = {
-            "kernel": "conv_tc_kernel (3x3 implicit GEMM, tcgen05)", "traffic": traffic, "traffic_source": traffic_src,
+            "kernel": ("block_fused_kernel (conv1 -> FiLM -> SiLU -> conv2 -> residual, one CTA-pair kernel per encoder block, tcgen05)"
+                       if res.get("fused") else "conv_tc_kernel (3x3 implicit GEMM, tcgen05)"),
+            "traffic": traffic, "traffic_source": traffic_src,
             "flops_per_launch": conv_flops, "bytes_per_launch": alg_bytes, "design_bytes_per_launch": design_bytes,
             "ms_per_launch": conv_launch_ms,
-            "launches_per_step": 2 * L, "conv_share_of_step": res["conv_ms"] / res["ms_step"],
+            "launches_per_step": n_launch, "conv_share_of_step": res["conv_ms"] / res["ms_step"],
             "tensor": {"achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                        "frac": tf / peaks["bf16_sustained"], "frac_of_burst_peak": tf / peaks["bf16_burst"]},
             "hbm": {"achieved": gbs_alg, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs_alg / peaks["hbm"],
-                    "basis": "algorithmic bytes 6C per LR px per launch (SURVEY 8(d))"},
+                    "basis": "algorithmic bytes 6C per LR px per convolution (SURVEY 8(d))"},
             "hbm_design": {"achieved": gbs_design, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs_design / peaks["hbm"],
-                           "basis": "bytes this design moves: fp32 residual stream + 16-bit shadow + hidden round trip"},
+                           "basis": ("bytes this design moves: fp32 residual stream + 16-bit shadow (12C per block; the hidden "
+                                     "tensor stays on the SM)") if res.get("fused") else
+                                    "bytes this design moves: fp32 residual stream + 16-bit shadow + hidden round trip"},
             "whole_step_tflops_per_gpu": total_flops / n_gpus / (res["ms_step"] * 1e-3) / 1e12,
             "whole_step_frac_of_burst_peak": total_flops / n_gpus / (res["ms_step"] * 1e-3) / 1e12 / peaks["bf16_burst"],
             "peak_source": peaks["source"] + "; tensor = sustained 16-bit dense (kernel timed inside a long step)",
@@ -537,7 +550,7 @@ def main():
     model_name, cfg, B, H, W, desc = res["model_name"], res["cfg"], res["B"], res["H"], res["W"], res["desc"]
     ms_step, value, e2e, clocks = res["ms_step"], res["value"], res["e2e"], res["clocks"]
     L = cfg["num_encoder_layers"]
-    launches_per_step = 2 * L + 2 + (1 if cfg["control_features"] else 0)
+    launches_per_step = (1 if res.get("fused") else 2) * L + 2 + (1 if cfg["control_features"] else 0)
     roofline = roofline_of(res, peaks)
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only

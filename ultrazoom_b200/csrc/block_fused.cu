@@ -476,19 +476,23 @@ __global__ void __launch_bounds__(fb::kThreads, 1) block_fused_kernel(const __gr
           for (int j = 0; j < 3; ++j) {
             FB_TIMED(1, mbar_wait(my_res + 8 * j, rpar));
             const uint32_t zrow = st_z + j * 2048 + lane * 64;
-            uint32_t o[8];
+            uint32_t o[8], addr[4];
+            float4 z[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {  // (all four loads first: the accessors are volatile, i.e. ordered)
+              addr[kk] = zrow + swz_chunk(lane, kk, 64) * 16;
+              z[kk] = lds128f(addr[kk]);
+            }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint32_t addr = zrow + swz_chunk(lane, kk, 64) * 16;
-              float4 z = lds128f(addr);
-              z.x += __uint_as_float(v[16 * j + 4 * kk + 0]);
-              z.y += __uint_as_float(v[16 * j + 4 * kk + 1]);
-              z.z += __uint_as_float(v[16 * j + 4 * kk + 2]);
-              z.w += __uint_as_float(v[16 * j + 4 * kk + 3]);
-              sts128(addr, __float_as_uint(z.x), __float_as_uint(z.y), __float_as_uint(z.z), __float_as_uint(z.w));
-              if (lane_live) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(z.x), fabsf(z.y))), fmaxf(fabsf(z.z), fabsf(z.w)));
-              o[2 * kk] = pack_op2(p.bf16, z.x, z.y);
-              o[2 * kk + 1] = pack_op2(p.bf16, z.z, z.w);
+              z[kk].x += __uint_as_float(v[16 * j + 4 * kk + 0]);
+              z[kk].y += __uint_as_float(v[16 * j + 4 * kk + 1]);
+              z[kk].z += __uint_as_float(v[16 * j + 4 * kk + 2]);
+              z[kk].w += __uint_as_float(v[16 * j + 4 * kk + 3]);
+              sts128(addr[kk], __float_as_uint(z[kk].x), __float_as_uint(z[kk].y), __float_as_uint(z[kk].z), __float_as_uint(z[kk].w));
+              if (lane_live) amax = fmaxf(fmaxf(amax, fmaxf(fabsf(z[kk].x), fabsf(z[kk].y))), fmaxf(fabsf(z[kk].z), fabsf(z[kk].w)));
+              o[2 * kk] = pack_op2(p.bf16, z[kk].x, z[kk].y);
+              o[2 * kk + 1] = pack_op2(p.bf16, z[kk].z, z[kk].w);
             }
             const uint32_t orow = st_o + j * 1024 + lane * 32;
             sts128(orow + swz_chunk(lane, 0, 32) * 16, o[0], o[1], o[2], o[3]);

@@ -818,19 +818,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           auto finish16 = [&](const uint32_t* v, uint32_t n0) {
             const uint32_t bz = n0 >> sh32, cz = (n0 - (bz << sh32)) >> 2;  // fp32 box, first 16-byte chunk in its row
             const uint32_t zrow = st_z + bz * box32 + lane * row32;
-            uint32_t o[8];
+            uint32_t o[8], addr[4];
+            float4 z[4];
+            // all four loads first: the shared-memory accessors are volatile (ordered), so a load / add / store per chunk
+            // would expose the full load latency four times per sixteen channels
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const uint32_t addr = zrow + swz_chunk(lane, cz + kk, row32) * 16;
-              float4 z = lds128f(addr);
-              z.x += __uint_as_float(v[4 * kk + 0]);
-              z.y += __uint_as_float(v[4 * kk + 1]);
-              z.z += __uint_as_float(v[4 * kk + 2]);
-              z.w += __uint_as_float(v[4 * kk + 3]);
-              sts128(addr, __float_as_uint(z.x), __float_as_uint(z.y), __float_as_uint(z.z), __float_as_uint(z.w));
-              amax = fmaxf(fmaxf(amax, fmaxf(fabsf(z.x), fabsf(z.y))), fmaxf(fabsf(z.z), fabsf(z.w)));
-              o[2 * kk] = pack_op2(p.epi.bf16, z.x, z.y);
-              o[2 * kk + 1] = pack_op2(p.epi.bf16, z.z, z.w);
+              addr[kk] = zrow + swz_chunk(lane, cz + kk, row32) * 16;
+              z[kk] = lds128f(addr[kk]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              z[kk].x += __uint_as_float(v[4 * kk + 0]);
+              z[kk].y += __uint_as_float(v[4 * kk + 1]);
+              z[kk].z += __uint_as_float(v[4 * kk + 2]);
+              z[kk].w += __uint_as_float(v[4 * kk + 3]);
+              sts128(addr[kk], __float_as_uint(z[kk].x), __float_as_uint(z[kk].y), __float_as_uint(z[kk].z), __float_as_uint(z[kk].w));
+              amax = fmaxf(fmaxf(amax, fmaxf(fabsf(z[kk].x), fabsf(z[kk].y))), fmaxf(fabsf(z[kk].z), fabsf(z[kk].w)));
+              o[2 * kk] = pack_op2(p.epi.bf16, z[kk].x, z[kk].y);
+              o[2 * kk + 1] = pack_op2(p.epi.bf16, z[kk].z, z[kk].w);
             }
             const uint32_t bo = n0 >> sh16, co = (n0 - (bo << sh16)) >> 3;
             const uint32_t orow = st_o + bo * box16 + lane * row16;
