@@ -286,6 +286,40 @@ int mz_ipc_frame_create(size_t bytes, void** dev_ptr, void* handle64);
 int mz_ipc_frame_open(const void* handle64, void** dev_ptr);
 int mz_ipc_frame_close(void* dev_ptr, int32_t owner);
 
+/* ---- operators of the reference's 0.3.0 U-Net on NHWC fp32 feature maps ----------------------
+ * Feature maps are (B,H,W,pitch) fp32 with the logical channels first; every operator can also write the 16-bit shadow
+ * (operand_dtype) the tcgen05 convolutions read as their A operand (out16_dev, same pitch; NULL = none).  The 3x3
+ * convolutions of these blocks (InvertedBottleneck model.py:731-778, SubpixelConv2d.conv :902-909) are mz_conv3x3 /
+ * mz_head_shuffle_add; what follows is everything else.  Weights are passed as [K][N] fp32 device matrices:
+ *   mix:    wt[k][n] = conv.weight[n][k][0][0]                 (K = 2C: x channels then z channels)
+ *   crush:  wt[(i*f + j)*Cin + c][n] = conv.weight[n][c][i][j]  (K = f*f*Cin)
+ *   assess: wt[(ky*3 + kx)*C + c][n] = conv.weight[n][c][ky][kx] (K = 9C)
+ * (the Python mirror, ultrazoom_b200/unet.py, builds them from the reference's state_dict tensors). */
+
+/* AdaptiveResidualMix.forward (model.py:826-839): beta = sigmoid(conv1x1(cat[x, z])); w = sigmoid(alpha) * beta;
+ * out = (1 - w) * x + w * z.  x, z, out: (npix, pitch) fp32. */
+int mz_adaptive_mix(const float* x_dev, const float* z_dev, const float* wt_dev, float alpha_logit, float* out_dev,
+                    void* out16_dev, int64_t npix, int32_t C, int32_t pitch, int32_t operand_dtype, void* stream);
+
+/* PixelCrush.forward (model.py:881-882): Conv2d(Cin, Cout, kernel_size=f, stride=f, bias=False), f in {2, 3, 4};
+ * (B,H,W,pitch_in) -> (B, H/f, W/f, pitch_out) (floor, as the convolution does). */
+int mz_pixel_crush(const float* in_dev, const float* wt_dev, float* out_dev, void* out16_dev, int32_t B, int32_t H, int32_t W,
+                   int32_t Cin, int32_t Cout, int32_t factor, int32_t pitch_in, int32_t pitch_out, int32_t operand_dtype,
+                   void* stream);
+
+/* QualityAssessor.forward (model.py:1024-1032): Conv2d(C, F, 3, padding=1) + bias -> AdaptiveAvgPool2d(1) -> (B, F). */
+int mz_quality_assessor(const float* in_dev, const float* wt_dev, const float* bias_dev, float* out_dev, int32_t B, int32_t H,
+                        int32_t W, int32_t C, int32_t F, int32_t pitch_in, void* stream);
+
+/* PixelShuffle(r) on NHWC (mid-network SubpixelConv2d, model.py:911,928; Decoder :569-571):
+ * out[b, h r + i, w r + j, c] = in[b, h, w, c r r + i r + j]; in (B,H,W,pitch_in >= C r r) -> out (B,rH,rW,pitch_out). */
+int mz_pixel_shuffle_nhwc(const float* in_dev, float* out_dev, void* out16_dev, int32_t B, int32_t H, int32_t W, int32_t C,
+                          int32_t r, int32_t pitch_in, int32_t pitch_out, int32_t operand_dtype, void* stream);
+
+/* Decoder.crop_feature_maps (model.py:650-689): centre-crop or zero-pad (B,H,W,C) to (B,target_h,target_w,C). */
+int mz_crop_feature_maps(const float* in_dev, float* out_dev, int32_t B, int32_t H, int32_t W, int32_t C, int32_t target_h,
+                         int32_t target_w, int32_t pitch_in, int32_t pitch_out, void* stream);
+
 /* Hardware probes used by tests and DESIGN.md (not on the hot path).
  * mz_probe_umma: one 128 x 64 x kc UMMA whose A descriptor starts `row_shift` rows into a
  * TMA-swizzled tile; base_offset_mode 0 leaves the descriptor's base_offset 0, 1 sets it to

@@ -141,5 +141,60 @@ def main() -> None:
     print("leaf_ops written")
 
 
+def make_unet_ops() -> None:
+    """Known-answer vectors of the 0.3.0 U-Net operators, computed by the reference's OWN leaf
+    classes (they import and run although ``MewZoom`` itself cannot be constructed): inputs, the leaf's state_dict and
+    its output, per operator.  tests/test_gpu_unet_ops.py replays them through ultrazoom_b200.unet."""
+    from ultrazoom.model import (  # type: ignore  (the reference)
+        AdaptiveResidualMix, Decoder, EncoderBlock, PixelCrush, QualityAssessor, SR2XBlock, SuperResolver)
+
+    torch.manual_seed(2024)
+    g = torch.Generator().manual_seed(99)
+    out = {}
+
+    def put(prefix, module, inputs, result):
+        for i, t in enumerate(inputs):
+            out[f"{prefix}/in{i}"] = t.numpy()
+        for k, v in module.state_dict().items():
+            out[f"{prefix}/w:{k}"] = v.detach().numpy()
+        out[f"{prefix}/out"] = result.detach().numpy()
+
+    with torch.inference_mode():
+        C = 16
+        mix = AdaptiveResidualMix(C).eval()                        # model.py:795-839
+        mix.alpha.fill_(0.7)                                       # (0 is the init value: sigmoid(0) = 0.5)
+        x, z = torch.randn(2, C, 9, 13, generator=g), torch.randn(2, C, 9, 13, generator=g)
+        put("mix", mix, [x, z], mix.forward(x, z))
+        for f, hw in ((2, (10, 14)), (3, (10, 14)), (4, (9, 17))):  # model.py:842-882 (odd sizes: the conv floors)
+            crush = PixelCrush(C, 2 * C, f).eval()
+            x = torch.randn(2, C, *hw, generator=g)
+            put(f"crush{f}", crush, [x], crush.forward(x))
+        up = SubpixelConv2d(2 * C, C, 2).eval()                    # mid-network upsampler, Decoder model.py:569-571
+        x = torch.randn(1, 2 * C, 7, 9, generator=g)
+        put("subpixel", up, [x], up.forward(x))
+        for name, size in (("crop_smaller", (6, 8)), ("crop_larger", (11, 13)), ("crop_mixed", (12, 7))):
+            x = torch.randn(1, C, 9, 10, generator=g)              # Decoder.crop_feature_maps model.py:650-689
+            out[f"{name}/in0"] = x.numpy()
+            out[f"{name}/size"] = np.array(size, dtype=np.int64)
+            out[f"{name}/out"] = Decoder.crop_feature_maps(x, size).numpy()
+        blk = EncoderBlock(C, 2).eval()                            # model.py:487-511 (InvertedBottleneck + gated mix)
+        blk.skip.alpha.fill_(-0.3)
+        x = torch.randn(1, C, 10, 18, generator=g)
+        put("encoder_block", blk, [x], blk.forward(x))
+        sr = SR2XBlock(C, 2, C).eval()                             # model.py:975-1001
+        x = torch.randn(1, C, 6, 10, generator=g)
+        put("sr2x", sr, [x], sr.forward(x))
+        head = SuperResolver(C, 2, 4).eval()                       # model.py:933-972: 16 ch -> x2 -> x2 -> 3 ch
+        x = torch.randn(1, C, 5, 7, generator=g)
+        put("super_resolver", head, [x], head.forward(x))
+        qa = QualityAssessor(2 * C, 3).eval()                      # model.py:1004-1032
+        x = torch.randn(2, 2 * C, 8, 11, generator=g)
+        put("quality", qa, [x], qa.forward(x))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "unet_ops.npz"), **out)
+    print(f"unet_ops written ({len(out)} arrays)")
+
+
 if __name__ == "__main__":
-    main()
+    if "--unet-only" not in sys.argv:
+        main()
+    make_unet_ops()
