@@ -430,6 +430,15 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         return self._run(x, c, _native.FLAG_CLAMP01)
 
     @torch.inference_mode()
+    def test_compare(self, x: Tensor, c: Optional[Tensor] = None):
+        """``(upscale(x, c), bicubic(x))``, both clamped to [0, 1]: what the reference's evaluation script asks of the
+        0.2.x model (validate.py:97).  The bicubic image comes from the stand-alone bicubic kernel (mz_bicubic_f32)."""
+        from . import ops
+
+        return self.upscale(x, c), ops.bicubic(x.float() if x.dtype != torch.uint8 else x.float() / 255.0,
+                                               self.upscale_ratio).clamp_(0, 1)
+
+    @torch.inference_mode()
     def upscale_into(self, x: Tensor, c: Optional[Tensor], frame: Tensor, window: tuple, at: tuple) -> None:
         """Halo-tiled inference without a tile output: ``upscale`` the LR tile ``x`` and write only its core -- the LR
         pixels ``window = (y0, y1, x0, x1)`` of the tile -- straight into ``frame`` (B,3,rH',rW'), whose HR pixel
