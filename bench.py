@@ -256,6 +256,19 @@ def main():
 
     tune_kw = {k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)}
 
+    def apply_tune(model):
+        """--tune k=v,...: plain keys apply to every convolution; c1.k / c2.k / head.k to conv1 / conv2 / the head only."""
+        if not tune_kw:
+            return
+        per = {-1: {}, 0: {}, 1: {}, 2: {}}
+        for k, v in tune_kw.items():
+            which, _, name = k.rpartition(".")
+            per[{"": -1, "c1": 0, "c2": 1, "head": 2}[which]][name] = v
+        for which in (0, 1, 2):
+            kw = {**per[-1], **per[which]}
+            if kw:
+                model.set_conv_tune(which, dev, **kw)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -271,8 +284,7 @@ def main():
         r = cfg["upscale_ratio"]
         torch.manual_seed(0)
         model = MewZoom(**cfg, operand_dtype=args.operands, residual_stream=args.residual_stream).to(dev).eval()
-        if tune_kw:
-            model.set_conv_tune(-1, dev, **tune_kw)
+        apply_tune(model)
         eng = model._engine(dev)
         g = torch.Generator().manual_seed(1234 + rank)
         x_host = torch.rand(B, 3, H, W, generator=g)
@@ -370,8 +382,7 @@ def main():
         r, L = cfg["upscale_ratio"], cfg["num_encoder_layers"]
         torch.manual_seed(0)
         model = MewZoom(**cfg, operand_dtype=args.operands, residual_stream=args.residual_stream).to(dev).eval()
-        if tune_kw:
-            model.set_conv_tune(-1, dev, **tune_kw)
+        apply_tune(model)
         eng = model._engine(dev)
         g = torch.Generator().manual_seed(1234)             # every rank holds the same LR frame
         x_host = torch.rand(B, 3, H, W, generator=g)
