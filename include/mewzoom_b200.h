@@ -151,6 +151,21 @@ int mz_upscale_window(mz_model* m, const void* x_dev, const float* c_dev, int32_
                       int32_t win_y1, int32_t win_x0, int32_t win_x1, void* workspace_dev, size_t workspace_bytes,
                       uint32_t flags, void* stream);
 
+/* The same call cut into STAGES along the depth of the network, for halo-tiled inference with a periodic halo refresh
+ * ("per-layer halo exchange" made coarse): this call runs the encoder blocks [layer_begin, layer_end)
+ * on the state in the workspace; the FiLM table and the stem run first when layer_begin == 0, the head (into y_dev,
+ * windowed as in mz_upscale_window, or dense when win_y1 <= 0) runs last when layer_end == num_encoder_layers.  Between
+ * two stages the caller may overwrite halo pixels of the residual stream with a neighbour tile's values: the workspace
+ * holds zf (B,H,W,Cp) fp32 and its 16-bit shadow zb (B,H,W,zb_pitch) at the offsets mz_workspace_layout returns (from
+ * the 1024-byte-aligned workspace pointer).  Models that run fused blocks keep the 16-bit stream in the HIDDEN buffer
+ * (offset hidden_offset, pitch Cp) after an odd number of blocks (mz_model_fused_block). */
+int mz_upscale_stage(mz_model* m, const void* x_dev, const float* c_dev, int32_t c_rows, void* y_dev, int64_t y_row_pitch,
+                     int64_t y_plane_pitch, int32_t B, int32_t H, int32_t W, int32_t win_y0, int32_t win_y1, int32_t win_x0,
+                     int32_t win_x1, void* workspace_dev, size_t workspace_bytes, uint32_t flags, void* stream,
+                     int32_t layer_begin, int32_t layer_end);
+int mz_workspace_layout(const mz_model* m, int32_t B, int32_t H, int32_t W, size_t* zf_offset, size_t* zb_offset,
+                        size_t* hidden_offset, int32_t* channels_padded, int32_t* zb_pitch);
+
 /* Enable peer access between two visible devices in this process, both directions (idempotent).  Needed before kernels
  * or copies of device `a` touch memory of device `b` that was mapped from a CUDA IPC handle. */
 int mz_enable_peer_access(int32_t a, int32_t b);

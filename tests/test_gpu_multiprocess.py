@@ -62,6 +62,58 @@ def _worker(rank: int, world: int, port: int, mode: str, out_path: str):
         dist.destroy_process_group()
 
 
+def _refresh_worker(rank: int, world: int, port: int, out_path: str):
+    import torch.distributed as dist
+
+    from ultrazoom_b200 import MODEL_CONFIGS, MewZoom
+    from ultrazoom_b200.sharding import share_frame, upscale_tiled_refresh
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        results = []
+        for name, L, k in (("MewZoom-4X-Ctrl", 4, 2), ("MewZoom-2X-Ctrl", 5, 1)):
+            cfg = dict(MODEL_CONFIGS[name])
+            cfg["num_encoder_layers"] = L
+            r = cfg["upscale_ratio"]
+            torch.manual_seed(71)
+            m = MewZoom(**cfg).to(dev).eval()
+            g = torch.Generator().manual_seed(72)
+            H, W = 60, 300
+            x, c = torch.rand(1, 3, H, W, generator=g).to(dev), torch.rand(1, 3, generator=g).to(dev)
+            shared = share_frame((1, 3, H * r, W * r), torch.float32, 0, rank, dev)
+            for rows, cols in ((1, 2), (2, 2)):                          # one tile per rank / two tiles per rank
+                upscale_tiled_refresh(m, x, c, r, L, rows, cols, k, shared.tensor, rank, world, align_w=128)
+                torch.cuda.synchronize()
+                dist.barrier()
+                if rank == 0:
+                    results.append(bool(torch.equal(shared.tensor, m.upscale(x, c))))
+                    shared.tensor.zero_()
+                    torch.cuda.synchronize()
+                dist.barrier()
+            shared.close()
+        if rank == 0:
+            with open(out_path, "w") as f:
+                f.write("ok" if all(results) and len(results) == 4 else f"mismatch {results}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_halo_refresh_across_two_gpus(tmp_path):
+    """Periodic halo refresh between PROCESSES: halo strips of the fp32 stream and its 16-bit shadow travel as grouped
+    NCCL isend / irecv between the neighbours' GPUs (no collective reduction), cores land in rank 0's IPC frame; the
+    result equals the un-tiled frame bit for bit, with one and with two tiles per rank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "result.txt")
+    mp.spawn(_refresh_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
+
+
 @pytest.mark.parametrize("mode", ["fused", "copy", "uint8"])
 def test_non_owner_rank_fills_the_owners_frame(tmp_path, mode):
     if torch.cuda.device_count() < 2:

@@ -392,3 +392,33 @@ def test_windowed_output_assembles_the_frame(dev, name):
     assert torch.equal(frame8, full8)
     with pytest.raises(AssertionError):                                  # a window that does not fit the frame
         m.upscale_into(x, c, frame, (0, 45, 0, 290), (r, 0))
+
+
+@pytest.mark.parametrize("name,L,k", [("MewZoom-2X-Ctrl", 5, 1), ("MewZoom-2X-Ctrl", 6, 2), ("MewZoom-4X-Ctrl", 4, 2), ("MewZoom-3X-Ctrl", 3, 3)])
+def test_halo_refresh_tiling_is_bit_exact(dev, name, L, k):
+    """sharding.upscale_tiled_refresh: tiles carry a halo of only 2k+1 pixels, run k encoder blocks at a time
+    (mz_upscale_stage) and refresh their halo ring from the neighbours' cores in between.  All tiles in this process
+    (device-to-device copies; the 2-process form is tests/test_gpu_multiprocess.py): the frame equals the un-tiled
+    result bit for bit -- fused blocks (2X: the 16-bit stream alternates between two buffers) and two-kernel blocks."""
+    from ultrazoom_b200 import MODEL_CONFIGS, MewZoom
+    from ultrazoom_b200.sharding import upscale_tiled_refresh
+
+    torch.manual_seed(61)
+    cfg = dict(MODEL_CONFIGS[name])
+    cfg["num_encoder_layers"] = L
+    r = cfg["upscale_ratio"]
+    m = MewZoom(**cfg).to(dev).eval()
+    g = torch.Generator().manual_seed(62)
+    x, c = torch.rand(1, 3, 50, 300, generator=g).to(dev), torch.rand(1, 3, generator=g).to(dev)
+    full = m.upscale(x, c)
+    for rows, cols in ((2, 2), (1, 3)):
+        frame = torch.full_like(full, -1.0)
+        state = upscale_tiled_refresh(m, x, c, r, L, rows, cols, k, frame, align_w=128)
+        assert torch.equal(frame, full), (rows, cols, (frame - full).abs().max().item())
+        frame.fill_(-1.0)
+        upscale_tiled_refresh(m, x, c, r, L, rows, cols, k, frame, align_w=128, state=state)   # cached plan + workspaces
+        assert torch.equal(frame, full)
+    x8 = (x * 255).to(torch.uint8)
+    full8, frame8 = m.upscale(x8, c), torch.zeros(1, 3, 50 * r, 300 * r, dtype=torch.uint8, device=dev)
+    upscale_tiled_refresh(m, x8, c, r, L, 2, 2, k, frame8, align_w=128)
+    assert torch.equal(frame8, full8)

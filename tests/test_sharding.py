@@ -154,3 +154,28 @@ def test_run_tile_into_windows_tile_the_frame_exactly_once(H, W, rows, cols, hal
         run_tile_into(rec, x, None, t, r, frame)
     assert len(rec.calls) == len(plan)
     assert torch.equal(frame, x.repeat_interleave(r, 2).repeat_interleave(r, 3))   # every HR pixel written exactly once
+
+
+def test_refresh_rectangles_cover_every_halo_exactly_once():
+    """Periodic halo refresh (sharding.upscale_tiled_refresh): what tile i receives from its neighbours -- the parts of
+    its haloed region inside their cores -- covers its halo exactly once, never its core; tile rows start on multiples
+    of ROW_ALIGN (the fused block's accumulator ring is tied to the image row: bit-exact tiling)."""
+    import numpy as np
+
+    from ultrazoom_b200.sharding import ROW_ALIGN, plan_tiles, refresh_rects
+
+    for (H, W, rows, cols, hw, aw) in [(1080, 1920, 2, 4, 21, 128), (70, 300, 2, 2, 5, 1), (45, 290, 3, 1, 7, 128), (64, 64, 1, 1, 9, 1)]:
+        plan = plan_tiles(H, W, rows, cols, hw, aw)
+        rects = refresh_rects(plan)
+        for t in plan:
+            assert t.hy0 % ROW_ALIGN == 0 and t.hy0 <= max(0, t.y0 - hw)
+            cover = np.zeros((H, W), int)
+            for (i, j), r in rects.items():
+                if i == t.index:
+                    o = plan[j]
+                    assert o.y0 <= r[0] < r[1] <= o.y1 and o.x0 <= r[2] < r[3] <= o.x1      # inside the sender's core
+                    cover[r[0]:r[1], r[2]:r[3]] += 1
+            want = np.zeros((H, W), int)
+            want[t.hy0:t.hy1, t.hx0:t.hx1] = 1
+            want[t.y0:t.y1, t.x0:t.x1] = 0
+            assert (cover == want).all()

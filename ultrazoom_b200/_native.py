@@ -90,6 +90,10 @@ SIGNATURES = {
     "mz_upscale": (C.c_int, [_P, _P, _P, _I, _P, _I, _I, _I, _P, C.c_size_t, C.c_uint32, _P]),
     "mz_upscale_window": (C.c_int, [_P, _P, _P, _I, _P, C.c_int64, C.c_int64, _I, _I, _I, _I, _I, _I, _I, _P, C.c_size_t,
                                     C.c_uint32, _P]),
+    "mz_upscale_stage": (C.c_int, [_P, _P, _P, _I, _P, C.c_int64, C.c_int64, _I, _I, _I, _I, _I, _I, _I, _P, C.c_size_t,
+                                   C.c_uint32, _P, _I, _I]),
+    "mz_workspace_layout": (C.c_int, [_P, _I, _I, _I, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                      C.POINTER(_I), C.POINTER(_I)]),
     "mz_enable_peer_access": (C.c_int, [_I, _I]),
     "mz_ipc_frame_create": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), _P]),
     "mz_ipc_frame_open": (C.c_int, [_P, C.POINTER(C.c_void_p)]),

@@ -552,10 +552,16 @@ struct OutWindow {
   long long row_pitch, plane_pitch;
 };
 
+// layer_begin / layer_end: the encoder blocks [layer_begin, layer_end) of this call (mz_upscale_stage).  The FiLM table and
+// the stem run when layer_begin == 0, the head when layer_end == L; in between the state lives in the workspace.
 static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, int32_t c_rows, void* y_dev_v, int32_t B,
                         int32_t H, int32_t W, void* workspace_dev, size_t workspace_bytes, uint32_t flags, void* stream,
-                        const OutWindow* win) {
+                        const OutWindow* win, int layer_begin = 0, int layer_end = -1) {
   MZ_REQUIRE(m && x_dev_v && y_dev_v && workspace_dev, "upscale: null pointer");
+  if (layer_end < 0) layer_end = m->L;
+  MZ_REQUIRE(0 <= layer_begin && layer_begin <= layer_end && layer_end <= m->L, "upscale: bad layer range [%d, %d) of %d",
+             layer_begin, layer_end, m->L);
+  const bool front = layer_begin == 0, back = layer_end == m->L;
   const bool io8 = (flags & MZ_FLAG_IO_U8) != 0;
   MZ_REQUIRE(!io8 || ((flags & MZ_FLAG_CLAMP01) && !(flags & MZ_FLAG_SKIP_FROM_BUFFER)),
              "upscale: 8-bit image I/O needs MZ_FLAG_CLAMP01 and recomputes the skip (no MZ_FLAG_SKIP_FROM_BUFFER)");
@@ -594,17 +600,19 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
   const bool simt = (flags & MZ_FLAG_SIMT_CONV) != 0;
   int rc;
 
-  if (m->F > 0) {
+  if (front && m->F > 0) {
     rc = launch_film(c_dev, c_rows, m->ctrl_w, m->ctrl_b, film, m->L, B, m->F, m->hC, m->hCp, m->ns, s);
     if (rc != MZ_OK) return rc;
   }
-  rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, m->split ? nullptr : zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s,
-                   m->sat_dev);
+  rc = MZ_OK;
+  if (front)
+    rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, m->split ? nullptr : zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s,
+                     m->sat_dev);
   const int zpitch = m->split ? 2 * m->Cp : 0;  // channel pitch of the convolutions that read the stream
   if (rc != MZ_OK) return rc;
 
   const int slot = m->timing_calls % kTimingSlots;
-  if (m->timing) MZ_CUDA(cudaEventRecord(m->ev[2 * slot], s));
+  if (m->timing && front) MZ_CUDA(cudaEventRecord(m->ev[2 * slot], s));
   // one slice of conv1's / conv2's filter bank
   const size_t c1s = static_cast<size_t>(9) * m->ns * m->Cz, c2s = static_cast<size_t>(9) * m->ns2 * m->hCp;
   const int S = m->S, S2 = m->S2;
@@ -615,9 +623,10 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
     set_error("upscale: the fused encoder block was required (tune.block = 1) but does not apply to this model / call");
     return MZ_ERR_UNSUPPORTED;
   }
-  uint16_t* zcur = zb;
-  uint16_t* znxt = hid;
-  for (int l = 0; l < m->L && fused; ++l) {
+  // (after an odd number of fused blocks the 16-bit stream lives in the hidden buffer: mz_workspace_layout documents it)
+  uint16_t* zcur = (fused && (layer_begin & 1)) ? hid : zb;
+  uint16_t* znxt = (fused && (layer_begin & 1)) ? zb : hid;
+  for (int l = layer_begin; l < layer_end && fused; ++l) {
     FusedBlockArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.zb_in = zcur;
@@ -639,7 +648,7 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
     zcur = znxt;
     znxt = t;
   }
-  for (int l = 0; l < m->L && !fused; ++l) {
+  for (int l = layer_begin; l < layer_end && !fused; ++l) {
     ConvArgs a;
     for (int sl = 0; sl < S; ++sl) {
       memset(&a, 0, sizeof(a));
@@ -682,10 +691,11 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
     }
   }
 
-  if (m->timing) {
+  if (m->timing && back) {
     MZ_CUDA(cudaEventRecord(m->ev[2 * slot + 1], s));
     ++m->timing_calls;
   }
+  if (!back) return MZ_OK;
 
   int skip_mode = 2;
   if (flags & MZ_FLAG_SKIP_FROM_BUFFER) {
@@ -750,6 +760,36 @@ int mz_upscale_window(mz_model* m, const void* x_dev, const float* c_dev, int32_
              "upscale_window: y and its pitches must be aligned to %d bytes", vec);
   const OutWindow w{win_y0, win_y1, win_x0, win_x1, y_row_pitch, y_plane_pitch};
   return upscale_impl(m, x_dev, c_dev, c_rows, y_dev, B, H, W, workspace_dev, workspace_bytes, flags, stream, &w);
+}
+
+int mz_upscale_stage(mz_model* m, const void* x_dev, const float* c_dev, int32_t c_rows, void* y_dev, int64_t y_row_pitch,
+                     int64_t y_plane_pitch, int32_t B, int32_t H, int32_t W, int32_t win_y0, int32_t win_y1, int32_t win_x0,
+                     int32_t win_x1, void* workspace_dev, size_t workspace_bytes, uint32_t flags, void* stream,
+                     int32_t layer_begin, int32_t layer_end) {
+  MZ_REQUIRE(m, "upscale_stage: null model");
+  MZ_REQUIRE(!(flags & MZ_FLAG_SKIP_FROM_BUFFER), "upscale_stage: the bicubic skip is recomputed (no MZ_FLAG_SKIP_FROM_BUFFER)");
+  if (win_y1 <= 0)  // dense output
+    return upscale_impl(m, x_dev, c_dev, c_rows, y_dev, B, H, W, workspace_dev, workspace_bytes, flags, stream, nullptr,
+                        layer_begin, layer_end);
+  MZ_REQUIRE(0 <= win_y0 && win_y0 < win_y1 && win_y1 <= H && 0 <= win_x0 && win_x0 < win_x1 && win_x1 <= W,
+             "upscale_stage: window [%d, %d) x [%d, %d) is not inside the %d x %d input", win_y0, win_y1, win_x0, win_x1, H, W);
+  const OutWindow w{win_y0, win_y1, win_x0, win_x1, y_row_pitch, y_plane_pitch};
+  return upscale_impl(m, x_dev, c_dev, c_rows, y_dev, B, H, W, workspace_dev, workspace_bytes, flags, stream, &w, layer_begin,
+                      layer_end);
+}
+
+int mz_workspace_layout(const mz_model* m, int32_t B, int32_t H, int32_t W, size_t* zf_offset, size_t* zb_offset,
+                        size_t* hidden_offset, int32_t* channels_padded, int32_t* zb_pitch) {
+  MZ_REQUIRE(m && zf_offset && zb_offset && hidden_offset && channels_padded && zb_pitch, "workspace_layout: null pointer");
+  MZ_REQUIRE(B > 0 && H > 0 && W > 0, "workspace_layout: empty input");
+  MZ_REQUIRE(!m->split, "workspace_layout: the split residual stream has no separate fp32 / 16-bit tensors");
+  const WsPlan wp = plan_ws(m, B, H, W);
+  *zf_offset = wp.zf;
+  *zb_offset = wp.zb;
+  *hidden_offset = wp.hid;
+  *channels_padded = m->Cp;
+  *zb_pitch = m->Cz;
+  return MZ_OK;
 }
 
 // one chunk (B images) on one lane: H2D, kernels, D2H -- all asynchronous on the lane's stream

@@ -478,6 +478,66 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
             ws.numel() - (ws_ptr - ws.data_ptr()), flags, stream.cuda_stream))
         eng.end(stream)
 
+    @torch.inference_mode()
+    def upscale_stage(self, x: Tensor, c: Optional[Tensor], frame: Tensor, window: tuple, at: tuple, layer_begin: int,
+                      layer_end: int, ws: Tensor) -> None:
+        """``upscale_into`` cut into stages along the depth of the network (mz_upscale_stage): run the encoder blocks
+        ``[layer_begin, layer_end)`` on the state kept in the caller's workspace ``ws`` (``stage_workspace``); the stem
+        runs first when ``layer_begin == 0``, the head -- storing the window into ``frame`` -- last when ``layer_end ==
+        num_encoder_layers``.  Between stages ``sharding.upscale_tiled_refresh`` overwrites the tile's halo with the
+        neighbours' values (``stage_views``)."""
+        c = self._check_inputs(x, c)
+        assert x.is_cuda and x.dtype in (torch.float32, torch.uint8), "upscale_stage takes a CUDA image (float32 or uint8)"
+        dev = x.device
+        eng = self._engine(dev)
+        io8 = x.dtype == torch.uint8
+        flags = _native.FLAG_CLAMP01 | self._flags_extra
+        if io8:
+            flags |= _native.FLAG_IO_U8 | (_native.FLAG_U8_TRUNC if self.u8_truncate else 0)
+        x = x.contiguous()
+        if c is not None:
+            c = c.detach().to(device=dev, dtype=torch.float32).contiguous()
+        B, _, H, W = x.shape
+        r = self.upscale_ratio
+        y0, y1, x0, x1 = window
+        fy, fx = at
+        assert frame.is_cuda and frame.dim() == 4 and frame.shape[0] == B and frame.shape[1] == 3 and frame.stride(3) == 1
+        assert frame.stride(0) == 3 * frame.stride(1), "frame planes must be evenly spaced"
+        if frame.device != dev:
+            _native.check(eng.lib.mz_enable_peer_access(dev.index or 0, frame.device.index or 0))
+        stream = torch.cuda.current_stream(dev)
+        ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        dst = frame[0, 0, fy, fx].data_ptr()
+        _native.check(eng.lib.mz_upscale_stage(
+            eng.handle, x.data_ptr(), c.data_ptr() if c is not None else None, c.shape[0] if c is not None else 0,
+            dst, frame.stride(2), frame.stride(1), B, H, W, y0, y1, x0, x1, ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()),
+            flags, stream.cuda_stream, layer_begin, layer_end))
+
+    def stage_workspace(self, shape, device: torch.device) -> Tensor:
+        """A private workspace for ``upscale_stage`` calls on a (B,3,H,W) tile (the state between stages lives in it)."""
+        eng = self._engine(torch.device(device))
+        need = C.c_size_t()
+        _native.check(eng.lib.mz_workspace_bytes(eng.handle, shape[0], shape[2], shape[3], C.byref(need)))
+        return torch.empty(need.value + 1024, dtype=torch.uint8, device=device)
+
+    def stage_views(self, ws: Tensor, shape, blocks_done: int):
+        """``(zf, z16)``: the fp32 residual stream (B,H,W,Cp) and its 16-bit shadow (B,H,W,pitch) inside ``ws`` after
+        ``blocks_done`` encoder blocks, as tensors sharing the workspace's memory (mz_workspace_layout)."""
+        eng = self._engine(ws.device)
+        B, _, H, W = shape
+        zf_o, zb_o, hid_o = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        cp, zp = C.c_int32(), C.c_int32()
+        _native.check(eng.lib.mz_workspace_layout(eng.handle, B, H, W, C.byref(zf_o), C.byref(zb_o), C.byref(hid_o),
+                                                  C.byref(cp), C.byref(zp)))
+        base = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr()
+        npix = B * H * W
+        dt16 = torch.bfloat16 if eng.operand_dtype == "bfloat16" else torch.float16
+        zf = ws[base + zf_o.value: base + zf_o.value + npix * cp.value * 4].view(torch.float32).view(B, H, W, cp.value)
+        in_hidden = bool(eng.lib.mz_model_fused_block(eng.handle)) and (blocks_done & 1)
+        off, pitch = (hid_o.value, cp.value) if in_hidden else (zb_o.value, zp.value)
+        z16 = ws[base + off: base + off + npix * pitch * 2].view(dt16).view(B, H, W, pitch)
+        return zf, z16
+
     def capture(self, x: Tensor, c: Optional[Tensor] = None, clamp: bool = True) -> "GraphedUpscale":
         """Record one ``upscale`` (``clamp=False``: ``forward``) call at the shape of ``x`` into a CUDA graph.
 
