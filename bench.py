@@ -491,6 +491,11 @@ def main():
                           "api": "MewZoom.upscale_into per tile (pinned host tile -> device), assembled frame -> pinned host on rank 0"}
         barrier()
         frame = None
+        if refresh_state.get("s"):
+            from ultrazoom_b200.sharding import close_refresh_state
+
+            close_refresh_state(refresh_state["s"])
+            barrier()
         shared.close()
         del model, eng, x, c
         torch.cuda.empty_cache()

@@ -260,64 +260,142 @@ def refresh_rects(plan: Sequence[Tile]):
     return out
 
 
+class _StageBuffer:
+    """Workspace of one tile for staged execution, allocated so that OTHER processes of the node can map it (CUDA IPC):
+    neighbours pull their halo strips straight out of it over NVLink.  ``tensor`` is the uint8 view ``upscale_stage`` takes."""
+
+    def __init__(self, nbytes: int, device: torch.device):
+        import ctypes as C
+
+        from . import _native
+
+        self.lib = _native.load()
+        self.ptr = C.c_void_p()
+        self.handle = C.create_string_buffer(64)
+        self.nbytes = nbytes
+        with torch.cuda.device(device):
+            _native.check(self.lib.mz_ipc_frame_create(nbytes, C.byref(self.ptr), self.handle))
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr.value, False), "version": 2}
+
+        self.tensor = torch.as_tensor(_Mem())          # zero-copy view (on the device CUDA reports for the allocation)
+        self.base = (-self.ptr.value) % 1024          # offset of the 1024-byte-aligned workspace inside the allocation
+
+    def close(self) -> None:
+        if self.ptr:
+            from . import _native
+
+            self.tensor = None
+            _native.check(self.lib.mz_ipc_frame_close(self.ptr, 1))
+            self.ptr = None
+
+
 def upscale_tiled_refresh(model, x: Tensor, c: Optional[Tensor], r: int, num_encoder_layers: int, rows: int, cols: int,
                           refresh_every: int, frame: Tensor, rank: int = 0, world: int = 1, group=None, align_w: int = 1,
                           state: Optional[dict] = None) -> dict:
     """Halo-tiled ``upscale`` of ONE frame with a halo refresh every ``refresh_every`` encoder blocks.  Tile i of the
     ``rows x cols`` grid belongs to rank ``i % world``; every tile's core lands in ``frame`` (``share_frame`` when the
-    ranks are processes).  ``state`` (returned) caches the plan, tile crops and workspaces between calls."""
+    ranks are processes).  ``state`` (returned) caches the plan, tile crops, workspaces and peer mappings between calls.
+
+    Refresh = ONE-SIDED GETS: every tile's workspace is mapped by its neighbours (CUDA IPC, opened with the puller's GPU
+    current), and a tile pulls each halo rectangle of the fp32 stream and of the 16-bit shadow out of the neighbour's
+    core with one 2-D copy (mz_put_plane_async: rows of (x1 - x0) * C elements at the two tiles' row pitches) over
+    NVLink.  Two tiny stream-ordered all-reduces per refresh order the gets against the neighbours' kernels ("everyone
+    has finished the group" / "everyone has finished pulling"); no data moves through a collective."""
+    import ctypes as C
+
     import torch.distributed as dist
+
+    from . import _native
 
     L, k = num_encoder_layers, refresh_every
     assert 1 <= k <= L, "refresh_every must be in [1, num_encoder_layers]"
     B, _, H, W = x.shape
+    multi = world > 1
+    lib = _native.load()
     if state is None:
         plan = plan_tiles(H, W, rows, cols, 2 * k + 1, align_w)
-        assert len(plan) % world == 0 or world == 1, "tiles must divide evenly over the ranks"
         mine = [t for t in plan if t.index % world == rank]
-        state = {"plan": plan, "mine": mine, "rects": refresh_rects(plan), "ws": {}, "xt": {}}
+        rects = refresh_rects(plan)
+        state = {"plan": plan, "mine": mine, "rects": rects, "buf": {}, "xt": {}, "peer": {}, "layout": {},
+                 "token": torch.zeros(1, device=x.device)}
+        eng = model._engine(x.device)
+        for t in plan:                                  # workspace layout of EVERY tile (a peer's offsets are computed here)
+            zf_o, zb_o, hid_o, cp, zp = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_int32(), C.c_int32()
+            _native.check(lib.mz_workspace_layout(eng.handle, B, t.hy1 - t.hy0, t.hx1 - t.hx0, C.byref(zf_o), C.byref(zb_o),
+                                                  C.byref(hid_o), C.byref(cp), C.byref(zp)))
+            state["layout"][t.index] = (zf_o.value, zb_o.value, hid_o.value, cp.value, zp.value)
+        state["fused"] = bool(lib.mz_model_fused_block(eng.handle))
         for t in mine:
             xt = x[:, :, t.hy0:t.hy1, t.hx0:t.hx1].contiguous()
             state["xt"][t.index] = xt
-            state["ws"][t.index] = model.stage_workspace(xt.shape, x.device)
-    plan, mine, rects = state["plan"], state["mine"], state["rects"]
+            need = C.c_size_t()
+            _native.check(lib.mz_workspace_bytes(eng.handle, B, xt.shape[2], xt.shape[3], C.byref(need)))
+            state["buf"][t.index] = _StageBuffer(need.value + 1024, x.device)
+        # base addresses (of the aligned workspace) of every tile some tile of mine pulls from
+        local = {i: b.ptr.value + b.base for i, b in state["buf"].items()}
+        if multi:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, {i: (b.handle.raw, b.base) for i, b in state["buf"].items()}, group=group)
+            with torch.cuda.device(x.device):
+                for (i, j) in rects:
+                    if i % world == rank and j % world != rank and j not in state["peer"]:
+                        raw, base = gathered[j % world][j]
+                        p = C.c_void_p()
+                        _native.check(lib.mz_ipc_frame_open(raw, C.byref(p)))
+                        state["peer"][j] = p.value + base
+                        state.setdefault("mappings", []).append(p)
+        state["addr"] = {**state["peer"], **local}
+    plan, mine, rects, addr = state["plan"], state["mine"], state["rects"], state["addr"]
     by_index = {t.index: t for t in plan}
     bounds = list(range(0, L, k)) + [L]
+    es16 = 2
+    stream = torch.cuda.current_stream(x.device)
 
-    def local(t: Tile, rect):  # global rectangle -> slices in tile t's haloed region
-        return slice(rect[0] - t.hy0, rect[1] - t.hy0), slice(rect[2] - t.hx0, rect[3] - t.hx0)
+    def planes(idx: int, blocks_done: int):
+        """(offset, channel pitch, element size) of the fp32 stream and of the current 16-bit stream of tile idx."""
+        zf_o, zb_o, hid_o, cp, zp = state["layout"][idx]
+        in_hidden = state["fused"] and (blocks_done & 1)
+        return ((zf_o, cp, 4), (hid_o, cp, es16) if in_hidden else (zb_o, zp, es16))
 
     for g in range(len(bounds) - 1):
         l0, l1 = bounds[g], bounds[g + 1]
         if g > 0:
-            views = {t.index: model.stage_views(state["ws"][t.index], state["xt"][t.index].shape, l0) for t in mine}
-            ops, unpack = [], []
-            for (i, j), rect in sorted(rects.items()):
-                oi, oj = i % world, j % world                       # i receives from j
-                if oj == rank and oi == rank:                       # both tiles live here: a device-to-device copy
-                    (sy, sx), (dy, dx) = local(by_index[j], rect), local(by_index[i], rect)
-                    for src, dst in zip(views[j], views[i]):
-                        dst[:, dy, dx].copy_(src[:, sy, sx])
-                elif oj == rank:                                    # my tile j sends
-                    sy, sx = local(by_index[j], rect)
-                    buf = torch.cat([v[:, sy, sx].reshape(-1).view(torch.uint8) for v in views[j]])
-                    ops.append(dist.P2POp(dist.isend, buf, oi if group is None else dist.get_global_rank(group, oi), group))
-                elif oi == rank:                                    # my tile i receives
-                    dy, dx = local(by_index[i], rect)
-                    parts = [v[:, dy, dx] for v in views[i]]
-                    buf = torch.empty(sum(p.numel() * p.element_size() for p in parts), dtype=torch.uint8, device=x.device)
-                    ops.append(dist.P2POp(dist.irecv, buf, oj if group is None else dist.get_global_rank(group, oj), group))
-                    unpack.append((buf, parts))
-            if ops:
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
-            for buf, parts in unpack:
-                o = 0
-                for p in parts:
-                    n = p.numel() * p.element_size()
-                    p.copy_(buf[o:o + n].view(p.dtype).view(p.shape))
-                    o += n
+            if multi:
+                dist.all_reduce(state["token"], group=group)          # every rank's group g-1 kernels precede its arrival
+            with torch.cuda.device(x.device):
+                for (i, j), rect in rects.items():
+                    if i % world != rank:
+                        continue                                        # tile i (mine) pulls rect out of tile j's core
+                    ti, tj = by_index[i], by_index[j]
+                    Wi, Wj, Hi, Hj = ti.hx1 - ti.hx0, tj.hx1 - tj.hx0, ti.hy1 - ti.hy0, tj.hy1 - tj.hy0
+                    h, w = rect[1] - rect[0], rect[3] - rect[2]
+                    for (so, sp, es), (do, dp, _) in zip(planes(j, l0), planes(i, l0)):
+                        for b in range(B):
+                            src = addr[j] + so + ((b * Hj + rect[0] - tj.hy0) * Wj + rect[2] - tj.hx0) * sp * es
+                            dst = addr[i] + do + ((b * Hi + rect[0] - ti.hy0) * Wi + rect[2] - ti.hx0) * dp * es
+                            # (rows of min(sp, dp) channels: the pitches agree -- same model, same padding)
+                            _native.check(lib.mz_put_plane_async(dst, Wi * dp * es, src, Wj * sp * es, w * sp * es, h,
+                                                                 stream.cuda_stream))
+            if multi:
+                dist.all_reduce(state["token"], group=group)          # nobody overwrites a core that is still being pulled
         for t in mine:
             model.upscale_stage(state["xt"][t.index], c, frame, (t.y0 - t.hy0, t.y1 - t.hy0, t.x0 - t.hx0, t.x1 - t.hx0),
-                                (t.y0 * r, t.x0 * r), l0, l1, state["ws"][t.index])
+                                (t.y0 * r, t.x0 * r), l0, l1, state["buf"][t.index].tensor)
     return state
+
+
+
+def close_refresh_state(state: Optional[dict]) -> None:
+    """Release what ``upscale_tiled_refresh`` cached: peer mappings first, then this rank's own workspaces (call it on
+    every rank, after a barrier: a workspace must not disappear while a neighbour still maps it)."""
+    if not state:
+        return
+    from . import _native
+
+    lib = _native.load()
+    for p in state.pop("mappings", []):
+        _native.check(lib.mz_ipc_frame_close(p, 0))
+    for b in state.pop("buf", {}).values():
+        b.close()
