@@ -267,9 +267,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           pa ^= 1u;
           a_wrapped = true;
         }
-        // one weight stage = the three horizontal taps of filter row dy: [3][N][kc] (a resident bank was requested
-        // before the loop)
-        for (int dy = 0; dy < 3 && !p.res_b; ++dy) {
+        // (streamed weights are issued by warp 3: see below)
+      }
+    }
+  } else if (warp == 3 && !p.res_b) {
+    // =============================== weight producer (streamed filter banks) ===============================
+    // Its own warp, so that the activation loads above never queue behind a full weight ring: with one producer loop
+    // the next chunk's activation tile could only be requested after all three weight stages of the current chunk had
+    // found a free slot, which limited the activation prefetch to about one chunk and left the tensor pipe waiting for
+    // loads (96-channel conv2: 28 % of the kernel in wait_a_full).  Weights do not depend on the previous kernel: no
+    // griddepcontrol.wait here.
+    uint32_t sb = 0, pb = 0;
+    bool b_wrapped = false;
+    const uint32_t tap_bytes = p.epi.n_pad * row_bytes;
+    auto issue_b = [&](int c, int dy, uint32_t sbi) {
+      const uint32_t full_b = bar_b_full + 8 * sbi;
+      const uint32_t dstB = b_base + sbi * p.b_stage_bytes;
+      if (PAIR) {
+        if (lane == 0) {  // this CTA's half of the weight rows; stage layout [3 taps][N/2][kc]
+          if (cta_rank == 0) mbar_expect_tx(full_b, 2 * p.b_tx_bytes);
+          tma2_load_3d(dstB, &p.tmB, mapa_u32(full_b, 0), c * p.kc, cta_rank * p.b_slice_rows, dy * 3);
+        }
+      } else if (lane == 0 && (p.dbg & 1) && b_wrapped) {
+        mbar_arrive(full_b);
+      } else if (lane == 0) {
+        mbar_expect_tx(full_b, p.b_tx_bytes);
+        if (p.cluster > 1) {
+          for (int dx = 0; dx < 3; ++dx)
+            tma_load_3d_mcast(dstB + dx * tap_bytes + cta_rank * p.b_slice_rows * row_bytes, &p.tmB, full_b,
+                              c * p.kc, cta_rank * p.b_slice_rows, dy * 3 + dx, cta_mask);
+        } else {
+          for (int sub = 0; sub < p.subs; ++sub)  // stage layout [sub][3 taps][N][kc]
+            tma_load_3d(dstB + sub * 3 * tap_bytes, &p.tmB, full_b, (c * p.subs + sub) * p.kc, 0, dy * 3);
+        }
+      }
+    };
+    for (int round = 0; round < p.n_rounds; ++round) {
+      for (int c = 0; c < p.n_chunks; ++c) {
+        // one weight stage = the three horizontal taps of filter row dy: [3][N][kc]
+        for (int dy = 0; dy < 3; ++dy) {
           MZ_TIMED(1, mbar_wait(bar_b_empty + 8 * sb, pb ^ 1u));
           issue_b(c, dy, sb);
           if (++sb == static_cast<uint32_t>(p.b_stages)) {
