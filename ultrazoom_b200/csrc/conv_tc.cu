@@ -37,6 +37,8 @@ struct TcParams {
   int stage_bytes;  // epilogue staging (all four warps)
   int o_ring;       // mode 0: warp-private ring of output boxes (2 or 4)
   int res_rows;     // mode 1: row buffers (fp32 residual tile + 16-bit tile) per epilogue warp: 1, or all its rows
+  int sliced;       // mode 1, res_rows == 1: the row is finished box by box (e16 == e32), each box with its own residual barrier,
+                    // and the NEXT row's boxes are requested as soon as this row's stores of them have been read
   int epi_warps;    // 4 or 8 epilogue warps; with 8, two warps share a TMEM lane quarter and split the rows / boxes
   EpiParams epi;
   int kc, n_chunks;  // channels per swizzled sub-tile; pipeline chunks per patch (each = subs sub-tiles)
@@ -73,7 +75,7 @@ __host__ __device__ inline SmemPlan plan_smem(const TcParams& p) {
   s.a = 0;
   s.b = s.a + p.a_stages * p.a_stage_bytes;
   s.bars = s.b + p.b_stages * p.b_stage_bytes;
-  const uint32_t nbars = 2 * p.a_stages + 2 * p.b_stages + 4 + 8;  // + one residual-load barrier per epilogue warp
+  const uint32_t nbars = 2 * p.a_stages + 2 * p.b_stages + 4 + 64;  // + up to eight residual-load barriers per epilogue warp
   s.tmem_ptr = s.bars + nbars * 8;
   s.film = s.tmem_ptr + 16;  // [2][n_pad <= 256] fp32: FiLM scale / shift rows of the current image
   s.stage = (s.film + 2 * 256 * 4 + 1023u) & ~1023u;  // epilogue staging: swizzled boxes for TMA store / load
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bar_acc_full + 8 * i, 1);
       mbar_init(bar_acc_empty + 8 * i, (PAIR ? 2 : 1) * p.epi_warps);  // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    for (int i = 0; i < 8; ++i) mbar_init(bar_res + 8 * i, 1);
+    for (int i = 0; i < 64; ++i) mbar_init(bar_res + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -694,8 +696,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t row_stage = 32 * n_pad * (MODE == 3 ? 4 : 6);
     const uint32_t st_base = base + sp.stage + ew * (MODE == 0 ? p.o_ring * box16 : p.res_rows * row_stage);
     const bool all_rows = p.res_rows > 1;
-    const uint32_t my_res = bar_res + 8 * ew;
+    const uint32_t my_res = bar_res + 64 * ew;  // (eight barriers per warp: one per residual box in the sliced form)
     const int n_epi_threads = p.epi_warps * 32;
+    bool preloaded = false, pending_last = false;  // sliced form: what of the current row's residual was requested ahead
     for (int round = 0; round < p.n_rounds; ++round) {
       const int unit_raw = round * static_cast<int>(gridDim.x) + static_cast<int>(blockIdx.x);
       const bool unit_ok = unit_raw < p.n_units;  // CTA-uniform
@@ -718,6 +721,144 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         named_bar_sync(1, n_epi_threads);
         film_b = b;
+      }
+
+      if (MODE == 1 && p.sliced) {
+        // ---- sliced residual epilogue (one row buffer per warp) ----
+        // The fp32 row tile and its 16-bit shadow are handled box by box (e32 channels x 32 pixels; e16 == e32): box j is
+        // waited for, updated and stored on its own, and box j of the NEXT row of this warp -- in this patch or the next
+        // one -- is requested one box later, when the stores of box j have been read (bulk_wait_read<1>).  Residual loads
+        // therefore run a row ahead, and neither their latency nor the store read-out sits between two rows.
+        const uint32_t st_z = st_base, st_o = st_z + 32 * n_pad * 4;
+        const uint32_t slice_bytes = 32 * p.e32 * 4;
+        auto finish16s = [&](const uint32_t* v, uint32_t n0) {
+          const uint32_t bz = n0 >> sh32, cz = (n0 - (bz << sh32)) >> 2;
+          const uint32_t zrow = st_z + bz * box32 + lane * row32;
+          uint32_t o[8], addr[4];
+          float4 z[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            addr[kk] = zrow + swz_chunk(lane, cz + kk, row32) * 16;
+            z[kk] = lds128f(addr[kk]);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            z[kk].x += __uint_as_float(v[4 * kk + 0]);
+            z[kk].y += __uint_as_float(v[4 * kk + 1]);
+            z[kk].z += __uint_as_float(v[4 * kk + 2]);
+            z[kk].w += __uint_as_float(v[4 * kk + 3]);
+            sts128(addr[kk], __float_as_uint(z[kk].x), __float_as_uint(z[kk].y), __float_as_uint(z[kk].z), __float_as_uint(z[kk].w));
+            amax = fmaxf(fmaxf(amax, fmaxf(fabsf(z[kk].x), fabsf(z[kk].y))), fmaxf(fabsf(z[kk].z), fabsf(z[kk].w)));
+            o[2 * kk] = pack_op2(p.epi.bf16, z[kk].x, z[kk].y);
+            o[2 * kk + 1] = pack_op2(p.epi.bf16, z[kk].z, z[kk].w);
+          }
+          const uint32_t bo = n0 >> sh16, co = (n0 - (bo << sh16)) >> 3;
+          const uint32_t orow = st_o + bo * box16 + lane * row16;
+          sts128(orow + swz_chunk(lane, co, row16) * 16, o[0], o[1], o[2], o[3]);
+          sts128(orow + swz_chunk(lane, co + 1, row16) * 16, o[4], o[5], o[6], o[7]);
+        };
+        bool acc_waited = false;
+        for (int r = half; r < ROWS; r += nh) {
+          const int y = y0 + r;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                 (as * ROWS + (FUSE ? ROWS - 1 - r : r)) * p.acc_stride;
+          const bool valid = live && y < p.epi.H;  // (warp-uniform)
+          if (valid && lane == 0) {
+            if (!preloaded) {  // nothing of this row was requested ahead (first row, or the previous one was skipped)
+              bulk_wait_read<0>();
+              for (uint32_t j = 0; j < nb32; ++j) {
+                mbar_expect_tx(my_res + 8 * j, slice_bytes);
+                tma_load_4d(st_z + j * box32, &p.tmZ, my_res + 8 * j, j * p.e32, xw, y, b);
+              }
+            } else if (pending_last) {
+              bulk_wait_read<0>();
+              mbar_expect_tx(my_res + 8 * (nb32 - 1), slice_bytes);
+              tma_load_4d(st_z + (nb32 - 1) * box32, &p.tmZ, my_res + 8 * (nb32 - 1), (nb32 - 1) * p.e32, xw, y, b);
+            }
+          }
+          if (!acc_waited) {
+            MZ_TIMED(0, mbar_wait(bar_acc_full + 8 * as, pacc));
+            __syncwarp();
+            tc_fence_after();
+            acc_waited = true;
+          }
+          if (!valid) {  // below the image / surplus patch: nothing to store (FUSE still re-zeroes its accumulators)
+            if (FUSE)
+              for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) tmem_zero16(taddr + n0);
+            preloaded = pending_last = false;
+            continue;
+          }
+          // this warp's next row: in this patch, or the first one of its next patch
+          int nb_ = b, ny = y + nh, nxw = xw;
+          bool nvalid = r + nh < ROWS;
+          if (!nvalid) {
+            const int nunit = unit_raw + static_cast<int>(gridDim.x);
+            if (round + 1 < p.n_rounds && nunit < p.n_units) {
+              nb_ = nunit / units_per_img;
+              const int nrem = nunit - nb_ * units_per_img;
+              const int nty = nrem / p.tiles_x, ntx = nrem - nty * p.tiles_x;
+              ny = nty * ROWS + half;
+              nxw = ntx * kTileW + q * 32;
+              nvalid = half < ROWS;
+            }
+          }
+          nvalid = nvalid && ny < p.epi.H && !(p.dbg & 4);
+          for (uint32_t j = 0; j < nb32; ++j) {
+            mbar_wait(my_res + 8 * j, rpar);
+            const uint32_t n0 = j * p.e32;
+            if (p.e32 == 32) {
+              uint32_t v[32];
+              tmem_ld32(taddr + n0, v);
+              tmem_ld_wait();
+              if (FUSE) {
+                tmem_zero16(taddr + n0);
+                tmem_zero16(taddr + n0 + 16);
+              }
+              finish16s(v, n0);
+              finish16s(v + 16, n0 + 16);
+            } else {
+              uint32_t v[16];
+              tmem_ld16(taddr + n0, v);
+              tmem_ld_wait();
+              if (FUSE) tmem_zero16(taddr + n0);
+              finish16s(v, n0);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&p.tmZ, st_z + j * box32, j * p.e32, xw, y, b);
+              tma_store_4d(&p.tmO, st_o + j * box16, j * p.e16, xw, y, b);
+              bulk_commit();
+              if (j >= 1 && nvalid) {  // box j-1: its stores (one group back) have been read -> the next row's box j-1
+                bulk_wait_read<1>();
+                mbar_expect_tx(my_res + 8 * (j - 1), slice_bytes);
+                tma_load_4d(st_z + (j - 1) * box32, &p.tmZ, my_res + 8 * (j - 1), (j - 1) * p.e32, nxw, ny, nb_);
+              }
+            }
+          }
+          rpar ^= 1u;
+          preloaded = nvalid && nb32 > 1;
+          pending_last = preloaded;
+        }
+        if (!acc_waited) {  // (a warp without rows in this patch still takes part in the accumulator hand-off)
+          MZ_TIMED(0, mbar_wait(bar_acc_full + 8 * as, pacc));
+          __syncwarp();
+          tc_fence_after();
+        }
+        if (FUSE) tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR)
+            mbar_arrive_remote(mapa_u32(bar_acc_empty + 8 * as, 0));
+          else
+            mbar_arrive(bar_acc_empty + 8 * as);
+        }
+        if (++as == static_cast<uint32_t>(p.acc_stages)) {
+          as = 0;
+          pacc ^= 1u;
+        }
+        continue;
       }
 
       // residual row-tiles of this warp's rows (r = half, half + nh, ...): TMA load into the warp's staging once its
@@ -1073,7 +1214,8 @@ static uint32_t pow2_cols(uint32_t c) {
 }
 
 // staging: 2 = deep (four output boxes / every accumulator row's residual in flight per warp), 1 = two boxes / one row,
-// 0 = slim (two boxes of at most 32 channels) -- what is left beside a resident filter bank
+// 0 = slim (two boxes of at most 32 channels) -- what is left beside a resident filter bank, -1 = two boxes of 16
+// channels (1 KB each: eight epilogue warps beside a 166 KB bank and three activation stages)
 static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stages, int halo_mode, int a_stages,
                           int b_stages, int staging, bool res_b) {
   const int nh = p.epi_warps / 4;
@@ -1105,9 +1247,12 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   p.b_kp = p.subs > 1 ? (3 * n_local * kc * 2) >> 4 : 2;
   p.tmem_cols = pow2_cols(static_cast<uint32_t>(acc_stages * rows * p.acc_stride));
   const int n = p.epi.n_pad;
-  p.e16 = (n % 64 == 0 && staging > 0) ? 64 : (n % 32 == 0 ? 32 : 16);
+  p.e16 = (n % 64 == 0 && staging > 0) ? 64 : ((n % 32 == 0 && staging >= 0) ? 32 : 16);  // staging -1: 16-channel boxes
   p.e32 = n % 32 == 0 ? 32 : 16;
   if (p.epi.mode == 3) p.e32 = (2 * n) % 64 == 0 ? 64 : ((2 * n) % 32 == 0 ? 32 : 16);  // boxes of the [hi | lo] tile
+  static const bool no_sliced = getenv("MZ_NO_SLICED_EPILOGUE") != nullptr;
+  p.sliced = (p.epi.mode == 1 && p.res_rows == 1 && !no_sliced) ? 1 : 0;
+  if (p.sliced) p.e16 = p.e32;  // one 16-bit box per fp32 box
   p.stage_bytes = p.epi.mode == 0   ? p.epi_warps * p.o_ring * 32 * p.e16 * 2
                   : p.epi.mode == 1 ? p.epi_warps * p.res_rows * 32 * n * 6
                   : p.epi.mode == 3 ? p.epi_warps * p.res_rows * 32 * n * 4
@@ -1290,7 +1435,7 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
             for (int as = as_first; as >= 2 && !found; --as) {
               // pass 0 of a one-row search only accepts the deepest activation ring; pass 1 takes whatever fits
               if (stages_first && outer == 0 && as != as_first) break;
-              for (int staging = 2; staging >= 0 && !found; --staging) {
+              for (int staging = 2; staging >= (stages_first && e.mode == 0 ? -1 : 0) && !found; --staging) {
                 fill_geometry(p, a.cin_p, kc, rows, 2, 0, as, 0, staging, true);
                 if (fits(p)) found = true;
               }
