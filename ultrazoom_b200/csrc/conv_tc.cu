@@ -1420,20 +1420,20 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
       return;
     const int rcap = rows_cap(2);
     const int rmin = (rcap >= 2 && !tune.rows) ? 2 : 1;  // a one-row patch reads every activation row three times
-    for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {  // wide K chunks first: fewer hand-offs per patch
-      // ONE-ROW patches (the 96-channel conv1: TMEM holds one 192-column row per stage): a third activation stage beats a
-      // second set of epilogue warps -- one K chunk of a one-row patch is ~0.55 us of UMMAs against ~1 us of TMA latency,
-      // so with two stages the tensor pipe waits for loads (15.23 -> 14.9 ms per 4X-Ctrl frame).  Patches of two rows
-      // have twice the work per chunk and prefer the eight epilogue warps (3X-Ctrl: 8.5 vs 9.4 ms).
-      const bool stages_first = rcap == 1;
-      for (int outer = 0; outer < 2 && !found; ++outer) {
+    // ONE-ROW patches (the 96-channel conv1: TMEM holds one 192-column row per stage): a third activation stage beats
+    // wider K chunks and a second set of epilogue warps -- one K chunk of a one-row patch is ~0.55 us of UMMAs against
+    // ~1 us of TMA latency, so with two stages the tensor pipe waits for loads (15.23 -> 14.9 ms per 4X-Ctrl frame).  Pass
+    // 0 of such a search only accepts the deepest activation ring, over every K chunk and warp count; pass 1 takes whatever
+    // fits.  Patches of two rows have twice the work per chunk and prefer the eight epilogue warps (3X-Ctrl: 8.5 vs 9.4 ms).
+    const bool stages_first = rcap == 1;
+    for (int outer = 0; outer < (stages_first ? 2 : 1) && !found; ++outer) {
+      for (int kc = kc_first; kc >= 16 && !found; kc >>= 1) {  // wide K chunks first: fewer hand-offs per patch
         const int as_first = tune.a_stages ? tune.a_stages : 3;
         for (int ew = ew_first; ew >= ew_last && !found; ew -= 4) {
           p.epi_warps = ew;
           for (int rows = rcap; rows >= rmin && !found; --rows) {
             if (rows == 3) continue;
             for (int as = as_first; as >= 2 && !found; --as) {
-              // pass 0 of a one-row search only accepts the deepest activation ring; pass 1 takes whatever fits
               if (stages_first && outer == 0 && as != as_first) break;
               for (int staging = 2; staging >= (stages_first && e.mode == 0 ? -1 : 0) && !found; --staging) {
                 fill_geometry(p, a.cin_p, kc, rows, 2, 0, as, 0, staging, true);
@@ -1444,9 +1444,8 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
             if (tune.rows) break;
           }
         }
-        if (!stages_first) break;
+        if (tune.kc) break;
       }
-      if (tune.kc) break;
     }
   };
   auto try_stream = [&]() {
