@@ -190,3 +190,19 @@ def test_build_is_idempotent_under_the_lock():
     from ultrazoom_b200 import build as b
 
     assert b.build_locked() == b.LIB and os.path.exists(b.LIB)
+
+
+def test_bench_arms_describe_one_workload():
+    """the driver compares the `config` objects of `bench.py` and `bench.py --impl reference`; both come
+    from one function, for every workload."""
+    import argparse
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    args = argparse.Namespace(io="float32", residual_stream="auto", operands="float16", tune="")
+    for w in bench.WORKLOADS:
+        a, b = bench.config_of(w, 1, args), bench.config_of(w, 1, args)
+        assert a == b and {"workload", "batch_per_gpu", "lr_h", "lr_w", "parallelism"} <= set(a)
+    assert "halo-padded tile" in bench.config_of("cfg5", 8, args)["parallelism"]
