@@ -53,7 +53,7 @@ def config_of(workload: str, world: int, args) -> dict:
                            f"replica per GPU x{world}, batch-sharded, no collective",
             "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
             "weights": "random init (seed 0)", "image_io": args.io,
-            "residual_stream": ("fp32" if args.residual_stream != "split" else "two 16-bit planes hi + lo (z to 2^-22)"),
+            "residual_stream": "fp32",
             "accumulate": "fp32", "mma_operands": args.operands,
             "tune": {k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)}}
 
@@ -222,7 +222,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--operands", default="float16", choices=["float16", "bfloat16"])
-    ap.add_argument("--residual-stream", default="auto", choices=["auto", "float32", "split"])
+    ap.add_argument("--residual-stream", default="auto", choices=["auto", "float32"])
     ap.add_argument("--tune", default="", help="comma list k=v of mz_conv_tune fields, e.g. cluster=4,rows=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

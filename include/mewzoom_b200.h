@@ -68,18 +68,14 @@ typedef struct mz_config {
                               /* at the same tcgen05 rate; accumulation is fp32 either way.  */
                               /* fp16's 10-bit mantissa keeps max|err| vs the fp32 reference */
                               /* ~8x smaller.                                    */
-  int32_t residual_stream;    /* how the residual stream z lives in HBM between blocks:      */
-                              /* MZ_STREAM_AUTO (0): the library's choice -- currently fp32  */
-                              /* MZ_STREAM_FP32 (1): fp32 z + a 16-bit shadow (14C bytes/px  */
-                              /*   moved by conv2)                                           */
-                              /* MZ_STREAM_SPLIT (2): two 16-bit planes [hi | lo], hi =      */
-                              /*   round16(z) doubling as the next conv's operand, lo =      */
-                              /*   round16(z - hi): z to 2^-22 (fp16) at 12C bytes/px        */
+  int32_t residual_stream;    /* MZ_STREAM_AUTO (0) or MZ_STREAM_FP32 (1): the residual stream */
+                              /* lives in HBM as fp32 z + a 16-bit shadow (the next block's  */
+                              /* tensor-core operand).  (A third form, two 16-bit planes hi +  */
+                              /* lo, was measured no faster in round 1 and removed in round 2.) */
 } mz_config;
 
 #define MZ_STREAM_AUTO 0
 #define MZ_STREAM_FP32 1
-#define MZ_STREAM_SPLIT 2
 
 #define MZ_DTYPE_F16 0
 #define MZ_DTYPE_BF16 1
@@ -244,7 +240,6 @@ int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, 
 /* FanOutProjection (model.py:212-242) fused with the NCHW->NHWC layout change:
  * zf (B,H,W,Cp) fp32 residual stream and zb (B,H,W,zb_pitch) 16-bit MMA operand (operand_dtype);
  * zb_pitch = 0 means Cp, a larger pitch is zero-filled (mz_zb_pitch gives the pitch mz_upscale uses).
- * zf_dev == NULL selects the split stream: zb_dev is then z16 (B,H,W,2*Cp) = [hi | lo] per pixel.
  * w_dev is (Cp,3) fp32 and bias_dev (Cp,) fp32, zero-padded beyond the logical channel count. */
 int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev,
                  int32_t B, int32_t H, int32_t W, int32_t Cp, int32_t zb_pitch, int32_t operand_dtype, void* stream);
@@ -255,9 +250,7 @@ int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, 
  *   mode 0: out16 = SiLU(scale[b,n]*acc + shift[b,n])   (conv1 + control + SiLU); film_dev is
  *           (B,2,cout_p) fp32 -- scale row then shift row per image -- or NULL for scale 1, shift 0
  *   mode 1: zf += acc ; out16 = round16(zf)              (conv2 + ResidualConnection, model.py:789-792)
- *   mode 3: the same on the split stream: out16_dev is z16 (B,H,W,2*cout_p) = [hi | lo], updated in place:
- *           z = hi + lo + acc ; hi = round16(z) ; lo = round16(z - hi)
- * in_pitch: channel pitch of the input in elements (0 = cin_p; 2*cin_p when the input is the hi half of a z16).
+ * in_pitch: channel pitch of the input in elements (0 = cin_p; larger: the first cin_p channels of a wider tensor).
  * out_pitch: channel pitch of out16 in elements (0 = cout_p); channels beyond cout_p are left untouched.
  * use_tc = 1: tcgen05/TMEM/TMA kernel; 0: SIMT diagnostic kernel.  tune may be NULL. */
 int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev,

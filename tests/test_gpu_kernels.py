@@ -271,59 +271,8 @@ def test_shifted_umma_descriptor_probe(dev):
             assert ops.probe_umma(kc, shift, 0) == 0.0
 
 
-def _split16(z, dt):
-    hi = z.to(dt)
-    return hi, (z - hi.float()).to(dt)
-
-
-def test_stem_pack_split_stream(dev):
-    """Split residual stream: z16 = [hi | lo] per pixel, hi = round16(z), lo = round16(z - hi)."""
-    ops, _ = _ops()
-    g = torch.Generator().manual_seed(6)
-    x = torch.rand(2, 3, 6, 7, generator=g)
-    for C_ in (48, 54):
-        w, b = torch.randn(C_, 3, 1, 1, generator=g) * 0.5, torch.randn(C_, generator=g) * 0.1
-        ref = F.conv2d(x, w, b).permute(0, 2, 3, 1)
-        for dt in DTYPES:
-            _, z16 = ops.stem_pack(x.to(dev), w, b, dtype=dt, split=True)
-            Cp = ops.padded_channels(C_)
-            z16 = z16.cpu()
-            assert tuple(z16.shape) == (2, 6, 7, 2 * Cp)
-            hi, lo = z16[..., :Cp], z16[..., Cp:]
-            assert (hi.float()[..., :C_] + lo.float()[..., :C_] - ref).abs().max().item() <= (2e-6 if dt == torch.float16 else 5e-5)
-            assert (hi.float()[..., :C_] - ref.to(dt).float()).abs().max().item() <= 2 * _ulp(dt) * ref.abs().max().item()
-            if Cp > C_:
-                assert z16[..., C_:Cp].abs().max().item() == 0.0 and z16[..., Cp + C_:].abs().max().item() == 0.0
-
-
-@pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("cin,cout,shape,tune", [
-    (96, 48, (2, 13, 150), {}), (192, 96, (1, 21, 300), {}), (108, 54, (1, 10, 70), {}), (32, 16, (1, 1, 5), {}),
-    (96, 48, (2, 41, 300), dict(max_ctas=3)), (192, 96, (2, 30, 260), dict(pair=1, max_ctas=4)),
-    (96, 48, (2, 13, 150), dict(resident=2, epi_warps=4)), (96, 48, (1, 7, 129), dict(rows=4)), (128, 64, (1, 9, 257), {}),
-])
-def test_conv2_split_residual(dev, cin, cout, shape, tune, dt):
-    """mode 3: z = hi + lo + acc on the split stream, updated in place; tcgen05 and SIMT twins."""
-    ops, native = _ops()
-    inp, w, _, zf0, acc = _conv_operands(cin, cout, shape, 18, ops, dt)
-    cout_p = zf0.shape[-1]
-    hi0, lo0 = _split16(zf0, dt)
-    zref = hi0.float()[..., :cout] + lo0.float()[..., :cout] + acc
-    wp = ops.pack_conv_weight(w, dev, dtype=dt)
-    tol = 1e-4 if dt == torch.float16 else 2e-4 * max(1.0, zref.abs().max().item())
-    for use_tc in (True, False):
-        z16 = torch.cat([hi0, lo0], dim=-1).to(dev).contiguous()
-        out = ops.conv3x3(inp.to(dev), wp, 3, None, None, use_tc=use_tc, tune=native.tune(**tune), z16=z16).cpu()
-        hi, lo = out[..., :cout_p], out[..., cout_p:]
-        assert (hi.float()[..., :cout] + lo.float()[..., :cout] - zref).abs().max().item() <= tol
-        # hi is the 16-bit rounding of the new value (what the next convolution reads), lo the remainder
-        assert (hi.float()[..., :cout] - zref).abs().max().item() <= 2 * _ulp(dt) * max(1.0, zref.abs().max().item()) + tol
-        if cout_p > cout:
-            assert hi[..., cout:].abs().max().item() == 0.0 and lo[..., cout:].abs().max().item() == 0.0
-
-
-def test_conv1_and_head_read_the_hi_half_of_the_split_stream(dev):
-    """in_pitch: a convolution whose input is z16 reads only its first cin_p channels (the hi plane)."""
+def test_conv1_and_head_read_the_first_channels_of_a_wider_tensor(dev):
+    """in_pitch: a convolution whose input tensor is wider than its cin_p reads only the first cin_p channels."""
     ops, native = _ops()
     inp, w, film, _, acc = _conv_operands(48, 96, (2, 13, 150), 19, ops, torch.float16)
     junk = torch.randn(inp.shape).to(torch.float16)

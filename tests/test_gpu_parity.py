@@ -92,28 +92,6 @@ def test_named_models_against_oracle(dev, name, shape):
         assert max_abs_err(got_b, ref_b) <= tol_b and psnr(got_b, ref_b) >= 50.0
 
 
-def test_residual_stream_variants_agree(dev):
-    """fp32 stream (mode 1) and split 16-bit stream (mode 3) carry the same value to 2^-22, but the two sums round a
-    few 16-bit operands (hi = round16(z)) to the neighbouring value; 40 layers amplify those flips to the size of the
-    operand-quantisation noise itself.  Both variants must stay inside the stated envelope of the reference."""
-    o = make_oracle("MewZoom-4X-Ctrl", seed=0)
-    cfg = dict(upscale_ratio=4, num_channels=96, hidden_ratio=2, num_encoder_layers=40, control_features=3)
-    from ultrazoom_b200 import MewZoom
-
-    g = torch.Generator().manual_seed(77)
-    x, c = torch.rand(1, 3, 40, 140, generator=g), torch.rand(1, 3, generator=g)
-    with torch.inference_mode():
-        ref = o.upscale(x, c)
-    outs = {}
-    for rs in ("float32", "split"):
-        m = MewZoom(**cfg, residual_stream=rs)
-        m.load_state_dict(o.state_dict())
-        m = m.to(dev).eval()
-        outs[rs] = m.upscale(x.to(dev), c.to(dev)).cpu()
-        assert max_abs_err(outs[rs], ref) <= 8e-3
-    assert max_abs_err(outs["float32"], outs["split"]) <= 8e-3
-
-
 @pytest.mark.parametrize("name", ["MewZoom-2X-Ctrl", "MewZoom-3X-Ctrl", "MewZoom-4X-Ctrl"])
 def test_ragged_shapes_against_the_simt_twin(dev, name):
     """Edge and ragged shapes (single row / column, widths around the 128-pixel tile, odd batches): the tcgen05 path,

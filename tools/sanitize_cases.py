@@ -1,6 +1,6 @@
 """Small-shape run of every kernel variant behind the C ABI, for `compute-sanitizer --tool memcheck|racecheck|synccheck`
 (tools/sanitize.sh; SURVEY.md section 5 "race detection"): bicubic r = 2/3/4, stem, FiLM table, device weight packer, the
-tcgen05 convolution in every epilogue MODE (0 conv1+FiLM+SiLU, 1 conv2+residual, 2 head, 3 split stream) and VAR (0 plain,
+tcgen05 convolution in every epilogue MODE (0 conv1+FiLM+SiLU, 1 conv2+residual, 2 head) and VAR (0 plain,
 1 CTA pair / cta_group::2, 2 vertical taps fused along N), resident and streamed filter banks, 4 and 8 epilogue warps,
 the SIMT twin, and whole small models through mz_upscale (dependent launches included).  Every result is also checked
 against the SIMT twin so that a sanitizer-induced timing change that exposes a protocol bug shows up as a mismatch."""
@@ -51,7 +51,7 @@ def main():
         cfg = dict(MODEL_CONFIGS[name])
         cfg["num_encoder_layers"] = 2
         torch.manual_seed(1)
-        for rs in ("float32", "split"):
+        for rs in ("float32",):
             m = MewZoom(**cfg, residual_stream=rs).to(dev).eval()
             x, c = torch.rand(shape, generator=g).to(dev), torch.rand(shape[0], 3, generator=g).to(dev)
             y = m.upscale(x, c)

@@ -32,8 +32,8 @@ DTYPE_F16, DTYPE_BF16 = 0, 1
 W_STEM_WEIGHT, W_STEM_BIAS, W_CONV1, W_CONV2, W_CTRL_WEIGHT, W_CTRL_BIAS, W_HEAD = range(7)
 
 
-STREAM_AUTO, STREAM_FP32, STREAM_SPLIT = 0, 1, 2
-STREAM_CODES = {"auto": STREAM_AUTO, "float32": STREAM_FP32, "split": STREAM_SPLIT}
+STREAM_AUTO, STREAM_FP32 = 0, 1
+STREAM_CODES = {"auto": STREAM_AUTO, "float32": STREAM_FP32}
 
 
 class MzConfig(C.Structure):

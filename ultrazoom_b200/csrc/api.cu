@@ -76,7 +76,7 @@ int mz_bicubic_f32(const float* x_dev, float* y_dev, int32_t planes, int32_t H, 
 
 int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, float* zf_dev, void* zb_dev, int32_t B,
                  int32_t H, int32_t W, int32_t Cp, int32_t zb_pitch, int32_t operand_dtype, void* stream) {
-  MZ_REQUIRE(x_dev && w_dev && bias_dev && zb_dev, "stem: null pointer");  // zf_dev == NULL: split stream into zb_dev
+  MZ_REQUIRE(x_dev && w_dev && bias_dev && zf_dev && zb_dev, "stem: null pointer");
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
   return launch_stem(x_dev, nullptr, w_dev, bias_dev, zf_dev, static_cast<uint16_t*>(zb_dev), operand_dtype, B, H, W, Cp, zb_pitch,
                      static_cast<cudaStream_t>(stream));
@@ -89,7 +89,7 @@ int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const 
   MZ_REQUIRE(out_pitch == 0 || (out_pitch >= cout_p && out_pitch % 8 == 0), "conv: out_pitch %d must be 0 or a multiple of 8 >= cout_p", out_pitch);
   MZ_REQUIRE(in_dev && wpacked_dev && out_bf16_dev, "conv: null pointer");
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
-  MZ_REQUIRE(mode == 0 || mode == 1 || mode == 3, "conv: mode must be 0, 1 or 3, %d given", mode);
+  MZ_REQUIRE(mode == 0 || mode == 1, "conv: mode must be 0 or 1, %d given", mode);
   MZ_REQUIRE(mode != 1 || zf_dev, "conv: mode 1 needs the fp32 residual stream");
   ConvArgs a;
   memset(&a, 0, sizeof(a));

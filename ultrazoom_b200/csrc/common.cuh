@@ -438,13 +438,6 @@ __device__ __forceinline__ float2 unpack_op2(int bf16, uint32_t u) {
   if (bf16) return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
   return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
-// Split of the residual stream into two 16-bit planes: hi = round16(z) (what the next convolution reads as its MMA
-// operand), lo = round16(z - hi); hi + lo carries z to 2^-22 relative (fp16) / 2^-17 (bf16).
-__device__ __forceinline__ void split_op2(int bf16, float z0, float z1, uint32_t& hi, uint32_t& lo) {
-  hi = bf16 ? pack_bf16x2(z0, z1) : pack_f16x2(z0, z1);
-  const float2 h = unpack_op2(bf16, hi);
-  lo = bf16 ? pack_bf16x2(z0 - h.x, z1 - h.y) : pack_f16x2(z0 - h.x, z1 - h.y);
-}
 __device__ __forceinline__ float op_to_float(int bf16, uint16_t v) {
   return bf16 ? __uint_as_float(static_cast<uint32_t>(v) << 16) : __half2float(__ushort_as_half(v));
 }

@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
-    if (MODE != 2 && MODE != 3) tma_prefetch_desc(&p.tmO);
-    if (MODE == 1 || MODE == 3) tma_prefetch_desc(&p.tmZ);
+    if (MODE != 2) tma_prefetch_desc(&p.tmO);
+    if (MODE == 1) tma_prefetch_desc(&p.tmZ);
     for (int i = 0; i < p.a_stages; ++i) {
       mbar_init(bar_a_full + 8 * i, 1);
       mbar_init(bar_a_empty + 8 * i, 1);
@@ -686,14 +686,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     float amax = 0.f;  // fp16 range guard: largest magnitude this thread rounded into a 16-bit operand (EpiParams::sat)
     uint32_t as = 0, pacc = 0, rpar = 0, ring = 0;
     const uint32_t n_pad = p.epi.n_pad;
-    // residual tiles: mode 1 fp32 (n_pad channels), mode 3 the 16-bit pair [hi | lo] (2 * n_pad channels)
-    const uint32_t row16 = p.e16 * 2, row32 = p.e32 * (MODE == 3 ? 2 : 4);  // staging row bytes (= TMA box inner extent)
+    const uint32_t row16 = p.e16 * 2, row32 = p.e32 * 4;  // staging row bytes (= TMA box inner extent): 16-bit / fp32 boxes
     const uint32_t box16 = 32 * row16, box32 = 32 * row32;        // one warp-box: 32 pixels
-    const uint32_t nb16 = n_pad / p.e16, nb32 = (MODE == 3 ? 2 * n_pad : n_pad) / p.e32;
+    const uint32_t nb16 = n_pad / p.e16, nb32 = n_pad / p.e32;
     const uint32_t sh16 = 31 - __clz(p.e16), sh32 = 31 - __clz(p.e32);  // box widths are powers of two
     // warp-private staging: mode 0 -> ring of 16-bit boxes; mode 1 -> res_rows x (fp32 row-tile + 16-bit row-tile)
-    // one accumulator row of this warp: mode 1 fp32 tile + 16-bit tile; mode 3 the [hi | lo] tile, updated in place
-    const uint32_t row_stage = 32 * n_pad * (MODE == 3 ? 4 : 6);
+    // one accumulator row of this warp: fp32 tile + 16-bit tile
+    const uint32_t row_stage = 32 * n_pad * 6;
     const uint32_t st_base = base + sp.stage + ew * (MODE == 0 ? p.o_ring * box16 : p.res_rows * row_stage);
     const bool all_rows = p.res_rows > 1;
     const uint32_t my_res = bar_res + 64 * ew;  // (eight barriers per warp: one per residual box in the sliced form)
@@ -865,7 +864,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       // previous stores have finished reading it.  With a buffer per row (res_rows > 1) all of them are requested up
       // front on one barrier; otherwise row k+1 is requested when row k has been stored.
       auto load_residual = [&](int k_lo, int k_hi) {  // k indexes this warp's rows: r = half + k * nh
-        if ((MODE == 1 || MODE == 3) && live && lane == 0) {
+        if (MODE == 1 && live && lane == 0) {
           int nrows = 0;
           for (int k = k_lo; k < k_hi; ++k) nrows += (half + k * nh < ROWS && y0 + half + k * nh < p.epi.H) ? 1 : 0;
           if (nrows > 0) {
@@ -882,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       };
       constexpr int kMyRowsMax = ROWS;  // upper bound of rows per warp
       load_residual(0, all_rows ? kMyRowsMax : 1);
-      if ((MODE == 1 || MODE == 3) && lane == 0 && !(p.dbg & 4)) {
+      if (MODE == 1 && lane == 0 && !(p.dbg & 4)) {
         // L2 prefetch of the residual tiles this warp will need for the NEXT patch: by then they are an L2 hit
         // (~0.5 us) instead of an HBM round trip that a single row buffer cannot hide
         const int nunit = unit_raw + static_cast<int>(gridDim.x);
@@ -942,47 +941,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               epi_head_r<2>(p.epi, b, y, x, acc);
             else
               epi_head_r<3>(p.epi, b, y, x, acc);
-          }
-        } else if (MODE == 3) {
-          if (k > 0 && !all_rows) load_residual(k, k + 1);
-          if (k == 0 || !all_rows) {
-            mbar_wait(my_res, rpar);
-            rpar ^= 1u;
-          }
-          const uint32_t st_z = st_base + (all_rows ? k : 0) * row_stage;
-          for (uint32_t n0 = 0; n0 < n_pad; n0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + n0, v);
-            tmem_ld_wait();
-            if (FUSE) tmem_zero16(taddr + n0);
-            // hi channels n0..n0+15 and lo channels n_pad+n0.. of this pixel: two 16-byte chunks each
-            const uint32_t nl = n_pad + n0;
-            const uint32_t bh = n0 >> sh32, ch = (n0 - (bh << sh32)) >> 3, bl = nl >> sh32, cl = (nl - (bl << sh32)) >> 3;
-            const uint32_t hrow = st_z + bh * box32 + lane * row32, lrow = st_z + bl * box32 + lane * row32;
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              const uint32_t ha = hrow + swz_chunk(lane, ch + kk, row32) * 16, la = lrow + swz_chunk(lane, cl + kk, row32) * 16;
-              const float4 hv = lds128f(ha), lv = lds128f(la);
-              const uint32_t hw[4] = {__float_as_uint(hv.x), __float_as_uint(hv.y), __float_as_uint(hv.z), __float_as_uint(hv.w)};
-              const uint32_t lw[4] = {__float_as_uint(lv.x), __float_as_uint(lv.y), __float_as_uint(lv.z), __float_as_uint(lv.w)};
-              uint32_t ho[4], lo[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 h = unpack_op2(p.epi.bf16, hw[j]), l = unpack_op2(p.epi.bf16, lw[j]);
-                const float z0 = h.x + l.x + __uint_as_float(v[8 * kk + 2 * j]);
-                const float z1 = h.y + l.y + __uint_as_float(v[8 * kk + 2 * j + 1]);
-                amax = fmaxf(amax, fmaxf(fabsf(z0), fabsf(z1)));
-                split_op2(p.epi.bf16, z0, z1, ho[j], lo[j]);
-              }
-              sts128(ha, ho[0], ho[1], ho[2], ho[3]);
-              sts128(la, lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            for (uint32_t bx = 0; bx < nb32; ++bx) tma_store_4d(&p.tmZ, st_z + bx * box32, bx * p.e32, xw, y, b);
-            bulk_commit();
           }
         } else if (MODE == 1) {
           if (k > 0 && !all_rows) load_residual(k, k + 1);
@@ -1153,13 +1111,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // ----------------------------------------------------------------------------------------------
 // ---- kernel lookup -------------------------------------------------------------------------------------------------
 // One lookup function per epilogue mode, so that the build can compile the instantiations of each mode in its own
-// translation unit: build.py compiles this file five times, with -DMZ_TC_PART=<mode> for the kernels of modes 0..3 and
+// translation unit: build.py compiles this file four times, with -DMZ_TC_PART=<mode> for the kernels of modes 0..2 and
 // -DMZ_TC_PART=4 for the host side.  Without the define (a plain `nvcc -c conv_tc.cu`) everything lands in one object.
 //   var 0: one CTA per patch, 1: CTA pair (cta_group::2), 2: fused rows.  Returns nullptr for a shape that has no kernel.
 const void* tc_kernel_mode0(int ks, int rows, int var);
 const void* tc_kernel_mode1(int ks, int rows, int var);
 const void* tc_kernel_mode2(int ks, int rows, int var);
-const void* tc_kernel_mode3(int ks, int rows, int var);
 
 template <int M, int K>
 static const void* tc_kernel_rows(int rows, int var) {
@@ -1198,9 +1155,6 @@ const void* tc_kernel_mode1(int ks, int rows, int var) { return tc_kernel_lookup
 #endif
 #if !defined(MZ_TC_PART) || MZ_TC_PART == 2
 const void* tc_kernel_mode2(int ks, int rows, int var) { return tc_kernel_lookup<2>(ks, rows, var); }
-#endif
-#if !defined(MZ_TC_PART) || MZ_TC_PART == 3
-const void* tc_kernel_mode3(int ks, int rows, int var) { return tc_kernel_lookup<3>(ks, rows, var); }
 #endif
 
 #if !defined(MZ_TC_PART) || MZ_TC_PART == 4  // ---- host side ----------------------------------------------------------
@@ -1249,13 +1203,11 @@ static void fill_geometry(TcParams& p, int cin_p, int kc, int rows, int acc_stag
   const int n = p.epi.n_pad;
   p.e16 = (n % 64 == 0 && staging > 0) ? 64 : ((n % 32 == 0 && staging >= 0) ? 32 : 16);  // staging -1: 16-channel boxes
   p.e32 = n % 32 == 0 ? 32 : 16;
-  if (p.epi.mode == 3) p.e32 = (2 * n) % 64 == 0 ? 64 : ((2 * n) % 32 == 0 ? 32 : 16);  // boxes of the [hi | lo] tile
   static const bool no_sliced = getenv("MZ_NO_SLICED_EPILOGUE") != nullptr;
   p.sliced = (p.epi.mode == 1 && p.res_rows == 1 && !no_sliced) ? 1 : 0;
   if (p.sliced) p.e16 = p.e32;  // one 16-bit box per fp32 box
   p.stage_bytes = p.epi.mode == 0   ? p.epi_warps * p.o_ring * 32 * p.e16 * 2
                   : p.epi.mode == 1 ? p.epi_warps * p.res_rows * 32 * n * 6
-                  : p.epi.mode == 3 ? p.epi_warps * p.res_rows * 32 * n * 4
                                     : 0;
 }
 
@@ -1363,7 +1315,7 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
   MZ_REQUIRE(a.cin_p > 0 && a.cin_p % 16 == 0, "conv: cin_p must be a positive multiple of 16, %d given", a.cin_p);
   MZ_REQUIRE(e.n_pad >= 16 && e.n_pad % 16 == 0 && e.n_pad <= 256,
              "conv: n_pad must be a multiple of 16 in [16, 256], %d given", e.n_pad);
-  MZ_REQUIRE(e.mode >= 0 && e.mode <= 3, "conv: bad epilogue mode %d", e.mode);
+  MZ_REQUIRE(e.mode >= 0 && e.mode <= 2, "conv: bad epilogue mode %d", e.mode);
   MZ_REQUIRE(e.mode != 2 || e.n_pad <= 48, "head conv: n_pad must be <= 48, %d given", e.n_pad);
   MZ_REQUIRE(tune.halo_mode >= 0 && tune.halo_mode <= 1, "conv: bad halo_mode %d", tune.halo_mode);
   MZ_REQUIRE(tune.cluster == 0 || tune.cluster == 1 || tune.cluster == 2 || tune.cluster == 4,
@@ -1542,7 +1494,7 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(a.cin_p), static_cast<uint64_t>(e.W), static_cast<uint64_t>(e.H),
                               static_cast<uint64_t>(e.B)};
-    const uint64_t ip = a.in_pitch ? a.in_pitch : a.cin_p;  // pixel pitch in elements (2 * cin_p inside z16)
+    const uint64_t ip = a.in_pitch ? a.in_pitch : a.cin_p;  // pixel pitch in elements (a wider tensor's first cin_p channels)
     const uint64_t strides[3] = {ip * 2, static_cast<uint64_t>(e.W) * ip * 2, static_cast<uint64_t>(e.H) * e.W * ip * 2};
     const uint32_t box[4] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.pw),
                              static_cast<uint32_t>(p.rows + 2), 1u};
@@ -1562,14 +1514,7 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
     return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                             : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   };
-  if (e.mode == 3) {  // the split residual stream z16 (2 * n_pad channels of 16 bits), loaded and stored by the epilogue
-    const uint64_t n2 = static_cast<uint64_t>(2) * e.n_pad;
-    const uint64_t dims[4] = {n2, static_cast<uint64_t>(e.W), static_cast<uint64_t>(e.H), static_cast<uint64_t>(e.B)};
-    const uint64_t st[3] = {n2 * 2, static_cast<uint64_t>(e.W) * n2 * 2, static_cast<uint64_t>(e.H) * e.W * n2 * 2};
-    const uint32_t box[4] = {static_cast<uint32_t>(p.e32), 32u, 1u, 1u};
-    int rc = encode_tmap(&p.tmZ, tdt, 4, e.out_bf16, dims, st, box, swz_of(p.e32 * 2));
-    if (rc != MZ_OK) return rc;
-  } else if (e.mode != 2) {
+  if (e.mode != 2) {
     const uint64_t dims[4] = {static_cast<uint64_t>(e.n_pad), static_cast<uint64_t>(e.W), static_cast<uint64_t>(e.H),
                               static_cast<uint64_t>(e.B)};
     const uint64_t op = e.out_pitch ? e.out_pitch : e.n_pad;
@@ -1610,7 +1555,6 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
   const int var = p.fuse_g ? 2 : (p.pair ? 1 : 0);
   const void* fn = e.mode == 0   ? tc_kernel_mode0(ks, p.rows, var)
                    : e.mode == 1 ? tc_kernel_mode1(ks, p.rows, var)
-                   : e.mode == 3 ? tc_kernel_mode3(ks, p.rows, var)
                                  : tc_kernel_mode2(ks, p.rows, var);
   if (!fn) {
     set_error("conv: no %s kernel for mode %d, %d k-steps, %d rows", var == 2 ? "fused-row" : (var == 1 ? "CTA-pair" : "tcgen05"),

@@ -29,9 +29,6 @@ void make_bicubic_table(int r, BicubicTable* t);
 //   mode 0: hidden = SiLU(scale[b,n] * acc + shift[b,n])   -> bf16 NHWC      (conv1 + control + SiLU)
 //   mode 1: zf += acc ; zb = bf16(zf)                                         (conv2 + ResidualConnection)
 //   mode 2: y = [clamp](skip + PixelShuffle_r(acc))         -> fp32 NCHW      (SubpixelConv2d + skip)
-//   mode 3: z = hi + lo + acc ; hi = round16(z) ; lo = round16(z - hi)        (conv2 + ResidualConnection on the
-//           SPLIT residual stream z16 (B,H,W,2*n_pad) = [hi | lo] per pixel, updated in place: 12C instead of
-//           14C bytes per pixel, hi doubles as the next convolution's operand)
 // ----------------------------------------------------------------------------------------------
 struct EpiParams {
   int mode;
@@ -39,7 +36,7 @@ struct EpiParams {
   int bf16;           // MMA-operand element type of every 16-bit tensor: 0 = fp16, 1 = bf16
   int n_pad;          // GEMM N (multiple of 16) == channel pitch of the 16-bit / fp32 NHWC outputs
   const float* film;  // mode 0: [B][2][n_pad] (scale row then shift row per image) or nullptr
-  uint16_t* out_bf16;       // mode 0: hidden; mode 1: zb (fp16 or bf16 bits); mode 3: z16 = [hi | lo], pitch 2 * n_pad
+  uint16_t* out_bf16;       // mode 0: hidden; mode 1: zb (fp16 or bf16 bits)
   int out_pitch;            // channel pitch of out_bf16 in elements (0 = n_pad); > n_pad when the consumer wants
                             // zero-padded channels (48-channel zb is kept at pitch 64: 128-byte TMA rows)
   float* zf;                // mode 1: fp32 residual stream, updated in place
@@ -85,7 +82,7 @@ struct ConvArgs {
   const uint16_t* in;  // (B,H,W,cin_p) fp16 | bf16
   const uint16_t* w;   // [9][n_pad][cin_p] fp16 | bf16, tap = ky*3+kx
   int cin_p;
-  int in_pitch;        // channel pitch of `in` in elements (0 = cin_p); 2 * cin_p when `in` is the hi half of z16
+  int in_pitch;        // channel pitch of `in` in elements (0 = cin_p): a wider tensor's first cin_p channels are read
   EpiParams epi;
 };
 
@@ -142,8 +139,7 @@ int prepare_block_fused(const FusedBlockArgs& a, int device, ConvLaunch* out);
 int run_block_fused(ConvLaunch& launch, cudaStream_t s);
 
 int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s);
-// zf != nullptr: fp32 stream zf + 16-bit shadow zb (pitch zb_pitch).  zf == nullptr: split stream, zb is z16 = [hi | lo]
-// with pitch 2 * Cp.
+// fp32 stream zf + 16-bit shadow zb (pitch zb_pitch).
 // x8 != nullptr: the image is 8-bit (B,3,H,W) and read as x8 / 255.
 int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* bias, float* zf, uint16_t* zb, int bf16,
                 int B, int H, int W, int Cp, int zb_pitch, cudaStream_t s, unsigned int* sat = nullptr);
@@ -227,17 +223,6 @@ __device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, in
     uint16_t* dst = p.out_bf16 + pix * (p.out_pitch ? p.out_pitch : p.n_pad) + n0;
     st_global_v4(dst, o[0], o[1], o[2], o[3]);
     st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
-  } else if (MODE == 3) {
-    uint32_t* zh = reinterpret_cast<uint32_t*>(p.out_bf16 + pix * 2 * p.n_pad + n0);
-    uint32_t* zl = reinterpret_cast<uint32_t*>(p.out_bf16 + pix * 2 * p.n_pad + p.n_pad + n0);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float2 h = unpack_op2(p.bf16, zh[q]), l = unpack_op2(p.bf16, zl[q]);
-      uint32_t hi, lo;
-      split_op2(p.bf16, h.x + l.x + acc[2 * q], h.y + l.y + acc[2 * q + 1], hi, lo);
-      zh[q] = hi;
-      zl[q] = lo;
-    }
   } else {
     const float4* zf = reinterpret_cast<const float4*>(p.zf + pix * (p.zf_pitch ? p.zf_pitch : p.n_pad) + n0);
     float4 zin[4];

@@ -24,7 +24,6 @@ struct mz_model {
   // S2 launches of ns2 channels each (Cp = S2 * ns2), each adding into its channel slice of the residual stream.
   // S = S2 = 1 for every named model.
   int S = 1, ns = 0, S2 = 1, ns2 = 0;
-  bool split = false;  // residual stream as two 16-bit planes z16 = [hi | lo] (pitch 2 * Cp) instead of fp32 zf + zb
   float* stem_w = nullptr;  // (Cp,3)
   float* stem_b = nullptr;  // (Cp)
   uint16_t* conv1 = nullptr;  // L x S x [9][ns][Cz]
@@ -107,9 +106,9 @@ WsPlan plan_ws(const mz_model* m, int B, int H, int W) {
   WsPlan p;
   size_t off = 0;
   p.zf = off;
-  if (!m->split) off = align_up(off + npix * m->Cp * sizeof(float), 1024);
-  p.zb = off;  // split stream: z16 = [hi | lo], 2 * Cp channels of 16 bits per pixel
-  off = align_up(off + npix * (m->split ? 2 * m->Cp : m->Cz) * sizeof(uint16_t), 1024);
+  off = align_up(off + npix * m->Cp * sizeof(float), 1024);
+  p.zb = off;
+  off = align_up(off + npix * m->Cz * sizeof(uint16_t), 1024);
   p.hid = off;
   off = align_up(off + npix * m->hCp * sizeof(uint16_t), 1024);
   p.film = off;
@@ -219,8 +218,8 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
              "control_features must be in [0, 64], %d given.", cfg->control_features);
   MZ_REQUIRE(cfg->operand_dtype == MZ_DTYPE_F16 || cfg->operand_dtype == MZ_DTYPE_BF16,
              "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given.", cfg->operand_dtype);
-  MZ_REQUIRE(cfg->residual_stream >= MZ_STREAM_AUTO && cfg->residual_stream <= MZ_STREAM_SPLIT,
-             "residual_stream must be MZ_STREAM_AUTO, MZ_STREAM_FP32 or MZ_STREAM_SPLIT, %d given.", cfg->residual_stream);
+  MZ_REQUIRE(cfg->residual_stream == MZ_STREAM_AUTO || cfg->residual_stream == MZ_STREAM_FP32,
+             "residual_stream must be MZ_STREAM_AUTO or MZ_STREAM_FP32, %d given.", cfg->residual_stream);
   const int hC = cfg->num_channels * cfg->hidden_ratio;
   MZ_REQUIRE(cfg->num_channels <= 512 && hC <= 1024, "num_channels %d / hidden width %d exceed 512 / 1024 channels",
              cfg->num_channels, hC);
@@ -254,13 +253,6 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   m->headN = 3 * m->r * m->r;
   m->headNp = mz_padded_channels(m->headN);
   m->bf16 = cfg->operand_dtype == MZ_DTYPE_BF16;
-  m->split = cfg->residual_stream == MZ_STREAM_SPLIT;  // (AUTO = fp32: measured equal or faster on all three models)
-  if (m->split) m->Cz = m->Cp;  // weights are packed against the logical pitch; the activation pitch is 2 * Cp
-  if (m->split && m->S2 > 1) {
-    set_error("residual_stream split is not available above 128 channels (%d given)", m->C);
-    delete m;
-    return MZ_ERR_UNSUPPORTED;
-  }
   m->have.assign(3 + 4 * m->L, 0);
   const int n_convs = (m->S + m->S2) * m->L + 1;
   m->prepared.resize(2 * n_convs);
@@ -283,7 +275,7 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   alloc(reinterpret_cast<void**>(&m->conv1), sizeof(uint16_t) * c1 * m->L);
   alloc(reinterpret_cast<void**>(&m->conv2), sizeof(uint16_t) * c2 * m->L);
   alloc(reinterpret_cast<void**>(&m->head), sizeof(uint16_t) * 9 * m->headNp * m->Cz);
-  m->fused_ok = !m->split && m->S == 1 && m->S2 == 1 && fused_block_applies(m->Cp, m->hCp, m->Cz);
+  m->fused_ok = m->S == 1 && m->S2 == 1 && fused_block_applies(m->Cp, m->hCp, m->Cz);
   if (m->fused_ok) {
     alloc(reinterpret_cast<void**>(&m->conv2s), sizeof(uint16_t) * c2 * m->L);
     m->fprepared.resize(2 * m->L);
@@ -606,9 +598,8 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
   }
   rc = MZ_OK;
   if (front)
-    rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, m->split ? nullptr : zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s,
+    rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s,
                      m->sat_dev);
-  const int zpitch = m->split ? 2 * m->Cp : 0;  // channel pitch of the convolutions that read the stream
   if (rc != MZ_OK) return rc;
 
   const int slot = m->timing_calls % kTimingSlots;
@@ -655,7 +646,6 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
       a.in = zb;
       a.w = m->conv1 + (static_cast<size_t>(l) * S + sl) * c1s;
       a.cin_p = m->Cz;
-      a.in_pitch = zpitch;
       a.epi.mode = 0;
       a.epi.bf16 = m->bf16;
       a.epi.B = B;
@@ -675,7 +665,7 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
       a.in = hid;
       a.w = m->conv2 + (static_cast<size_t>(l) * S2 + sl) * c2s;
       a.cin_p = m->hCp;
-      a.epi.mode = m->split ? 3 : 1;
+      a.epi.mode = 1;
       a.epi.bf16 = m->bf16;
       a.epi.B = B;
       a.epi.H = H;
@@ -708,7 +698,6 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
   a.in = zcur;
   a.w = m->head;
   a.cin_p = m->Cz;
-  a.in_pitch = zpitch;
   a.epi.mode = 2;
   a.epi.bf16 = m->bf16;
   a.epi.B = B;
@@ -782,7 +771,6 @@ int mz_workspace_layout(const mz_model* m, int32_t B, int32_t H, int32_t W, size
                         size_t* hidden_offset, int32_t* channels_padded, int32_t* zb_pitch) {
   MZ_REQUIRE(m && zf_offset && zb_offset && hidden_offset && channels_padded && zb_pitch, "workspace_layout: null pointer");
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "workspace_layout: empty input");
-  MZ_REQUIRE(!m->split, "workspace_layout: the split residual stream has no separate fp32 / 16-bit tensors");
   const WsPlan wp = plan_ws(m, B, H, W);
   *zf_offset = wp.zf;
   *zb_offset = wp.zb;

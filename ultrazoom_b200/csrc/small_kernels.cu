@@ -175,19 +175,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
       for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(o[i]));
       if (!(amax <= MZ_F16_MAX)) *sat = 1u;
     }
-    if (real && zf != nullptr) {
+    if (real) {
       float4* f = reinterpret_cast<float4*>(zf + pix * Cp + g * 8);
       f[0] = make_float4(o[0], o[1], o[2], o[3]);
       f[1] = make_float4(o[4], o[5], o[6], o[7]);
-    }
-    if (zf == nullptr) {  // split stream: z16 = [hi | lo], pitch 2 * Cp (Cz == Cp here)
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) split_op2(bf16, o[2 * i], o[2 * i + 1], hi[i], lo[i]);
-      uint16_t* dst = zb + pix * 2 * Cp + g * 8;
-      st_global_v4(dst, hi[0], hi[1], hi[2], hi[3]);
-      st_global_v4(dst + Cp, lo[0], lo[1], lo[2], lo[3]);
-      continue;
     }
     st_global_v4(zb + pix * Cz + g * 8, pack_op2(bf16, o[0], o[1]), pack_op2(bf16, o[2], o[3]),
                  pack_op2(bf16, o[4], o[5]), pack_op2(bf16, o[6], o[7]));
@@ -198,7 +189,8 @@ int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* 
                 int B, int H, int W, int Cp, int zb_pitch, cudaStream_t s, unsigned int* sat) {
   MZ_REQUIRE(Cp > 0 && Cp % 8 == 0, "stem: padded channel count must be a multiple of 8, %d given", Cp);
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "stem: empty input");
-  const int Cz = (zb_pitch && zf != nullptr) ? zb_pitch : Cp;
+  MZ_REQUIRE(zf != nullptr, "stem: null fp32 stream");
+  const int Cz = zb_pitch ? zb_pitch : Cp;
   MZ_REQUIRE(Cz >= Cp && Cz % 8 == 0, "stem: zb pitch %d must be a multiple of 8 and >= %d", Cz, Cp);
   const int groups = Cz / 8;
   MZ_REQUIRE(groups <= 256, "stem: zb pitch %d exceeds 2048 channels", Cz);
@@ -344,7 +336,7 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvArgs a) {
       float h[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) h[i] = acc[i];
-      constexpr int M01 = MODE == 2 ? 0 : MODE;  // (epilogue mode 0, 1 or 3)
+      constexpr int M01 = MODE == 2 ? 0 : MODE;  // (epilogue mode 0 or 1)
       epi_store16<M01>(p, b, y, x, n0, h,
                        p.film != nullptr ? p.film + static_cast<size_t>(b) * 2 * p.n_pad : nullptr);
     }
@@ -363,8 +355,6 @@ int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
     conv_simt_kernel<0><<<gb, 128, 0, s>>>(a);
   else if (p.mode == 1)
     conv_simt_kernel<1><<<gb, 128, 0, s>>>(a);
-  else if (p.mode == 3)
-    conv_simt_kernel<3><<<gb, 128, 0, s>>>(a);
   else
     conv_simt_kernel<2><<<gb, 128, 0, s>>>(a);
   MZ_CUDA(cudaGetLastError());

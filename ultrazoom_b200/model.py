@@ -203,9 +203,8 @@ class MewZoom(nn.Module, PyTorchModelHubMixin):
         magnitude into an fp16 operand raises a flag (``saturated()``); with "float16" the next call then raises
         instead of returning clipped images, with "auto" every call is checked (one stream synchronisation) and a
         saturated one is re-run -- like all later ones -- with bfloat16 operands.
-        ``residual_stream``: how the residual stream lives in HBM between blocks -- "float32" (fp32 + a 16-bit shadow),
-        "split" (two 16-bit planes hi + lo: the same value to 2^-22 with 14 % less conv2 traffic; measured no faster,
-        kept as a tested option) or "auto" (the library's choice: float32)."""
+        ``residual_stream``: "auto" | "float32" -- the residual stream lives in HBM as fp32 + a 16-bit shadow (the next
+        block's tensor-core operand)."""
         super().__init__()
         if str(operand_dtype) != "auto":
             _native.dtype_code(operand_dtype)

@@ -59,9 +59,8 @@ def pack_conv_weight(w: Tensor, device: torch.device, cout_p: Optional[int] = No
 
 
 def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None, dtype: torch.dtype = torch.float16,
-              zb_pitch: int = 0, split: bool = False):
-    """FanOutProjection + NCHW->NHWC: returns (zf fp32 (B,H,W,Cp), zb fp16|bf16 (B,H,W,zb_pitch or Cp)), or with
-    ``split`` (None, z16 (B,H,W,2*Cp) = [hi | lo])."""
+              zb_pitch: int = 0):
+    """FanOutProjection + NCHW->NHWC: returns (zf fp32 (B,H,W,Cp), zb fp16|bf16 (B,H,W,zb_pitch or Cp))."""
     _need_cuda(x)
     lib = _native.load()
     x = x.to(torch.float32).contiguous()
@@ -72,11 +71,10 @@ def stem_pack(x: Tensor, weight: Tensor, bias: Tensor, cp: Optional[int] = None,
     b = torch.zeros((cp,), dtype=torch.float32, device=x.device)
     w[:Cc] = weight.detach().reshape(Cc, 3).to(x.device, torch.float32)
     b[:Cc] = bias.detach().to(x.device, torch.float32)
-    zf = None if split else torch.empty((B, H, W, cp), dtype=torch.float32, device=x.device)
-    zb = torch.empty((B, H, W, 2 * cp if split else (zb_pitch or cp)), dtype=dtype, device=x.device)
+    zf = torch.empty((B, H, W, cp), dtype=torch.float32, device=x.device)
+    zb = torch.empty((B, H, W, zb_pitch or cp), dtype=dtype, device=x.device)
     with torch.cuda.device(x.device):
-        _native.check(lib.mz_stem_pack(x.data_ptr(), w.data_ptr(), b.data_ptr(), zf.data_ptr() if zf is not None else None,
-                                       zb.data_ptr(),
+        _native.check(lib.mz_stem_pack(x.data_ptr(), w.data_ptr(), b.data_ptr(), zf.data_ptr(), zb.data_ptr(),
                                        B, H, W, cp, zb_pitch, _native.dtype_code(dtype), _stream(x)))
     return zf, zb
 
@@ -98,25 +96,20 @@ def control_film(c: Tensor, weight: Tensor, bias: Tensor, B: int, hcp: Optional[
 
 
 def conv3x3(inp: Tensor, wpacked: Tensor, mode: int, film: Optional[Tensor] = None, zf: Optional[Tensor] = None,
-            use_tc: bool = True, tune: Optional[_native.MzConvTune] = None, out_pitch: int = 0,
-            z16: Optional[Tensor] = None) -> Tensor:
+            use_tc: bool = True, tune: Optional[_native.MzConvTune] = None, out_pitch: int = 0) -> Tensor:
     """3x3 conv on NHWC fp16|bf16 with the fused block epilogues; returns the 16-bit NHWC output (dtype of `inp`).
 
-    mode 0: SiLU(scale*acc+shift) with film (B,2,cout_p) or None; mode 1: zf += acc (in place), returns round16(zf);
-    mode 3: the split stream z16 (B,H,W,2*cout_p) = [hi | lo] is updated in place and returned.
-    The input may be wider than the weights' cin_p (its first cin_p channels are used: the hi half of a z16)."""
+    mode 0: SiLU(scale*acc+shift) with film (B,2,cout_p) or None; mode 1: zf += acc (in place), returns round16(zf).
+    The input may be wider than the weights' cin_p (its first cin_p channels are used)."""
     _need_cuda(inp, wpacked)
     assert inp.dtype in (torch.float16, torch.bfloat16) and wpacked.dtype == inp.dtype
     inp = inp.contiguous()
     B, H, W, in_pitch = inp.shape
     _, cout_p, cin_p = wpacked.shape
     assert in_pitch >= cin_p, "weight / activation channel mismatch"
-    if mode == 3:
-        assert z16 is not None and z16.is_contiguous() and tuple(z16.shape) == (B, H, W, 2 * cout_p) and z16.dtype == inp.dtype
-        out = z16
-    else:
-        alloc = torch.zeros if out_pitch > cout_p else torch.empty   # pad channels are never written by the kernel
-        out = alloc((B, H, W, out_pitch or cout_p), dtype=inp.dtype, device=inp.device)
+    assert mode in (0, 1), "mode must be 0 (conv1 + FiLM + SiLU) or 1 (conv2 + residual)"
+    alloc = torch.zeros if out_pitch > cout_p else torch.empty   # pad channels are never written by the kernel
+    out = alloc((B, H, W, out_pitch or cout_p), dtype=inp.dtype, device=inp.device)
     if mode == 1:
         assert zf is not None and zf.is_contiguous() and tuple(zf.shape) == (B, H, W, cout_p)
     with torch.cuda.device(inp.device):
