@@ -36,7 +36,7 @@ struct mz_model {
   struct FusedKey {
     FusedBlockArgs a;
   };
-  std::vector<ConvLaunch> fprepared;  // two ways per layer, like `prepared`
+  std::vector<ConvLaunch> fprepared;  // kWays per layer, like `prepared`
   std::vector<FusedKey> fkeys;
   std::vector<uint8_t> fvictim;
   float* ctrl_w = nullptr;         // (L, 2hC, F)
@@ -81,6 +81,9 @@ struct mz_model {
 };
 
 static constexpr int kTimingSlots = 64;
+// Prepared launches per convolution: the two host lanes, the engine's own workspace and a captured graph's private one
+// are four buffer sets that may alternate; the victim is chosen round-robin.
+static constexpr int kWays = 4;
 
 namespace {
 
@@ -155,17 +158,16 @@ static int run_conv(mz_model* m, int slot, const ConvArgs& a, const ConvTcTune& 
     key.a.epi.wy0 = key.a.epi.wy1 = key.a.epi.wx0 = key.a.epi.wx1 = 0;
     key.a.epi.y_row = key.a.epi.y_plane = 0;
   }
-  // two ways per convolution: the two host lanes (and a caller ping-ponging two buffer sets) alternate operands
-  for (int way = 0; way < 2; ++way) {
-    const int i = 2 * slot + way;
+  // kWays prepared launches per convolution: the host lanes, the engine workspace and captured graphs alternate operands
+  for (int way = 0; way < kWays; ++way) {
+    const int i = kWays * slot + way;
     if (m->prepared[i].valid && memcmp(&key, &m->keys[i], sizeof(key)) == 0) {
-      m->victim[slot] = static_cast<uint8_t>(way ^ 1);
       if (a.epi.mode == 2) patch_conv_epi(m->prepared[i], a.epi);
       return run_conv_tc(m->prepared[i], s);
     }
   }
-  const int i = 2 * slot + m->victim[slot];
-  m->victim[slot] ^= 1;
+  const int i = kWays * slot + m->victim[slot];
+  m->victim[slot] = static_cast<uint8_t>((m->victim[slot] + 1) % kWays);
   m->prepared[i].valid = false;
   const int rc = prepare_conv_tc(a, t, m->cfg.device, &m->prepared[i]);
   if (rc != MZ_OK) return rc;
@@ -178,15 +180,14 @@ static int run_fused(mz_model* m, int layer, const FusedBlockArgs& a, cudaStream
   mz_model::FusedKey key;
   memset(&key, 0, sizeof(key));
   key.a = a;
-  for (int way = 0; way < 2; ++way) {
-    const int i = 2 * layer + way;
+  for (int way = 0; way < kWays; ++way) {
+    const int i = kWays * layer + way;
     if (m->fprepared[i].valid && memcmp(&key, &m->fkeys[i], sizeof(key)) == 0) {
-      m->fvictim[layer] = static_cast<uint8_t>(way ^ 1);
       return run_block_fused(m->fprepared[i], s);
     }
   }
-  const int i = 2 * layer + m->fvictim[layer];
-  m->fvictim[layer] ^= 1;
+  const int i = kWays * layer + m->fvictim[layer];
+  m->fvictim[layer] = static_cast<uint8_t>((m->fvictim[layer] + 1) % kWays);
   m->fprepared[i].valid = false;
   const int rc = prepare_block_fused(a, m->cfg.device, &m->fprepared[i]);
   if (rc != MZ_OK) return rc;
@@ -255,8 +256,8 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   m->bf16 = cfg->operand_dtype == MZ_DTYPE_BF16;
   m->have.assign(3 + 4 * m->L, 0);
   const int n_convs = (m->S + m->S2) * m->L + 1;
-  m->prepared.resize(2 * n_convs);
-  m->keys.resize(2 * n_convs);
+  m->prepared.resize(kWays * n_convs);
+  m->keys.resize(kWays * n_convs);
   m->victim.assign(n_convs, 0);
   for (auto& k : m->keys) memset(&k, 0xff, sizeof(k));
   memset(m->tune, 0, sizeof(m->tune));
@@ -278,8 +279,8 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   m->fused_ok = m->S == 1 && m->S2 == 1 && fused_block_applies(m->Cp, m->hCp, m->Cz);
   if (m->fused_ok) {
     alloc(reinterpret_cast<void**>(&m->conv2s), sizeof(uint16_t) * c2 * m->L);
-    m->fprepared.resize(2 * m->L);
-    m->fkeys.resize(2 * m->L);
+    m->fprepared.resize(kWays * m->L);
+    m->fkeys.resize(kWays * m->L);
     m->fvictim.assign(m->L, 0);
     for (auto& k : m->fkeys) memset(&k, 0xff, sizeof(k));
   }
