@@ -102,9 +102,10 @@ def _refresh_worker(rank: int, world: int, port: int, out_path: str):
 
 
 def test_halo_refresh_across_two_gpus(tmp_path):
-    """Periodic halo refresh between PROCESSES: halo strips of the fp32 stream and its 16-bit shadow travel as grouped
-    NCCL isend / irecv between the neighbours' GPUs (no collective reduction), cores land in rank 0's IPC frame; the
-    result equals the un-tiled frame bit for bit, with one and with two tiles per rank."""
+    """Periodic halo refresh between PROCESSES: every rank reads the halo strips of the fp32 stream and its 16-bit shadow
+    out of its neighbours' IPC-mapped stage buffers (one-sided gets over NVLink, ordered by two 1-element all-reduces per
+    refresh), cores land in rank 0's IPC frame; the result equals the un-tiled frame bit for bit, with one and with two
+    tiles per rank."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
