@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--halo-refresh", type=int, default=-1,
                     help="cfg5: refresh the tiles' halo every K encoder blocks (halo 2K+1 instead of 2L+1 pixels, strips "
                          "exchanged between neighbour GPUs); 0 = full halo, no exchange; -1 = the default (see measure_tiled)")
+    ap.add_argument("--unet-ops", action="store_true", help="add the U-Net operator microbenchmarks to the line (default with cfg2 at N = 1)")
     ap.add_argument("--no-also", action="store_true",
                     help="skip the secondary records (4X-Ctrl frame, 3X-Ctrl frame, halo-tiled 8K frame)")
     args = ap.parse_args()
@@ -566,6 +567,44 @@ def main():
         return {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": tf / peaks["bf16_sustained"], **common}
 
+    def measure_unet_ops():
+        """The 0.3.0 U-Net operators that are not 3x3 convolutions, each against its HBM roofline:
+        algorithmic bytes = every input and output element once, fp32.  Inputs are larger than L2 (126 MB)."""
+        from ultrazoom_b200 import unet as N
+
+        g = torch.Generator().manual_seed(5)
+        out = {}
+
+        def timed(fn, nbytes, iters=10):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            return {"ms": ms, "algorithmic_bytes": nbytes, "gb_per_s": nbytes / ms / 1e6}
+
+        C = 96
+        x = torch.randn(1, 540, 960, C, generator=g).to(dev)
+        z = torch.randn(1, 540, 960, C, generator=g).to(dev)
+        w = (torch.randn(C, 2 * C, 1, 1, generator=g) / (2 * C) ** 0.5).to(dev)
+        a = torch.tensor(0.25)
+        for math in ("tf32", "fp32"):
+            out[f"adaptive_residual_mix_c96_960x540_{math}"] = timed(lambda: N.adaptive_residual_mix(x, z, w, a, math), 3 * x.numel() * 4)
+        xi = torch.randn(1, 1080, 1920, 48, generator=g).to(dev)
+        wc = (torch.randn(96, 48, 2, 2, generator=g) / (4 * 48) ** 0.5).to(dev)
+        for math in ("tf32", "fp32"):
+            out[f"pixel_crush_f2_48to96_1920x1080_{math}"] = timed(lambda: N.pixel_crush(xi, wc, 2, math),
+                                                                   (xi.numel() + 540 * 960 * 96) * 4)
+        xs = torch.randn(1, 540, 960, 192, generator=g).to(dev)
+        out["pixel_shuffle_nhwc_r2_192to48_960x540"] = timed(lambda: N.pixel_shuffle_nhwc(xs, 2), 2 * xs.numel() * 4)
+        out["crop_feature_maps_c96_960x540_to_956x536"] = timed(lambda: N.crop_feature_maps(x, (536, 956)), 2 * 536 * 956 * C * 4)
+        return out
+
     main_res = measure(args.workload, args.steps, args.warmup, not args.no_e2e, True)
     # The north_star's efficiency target is stated on MewZoom-4X-Ctrl and its hard multi-GPU case is the spatial split:
     # the default line carries those as first-class records (own clocks; 4X-Ctrl with its own e2e) under "also".
@@ -579,6 +618,7 @@ def main():
             # the north_star names bf16 operands: the same headline workload with them (same tcgen05 rate and bytes; the
             # default is fp16 because bf16 misses BASELINE's 2e-2 max-abs on the 40-layer model: tests/test_gpu_fullsize.py)
             also["cfg2_bf16"] = measure("cfg2", k, args.warmup, False, True, operands="bfloat16")
+    unet_ops = measure_unet_ops() if (args.workload == "cfg2" and not args.no_also and world == 1) or args.unet_ops else None
 
     if rank != 0:
         if world > 1:
@@ -625,6 +665,14 @@ def main():
             if "tiling" in ar:
                 rec["tiling"] = ar["tiling"]
             line["also"][name] = rec
+    if unet_ops:
+        for rec in unet_ops.values():
+            rec["frac_of_hbm_peak"] = rec["gb_per_s"] / peaks["hbm"]
+        line.setdefault("also", {})["unet_ops"] = {
+            "what": "0.3.0 U-Net operators beside the 3x3 convolutions (SURVEY 8(f) rank 3): one launch each, fp32 NHWC feature "
+                    "maps larger than L2, HBM roofline over algorithmic bytes (every input and output element once); "
+                    "tf32 = tcgen05 kind::tf32 GEMM from the fp32 maps (default), fp32 = the exact SIMT twin",
+            "hbm_peak_gb_per_s": peaks["hbm"], "ops": unet_ops}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

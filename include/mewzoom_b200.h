@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MZ_ABI_VERSION 3
+#define MZ_ABI_VERSION 4
 
 typedef enum mz_status {
   MZ_OK = 0,
@@ -298,22 +298,28 @@ int mz_ipc_frame_close(void* dev_ptr, int32_t owner);
  * Feature maps are (B,H,W,pitch) fp32 with the logical channels first; every operator can also write the 16-bit shadow
  * (operand_dtype) the tcgen05 convolutions read as their A operand (out16_dev, same pitch; NULL = none).  The 3x3
  * convolutions of these blocks (InvertedBottleneck model.py:731-778, SubpixelConv2d.conv :902-909) are mz_conv3x3 /
- * mz_head_shuffle_add; what follows is everything else.  Weights are passed as [K][N] fp32 device matrices:
- *   mix:    wt[k][n] = conv.weight[n][k][0][0]                 (K = 2C: x channels then z channels)
- *   crush:  wt[(i*f + j)*Cin + c][n] = conv.weight[n][c][i][j]  (K = f*f*Cin)
- *   assess: wt[(ky*3 + kx)*C + c][n] = conv.weight[n][c][ky][kx] (K = 9C)
- * (the Python mirror, ultrazoom_b200/unet.py, builds them from the reference's state_dict tensors). */
+ * mz_head_shuffle_add; what follows is everything else.  Weights are passed as [N][K] fp32 device matrices, K-contiguous
+ * (N = output channels), i.e. the reference's conv.weight with the kernel taps moved in front of the input channels:
+ *   mix:    wt[n][k] = conv.weight[n][k][0][0]                 (K = 2C: x channels then z channels; a plain reshape)
+ *   crush:  wt[n][(i*f + j)*Cin + c] = conv.weight[n][c][i][j]  (K = f*f*Cin)
+ *   assess: wt[n][(ky*3 + kx)*C + c] = conv.weight[n][c][ky][kx] (K = 9C)
+ * (the Python mirror, ultrazoom_b200/unet.py, builds them from the reference's state_dict tensors).
+ * math: MZ_MATH_TF32 (default) runs the mix / crush GEMM on tcgen05 tensor cores straight from the fp32 feature maps
+ * (operands truncated to tf32, fp32 accumulation; pointers 16-byte aligned, C and pitches multiples of 4);
+ * MZ_MATH_FP32 is the exact fp32 SIMT twin of the same operator. */
+#define MZ_MATH_TF32 0
+#define MZ_MATH_FP32 1
 
 /* AdaptiveResidualMix.forward (model.py:826-839): beta = sigmoid(conv1x1(cat[x, z])); w = sigmoid(alpha) * beta;
  * out = (1 - w) * x + w * z.  x, z, out: (npix, pitch) fp32. */
 int mz_adaptive_mix(const float* x_dev, const float* z_dev, const float* wt_dev, float alpha_logit, float* out_dev,
-                    void* out16_dev, int64_t npix, int32_t C, int32_t pitch, int32_t operand_dtype, void* stream);
+                    void* out16_dev, int64_t npix, int32_t C, int32_t pitch, int32_t operand_dtype, int32_t math, void* stream);
 
 /* PixelCrush.forward (model.py:881-882): Conv2d(Cin, Cout, kernel_size=f, stride=f, bias=False), f in {2, 3, 4};
  * (B,H,W,pitch_in) -> (B, H/f, W/f, pitch_out) (floor, as the convolution does). */
 int mz_pixel_crush(const float* in_dev, const float* wt_dev, float* out_dev, void* out16_dev, int32_t B, int32_t H, int32_t W,
                    int32_t Cin, int32_t Cout, int32_t factor, int32_t pitch_in, int32_t pitch_out, int32_t operand_dtype,
-                   void* stream);
+                   int32_t math, void* stream);
 
 /* QualityAssessor.forward (model.py:1024-1032): Conv2d(C, F, 3, padding=1) + bias -> AdaptiveAvgPool2d(1) -> (B, F). */
 int mz_quality_assessor(const float* in_dev, const float* wt_dev, const float* bias_dev, float* out_dev, int32_t B, int32_t H,

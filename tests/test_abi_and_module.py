@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _native.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_native.SIGNATURES) == names
-    assert lib.mz_abi_version() == _native.ABI_VERSION == 3
+    assert lib.mz_abi_version() == _native.ABI_VERSION == 4
 
 
 def test_padded_channels_and_error_plumbing():

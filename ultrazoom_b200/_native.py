@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmewzoom_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 MZ_OK = 0
 MZ_ERR_INVALID = -1
@@ -28,6 +28,7 @@ FLAG_IO_U8 = 8
 FLAG_U8_TRUNC = 16
 
 DTYPE_F16, DTYPE_BF16 = 0, 1
+MATH_TF32, MATH_FP32 = 0, 1
 
 W_STEM_WEIGHT, W_STEM_BIAS, W_CONV1, W_CONV2, W_CTRL_WEIGHT, W_CTRL_BIAS, W_HEAD = range(7)
 
@@ -108,8 +109,8 @@ SIGNATURES = {
     "mz_head_shuffle_add": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(MzConvTune), _P]),
     "mz_pack_conv_weight": (C.c_int, [_P, _I, _I, _I, _I, _I, _P, C.POINTER(C.c_size_t)]),
     "mz_control_film": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "mz_adaptive_mix": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, C.c_int64, _I, _I, _I, _P]),
-    "mz_pixel_crush": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "mz_adaptive_mix": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, C.c_int64, _I, _I, _I, _I, _P]),
+    "mz_pixel_crush": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "mz_quality_assessor": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mz_pixel_shuffle_nhwc": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "mz_crop_feature_maps": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -20,7 +20,7 @@ OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libmewzoom_b200.so")
 # (source, extra defines, object name).  conv_tc.cu is compiled once per epilogue mode 0..2 (its template instantiations
 # dominate the build time) and once (part 4) for its host side; see the MZ_TC_PART comment in the file.
-SOURCES = [(f"{n}.cu", [], f"{n}.o") for n in ("host_util", "small_kernels", "api", "model", "probe", "block_fused", "unet_ops")] + [
+SOURCES = [(f"{n}.cu", [], f"{n}.o") for n in ("host_util", "small_kernels", "api", "model", "probe", "block_fused", "unet_ops", "unet_tc")] + [
     ("conv_tc.cu", [f"-DMZ_TC_PART={part}"], f"conv_tc_p{part}.o") for part in (0, 1, 2, 4)
 ]
 NVCC_FLAGS = [

@@ -138,6 +138,27 @@ int stack_conv2_bank(const uint16_t* packed, uint16_t* stacked, cudaStream_t s);
 int prepare_block_fused(const FusedBlockArgs& a, int device, ConvLaunch* out);
 int run_block_fused(ConvLaunch& launch, cudaStream_t s);
 
+// ---- AdaptiveResidualMix / PixelCrush as one tcgen05 kind::tf32 GEMM on the fp32 feature maps (unet_tc.cu) ----
+struct SgArgs {
+  const float* a0;    // x | input feature map
+  const float* a1;    // z | nullptr
+  const float* wt;    // [N][K] fp32 (conv.weight as the reference stores it, K = taps x C)
+  float* out;
+  void* out16;        // optional 16-bit shadow
+  int bf16;
+  int mix;            // 1: gated mix of (a0, a1); 0: f x f / stride f crush of a0
+  float gate;         // sigmoid(alpha)
+  int C, N, f;
+  long long rows;     // output rows (B * Ho | 1)
+  long long wo;       // output pixels per row (Wo | npix)
+  int H, Ho, W;       // crush: input rows per image, output rows per image, input width
+  long long in_rows;  // crush: B * H
+  int pitch_in, pitch_out;
+};
+bool seg_gemm_tc_applies(const float* a0, const float* a1, const float* wt, const float* out, const void* out16, int C, int N,
+                         int K, int pitch_in, int pitch_out);
+int launch_seg_gemm_tc(const SgArgs& a, cudaStream_t s);
+
 int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s);
 // fp32 stream zf + 16-bit shadow zb (pitch zb_pitch).
 // x8 != nullptr: the image is 8-bit (B,3,H,W) and read as x8 / 255.

@@ -9,9 +9,10 @@
 //   * mid-network SubpixelConv2d's PixelShuffle on NHWC (model.py:911,928; Decoder :569-571): pure re-indexing
 //   * Decoder.crop_feature_maps (model.py:650-689): centre crop / zero pad to a target size
 // The 3x3 convolutions of these blocks (InvertedBottleneck, SubpixelConv2d.conv) run on the tcgen05 kernel of conv_tc.cu.
-// One tiled SIMT GEMM serves the three gather forms: M = output pixels, N = output channels, K as above; 64 x 64 x 16
-// tiles, 256 threads, a 4 x 4 register tile per thread.  These operators are a few percent of a U-Net's work (its
-// convolutions are the 3x3 ones); they are written for exactness against the reference's leaf classes first.
+// One tiled SIMT GEMM serves the three gather forms in exact fp32: M = output pixels, N = output channels, K as above;
+// 64 x 64 x 16 tiles, 256 threads, a 4 x 4 register tile per thread.  For the mix and the crush it is the exact TWIN
+// (math = MZ_MATH_FP32) of the tcgen05 kind::tf32 kernel of unet_tc.cu, which is the default (MZ_MATH_TF32) and runs at
+// the HBM roofline; the quality head (a 3x3 convolution reduced to B x F numbers) only exists in this form.
 #include "kernels.cuh"
 
 namespace mz {
@@ -19,7 +20,7 @@ namespace mz {
 struct GemmArgs {
   const float* a0;   // x | input feature map (B,H,W,pitch_in)
   const float* a1;   // z (mix) or nullptr
-  const float* wt;   // weights as [K][N] fp32
+  const float* wt;   // weights as [N][K] fp32 (conv.weight as the reference stores it)
   const float* bias; // [N] or nullptr (pool epilogue adds it once per image)
   float* out;        // (M, pitch_out) fp32 | (B, N) pooled
   uint16_t* out16;   // optional 16-bit shadow of out (pitch_out) or nullptr
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(const GemmArgs g) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = k0 + bk, n = n0 + bn + e;
-      Bs[bk][bn + e] = (k < g.K && n < g.N) ? __ldg(g.wt + static_cast<size_t>(k) * g.N + n) : 0.f;
+      Bs[bk][bn + e] = (k < g.K && n < g.N) ? __ldg(g.wt + static_cast<size_t>(n) * g.K + k) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -147,50 +148,79 @@ __global__ void fill_bias_kernel(float* out, const float* bias, int B, int N) {
   if (i < B * N) out[i] = bias ? bias[i % N] : 0.f;
 }
 
-// PixelShuffle on NHWC: out[b, h r + i, w r + j, c] = in[b, h, w, c r r + i r + j]   (model.py:911,928 index rule)
-__global__ void pixel_shuffle_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, uint16_t* __restrict__ out16,
-                                          int bf16, int B, int H, int W, int C, int r, int pitch_in, int pitch_out) {
-  const long long total = static_cast<long long>(B) * H * r * W * r * C;
+// PixelShuffle on NHWC: out[b, h r + i, w r + j, c] = in[b, h, w, c r r + i r + j]   (model.py:911,928 index rule).
+// One thread per (input pixel, output channel): its r r input values are consecutive (a warp reads 32 r r consecutive
+// floats; 16-byte loads when VEC), and for each (i, j) the warp writes 32 consecutive channels of one output pixel.
+template <int R, bool VEC>
+__global__ void __launch_bounds__(256) pixel_shuffle_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                 uint16_t* __restrict__ out16, int bf16, int B, int H, int W, int C,
+                                                                 int pitch_in, int pitch_out) {
+  const long long total = static_cast<long long>(B) * H * W * C;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(idx % C);
-    long long t = idx / C;
-    const int ox = static_cast<int>(t % (W * r));
-    t /= (W * r);
-    const int oy = static_cast<int>(t % (H * r));
-    const int b = static_cast<int>(t / (H * r));
-    const int h = oy / r, i = oy - h * r, w = ox / r, j = ox - w * r;
-    const float v = __ldg(in + ((static_cast<size_t>(b) * H + h) * W + w) * pitch_in + c * r * r + i * r + j);
-    const size_t o = ((static_cast<size_t>(b) * H * r + oy) * (W * r) + ox) * pitch_out + c;
-    out[o] = v;
-    if (out16) out16[o] = bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v)) : __half_as_ushort(__float2half_rn(v));
+    const long long pix = idx / C;
+    const int w = static_cast<int>(pix % W);
+    const long long t = pix / W;
+    const int h = static_cast<int>(t % H);
+    const int b = static_cast<int>(t / H);
+    const float* src = in + static_cast<size_t>(pix) * pitch_in + c * (R * R);
+    float v[R * R];
+    if (VEC) {
+#pragma unroll
+      for (int e = 0; e < R * R / 4; ++e) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(src) + e);
+        v[4 * e] = q.x, v[4 * e + 1] = q.y, v[4 * e + 2] = q.z, v[4 * e + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < R * R; ++e) v[e] = __ldg(src + e);
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const size_t o = ((static_cast<size_t>(b) * H * R + h * R + i) * (static_cast<size_t>(W) * R) + w * R + j) * pitch_out + c;
+        out[o] = v[i * R + j];
+        if (out16)
+          out16[o] = bf16 ? __bfloat16_as_ushort(__float2bfloat16_rn(v[i * R + j])) : __half_as_ushort(__float2half_rn(v[i * R + j]));
+      }
   }
 }
 
-// Decoder.crop_feature_maps (model.py:650-689): centre crop (start = (h - th) / 2) or zero pad (top = (th - h) / 2) per axis
-__global__ void crop_pad_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int tH,
-                                     int tW, int pitch_in, int pitch_out) {
+// Decoder.crop_feature_maps (model.py:650-689): centre crop (start = (h - th) / 2) or zero pad (top = (th - h) / 2) per axis.
+// V = 4: channels in 16-byte groups (C and the pitches multiples of 4, aligned bases); V = 1: any layout.
+template <int V>
+__global__ void __launch_bounds__(256) crop_pad_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W,
+                                                            int C, int tH, int tW, int pitch_in, int pitch_out) {
   const int oy0 = H > tH ? (H - tH) / 2 : -((tH - H) / 2);  // input row of output row 0
   const int ox0 = W > tW ? (W - tW) / 2 : -((tW - W) / 2);
-  const long long total = static_cast<long long>(B) * tH * tW * C;
+  const int Cv = C / V;
+  const long long total = static_cast<long long>(B) * tH * tW * Cv;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(idx % C);
-    long long t = idx / C;
+    const int c = static_cast<int>(idx % Cv) * V;
+    long long t = idx / Cv;
     const int x = static_cast<int>(t % tW);
     t /= tW;
     const int y = static_cast<int>(t % tH);
     const int b = static_cast<int>(t / tH);
     const int iy = y + oy0, ix = x + ox0;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(in + ((static_cast<size_t>(b) * H + iy) * W + ix) * pitch_in + c);
-    out[((static_cast<size_t>(b) * tH + y) * tW + x) * pitch_out + c] = v;
+    const bool inside = iy >= 0 && iy < H && ix >= 0 && ix < W;
+    const size_t src = ((static_cast<size_t>(b) * H + iy) * W + ix) * pitch_in + c;
+    const size_t dst = ((static_cast<size_t>(b) * tH + y) * tW + x) * pitch_out + c;
+    if (V == 4) {
+      const float4 v = inside ? __ldg(reinterpret_cast<const float4*>(in + src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(out + dst) = v;
+    } else {
+      out[dst] = inside ? __ldg(in + src) : 0.f;
+    }
   }
 }
 
 static unsigned blocks_for(long long total) {
   long long b = (total + 255) / 256;
-  if (b > 148LL * 32) b = 148LL * 32;
+  if (b > 148LL * 64) b = 148LL * 64;
   return static_cast<unsigned>(b < 1 ? 1 : b);
 }
 
@@ -201,11 +231,33 @@ using namespace mz;
 extern "C" {
 
 int mz_adaptive_mix(const float* x_dev, const float* z_dev, const float* wt_dev, float alpha_logit, float* out_dev,
-                    void* out16_dev, int64_t npix, int32_t C, int32_t pitch, int32_t operand_dtype, void* stream) {
+                    void* out16_dev, int64_t npix, int32_t C, int32_t pitch, int32_t operand_dtype, int32_t math, void* stream) {
   MZ_REQUIRE(x_dev && z_dev && wt_dev && out_dev, "adaptive_mix: null pointer");
   MZ_REQUIRE(npix > 0 && npix < (1LL << 31) && C > 0 && pitch >= C, "adaptive_mix: bad shape (npix %lld, C %d, pitch %d)",
              static_cast<long long>(npix), C, pitch);
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
+  MZ_REQUIRE(math == MZ_MATH_TF32 || math == MZ_MATH_FP32, "math must be MZ_MATH_TF32 or MZ_MATH_FP32, %d given", math);
+  MZ_REQUIRE(out_dev != x_dev && out_dev != z_dev, "adaptive_mix: the output needs its own buffer");
+  if (math == MZ_MATH_TF32) {
+    MZ_REQUIRE(seg_gemm_tc_applies(x_dev, z_dev, wt_dev, out_dev, out16_dev, C, C, 2 * C, pitch, pitch),
+               "adaptive_mix (tf32): pointers must be 16-byte aligned, C and pitch multiples of 4 (8 with a 16-bit shadow)");
+    SgArgs a;
+    memset(&a, 0, sizeof(a));
+    a.a0 = x_dev;
+    a.a1 = z_dev;
+    a.wt = wt_dev;
+    a.out = out_dev;
+    a.out16 = out16_dev;
+    a.bf16 = operand_dtype == MZ_DTYPE_BF16;
+    a.mix = 1;
+    a.gate = 1.f / (1.f + expf(-alpha_logit));
+    a.C = a.N = C;
+    a.f = 1;
+    a.rows = 1;
+    a.wo = npix;
+    a.pitch_in = a.pitch_out = pitch;
+    return launch_seg_gemm_tc(a, static_cast<cudaStream_t>(stream));
+  }
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.a0 = x_dev;
@@ -225,13 +277,37 @@ int mz_adaptive_mix(const float* x_dev, const float* z_dev, const float* wt_dev,
 
 int mz_pixel_crush(const float* in_dev, const float* wt_dev, float* out_dev, void* out16_dev, int32_t B, int32_t H, int32_t W,
                    int32_t Cin, int32_t Cout, int32_t factor, int32_t pitch_in, int32_t pitch_out, int32_t operand_dtype,
-                   void* stream) {
+                   int32_t math, void* stream) {
   MZ_REQUIRE(in_dev && wt_dev && out_dev, "pixel_crush: null pointer");
   MZ_REQUIRE(factor == 2 || factor == 3 || factor == 4, "Crush factor must be either 2, 3, or 4, %d given.", factor);
   MZ_REQUIRE(Cin > 0, "Input channels must be greater than 0.");
   MZ_REQUIRE(Cout > 0, "Output channels must be greater than 0.");
   MZ_REQUIRE(B > 0 && H >= factor && W >= factor && pitch_in >= Cin && pitch_out >= Cout, "pixel_crush: bad shape");
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
+  MZ_REQUIRE(math == MZ_MATH_TF32 || math == MZ_MATH_FP32, "math must be MZ_MATH_TF32 or MZ_MATH_FP32, %d given", math);
+  if (math == MZ_MATH_TF32) {
+    MZ_REQUIRE(seg_gemm_tc_applies(in_dev, nullptr, wt_dev, out_dev, out16_dev, Cin, Cout, factor * factor * Cin, pitch_in, pitch_out),
+               "pixel_crush (tf32): pointers must be 16-byte aligned, Cin and the pitches multiples of 4 (8 with a 16-bit shadow)");
+    SgArgs a;
+    memset(&a, 0, sizeof(a));
+    a.a0 = in_dev;
+    a.wt = wt_dev;
+    a.out = out_dev;
+    a.out16 = out16_dev;
+    a.bf16 = operand_dtype == MZ_DTYPE_BF16;
+    a.C = Cin;
+    a.N = Cout;
+    a.f = factor;
+    a.H = H;
+    a.W = W;
+    a.Ho = H / factor;
+    a.rows = static_cast<long long>(B) * a.Ho;
+    a.wo = W / factor;
+    a.in_rows = static_cast<long long>(B) * H;
+    a.pitch_in = pitch_in;
+    a.pitch_out = pitch_out;
+    return launch_seg_gemm_tc(a, static_cast<cudaStream_t>(stream));
+  }
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.a0 = in_dev;
@@ -289,9 +365,17 @@ int mz_pixel_shuffle_nhwc(const float* in_dev, float* out_dev, void* out16_dev, 
   MZ_REQUIRE(r == 2 || r == 3 || r == 4, "Upscale ratio must be either 2, 3, or 4, %d given.", r);
   MZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && pitch_in >= C * r * r && pitch_out >= C, "pixel_shuffle: bad shape");
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
-  const long long total = static_cast<long long>(B) * H * r * W * r * C;
-  pixel_shuffle_nhwc_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      in_dev, out_dev, static_cast<uint16_t*>(out16_dev), operand_dtype == MZ_DTYPE_BF16, B, H, W, C, r, pitch_in, pitch_out);
+  const long long total = static_cast<long long>(B) * H * W * C;
+  const bool vec = (reinterpret_cast<uintptr_t>(in_dev) & 15u) == 0 && pitch_in % 4 == 0 && r != 3;
+  const unsigned nb = blocks_for(total);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  uint16_t* o16 = static_cast<uint16_t*>(out16_dev);
+  const int bf = operand_dtype == MZ_DTYPE_BF16;
+  if (r == 2 && vec) pixel_shuffle_nhwc_kernel<2, true><<<nb, 256, 0, s>>>(in_dev, out_dev, o16, bf, B, H, W, C, pitch_in, pitch_out);
+  else if (r == 2) pixel_shuffle_nhwc_kernel<2, false><<<nb, 256, 0, s>>>(in_dev, out_dev, o16, bf, B, H, W, C, pitch_in, pitch_out);
+  else if (r == 3) pixel_shuffle_nhwc_kernel<3, false><<<nb, 256, 0, s>>>(in_dev, out_dev, o16, bf, B, H, W, C, pitch_in, pitch_out);
+  else if (vec) pixel_shuffle_nhwc_kernel<4, true><<<nb, 256, 0, s>>>(in_dev, out_dev, o16, bf, B, H, W, C, pitch_in, pitch_out);
+  else pixel_shuffle_nhwc_kernel<4, false><<<nb, 256, 0, s>>>(in_dev, out_dev, o16, bf, B, H, W, C, pitch_in, pitch_out);
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }
@@ -301,9 +385,15 @@ int mz_crop_feature_maps(const float* in_dev, float* out_dev, int32_t B, int32_t
   MZ_REQUIRE(in_dev && out_dev, "crop_feature_maps: null pointer");
   MZ_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && target_h > 0 && target_w > 0 && pitch_in >= C && pitch_out >= C,
              "crop_feature_maps: bad shape");
-  const long long total = static_cast<long long>(B) * target_h * target_w * C;
-  crop_pad_nhwc_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, B, H, W, C, target_h,
-                                                                                        target_w, pitch_in, pitch_out);
+  const bool vec = ((reinterpret_cast<uintptr_t>(in_dev) | reinterpret_cast<uintptr_t>(out_dev)) & 15u) == 0 && C % 4 == 0 &&
+                   pitch_in % 4 == 0 && pitch_out % 4 == 0;
+  const long long total = static_cast<long long>(B) * target_h * target_w * (vec ? C / 4 : C);
+  if (vec)
+    crop_pad_nhwc_kernel<4><<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, B, H, W, C, target_h,
+                                                                                             target_w, pitch_in, pitch_out);
+  else
+    crop_pad_nhwc_kernel<1><<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(in_dev, out_dev, B, H, W, C, target_h,
+                                                                                             target_w, pitch_in, pitch_out);
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }
