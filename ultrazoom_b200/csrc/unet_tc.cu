@@ -9,15 +9,23 @@
 // A tile of a tap is one TMA box of a 4-D view (channel, j, xo, input row) of the feature map -- 128 pixels x 32 channels
 // = 128-byte rows, 128-byte swizzle, the K-major operand layout as it lands; channels past C arrive as zeros (TMA
 // out-of-bounds fill), so C needs no padding and the weight matrix [N][K] is read as the reference stores it
-// (conv.weight reshaped), one TMA box per 32-channel chunk, resident for the life of the CTA.
+// (conv.weight reshaped), one TMA box per 32-channel chunk.  On a dense map (pitch = C) the f pixels under one output
+// pixel of the crush are f C consecutive floats, so a whole input row is one K segment.  The [ns][K] weight slice of the
+// CTA stays in shared memory when it fits beside three ring stages (else N is sliced over CTAs, or -- deep K -- the weight
+// chunks travel through the ring with their A chunks: whichever moves fewer bytes per tile through L2).
 //
-// Roles (192 | 320 threads, persistent over tiles): warp 0 TMA producer (weights once, then a ring of A chunks), warp 1 TMEM
-// allocation + UMMA issue (4 x K = 8 per chunk, two accumulator stages), warps 2-5 (2-9) epilogue: per 16-channel slice
-// tcgen05.ld -> (mix: x and z slices of the warp's 32 pixels, TMA-loaded two slices ahead into the warp's own slots --
+// Roles (192 | 320 threads, persistent over tiles): warp 0 TMA producer (a ring of 3-6 A chunks), warp 1 TMEM allocation
+// + UMMA issue (4 x K = 8 per chunk, two accumulator stages), 4 (crush) or 8 (mix) epilogue warps: per 16-channel slice
+// tcgen05.ld -> (mix: the x and z slices of the warp's 32 pixels, TMA-loaded two slices ahead into the warp's own slots --
 // L2 hits, the producer fetched them for the GEMM a moment ago) -> fp32 slice (+ optional 16-bit shadow) written in
 // place -> TMA store.  Everything a pixel needs is read from HBM once and written once: 12 C bytes per pixel for the mix,
-// 4 (f f Cin + Cout) for the crush -- the kernel is HBM-bound from C ~ 32 up (tf32 tensor time is a fifth of the HBM time
-// at C = 96).
+// 4 (f f Cin + Cout) for the crush; tf32 tensor time is a fifth of the HBM time at C = 96, so the roofline is HBM.
+// Measured (one B200, maps larger than L2; tools/unet_shapes.py): mix 4.2-5.9 TB/s over C = 32 .. 192, crush 5.2-5.9 TB/s
+// (0.64-0.90 of the 6.55 TB/s copy peak) -- the fp32 SIMT twin of unet_ops.cu runs the same shapes at 0.4-0.5 TB/s.
+// What it took beyond the first correct version (0.39 of peak): every role is ONE warp per scheduler with nothing to hide
+// instruction latency behind, so the producer and the epilogue loops carry cursors instead of dividing (an integer
+// division per chunk in the single producer thread alone held the crush at 2.9 TB/s), the mix epilogue runs on eight
+// warps, and its shared-memory loads are issued before the math.
 #include <vector>
 
 #include "kernels.cuh"
