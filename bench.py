@@ -603,6 +603,14 @@ def main():
         xs = torch.randn(1, 540, 960, 192, generator=g).to(dev)
         out["pixel_shuffle_nhwc_r2_192to48_960x540"] = timed(lambda: N.pixel_shuffle_nhwc(xs, 2), 2 * xs.numel() * 4)
         out["crop_feature_maps_c96_960x540_to_956x536"] = timed(lambda: N.crop_feature_maps(x, (536, 956)), 2 * 536 * 956 * C * 4)
+        # one decoder stage end to end (DecoderBlock + SubpixelConv2d x2, reference model.py:975-1001): three 3x3 convolutions
+        # on conv_tc_kernel (96 -> 192 -> 96, 96 -> 4 x 48), the gated mix, the NHWC shuffle; random-init weights
+        torch.manual_seed(9)
+        blk = N.SR2XBlock(C, 2, 48).to(dev)
+        rec = timed(lambda: blk.forward(x), 0, iters=5)
+        flops = 2 * 9 * (C * 2 * C * 2 + C * 4 * 48) * 540 * 960
+        out["sr2x_block_c96_to_c48_960x540"] = {"ms": rec["ms"], "conv_tflops": flops / rec["ms"] / 1e9,
+                                                "note": "composite: 3 tcgen05 3x3 convolutions + mix + shuffle + the casts between them"}
         return out
 
     main_res = measure(args.workload, args.steps, args.warmup, not args.no_e2e, True)
@@ -667,7 +675,8 @@ def main():
             line["also"][name] = rec
     if unet_ops:
         for rec in unet_ops.values():
-            rec["frac_of_hbm_peak"] = rec["gb_per_s"] / peaks["hbm"]
+            if "gb_per_s" in rec:
+                rec["frac_of_hbm_peak"] = rec["gb_per_s"] / peaks["hbm"]
         line.setdefault("also", {})["unet_ops"] = {
             "what": "0.3.0 U-Net operators beside the 3x3 convolutions (SURVEY 8(f) rank 3): one launch each, fp32 NHWC feature "
                     "maps larger than L2, HBM roofline over algorithmic bytes (every input and output element once); "

@@ -252,11 +252,14 @@ int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, 
  *   mode 1: zf += acc ; out16 = round16(zf)              (conv2 + ResidualConnection, model.py:789-792)
  * in_pitch: channel pitch of the input in elements (0 = cin_p; larger: the first cin_p channels of a wider tensor).
  * out_pitch: channel pitch of out16 in elements (0 = cout_p); channels beyond cout_p are left untouched.
+ * zf_pitch: channel pitch of zf in elements (0 = cout_p).  With both pitches a convolution wider than one launch (more than
+ *   256 output channels in mode 0, 128 in mode 1) runs as one launch per slice of output channels, each with its own packed
+ *   bank (and FiLM rows) and its out16 / zf pointers advanced to the slice's first channel.
  * use_tc = 1: tcgen05/TMEM/TMA kernel; 0: SIMT diagnostic kernel.  tune may be NULL. */
 int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev,
                void* out16_dev, float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t in_pitch,
-               int32_t cout_p, int32_t out_pitch, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune,
-               void* stream);
+               int32_t cout_p, int32_t out_pitch, int32_t zf_pitch, int32_t operand_dtype, int32_t use_tc,
+               const mz_conv_tune* tune, void* stream);
 
 /* SubpixelConv2d (model.py:885-930) + global skip (model.py:162) + optional clamp (:177):
  * y = [clamp](skip + PixelShuffle_r(conv3x3(z))).  skip_mode 0: none, 1: read y_dev in place

@@ -146,6 +146,32 @@ def test_sixteen_bit_shadow_is_the_rounded_output(dev, math, dt):
     _close(out, want, TF32_TOL * want.abs().max().item() if math == "tf32" else 2e-5)
 
 
+@pytest.mark.parametrize("C,hidden_ratio,shape", [(96, 2, (1, 24, 150)), (192, 2, (1, 10, 140)), (384, 2, (1, 6, 40)), (64, 4, (2, 9, 70))])
+def test_blocks_at_the_widths_of_the_default_unet(dev, C, hidden_ratio, shape):
+    """The stage widths of the reference's default U-Net (48 / 96 / 192 / 384 channels): convolutions wider than one launch
+    (more than 256 hidden channels, more than 128 output channels -- e.g. SubpixelConv2d's C -> 4C) run as slices of output
+    channels; blocks against the pinned oracle on the same weights."""
+    from ultrazoom_b200 import unet as N
+
+    torch.manual_seed(C + hidden_ratio)
+    B, H, W = shape
+    x = torch.randn(B, C, H, W)
+    blk = N.SR2XBlock(C, hidden_ratio, C // 2)
+    sd = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    want = U.sr2x_block(x, sd)
+    got = blk.to(dev).forward(N.to_nhwc(x).to(dev))
+    assert tuple(got.shape) == (B, 2 * H, 2 * W, C // 2)
+    _close(got, want, 8e-3 * want.abs().max().item())
+    ib = N.InvertedBottleneck(C, hidden_ratio)
+    want = U.inverted_bottleneck(x, ib.conv1.weight.detach(), ib.conv2.weight.detach())
+    _close(ib.to(dev).forward(N.to_nhwc(x).to(dev)), want, 6e-3 * want.abs().max().item())
+    again = ib.forward(N.to_nhwc(x).to(dev))                              # packed banks come from the cache now
+    assert torch.equal(again, ib.forward(N.to_nhwc(x).to(dev)))
+    with torch.no_grad():
+        ib.conv2.weight.mul_(2.0)                                        # ... and are re-packed when a weight changes
+    _close(ib.forward(N.to_nhwc(x).to(dev)), 2.0 * want, 6e-3 * 2.0 * want.abs().max().item())
+
+
 @pytest.mark.parametrize("how", ["stream", "resident"])
 def test_streamed_and_resident_weights_agree(dev, how, monkeypatch):
     """The weight slice either stays in shared memory or its chunks travel with the activation chunks (deep K): the same

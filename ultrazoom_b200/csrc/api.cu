@@ -84,9 +84,11 @@ int mz_stem_pack(const float* x_dev, const float* w_dev, const float* bias_dev, 
 
 int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const float* film_dev, void* out_bf16_dev,
                float* zf_dev, int32_t B, int32_t H, int32_t W, int32_t cin_p, int32_t in_pitch, int32_t cout_p,
-               int32_t out_pitch, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune, void* stream) {
+               int32_t out_pitch, int32_t zf_pitch, int32_t operand_dtype, int32_t use_tc, const mz_conv_tune* tune,
+               void* stream) {
   MZ_REQUIRE(in_pitch == 0 || (in_pitch >= cin_p && in_pitch % 8 == 0), "conv: in_pitch %d must be 0 or a multiple of 8 >= cin_p", in_pitch);
   MZ_REQUIRE(out_pitch == 0 || (out_pitch >= cout_p && out_pitch % 8 == 0), "conv: out_pitch %d must be 0 or a multiple of 8 >= cout_p", out_pitch);
+  MZ_REQUIRE(zf_pitch == 0 || (zf_pitch >= cout_p && zf_pitch % 4 == 0), "conv: zf_pitch %d must be 0 or a multiple of 4 >= cout_p", zf_pitch);
   MZ_REQUIRE(in_dev && wpacked_dev && out_bf16_dev, "conv: null pointer");
   MZ_REQUIRE(dtype_ok(operand_dtype), "operand_dtype must be MZ_DTYPE_F16 or MZ_DTYPE_BF16, %d given", operand_dtype);
   MZ_REQUIRE(mode == 0 || mode == 1, "conv: mode must be 0 or 1, %d given", mode);
@@ -107,6 +109,7 @@ int mz_conv3x3(const void* in_dev, const void* wpacked_dev, int32_t mode, const 
   a.epi.out_bf16 = static_cast<uint16_t*>(out_bf16_dev);
   a.epi.out_pitch = out_pitch;
   a.epi.zf = zf_dev;
+  a.epi.zf_pitch = zf_pitch;
   if (use_tc) return launch_conv_tc(a, to_tune(tune), current_device(), static_cast<cudaStream_t>(stream));
   return launch_conv_simt(a, static_cast<cudaStream_t>(stream));
 }

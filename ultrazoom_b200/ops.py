@@ -96,11 +96,14 @@ def control_film(c: Tensor, weight: Tensor, bias: Tensor, B: int, hcp: Optional[
 
 
 def conv3x3(inp: Tensor, wpacked: Tensor, mode: int, film: Optional[Tensor] = None, zf: Optional[Tensor] = None,
-            use_tc: bool = True, tune: Optional[_native.MzConvTune] = None, out_pitch: int = 0) -> Tensor:
+            use_tc: bool = True, tune: Optional[_native.MzConvTune] = None, out_pitch: int = 0,
+            out: Optional[Tensor] = None, channel_offset: int = 0) -> Tensor:
     """3x3 conv on NHWC fp16|bf16 with the fused block epilogues; returns the 16-bit NHWC output (dtype of `inp`).
 
     mode 0: SiLU(scale*acc+shift) with film (B,2,cout_p) or None; mode 1: zf += acc (in place), returns round16(zf).
-    The input may be wider than the weights' cin_p (its first cin_p channels are used)."""
+    The input may be wider than the weights' cin_p (its first cin_p channels are used).  ``out`` (B,H,W,P) 16-bit and
+    ``channel_offset``: this launch owns output channels [channel_offset, channel_offset + cout_p) of a wider ``out`` (and,
+    in mode 1, of a wider ``zf``) -- how a convolution wider than one launch is sliced."""
     _need_cuda(inp, wpacked)
     assert inp.dtype in (torch.float16, torch.bfloat16) and wpacked.dtype == inp.dtype
     inp = inp.contiguous()
@@ -108,15 +111,27 @@ def conv3x3(inp: Tensor, wpacked: Tensor, mode: int, film: Optional[Tensor] = No
     _, cout_p, cin_p = wpacked.shape
     assert in_pitch >= cin_p, "weight / activation channel mismatch"
     assert mode in (0, 1), "mode must be 0 (conv1 + FiLM + SiLU) or 1 (conv2 + residual)"
-    alloc = torch.zeros if out_pitch > cout_p else torch.empty   # pad channels are never written by the kernel
-    out = alloc((B, H, W, out_pitch or cout_p), dtype=inp.dtype, device=inp.device)
-    if mode == 1:
-        assert zf is not None and zf.is_contiguous() and tuple(zf.shape) == (B, H, W, cout_p)
+    zf_pitch = 0
+    if out is None:
+        assert channel_offset == 0
+        alloc = torch.zeros if out_pitch > cout_p else torch.empty   # pad channels are never written by the kernel
+        out = alloc((B, H, W, out_pitch or cout_p), dtype=inp.dtype, device=inp.device)
+        if mode == 1:
+            assert zf is not None and zf.is_contiguous() and tuple(zf.shape) == (B, H, W, cout_p)
+    else:
+        assert out.is_contiguous() and out.dtype == inp.dtype and tuple(out.shape[:3]) == (B, H, W)
+        out_pitch = out.shape[3]
+        assert 0 <= channel_offset and channel_offset + cout_p <= out_pitch and channel_offset % 8 == 0
+        if mode == 1:
+            assert zf is not None and zf.is_contiguous() and tuple(zf.shape[:3]) == (B, H, W)
+            zf_pitch = zf.shape[3]
+            assert channel_offset + cout_p <= zf_pitch
     with torch.cuda.device(inp.device):
         _native.check(_native.load().mz_conv3x3(
             inp.data_ptr(), wpacked.data_ptr(), mode, film.data_ptr() if film is not None else None,
-            out.data_ptr(), zf.data_ptr() if zf is not None else None, B, H, W, cin_p,
-            in_pitch if in_pitch != cin_p else 0, cout_p, out_pitch, _native.dtype_code(inp.dtype), 1 if use_tc else 0,
+            out.data_ptr() + 2 * channel_offset, zf.data_ptr() + 4 * channel_offset if zf is not None else None, B, H, W, cin_p,
+            in_pitch if in_pitch != cin_p else 0, cout_p, out_pitch if out_pitch != cout_p else 0,
+            zf_pitch if zf_pitch != cout_p else 0, _native.dtype_code(inp.dtype), 1 if use_tc else 0,
             C.byref(tune) if tune is not None else None, _stream(inp)))
     return out
 
