@@ -165,6 +165,11 @@ def test_blocks_at_the_widths_of_the_default_unet(dev, C, hidden_ratio, shape):
     ib = N.InvertedBottleneck(C, hidden_ratio)
     want = U.inverted_bottleneck(x, ib.conv1.weight.detach(), ib.conv2.weight.detach())
     _close(ib.to(dev).forward(N.to_nhwc(x).to(dev)), want, 6e-3 * want.abs().max().item())
+    # the block's output carries its 16-bit copy for the next convolution; an in-place edit retires it
+    y = blk.refiner.forward(N.to_nhwc(x).to(dev))
+    assert torch.equal(N._operand(y, torch.float16), y.to(torch.float16)) and N._operand(y, torch.float16) is y._mz16[0]
+    y.mul_(0.5)
+    assert N._operand(y, torch.float16) is not y._mz16[0] and torch.equal(N._operand(y, torch.float16), y.to(torch.float16))
     again = ib.forward(N.to_nhwc(x).to(dev))                              # packed banks come from the cache now
     assert torch.equal(again, ib.forward(N.to_nhwc(x).to(dev)))
     with torch.no_grad():
