@@ -49,11 +49,11 @@ constexpr int kStrip = 8;
 
 template <int R>
 __global__ void __launch_bounds__(128) bicubic_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W,
-                                                      int n_strips, BicubicTable bt) {
+                                                      int n_strips, int strip_rows, BicubicTable bt) {
   const int lx = blockIdx.x * 128 + threadIdx.x;
   if (lx >= W) return;
   const int pl = blockIdx.y / n_strips, strip = blockIdx.y - pl * n_strips;
-  const int ly0 = strip * kStrip, ly1 = min(ly0 + kStrip, H);
+  const int ly0 = strip * strip_rows, ly1 = min(ly0 + strip_rows, H);
   const float* plane = x + static_cast<size_t>(pl) * H * W;
   const size_t WR = static_cast<size_t>(W) * R;
   float* out = y + static_cast<size_t>(pl) * H * R * WR + static_cast<size_t>(lx) * R;
@@ -113,16 +113,21 @@ int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cu
   MZ_REQUIRE(planes > 0 && H > 0 && W > 0, "bicubic: empty input (planes %d, H %d, W %d)", planes, H, W);
   BicubicTable bt;
   make_bicubic_table(r, &bt);
-  const int n_strips = (H + kStrip - 1) / kStrip;
+  // strips of 8 LR rows (4 halo rows re-read per strip), shorter ones while the grid would not fill the GPU four times
+  // over: a pure store-bound kernel needs the stores of many threads in flight
+  int strip_rows = kStrip;
+  const long long bx = (W + 127) / 128;
+  while (strip_rows > 2 && bx * planes * ((H + strip_rows - 1) / strip_rows) < 148LL * 16 * 4) strip_rows /= 2;
+  const int n_strips = (H + strip_rows - 1) / strip_rows;
   const long long gy = static_cast<long long>(planes) * n_strips;
   MZ_REQUIRE(gy <= 65535, "bicubic: planes x row strips (%lld) exceeds the grid limit", gy);
   const dim3 grid((W + 127) / 128, static_cast<unsigned>(gy));
   if (r == 2)
-    bicubic_kernel<2><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, bt);
+    bicubic_kernel<2><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, strip_rows, bt);
   else if (r == 3)
-    bicubic_kernel<3><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, bt);
+    bicubic_kernel<3><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, strip_rows, bt);
   else
-    bicubic_kernel<4><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, bt);
+    bicubic_kernel<4><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, strip_rows, bt);
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }
@@ -153,9 +158,15 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
   const size_t npix = static_cast<size_t>(B) * plane;
   const size_t p0 = static_cast<size_t>(blockIdx.x) * ppb;
   const size_t p1 = p0 + ppb < npix ? p0 + ppb : npix;
-  for (size_t pix = p0 + threadIdx.y; pix < p1; pix += blockDim.y) {
-    const size_t b = pix / plane;
-    const size_t xo = b * 3 * plane + (pix - b * plane);
+  // (image index and offset inside the image are carried along: a 64-bit division per pixel was a third of the
+  // kernel's instructions)
+  size_t b = (p0 + threadIdx.y) / plane, rem = (p0 + threadIdx.y) - b * plane;
+  for (size_t pix = p0 + threadIdx.y; pix < p1; pix += blockDim.y, rem += blockDim.y) {
+    while (rem >= plane) {
+      rem -= plane;
+      ++b;
+    }
+    const size_t xo = b * 3 * plane + rem;
     float r0, r1, r2;
     if (x8 != nullptr) {
       // exact x8 / 255 (IEEE division, what ToDtype(float32, scale=True) computes): the network amplifies a 1-ulp
