@@ -935,12 +935,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
           }
           if (ok) {
+            const bool interior = xw >= 2 && xw + 33 < p.epi.W;  // (warp-uniform) no clamped column in this warp
             if (p.epi.r == 4)
-              epi_head_r<4>(p.epi, b, y, x, acc);
+              epi_head_r<4>(p.epi, b, y, x, acc, interior);
             else if (p.epi.r == 2)
-              epi_head_r<2>(p.epi, b, y, x, acc);
+              epi_head_r<2>(p.epi, b, y, x, acc, interior);
             else
-              epi_head_r<3>(p.epi, b, y, x, acc);
+              epi_head_r<3>(p.epi, b, y, x, acc, interior);
           }
         } else if (MODE == 1) {
           if (k > 0 && !all_rows) load_residual(k, k + 1);
@@ -1317,6 +1318,7 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
              "conv: n_pad must be a multiple of 16 in [16, 256], %d given", e.n_pad);
   MZ_REQUIRE(e.mode >= 0 && e.mode <= 2, "conv: bad epilogue mode %d", e.mode);
   MZ_REQUIRE(e.mode != 2 || e.n_pad <= 48, "head conv: n_pad must be <= 48, %d given", e.n_pad);
+  MZ_REQUIRE(static_cast<long long>(e.H) * e.W < (1LL << 31), "conv: an image plane of %d x %d pixels exceeds 2^31", e.H, e.W);
   MZ_REQUIRE(tune.halo_mode >= 0 && tune.halo_mode <= 1, "conv: bad halo_mode %d", tune.halo_mode);
   MZ_REQUIRE(tune.cluster == 0 || tune.cluster == 1 || tune.cluster == 2 || tune.cluster == 4,
              "conv: cluster must be 0 (auto), 1, 2 or 4, %d given", tune.cluster);

@@ -317,62 +317,94 @@ __device__ __forceinline__ void epi_head(const EpiParams& p, int b, int y, int x
 // colour, interpolated horizontally for the R phases (5 rows x R values) and then vertically (R x R values) --
 // 25 loads + 20R + 4R^2 FMAs per colour instead of 16 loads + 20 FMAs per HR pixel -- and every HR row segment of
 // the pixel (R contiguous floats) leaves in one vector store, so a warp writes 32*R contiguous floats.
-template <int R>
-__device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int x, const float (&acc)[48]) {
+// The epilogue warps are few (two per scheduler) and this code is latency-bound, so: the skip source's type is a
+// template parameter (one load per tap instead of a predicated fp32 / 8-bit pair), the clamped row / column offsets
+// are computed once for the three colours, and at R = 2 all 75 taps (R > 2: the 25 of a colour) are requested before
+// the first FMA; skip-from-buffer reads all its row segments before the first store (a store to y orders every
+// later load from y behind it).  Columns are only clamped in the first and last warp of an image row: the others
+// (interior) read each neighbourhood row through one pointer with immediate offsets.
+template <int R, typename T>
+__device__ __forceinline__ void epi_head_rt(const EpiParams& p, const T* __restrict__ lr, int b, int y, int x,
+                                            const float (&acc)[48], bool interior) {
   const int H = p.H, W = p.W;
   const long long first = head_out_index(p, b, 0, y, x, 0, 0);
   if (first < 0) return;  // outside the output window
   const size_t row_pitch = p.y_row ? static_cast<size_t>(p.y_row) : static_cast<size_t>(W) * R;
   const size_t plane_pitch = p.y_plane ? static_cast<size_t>(p.y_plane) : static_cast<size_t>(H) * R * W * R;
+  constexpr int NC = (R == 2) ? 3 : 1;  // colours whose taps are in flight together
+  float out[3][R][R];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float out[R][R];
+  for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int i = 0; i < R; ++i)
 #pragma unroll
-      for (int j = 0; j < R; ++j) out[i][j] = acc[c * R * R + i * R + j];
-    const size_t d0 = static_cast<size_t>(first) + c * plane_pitch;
-    float* dst = p.y + d0;
-    if (p.skip_mode == 2) {
-      const size_t pl = (static_cast<size_t>(b) * 3 + c) * H * W;
-      float hz[5][R];
+      for (int j = 0; j < R; ++j) out[c][i][j] = acc[c * R * R + i * R + j];
+
+  if (p.skip_mode == 2) {
+    const size_t HW = static_cast<size_t>(H) * W;
+    const T* img = lr + static_cast<size_t>(b) * 3 * HW;
+    int xo[5], ro[5];  // (a colour plane is below 2^31 pixels: prepare_conv_tc checks)
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const size_t ro = pl + static_cast<size_t>(min(max(y - 2 + k, 0), H - 1)) * W;
-        float nb[5];
+    for (int m = 0; m < 5; ++m) xo[m] = min(max(x - 2 + m, 0), W - 1);
 #pragma unroll
-        for (int m = 0; m < 5; ++m) {
-          const size_t xi = ro + min(max(x - 2 + m, 0), W - 1);
-          nb[m] = p.x8 != nullptr ? lr_px(p.x8 + xi) : lr_px(p.x + xi);
-        }
+    for (int k = 0; k < 5; ++k) ro[k] = min(max(y - 2 + k, 0), H - 1) * W;
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int s = (2 * j + 1 < R) ? 0 : 1;  // first tap relative to x-2 (phase offset -1 or 0)
-          float a = 0.f;
+    for (int c0 = 0; c0 < 3; c0 += NC) {
+      float nb[NC][5][5];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) a = fmaf(nb[s + m], p.bt.w[j][m], a);
-          hz[k][j] = a;
+      for (int cc = 0; cc < NC; ++cc) {
+        const T* pl = img + (c0 + cc) * HW;
+        if (interior) {  // warp-uniform: no column of the warp's neighbourhoods is clamped -> one pointer per row
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const T* rp = pl + (ro[k] + (x - 2));
+#pragma unroll
+            for (int m = 0; m < 5; ++m) nb[cc][k][m] = lr_px(rp + m);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 5; ++k)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) nb[cc][k][m] = lr_px(pl + (ro[k] + xo[m]));
         }
       }
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const int s = (2 * i + 1 < R) ? 0 : 1;
+      for (int cc = 0; cc < NC; ++cc) {
+        float hz[5][R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          float a = 0.f;
+        for (int k = 0; k < 5; ++k)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) a = fmaf(hz[s + k][j], p.bt.w[i][k], a);
-          out[i][j] += a;
+          for (int j = 0; j < R; ++j) {
+            const int s = (2 * j + 1 < R) ? 0 : 1;  // first tap relative to x-2 (phase offset -1 or 0)
+            float a = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) a = fmaf(nb[cc][k][s + m], p.bt.w[j][m], a);
+            hz[k][j] = a;
+          }
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const int s = (2 * i + 1 < R) ? 0 : 1;
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a = fmaf(hz[s + k][j], p.bt.w[i][k], a);
+            out[c0 + cc][i][j] += a;
+          }
         }
       }
     }
-    if (p.y8 != nullptr) {  // 8-bit output: R bytes per HR row segment (a warp writes 32 * R contiguous bytes)
+  }
+
+  if (p.y8 != nullptr) {  // 8-bit output: R bytes per HR row segment (a warp writes 32 * R contiguous bytes)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int i = 0; i < R; ++i) {
-        uint8_t* rowp = p.y8 + d0 + static_cast<size_t>(i) * row_pitch;
+        uint8_t* rowp = p.y8 + static_cast<size_t>(first) + c * plane_pitch + static_cast<size_t>(i) * row_pitch;
         uint32_t w = 0;
 #pragma unroll
-        for (int j = 0; j < R; ++j) w |= static_cast<uint32_t>(to_u8(out[i][j], p.u8_trunc)) << (8 * j);
+        for (int j = 0; j < R; ++j) w |= static_cast<uint32_t>(to_u8(out[c][i][j], p.u8_trunc)) << (8 * j);
         if (R == 4) {
           *reinterpret_cast<uint32_t*>(rowp) = w;
         } else if (R == 2) {
@@ -382,29 +414,62 @@ __device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int
           for (int j = 0; j < R; ++j) rowp[j] = static_cast<uint8_t>(w >> (8 * j));
         }
       }
-      continue;
-    }
+    return;
+  }
+
+  float* dst = p.y + static_cast<size_t>(first);
+  if (p.skip_mode == 1) {  // y already holds the bicubic image: all of this pixel's segments first, then the stores
+    float sk[3][R][R];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const float* rowp = dst + c * plane_pitch + static_cast<size_t>(i) * row_pitch;
+        if (R == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(rowp);
+          sk[c][i][0] = v.x, sk[c][i][1] = v.y, sk[c][i][R > 2 ? 2 : 0] = v.z, sk[c][i][R - 1] = v.w;
+        } else if (R == 2) {
+          const float2 v = *reinterpret_cast<const float2*>(rowp);
+          sk[c][i][0] = v.x, sk[c][i][1] = v.y;
+        } else {
+#pragma unroll
+          for (int j = 0; j < R; ++j) sk[c][i][j] = rowp[j];
+        }
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) out[c][i][j] += sk[c][i][j];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      float* rowp = dst + static_cast<size_t>(i) * row_pitch;
-      if (p.skip_mode == 1) {
-#pragma unroll
-        for (int j = 0; j < R; ++j) out[i][j] += rowp[j];
-      }
+      float* rowp = dst + c * plane_pitch + static_cast<size_t>(i) * row_pitch;
       if (p.clamp01) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) out[i][j] = fminf(fmaxf(out[i][j], 0.f), 1.f);
+        for (int j = 0; j < R; ++j) out[c][i][j] = fminf(fmaxf(out[c][i][j], 0.f), 1.f);
       }
       if (R == 4) {
-        *reinterpret_cast<float4*>(rowp) = make_float4(out[i][0], out[i][1], out[i][R > 2 ? 2 : 0], out[i][R - 1]);
+        *reinterpret_cast<float4*>(rowp) =
+            make_float4(out[c][i][0], out[c][i][1], out[c][i][R > 2 ? 2 : 0], out[c][i][R - 1]);
       } else if (R == 2) {
-        *reinterpret_cast<float2*>(rowp) = make_float2(out[i][0], out[i][1]);
+        *reinterpret_cast<float2*>(rowp) = make_float2(out[c][i][0], out[c][i][1]);
       } else {
 #pragma unroll
-        for (int j = 0; j < R; ++j) rowp[j] = out[i][j];
+        for (int j = 0; j < R; ++j) rowp[j] = out[c][i][j];
       }
     }
-  }
+}
+// interior: warp-uniform promise that x - 2 >= 0 and x + 2 < W for every lane of the calling warp
+template <int R>
+__device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int x, const float (&acc)[48], bool interior) {
+  if (p.x8 != nullptr)
+    epi_head_rt<R, uint8_t>(p, p.x8, b, y, x, acc, interior);
+  else
+    epi_head_rt<R, float>(p, p.x, b, y, x, acc, interior);
 }
 #endif  // __CUDACC__
 
