@@ -449,7 +449,7 @@ def main():
                "ms_step": ms_step, "conv_ms": conv_ms.value, "clocks": clocks, "value": out_px / (ms_step * 1e-3) / 1e6,
                "e2e": None, "scaling": "strong", "steps": steps, "fused": bool(eng.lib.mz_model_fused_block(eng.handle)), "npix_executed": int(sum((t_.hy1 - t_.hy0) * (t_.hx1 - t_.hx0) for t_ in mine)),
                "tiling": {"grid": f"{rows}x{cols}", "halo_lr_px": R, "halo_refresh_every_blocks": refresh or None,
-                          "exchange": ("halo strips of zf + zb between neighbour tiles, grouped NCCL isend / irecv" if refresh and world > 1
+                          "exchange": ("halo rectangles of zf + zb pulled out of the neighbour tiles' workspaces by one-sided 2-D gets over NVLink (CUDA IPC mappings); two one-element stream-ordered all-reduces per refresh order them" if refresh and world > 1
                                        else None),
                           "executed_over_algorithmic_work": executed,
                           "max_abs_diff_vs_untiled": err,
