@@ -1319,6 +1319,16 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
   MZ_REQUIRE(e.mode >= 0 && e.mode <= 2, "conv: bad epilogue mode %d", e.mode);
   MZ_REQUIRE(e.mode != 2 || e.n_pad <= 48, "head conv: n_pad must be <= 48, %d given", e.n_pad);
   MZ_REQUIRE(static_cast<long long>(e.H) * e.W < (1LL << 31), "conv: an image plane of %d x %d pixels exceeds 2^31", e.H, e.W);
+  {  // dense layouts: extents are whole 16-byte runs, inside the GEMM width, and not wider than the pitch
+    const int ie = a.in_extent ? a.in_extent : a.cin_p, oe = e.out_extent ? e.out_extent : e.n_pad;
+    const int ze = e.zf_extent ? e.zf_extent : e.n_pad;
+    MZ_REQUIRE(ie > 0 && ie <= a.cin_p && ie % 8 == 0 && (a.in_pitch == 0 ? ie == a.cin_p : ie <= a.in_pitch),
+               "conv: in_extent %d does not fit cin_p %d / in_pitch %d (multiple of 8)", ie, a.cin_p, a.in_pitch);
+    MZ_REQUIRE(e.mode == 2 || (oe > 0 && oe <= e.n_pad && oe % 8 == 0 && (e.out_pitch == 0 ? oe == e.n_pad : oe <= e.out_pitch)),
+               "conv: out_extent %d does not fit n_pad %d / out_pitch %d (multiple of 8)", oe, e.n_pad, e.out_pitch);
+    MZ_REQUIRE(e.mode != 1 || (ze > 0 && ze <= e.n_pad && ze % 4 == 0 && (e.zf_pitch == 0 ? ze == e.n_pad : ze <= e.zf_pitch)),
+               "conv: zf_extent %d does not fit n_pad %d / zf_pitch %d (multiple of 4)", ze, e.n_pad, e.zf_pitch);
+  }
   MZ_REQUIRE(tune.halo_mode >= 0 && tune.halo_mode <= 1, "conv: bad halo_mode %d", tune.halo_mode);
   MZ_REQUIRE(tune.cluster == 0 || tune.cluster == 1 || tune.cluster == 2 || tune.cluster == 4,
              "conv: cluster must be 0 (auto), 1, 2 or 4, %d given", tune.cluster);
@@ -1494,8 +1504,8 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
   const CUtensorMapSwizzle swz =
       p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   {
-    const uint64_t dims[4] = {static_cast<uint64_t>(a.cin_p), static_cast<uint64_t>(e.W), static_cast<uint64_t>(e.H),
-                              static_cast<uint64_t>(e.B)};
+    const uint64_t dims[4] = {static_cast<uint64_t>(a.in_extent ? a.in_extent : a.cin_p), static_cast<uint64_t>(e.W),
+                              static_cast<uint64_t>(e.H), static_cast<uint64_t>(e.B)};
     const uint64_t ip = a.in_pitch ? a.in_pitch : a.cin_p;  // pixel pitch in elements (a wider tensor's first cin_p channels)
     const uint64_t strides[3] = {ip * 2, static_cast<uint64_t>(e.W) * ip * 2, static_cast<uint64_t>(e.H) * e.W * ip * 2};
     const uint32_t box[4] = {static_cast<uint32_t>(p.kc), static_cast<uint32_t>(p.pw),
@@ -1517,8 +1527,8 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
                             : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   };
   if (e.mode != 2) {
-    const uint64_t dims[4] = {static_cast<uint64_t>(e.n_pad), static_cast<uint64_t>(e.W), static_cast<uint64_t>(e.H),
-                              static_cast<uint64_t>(e.B)};
+    uint64_t dims[4] = {static_cast<uint64_t>(e.out_extent ? e.out_extent : e.n_pad), static_cast<uint64_t>(e.W),
+                        static_cast<uint64_t>(e.H), static_cast<uint64_t>(e.B)};
     const uint64_t op = e.out_pitch ? e.out_pitch : e.n_pad;
     const uint64_t st16[3] = {op * 2, static_cast<uint64_t>(e.W) * op * 2, static_cast<uint64_t>(e.H) * e.W * op * 2};
     const uint32_t box16[4] = {static_cast<uint32_t>(p.e16), 32u, 1u, 1u};
@@ -1528,6 +1538,7 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
       const uint64_t zp = e.zf_pitch ? e.zf_pitch : e.n_pad;
       const uint64_t st32[3] = {zp * 4, static_cast<uint64_t>(e.W) * zp * 4, static_cast<uint64_t>(e.H) * e.W * zp * 4};
       const uint32_t box32[4] = {static_cast<uint32_t>(p.e32), 32u, 1u, 1u};
+      dims[0] = static_cast<uint64_t>(e.zf_extent ? e.zf_extent : e.n_pad);
       rc = encode_tmap(&p.tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e.zf, dims, st32, box32, swz_of(p.e32 * 4));
       if (rc != MZ_OK) return rc;
     }

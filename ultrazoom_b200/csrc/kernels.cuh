@@ -39,8 +39,12 @@ struct EpiParams {
   uint16_t* out_bf16;       // mode 0: hidden; mode 1: zb (fp16 or bf16 bits)
   int out_pitch;            // channel pitch of out_bf16 in elements (0 = n_pad); > n_pad when the consumer wants
                             // zero-padded channels (48-channel zb is kept at pitch 64: 128-byte TMA rows)
+  int out_extent;           // channels of out_bf16 that exist in memory (0 = n_pad; a multiple of 8).  < n_pad = DENSE
+                            // layout: the GEMM's zero padding lives in shared memory only -- the tensor maps end at the
+                            // extent, so TMA neither writes the padding nor fetches it (out-of-bounds reads are zeros)
   float* zf;                // mode 1: fp32 residual stream, updated in place
   int zf_pitch;             // channel pitch of zf in elements (0 = n_pad); > n_pad when this launch owns a channel slice
+  int zf_extent;            // channels of zf that exist in memory (0 = n_pad), as out_extent
   // mode 2
   const float* x;  // LR image (B,3,H,W) fp32 -- only for skip_mode 2
   float* y;        // HR image (B,3,rH,rW) fp32
@@ -83,6 +87,7 @@ struct ConvArgs {
   const uint16_t* w;   // [9][n_pad][cin_p] fp16 | bf16, tap = ky*3+kx
   int cin_p;
   int in_pitch;        // channel pitch of `in` in elements (0 = cin_p): a wider tensor's first cin_p channels are read
+  int in_extent;       // channels of `in` that exist in memory (0 = cin_p; a multiple of 8): see EpiParams::out_extent
   EpiParams epi;
 };
 
@@ -201,15 +206,16 @@ __device__ __forceinline__ void epi_residual16(const EpiParams& p, int b, int y,
     z.y += acc[4 * q + 1];
     z.z += acc[4 * q + 2];
     z.w += acc[4 * q + 3];
-    zf[q] = z;
+    if (n0 + 4 * q < (p.zf_extent ? p.zf_extent : p.n_pad)) zf[q] = z;
     amax = fmaxf(fmaxf(amax, fmaxf(fabsf(z.x), fabsf(z.y))), fmaxf(fabsf(z.z), fabsf(z.w)));
     o[2 * q] = pack_op2(p.bf16, z.x, z.y);
     o[2 * q + 1] = pack_op2(p.bf16, z.z, z.w);
   }
   if (!p.bf16 && p.sat != nullptr && !(amax <= MZ_F16_MAX)) *p.sat = 1u;
   uint16_t* dst = p.out_bf16 + pix * (p.out_pitch ? p.out_pitch : p.n_pad) + n0;
-  st_global_v4(dst, o[0], o[1], o[2], o[3]);
-  st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
+  const int oe = p.out_extent ? p.out_extent : p.n_pad;
+  if (n0 < oe) st_global_v4(dst, o[0], o[1], o[2], o[3]);
+  if (n0 + 8 < oe) st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
 }
 
 // modes 0 and 1: sixteen consecutive output channels n0..n0+15 of pixel (b, y, x).  `film_rows` (mode 0) points at
@@ -242,13 +248,15 @@ __device__ __forceinline__ void epi_store16(const EpiParams& p, int b, int y, in
     }
     if (!p.bf16 && p.sat != nullptr && !(amax <= MZ_F16_MAX)) *p.sat = 1u;
     uint16_t* dst = p.out_bf16 + pix * (p.out_pitch ? p.out_pitch : p.n_pad) + n0;
-    st_global_v4(dst, o[0], o[1], o[2], o[3]);
-    st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
+    const int oe = p.out_extent ? p.out_extent : p.n_pad;
+    if (n0 < oe) st_global_v4(dst, o[0], o[1], o[2], o[3]);
+    if (n0 + 8 < oe) st_global_v4(dst + 8, o[4], o[5], o[6], o[7]);
   } else {
     const float4* zf = reinterpret_cast<const float4*>(p.zf + pix * (p.zf_pitch ? p.zf_pitch : p.n_pad) + n0);
     float4 zin[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) zin[q] = zf[q];
+    for (int q = 0; q < 4; ++q)
+      zin[q] = n0 + 4 * q < (p.zf_extent ? p.zf_extent : p.n_pad) ? zf[q] : make_float4(0.f, 0.f, 0.f, 0.f);
     epi_residual16(p, b, y, x, n0, acc, zin);
   }
 }

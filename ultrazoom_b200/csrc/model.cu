@@ -18,6 +18,10 @@ using namespace mz;
 struct mz_model {
   mz_config cfg;
   int C, Cp, Cz, hC, hCp, L, r, F, headN, headNp, bf16;  // Cz: channel pitch of zb (>= Cp, zero padded)
+  // Channels per pixel IN MEMORY of the fp32 stream, its 16-bit shadow and the hidden tensor.  Equal to the GEMM widths
+  // (Cp, Cz, hCp) unless the layout is dense: channels rounded up to 8 only (54 -> 56, 108 -> 112 instead of 64 / 128) --
+  // the GEMM's zero padding then exists in shared memory only (ConvArgs::in_extent, EpiParams::out_extent / zf_extent).
+  int Cpm, Czm, hCm;
   // A hidden width above the 256 columns of one UMMA tile runs conv1 as S launches of ns output channels each
   // (hCp = S * ns): slice s has its own packed filter bank and FiLM rows and writes channels [s * ns, (s + 1) * ns) of
   // the hidden tensor.  Likewise conv2 above 128 output channels (its epilogue stages whole fp32 + 16-bit row tiles):
@@ -109,11 +113,11 @@ WsPlan plan_ws(const mz_model* m, int B, int H, int W) {
   WsPlan p;
   size_t off = 0;
   p.zf = off;
-  off = align_up(off + npix * m->Cp * sizeof(float), 1024);
+  off = align_up(off + npix * m->Cpm * sizeof(float), 1024);
   p.zb = off;
-  off = align_up(off + npix * m->Cz * sizeof(uint16_t), 1024);
+  off = align_up(off + npix * m->Czm * sizeof(uint16_t), 1024);
   p.hid = off;
-  off = align_up(off + npix * m->hCp * sizeof(uint16_t), 1024);
+  off = align_up(off + npix * m->hCm * sizeof(uint16_t), 1024);
   p.film = off;
   if (m->F > 0) off = align_up(off + static_cast<size_t>(m->L) * B * 2 * m->hCp * sizeof(float), 1024);
   p.total = off;
@@ -277,6 +281,16 @@ int mz_model_create(const mz_config* cfg, mz_model** out) {
   alloc(reinterpret_cast<void**>(&m->conv2), sizeof(uint16_t) * c2 * m->L);
   alloc(reinterpret_cast<void**>(&m->head), sizeof(uint16_t) * 9 * m->headNp * m->Cz);
   m->fused_ok = m->S == 1 && m->S2 == 1 && fused_block_applies(m->Cp, m->hCp, m->Cz);
+  // dense layout (3X-Ctrl: 54 / 108 channels move as 56 / 112 instead of 64 / 128: -12.5 % of every block's bytes);
+  // not with sliced convolutions (a slice's tensor map starts inside the pixel) -- MZ_NO_DENSE_LAYOUT=1 restores the
+  // padded pitches (diagnostic)
+  m->Cpm = m->Cp, m->Czm = m->Cz, m->hCm = m->hCp;
+  if (m->S == 1 && m->S2 == 1 && !m->fused_ok && getenv("MZ_NO_DENSE_LAYOUT") == nullptr) {
+    const int mask = env_int("MZ_DENSE_LAYOUT", 1);  // 1 = fp32 stream, 2 = 16-bit shadow, 4 = hidden tensor
+    if (mask & 1) m->Cpm = (m->C + 7) / 8 * 8;
+    if (mask & 2) m->Czm = (m->C + 7) / 8 * 8;
+    if (mask & 4) m->hCm = (m->hC + 7) / 8 * 8;
+  }
   if (m->fused_ok) {
     alloc(reinterpret_cast<void**>(&m->conv2s), sizeof(uint16_t) * c2 * m->L);
     m->fprepared.resize(kWays * m->L);
@@ -599,7 +613,7 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
   }
   rc = MZ_OK;
   if (front)
-    rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, zf, zb, m->bf16, B, H, W, m->Cp, m->Cz, s,
+    rc = launch_stem(x_dev, x8, m->stem_w, m->stem_b, zf, zb, m->bf16, B, H, W, m->Cpm, m->Czm, s,
                      m->sat_dev);
   if (rc != MZ_OK) return rc;
 
@@ -647,6 +661,8 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
       a.in = zb;
       a.w = m->conv1 + (static_cast<size_t>(l) * S + sl) * c1s;
       a.cin_p = m->Cz;
+      a.in_pitch = m->Czm != m->Cz ? m->Czm : 0;
+      a.in_extent = m->Czm != m->Cz ? m->Czm : 0;
       a.epi.mode = 0;
       a.epi.bf16 = m->bf16;
       a.epi.B = B;
@@ -655,7 +671,8 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
       a.epi.n_pad = m->ns;
       a.epi.film = m->F > 0 ? film + (static_cast<size_t>(l) * S + sl) * B * 2 * m->ns : nullptr;
       a.epi.out_bf16 = hid + static_cast<size_t>(sl) * m->ns;
-      a.epi.out_pitch = S > 1 ? m->hCp : 0;
+      a.epi.out_pitch = (S > 1 || m->hCm != m->hCp) ? m->hCm : 0;
+      a.epi.out_extent = m->hCm != m->hCp ? m->hCm : 0;
       a.epi.sat = m->sat_dev;
       rc = simt ? launch_conv_simt(a, s) : run_conv(m, l * (S + S2) + sl, a, m->tune[0], s);
       if (rc != MZ_OK) return rc;
@@ -666,6 +683,8 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
       a.in = hid;
       a.w = m->conv2 + (static_cast<size_t>(l) * S2 + sl) * c2s;
       a.cin_p = m->hCp;
+      a.in_pitch = m->hCm != m->hCp ? m->hCm : 0;
+      a.in_extent = m->hCm != m->hCp ? m->hCm : 0;
       a.epi.mode = 1;
       a.epi.bf16 = m->bf16;
       a.epi.B = B;
@@ -673,9 +692,11 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
       a.epi.W = W;
       a.epi.n_pad = m->ns2;
       a.epi.out_bf16 = zb + static_cast<size_t>(sl) * m->ns2;
-      a.epi.out_pitch = m->Cz;
+      a.epi.out_pitch = m->Czm;
+      a.epi.out_extent = m->Czm < m->ns2 ? m->Czm : 0;
       a.epi.zf = zf + static_cast<size_t>(sl) * m->ns2;
-      a.epi.zf_pitch = S2 > 1 ? m->Cp : 0;
+      a.epi.zf_pitch = (S2 > 1 || m->Cpm != m->Cp) ? m->Cpm : 0;
+      a.epi.zf_extent = m->Cpm != m->Cp ? m->Cpm : 0;
       a.epi.sat = m->sat_dev;
       rc = simt ? launch_conv_simt(a, s) : run_conv(m, l * (S + S2) + S + sl, a, m->tune[1], s);
       if (rc != MZ_OK) return rc;
@@ -699,6 +720,8 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
   a.in = zcur;
   a.w = m->head;
   a.cin_p = m->Cz;
+  a.in_pitch = m->Czm != m->Cz ? m->Czm : 0;
+  a.in_extent = m->Czm != m->Cz ? m->Czm : 0;
   a.epi.mode = 2;
   a.epi.bf16 = m->bf16;
   a.epi.B = B;
@@ -776,8 +799,8 @@ int mz_workspace_layout(const mz_model* m, int32_t B, int32_t H, int32_t W, size
   *zf_offset = wp.zf;
   *zb_offset = wp.zb;
   *hidden_offset = wp.hid;
-  *channels_padded = m->Cp;
-  *zb_pitch = m->Cz;
+  *channels_padded = m->Cpm;
+  *zb_pitch = m->Czm;
   return MZ_OK;
 }
 

@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvArgs a) {
         if (xx < 0 || xx >= p.W) continue;
         const uint16_t* src = a.in + ((static_cast<size_t>(b) * p.H + yy) * p.W + xx) * (a.in_pitch ? a.in_pitch : a.cin_p);
         const uint16_t* wt = a.w + (static_cast<size_t>(ky * 3 + kx) * p.n_pad + n0) * a.cin_p;
-        for (int k = 0; k < a.cin_p; ++k) {
+        const int kmax = a.in_extent ? a.in_extent : a.cin_p;  // (channels beyond the extent are zero padding)
+        for (int k = 0; k < kmax; ++k) {
           const float v = op_to_float(p.bf16, src[k]);
 #pragma unroll
           for (int i = 0; i < NACC; ++i)
