@@ -42,7 +42,18 @@ WORKLOADS = {
 }
 
 
-def config_of(workload: str, world: int, args) -> dict:
+def operands_for(workload: str, args) -> str:
+    """Tensor-core operand type of a workload.  `--operands auto` (default): bf16 -- the type BASELINE configs[1] and the
+    north_star name -- for the 20-layer 2X model, where it meets BASELINE's envelope at full size (max-abs 0.015, PSNR
+    55 dB vs <= 2e-2 / >= 45 dB: tests/test_gpu_fullsize.py) and runs 5 % faster than fp16 under the power cap (same
+    tcgen05 rate and bytes, lower multiplier power: DESIGN.md section 7); fp16 for the 30- / 40-layer models, where bf16
+    does not meet the envelope (0.018 / 0.026).  The same rule in both arms, so their `config` objects agree."""
+    if args.operands != "auto":
+        return args.operands
+    return "bfloat16" if WORKLOADS[workload][0].startswith("MewZoom-2X") else "float16"
+
+
+def config_of(workload: str, world: int, args, operands=None) -> dict:
     """The `config` object of the JSON line -- the same keys and values in both arms (`--impl reference` times the
     CPU path on THIS configuration), so that the driver can tell the two lines describe one workload."""
     model_name, B, H, W, desc = WORKLOADS[workload]
@@ -54,7 +65,7 @@ def config_of(workload: str, world: int, args) -> dict:
             "l2": "activations per step (>= 1 GB) exceed the 126 MB L2; no explicit flush",
             "weights": "random init (seed 0)", "image_io": args.io,
             "residual_stream": "fp32",
-            "accumulate": "fp32", "mma_operands": args.operands,
+            "accumulate": "fp32", "mma_operands": operands or operands_for(workload, args),
             "tune": {k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)}}
 
 
@@ -71,7 +82,7 @@ def conv_flops_per_launch(cfg, npix: int) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -86,7 +97,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
                  str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -221,7 +232,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--operands", default="float16", choices=["float16", "bfloat16"])
+    ap.add_argument("--operands", default="auto", choices=["auto", "float16", "bfloat16"],
+                    help="tensor-core operand type; auto = bf16 for the 20-layer 2X model, fp16 for the deeper ones (operands_for)")
     ap.add_argument("--residual-stream", default="auto", choices=["auto", "float32"])
     ap.add_argument("--tune", default="", help="comma list k=v of mz_conv_tune fields, e.g. cluster=4,rows=1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -287,7 +299,8 @@ def main():
         cfg = MODEL_CONFIGS[model_name]
         r = cfg["upscale_ratio"]
         torch.manual_seed(0)
-        model = MewZoom(**cfg, operand_dtype=operands or args.operands, residual_stream=args.residual_stream).to(dev).eval()
+        operands = operands or operands_for(workload, args)
+        model = MewZoom(**cfg, operand_dtype=operands, residual_stream=args.residual_stream).to(dev).eval()
         apply_tune(model)
         eng = model._engine(dev)
         g = torch.Generator().manual_seed(1234 + rank)
@@ -324,7 +337,7 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step = float(t.item()) / steps
-        res = {"workload": workload, "model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc, "ms_step": ms_step,
+        res = {"workload": workload, "operands": operands, "model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc, "ms_step": ms_step,
                "conv_ms": conv_ms.value, "clocks": clocks, "value": world * out_px / (ms_step * 1e-3) / 1e6,
                "e2e": None, "scaling": "weak", "steps": steps, "fused": fused}
         # ---- end to end through the public API with HOST buffers (H2D + kernels + D2H inside the timed region) ----
@@ -386,7 +399,8 @@ def main():
         cfg = MODEL_CONFIGS[model_name]
         r, L = cfg["upscale_ratio"], cfg["num_encoder_layers"]
         torch.manual_seed(0)
-        model = MewZoom(**cfg, operand_dtype=args.operands, residual_stream=args.residual_stream).to(dev).eval()
+        operands = operands_for("cfg5", args)
+        model = MewZoom(**cfg, operand_dtype=operands, residual_stream=args.residual_stream).to(dev).eval()
         apply_tune(model)
         eng = model._engine(dev)
         g = torch.Generator().manual_seed(1234)             # every rank holds the same LR frame
@@ -445,7 +459,7 @@ def main():
             full = model.upscale(x, c)
             err = float((full.float() - frame.float()).abs().max())
             del full
-        res = {"workload": "cfg5", "model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc,
+        res = {"workload": "cfg5", "operands": operands, "model_name": model_name, "cfg": cfg, "B": B, "H": H, "W": W, "desc": desc,
                "ms_step": ms_step, "conv_ms": conv_ms.value, "clocks": clocks, "value": out_px / (ms_step * 1e-3) / 1e6,
                "e2e": None, "scaling": "strong", "steps": steps, "fused": bool(eng.lib.mz_model_fused_block(eng.handle)), "npix_executed": int(sum((t_.hy1 - t_.hy0) * (t_.hx1 - t_.hx0) for t_ in mine)),
                "tiling": {"grid": f"{rows}x{cols}", "halo_lr_px": R, "halo_refresh_every_blocks": refresh or None,
@@ -613,6 +627,46 @@ def main():
                                                 "note": "composite: 3 tcgen05 3x3 convolutions + mix + shuffle + the casts between them"}
         return out
 
+    def measure_small_kernels():
+        """The non-encoder kernels of the path at the headline shape, one launch each through the per-kernel C-ABI entry
+        points (ultrazoom_b200.ops): HBM roofline over algorithmic bytes (inputs and outputs once)."""
+        from ultrazoom_b200 import ops
+        model_name, B, H, W, _ = WORKLOADS["cfg2"]
+        cfg = MODEL_CONFIGS[model_name]
+        Cc, r = cfg["num_channels"], cfg["upscale_ratio"]
+        Cp = ops.padded_channels(Cc)
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(B, 3, H, W, generator=g).to(dev)
+        zb = torch.randn(B, H, W, Cp, generator=g).to(torch.float16).to(dev)
+        wh = ops.pack_conv_weight(torch.randn(3 * r * r, Cc, 3, 3, generator=g) * 0.02, dev)
+        ws, bs = torch.randn(Cc, 3, 1, 1, generator=g), torch.randn(Cc, generator=g)
+        y = torch.empty(B, 3, H * r, W * r, device=dev)
+        npx = B * H * W
+        peaks_hbm = load_peaks()["hbm"]
+
+        def timed(fn, nbytes, iters=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / iters
+            return {"ms": ms, "algorithmic_bytes": nbytes, "gb_per_s": nbytes / ms / 1e6,
+                    "frac_of_hbm_peak": nbytes / ms / 1e6 / peaks_hbm}
+
+        return {
+            "what": f"one launch each at the headline shape ({B} x {W}x{H}, {Cc} channels, r = {r}); the timed call includes the "
+                    "ctypes wrapper's own output allocation",
+            "head_conv_shuffle_bicubic_skip_clamp": timed(
+                lambda: ops.head_shuffle_add(zb, wh, r, x=x, y=y, skip_mode=2, clamp01=True), npx * (2 * Cp + 12 + 12 * r * r)),
+            "stem_nchw_to_nhwc_fp32_and_16bit": timed(lambda: ops.stem_pack(x, ws, bs), npx * (12 + 6 * Cp)),
+            "bicubic_standalone": timed(lambda: ops.bicubic(x, r), npx * (12 + 12 * r * r)),
+        }
+
     main_res = measure(args.workload, args.steps, args.warmup, not args.no_e2e, True)
     # The north_star's efficiency target is stated on MewZoom-4X-Ctrl and its hard multi-GPU case is the spatial split:
     # the default line carries those as first-class records (own clocks; 4X-Ctrl with its own e2e) under "also".
@@ -622,11 +676,11 @@ def main():
         also["cfg4a"] = measure("cfg4a", k, args.warmup, not args.no_e2e, True)
         also["cfg3"] = measure("cfg3", k, args.warmup, False, True)
         also["cfg5"] = measure("cfg5", max(3, min(args.steps, 5)), args.warmup, False, True)
-        if args.operands == "float16":
-            # the north_star names bf16 operands: the same headline workload with them (same tcgen05 rate and bytes; the
-            # default is fp16 because bf16 misses BASELINE's 2e-2 max-abs on the 40-layer model: tests/test_gpu_fullsize.py)
-            also["cfg2_bf16"] = measure("cfg2", k, args.warmup, False, True, operands="bfloat16")
+        # the same headline workload with the other 16-bit operand type (same tcgen05 rate and bytes; see operands_for)
+        other = "float16" if main_res["operands"] == "bfloat16" else "bfloat16"
+        also["cfg2_fp16" if other == "float16" else "cfg2_bf16"] = measure("cfg2", k, args.warmup, False, True, operands=other)
     unet_ops = measure_unet_ops() if (args.workload == "cfg2" and not args.no_also and world == 1) or args.unet_ops else None
+    small = measure_small_kernels() if args.workload == "cfg2" and not args.no_also and world == 1 else None
 
     if rank != 0:
         if world > 1:
@@ -652,8 +706,8 @@ def main():
     line = {
         "metric": "output_mpx_per_s", "value": value, "unit": "Mpx/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": res["scaling"],
-        "vs_baseline": None, "dtype": "f16" if args.operands == "float16" else "bf16", "data": "synthetic",
-        "config": config_of(args.workload, world, args),
+        "vs_baseline": None, "dtype": "f16" if res["operands"] == "float16" else "bf16", "data": "synthetic",
+        "config": config_of(args.workload, world, args, res["operands"]),
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         "ms_per_frame": ms_step / B,
@@ -663,13 +717,11 @@ def main():
     if also:
         line["also"] = {}
         for name, ar in also.items():
-            rec = {"workload": ar["desc"] + (" -- bf16 tensor-core operands" if name.endswith("_bf16") else ""),
+            rec = {"workload": ar["desc"] + (f" -- {ar['operands']} tensor-core operands" if name.startswith("cfg2_") else ""),
                    "value": ar["value"], "unit": "Mpx/s", "scaling": ar["scaling"],
                    "steps": ar["steps"], "ms_per_frame": ar["ms_step"], "roofline": roofline_of(ar, peaks),
-                   "clocks": ar["clocks"], "e2e": ar["e2e"], "config": config_of(ar["workload"], world, args),
-                   "dtype": "bf16" if name.endswith("_bf16") else ("f16" if args.operands == "float16" else "bf16")}
-            if name.endswith("_bf16"):
-                rec["config"]["mma_operands"] = "bfloat16"
+                   "clocks": ar["clocks"], "e2e": ar["e2e"], "config": config_of(ar["workload"], world, args, ar["operands"]),
+                   "dtype": "f16" if ar["operands"] == "float16" else "bf16"}
             if "tiling" in ar:
                 rec["tiling"] = ar["tiling"]
             line["also"][name] = rec
@@ -682,6 +734,8 @@ def main():
                     "maps larger than L2, HBM roofline over algorithmic bytes (every input and output element once); "
                     "tf32 = tcgen05 kind::tf32 GEMM from the fp32 maps (default), fp32 = the exact SIMT twin",
             "hbm_peak_gb_per_s": peaks["hbm"], "ops": unet_ops}
+    if small:
+        line.setdefault("also", {})["small_kernels"] = small
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -206,3 +206,9 @@ def test_bench_arms_describe_one_workload():
         a, b = bench.config_of(w, 1, args), bench.config_of(w, 1, args)
         assert a == b and {"workload", "batch_per_gpu", "lr_h", "lr_w", "parallelism"} <= set(a)
     assert "halo-padded tile" in bench.config_of("cfg5", 8, args)["parallelism"]
+    # --operands auto (the default of both arms): bf16 for the 20-layer 2X model -- the type BASELINE configs[1] names --
+    # fp16 for the deeper models, where bf16 misses BASELINE's 2e-2 (tests/test_gpu_fullsize.py)
+    auto = argparse.Namespace(io="float32", residual_stream="auto", operands="auto", tune="")
+    assert bench.config_of("cfg2", 1, auto)["mma_operands"] == "bfloat16"
+    assert all(bench.config_of(w, 1, auto)["mma_operands"] == "float16" for w in ("cfg3", "cfg4a", "cfg4b", "cfg5"))
+    assert bench.config_of("cfg2", 1, auto, "float16")["mma_operands"] == "float16"
