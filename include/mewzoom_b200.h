@@ -159,6 +159,9 @@ int mz_upscale_stage(mz_model* m, const void* x_dev, const float* c_dev, int32_t
                      int64_t y_plane_pitch, int32_t B, int32_t H, int32_t W, int32_t win_y0, int32_t win_y1, int32_t win_x0,
                      int32_t win_x1, void* workspace_dev, size_t workspace_bytes, uint32_t flags, void* stream,
                      int32_t layer_begin, int32_t layer_end);
+/* channels_padded / zb_pitch: channels per pixel of zf / zb IN MEMORY.  They may be smaller than the GEMM width of the
+ * convolutions (a 54-channel model keeps its fp32 stream at 56 channels per pixel, its GEMMs run 64 wide: the zero
+ * padding is made by TMA in shared memory) -- always take them from this call. */
 int mz_workspace_layout(const mz_model* m, int32_t B, int32_t H, int32_t W, size_t* zf_offset, size_t* zb_offset,
                         size_t* hidden_offset, int32_t* channels_padded, int32_t* zb_pitch);
 

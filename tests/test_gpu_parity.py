@@ -294,6 +294,43 @@ def test_hidden_widths_beyond_one_umma_tile(dev, cfg, tol):
     assert (y - ys).abs().max().item() <= 2e-3
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(upscale_ratio=3, num_channels=54, hidden_ratio=2, num_encoder_layers=3, control_features=3),    # 56 / 112 of 64 / 128
+    dict(upscale_ratio=2, num_channels=80, hidden_ratio=2, num_encoder_layers=2, control_features=0),    # 80 / 160 of 96 / 160
+    dict(upscale_ratio=4, num_channels=20, hidden_ratio=4, num_encoder_layers=2, control_features=3),    # 24 / 80 of 32 / 96
+])
+def test_dense_layouts_are_bit_identical(dev, cfg, monkeypatch):
+    """A tensor may hold fewer channels in memory than its GEMM is wide (ConvArgs::in_extent, EpiParams::out_extent /
+    zf_extent: the tensor maps end at the extent, the zero padding exists in shared memory only).  Every combination --
+    fp32 stream, 16-bit shadow, hidden tensor (MZ_DENSE_LAYOUT bits 1 | 2 | 4; the default is the fp32 stream only) --
+    gives the padded layout's result bit for bit, on the tcgen05 path and on the SIMT twin, and the workspace shrinks."""
+    import ctypes as C
+
+    from ultrazoom_b200 import _native
+
+    o = make_oracle(cfg, seed=31)
+    g = torch.Generator().manual_seed(32)
+    x = torch.rand(2, 3, 41, 150, generator=g).to(dev)
+    c = torch.rand(2, 3, generator=g).to(dev) if cfg["control_features"] else None
+    outs, sizes = {}, {}
+    for mask in (0, 1, 2, 4, 7):
+        monkeypatch.setenv("MZ_DENSE_LAYOUT", str(mask))
+        m = _model_from(cfg, o.state_dict(), dev)
+        outs[mask] = m.upscale(x, c)
+        eng = m._engine(dev)
+        need = C.c_size_t()
+        _native.check(eng.lib.mz_workspace_bytes(eng.handle, 2, 41, 150, C.byref(need)))
+        sizes[mask] = need.value
+        m._flags_extra = _native.FLAG_SIMT_CONV
+        ys = m.upscale(x, c)
+        m._flags_extra = 0
+        assert (outs[mask] - ys).abs().max().item() <= 2e-3, mask
+        if mask:
+            assert torch.equal(outs[mask], outs[0]), (mask, (outs[mask] - outs[0]).abs().max().item())
+    assert max_abs_err(outs[0].cpu(), o.upscale(x.cpu(), None if c is None else c.cpu())) <= 6e-3
+    assert sizes[7] < sizes[0] and sizes[7] <= sizes[1] < sizes[0] and sizes[2] < sizes[0] and sizes[4] <= sizes[0]
+
+
 def test_put_core_assembles_the_frame(dev):
     """Spatial sharding, stitch step: each tile's HR core is put into the assembled frame with 2-D
     copies (mz_put_plane_async) -- into a device buffer (a peer GPU's in the multi-GPU run, tools/tiled_8k.py) or into

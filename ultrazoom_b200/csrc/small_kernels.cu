@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
   extern __shared__ float xs[];  // [3][ppb]: the block's pixels, colour planes apart
   // blockDim = (channel groups of 4, pixels per pass): a thread keeps ITS four channels' weights and bias in registers
   const int g = threadIdx.x;
-  const bool real = g * 4 < Cp;  // groups beyond Cp exist only in the 16-bit shadow (zero padding up to its pitch)
+  const bool real = g * 4 < Cp;  // groups beyond Cp exist only in the 16-bit shadow (zero padding up to its pitch Cz)
   float wr[4][3], br[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     }
     const size_t pix = p0 + j;
     if (real) *reinterpret_cast<float4*>(zf + pix * Cp + g * 4) = make_float4(o[0], o[1], o[2], o[3]);
-    st_global_v2(zb + pix * Cz + g * 4, pack_op2(bf16, o[0], o[1]), pack_op2(bf16, o[2], o[3]));
+    if (g * 4 < Cz) st_global_v2(zb + pix * Cz + g * 4, pack_op2(bf16, o[0], o[1]), pack_op2(bf16, o[2], o[3]));
   }
   if (!bf16 && sat != nullptr && !(amax <= MZ_F16_MAX)) *sat = 1u;  // fp16 range guard (see EpiParams::sat)
 }
@@ -208,9 +208,11 @@ int launch_stem(const float* x, const uint8_t* x8, const float* w, const float* 
   MZ_REQUIRE(B > 0 && H > 0 && W > 0, "stem: empty input");
   MZ_REQUIRE(zf != nullptr, "stem: null fp32 stream");
   const int Cz = zb_pitch ? zb_pitch : Cp;
-  MZ_REQUIRE(Cz >= Cp && Cz % 8 == 0, "stem: zb pitch %d must be a multiple of 8 and >= %d", Cz, Cp);
-  const int groups = Cz / 4;
-  MZ_REQUIRE(groups <= 256, "stem: zb pitch %d exceeds 1024 channels", Cz);
+  // (the shadow may be wider than the fp32 stream -- zero padding up to its pitch -- or narrower: a dense shadow beside a
+  // padded stream; padded channels are zeros either way)
+  MZ_REQUIRE(Cz > 0 && Cz % 8 == 0, "stem: zb pitch %d must be a positive multiple of 8", Cz);
+  const int groups = (Cz > Cp ? Cz : Cp) / 4;
+  MZ_REQUIRE(groups <= 256, "stem: %d channels per pixel exceed 1024", groups * 4);
   const int py = 256 / groups > 0 ? 256 / groups : 1;  // pixels per pass of a block
   const long long npix = static_cast<long long>(B) * H * W;
   // ~16 passes per block, but at least ~8 blocks per SM so that a small frame still fills the GPU
