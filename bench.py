@@ -267,6 +267,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a B200 (there is no CPU fallback for the product path)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from ultrazoom_b200.sharding import bind_process_to_gpu
+    # One process per GPU: node-local pinned buffers for the end-to-end leg.  Not at N = 1: the CPU baseline of that line
+    # uses every host core, and threads started under a narrowed affinity would keep it.
+    cpus = bind_process_to_gpu(local_rank) if world > 1 and not os.environ.get("MZ_NO_BIND") else None
 
     import ctypes as C
 
@@ -377,6 +381,8 @@ def main():
             res["e2e"] = {"value": world * out_px * steps / dt / 1e6, "unit": "Mpx/s",
                           "h2d_bytes_per_step": x_host.numel() * x_host.element_size() + (c_host.numel() * 4 if c_host is not None else 0),
                           "d2h_bytes_per_step": out_host.numel() * out_host.element_size(), "ms_per_step": 1e3 * dt / steps,
+                          "host_binding": (f"rank bound to the {len(cpus)} CPUs next to its GPU (NVML ideal-CPU set)" if cpus
+                                           else "none"),
                           "api": ("MewZoom.upscale_host(lane=i%2) + host_wait -> mz_upscale_host_async (stream of steps, two "
                                   "lanes, pinned host buffers)") if stream_mode else
                                  "MewZoom.upscale_host -> mz_upscale_host (pinned host buffers, batch pipelined in chunks)"}

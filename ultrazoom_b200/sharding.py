@@ -25,6 +25,26 @@ def halo_radius(num_encoder_layers: int) -> int:
     return 2 * num_encoder_layers + 1
 
 
+def bind_process_to_gpu(device_index: int) -> Optional[List[int]]:
+    """One process per GPU with HOST buffers: pin the calling thread (and the threads it starts later) to the CPUs
+    next to GPU ``device_index`` (NVML's ideal-CPU set: the GPU's NUMA node), so that the pinned staging buffers it
+    allocates afterwards are node-local and the H2D / D2H copies of eight ranks do not all cross one socket's memory
+    controller and the inter-socket link.  Call it first thing in the rank, before any pinned allocation.  Returns the
+    CPU list, or None when NVML / the device is not available (nothing is changed then)."""
+    try:
+        import os
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(props.uuid)).encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))
+    except Exception:       # noqa: BLE001 -- a placement hint: never fatal
+        return None
+
+
 def frames_for_rank(num_frames: int, rank: int, world: int) -> List[int]:
     assert world > 0 and 0 <= rank < world, f"bad rank {rank} / world {world}"
     return list(range(rank, num_frames, world))
