@@ -331,6 +331,21 @@ def test_dense_layouts_are_bit_identical(dev, cfg, monkeypatch):
     assert sizes[7] < sizes[0] and sizes[7] <= sizes[1] < sizes[0] and sizes[2] < sizes[0] and sizes[4] <= sizes[0]
 
 
+def test_skipped_zero_k_steps_change_nothing(dev, monkeypatch):
+    """conv2 of the 54-channel model reads a hidden tensor of 108 channels padded to 128: the eighth 16-channel k-step of
+    every tap multiplies zeros and is not issued (TcParams::kt_last).  The result equals the full K loop bit for bit."""
+    cfg = dict(upscale_ratio=3, num_channels=54, hidden_ratio=2, num_encoder_layers=4, control_features=3)
+    o = make_oracle(cfg, seed=41)
+    g = torch.Generator().manual_seed(42)
+    x = torch.rand(1, 3, 70, 300, generator=g).to(dev)
+    c = torch.rand(1, 3, generator=g).to(dev)
+    y = _model_from(cfg, o.state_dict(), dev).upscale(x, c)
+    monkeypatch.setenv("MZ_NO_KSKIP", "1")
+    y_full = _model_from(cfg, o.state_dict(), dev).upscale(x, c)
+    assert torch.equal(y, y_full), (y - y_full).abs().max().item()
+    assert max_abs_err(y.cpu(), o.upscale(x.cpu(), c.cpu())) <= 6e-3
+
+
 def test_put_core_assembles_the_frame(dev):
     """Spatial sharding, stitch step: each tile's HR core is put into the assembled frame with 2-D
     copies (mz_put_plane_async) -- into a device buffer (a peer GPU's in the multi-GPU run, tools/tiled_8k.py) or into

@@ -40,6 +40,8 @@ struct TcParams {
   int sliced;       // mode 1, res_rows == 1: the row is finished box by box (e16 == e32), each box with its own residual barrier,
                     // and the NEXT row's boxes are requested as soon as this row's stores of them have been read
   int epi_warps;    // 4 or 8 epilogue warps; with 8, two warps share a TMEM lane quarter and split the rows / boxes
+  int kt_last;      // k-steps issued for the LAST K chunk of a patch (resident banks): fewer than kc / 16 when the tail of
+                    // the input channels is zero padding (108 -> 128: the eighth k-step would multiply zeros)
   EpiParams epi;
   int kc, n_chunks;  // channels per swizzled sub-tile; pipeline chunks per patch (each = subs sub-tiles)
   int subs;          // 16-channel sub-tiles fused into one stage (3 for Cin = 48), else 1
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #define MZ_ISSUE_TAP(DXV)                                                                                         \
   if (issue) {                                                                                                    \
     _Pragma("unroll") for (int t = 0; t < KT; ++t) {                                                              \
+      if (t >= static_cast<int>(cur_kt)) break; /* (uniform) k-steps over zero padding are not issued */           \
       const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo_stage + (DXV) * TB + t * b_kp);        \
       _Pragma("unroll") for (int r = 0; r < ROWS; ++r) {                                                          \
         const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo_dy + (DXV) * DX + r * RP + t * a_kp); \
@@ -369,6 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }                                                                                                             \
   }
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+    uint32_t cur_kt = KT;  // k-steps of the current step's chunk (only the resident path ever lowers it)
     // Barrier state of the NEXT step is sampled (non-blocking mbarrier.test_wait) in the middle of the current
     // step, so in the common case -- the producer is ahead -- the blocking wait and its latency are skipped and
     // the tensor pipe never drains between stages.  The commit of the current stage is NOT delayed by this.
@@ -494,9 +498,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t cur_first = 0u;  // 0: the first UMMA of the step overwrites the accumulator (first chunk of a patch)
       int c = 0;
       bool first_round = true;
+      const uint32_t kt_last = static_cast<uint32_t>(p.kt_last);
+      cur_kt = n_chunks == 1 ? kt_last : KT;
       for (int step = 0; step < total_steps; ++step) {
         const uint32_t d_base = cur_d;
-        uint32_t n_a_lo = 0, n_b_lo = 0, n_d = 0, n_commit_a = 0, n_commit_acc = 0, n_first = 0;
+        uint32_t n_a_lo = 0, n_b_lo = 0, n_d = 0, n_commit_a = 0, n_commit_acc = 0, n_first = 0, n_kt = KT;
         uint32_t nsa = sa, npa = pa, nas = as, npacc = pacc;
         bool ready = true;
 #pragma unroll
@@ -533,6 +539,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             n_d = tmem_base + nas * acc_cols;
             n_commit_acc = c == n_chunks - 1 ? bar_acc_full + 8 * nas : 0u;  // (c is already the next step's chunk)
+            n_kt = c == n_chunks - 1 ? kt_last : KT;
             if (step + 1 < total_steps) {
               ready = test_uniform(bar_a_full + 8 * nsa, npa);
               if (last_chunk) ready = test_uniform(bar_acc_empty + 8 * nas, npacc ^ 1u) && ready;
@@ -567,6 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         cur_commit_a = n_commit_a;
         cur_commit_acc = n_commit_acc;
         cur_first = n_first;
+        cur_kt = n_kt;
       }
     } else {
       // ---- streamed weights: one hand-off per filter row (weight stage), same minimal-gap structure ----
@@ -1488,6 +1496,16 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
     return MZ_ERR_UNSUPPORTED;
   }
 
+  // k-steps over zero padding at the end of K (a.k_valid: the input channels that can be non-zero): not issued for the
+  // last chunk of a resident, un-fused bank (what the 54-channel model's conv2 runs: K = 108 -> 128, seven of eight)
+  p.kt_last = p.subs > 1 ? p.subs : p.kc / 16;  // (= the kernel's KT: every k-step)
+  {
+    const int kv = a.k_valid ? a.k_valid : a.cin_p;
+    MZ_REQUIRE(kv > 0 && kv <= a.cin_p, "conv: k_valid %d outside (0, %d]", kv, a.cin_p);
+    const bool no_kskip = getenv("MZ_NO_KSKIP") != nullptr;  // (diagnostic; read per prepared launch)
+    const int dead = (a.cin_p - kv) / 16;  // whole k-steps of zeros
+    if (!no_kskip && p.res_b && !p.fuse_g && p.subs == 1 && dead > 0 && dead < p.kc / 16) p.kt_last = p.kc / 16 - dead;
+  }
   p.tiles_x = ceil_div(e.W, kTileW);
   p.tiles_y = ceil_div(e.H, p.rows);
   const long long n_units = static_cast<long long>(e.B) * p.tiles_x * p.tiles_y;

@@ -87,6 +87,8 @@ struct ConvArgs {
   const uint16_t* w;   // [9][n_pad][cin_p] fp16 | bf16, tap = ky*3+kx
   int cin_p;
   int in_pitch;        // channel pitch of `in` in elements (0 = cin_p): a wider tensor's first cin_p channels are read
+  int k_valid;         // channels of `in` that can be non-zero (0 = cin_p): whole 16-channel k-steps beyond them are zero
+                       // padding and may be skipped by the kernel (results do not change: they would add zeros)
   int in_extent;       // channels of `in` that exist in memory (0 = cin_p; a multiple of 8): see EpiParams::out_extent
   EpiParams epi;
 };

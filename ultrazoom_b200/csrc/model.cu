@@ -683,6 +683,7 @@ static int upscale_impl(mz_model* m, const void* x_dev_v, const float* c_dev, in
       a.in = hid;
       a.w = m->conv2 + (static_cast<size_t>(l) * S2 + sl) * c2s;
       a.cin_p = m->hCp;
+      a.k_valid = S == 1 ? (m->hC + 15) / 16 * 16 : 0;  // (hidden channels >= hC are SiLU(0) = 0, written by conv1)
       a.in_pitch = m->hCm != m->hCp ? m->hCm : 0;
       a.in_extent = m->hCm != m->hCp ? m->hCm : 0;
       a.epi.mode = 1;
