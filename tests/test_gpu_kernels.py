@@ -262,6 +262,35 @@ def test_head_shuffle_skip_clamp(dev, r, tol, cin, shape, use_tc, dt):
     assert (got - u).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("r,tol", [(2, 1e-4), (3, 2e-4), (4, 1e-4)])
+@pytest.mark.parametrize("cin,shape", [(48, (2, 7, 190)), (96, (1, 9, 129)), (54, (1, 4, 131)), (48, (1, 13, 300))])
+def test_head_with_stacked_taps(dev, r, tol, cin, shape):
+    """The head with its vertical filter taps stacked along N (`VAR 2`, four-row patches, tune.fuse = 1): one UMMA per input
+    row and filter column feeds up to three output rows.  Heights that are not multiples of four exercise the re-zeroing
+    of accumulator rows below the image; both skip forms, clamp, and the plain shuffle match the PyTorch reference."""
+    ops, native = _ops()
+    g = torch.Generator().manual_seed(19 + r)
+    B, H, W = shape
+    dt = torch.float16
+    cin_p = ops.padded_channels(cin)
+    zb = torch.zeros(B, H, W, cin_p, dtype=dt)
+    zb[..., :cin] = torch.randn(B, H, W, cin, generator=g).to(dt)
+    w = torch.randn(3 * r * r, cin, 3, 3, generator=g) / (3.0 * cin ** 0.5)
+    x = torch.rand(B, 3, H, W, generator=g)
+    wp = ops.pack_conv_weight(w, dev, dtype=dt)
+    u = F.pixel_shuffle(F.conv2d(zb.float().permute(0, 3, 1, 2)[:, :cin], w.to(dt).float(), padding=1), r)
+    s = F.interpolate(x, scale_factor=r, mode="bicubic")
+    t = native.tune(fuse=1)
+    for _ in range(2):   # (twice: the second launch finds the accumulators as the first one left them)
+        got = ops.head_shuffle_add(zb.to(dev), wp, r, x=x.to(dev), skip_mode=2, clamp01=True, tune=t).cpu()
+        assert (got - (u + s).clamp(0, 1)).abs().max().item() <= tol
+    got = ops.head_shuffle_add(zb.to(dev), wp, r, skip_mode=0, tune=t).cpu()
+    assert (got - u).abs().max().item() <= tol
+    y = ops.bicubic(x.to(dev), r)
+    got = ops.head_shuffle_add(zb.to(dev), wp, r, x=None, y=y, skip_mode=1, clamp01=False, tune=t).cpu()
+    assert (got - (u + s)).abs().max().item() <= tol
+
+
 def test_shifted_umma_descriptor_probe(dev):
     """The hardware property the shared-halo conv relies on: a K-major swizzled A descriptor may
     start at ANY row of a TMA-written tile when base_offset stays 0."""

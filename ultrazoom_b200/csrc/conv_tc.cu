@@ -935,6 +935,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (j * 16 < p.epi.n_pad) {  // warp-uniform
               tmem_ld16(taddr + j * 16, v);
               tmem_ld_wait();
+              if (FUSE) tmem_zero16(taddr + j * 16);
 #pragma unroll
               for (int i = 0; i < 16; ++i) acc[j * 16 + i] = __uint_as_float(v[i]);
             } else {
@@ -1134,14 +1135,14 @@ static const void* tc_kernel_rows(int rows, int var) {
     if (rows == 2) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 2, 0>);
     if (rows == 4) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 4, 0>);
   }
-  if constexpr (M != 2) {  // the head has neither a pair nor a fused-row form
-    if constexpr (K != 3) {  // pairs: the shapes the 64/96/128-channel encoders use
-      if (var == 1 && rows == 1) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 1, 1>);
-      if (var == 1 && rows == 2) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 2, 1>);
-    }
-    if (var == 2 && rows == 2) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 2, 2>);
-    if (var == 2 && rows == 4) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 4, 2>);
+  if constexpr (M != 2 && K != 3) {  // pairs: the shapes the 64/96/128-channel encoders use (the head has no pair form)
+    if (var == 1 && rows == 1) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 1, 1>);
+    if (var == 1 && rows == 2) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 2, 1>);
   }
+  if constexpr (M != 2) {
+    if (var == 2 && rows == 2) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 2, 2>);
+  }
+  if (var == 2 && rows == 4) return reinterpret_cast<const void*>(conv_tc_kernel<M, K, 4, 2>);  // (head: four-row patches only)
   return nullptr;
 }
 
@@ -1376,13 +1377,14 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
     p.pair = on;
     p.b_slice_rows = on ? e.n_pad / 2 : e.n_pad / p.cluster;
   };
+  int want_rows = tune.rows;  // (the head's fused-row attempt below asks for four-row patches)
   auto rows_cap = [&](int acc_stages) {
     const int acc_stride = p.fuse_g ? e.n_pad : ((e.n_pad + 31) / 32) * 32;
     int rmax = 512 / (acc_stages * acc_stride);
     if (rmax > 4) rmax = 4;
     if (rmax > e.H) rmax = e.H;
     if (p.pair && rmax > 2) rmax = 2;  // pair kernels are instantiated for one and two accumulator rows
-    if (tune.rows) rmax = tune.rows;
+    if (want_rows) rmax = want_rows;
     return rmax;
   };
   // epilogue warps: eight (two per TMEM lane quarter) unless their staging does not fit beside the operand rings
@@ -1391,7 +1393,7 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
     if (tune.resident == 2 || p.cluster != 1 || tune.halo_mode != 0 || !(tune.acc_stages == 0 || tune.acc_stages == 2))
       return;
     const int rcap = rows_cap(2);
-    const int rmin = (rcap >= 2 && !tune.rows) ? 2 : 1;  // a one-row patch reads every activation row three times
+    const int rmin = (rcap >= 2 && !want_rows) ? 2 : 1;  // a one-row patch reads every activation row three times
     // ONE-ROW patches (the 96-channel conv1: TMEM holds one 192-column row per stage): a third activation stage beats
     // wider K chunks and a second set of epilogue warps -- one K chunk of a one-row patch is ~0.55 us of UMMAs against
     // ~1 us of TMA latency, so with two stages the tensor pipe waits for loads (15.23 -> 14.9 ms per 4X-Ctrl frame).  Pass
@@ -1413,7 +1415,7 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
               }
               if (tune.a_stages) break;
             }
-            if (tune.rows) break;
+            if (want_rows) break;
           }
         }
         if (tune.kc) break;
@@ -1444,7 +1446,7 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
           }
           if (tune.kc) break;
         }
-        if (tune.rows) break;
+        if (want_rows) break;
       }
       if (tune.acc_stages) break;
     }
@@ -1453,8 +1455,11 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
   const int fuse_g = (256 / e.n_pad) >= 3 ? 3 : (256 / e.n_pad);
   // Automatic with three stacked taps (N <= 85: the 48-channel conv2, -19 % tensor-only time, -3.5 % on the whole 2X-Ctrl
   // step); with two (N = 96 | 128) the 2N-wide windows measured slower than they save: opt-in (tune.fuse = 1) only.
-  const bool fuse_ok = e.mode != 2 && tune.fuse != 2 && (fuse_g >= 3 || (tune.fuse == 1 && fuse_g >= 2)) && e.H >= 2 &&
-                       (tune.rows == 0 || tune.rows >= 2) && tune.pair != 1;
+  // The head (mode 2, N = 16 / 32 / 48: every UMMA re-fetches its 4 KB activation tile for a few output columns) stacks
+  // its taps too, in four-row patches (six UMMAs per filter column and k-step instead of twelve): opt-in for now.
+  const bool head_fuse = e.mode == 2 && tune.fuse == 1 && e.H >= 4 && (tune.rows == 0 || tune.rows == 4);
+  const bool fuse_ok = (e.mode != 2 || head_fuse) && tune.fuse != 2 && (fuse_g >= 3 || (tune.fuse == 1 && fuse_g >= 2)) &&
+                       e.H >= 2 && (tune.rows == 0 || tune.rows >= 2) && tune.pair != 1;
   if (tune.pair == 1 && pair_ok) {
     set_pair(1);
     try_resident();
@@ -1462,8 +1467,10 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
     set_pair(0);
     if (fuse_ok) {
       p.fuse_g = fuse_g;
+      if (e.mode == 2) want_rows = 4;
       try_resident();
-      if (found && p.rows < 2) found = false;
+      want_rows = tune.rows;
+      if (found && p.rows < (e.mode == 2 ? 4 : 2)) found = false;
       if (!found) p.fuse_g = 0;
     }
     if (!found && tune.fuse == 1) {
