@@ -82,9 +82,11 @@ def conv_flops_per_launch(cfg, npix: int) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons every 100 ms.  The process is started BEFORE the warm-up steps (nvidia-smi
+    needs a few hundred ms to deliver its first line -- longer than a short timed region) and the samples whose own
+    timestamps fall inside the timed region (mark_begin() .. stop()) are the ones reported."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -93,6 +95,7 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.thread = None
+        self.t_begin = None
 
     def start(self):
         try:
@@ -105,6 +108,9 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
 
+    def mark_begin(self):
+        self.t_begin = time.time()
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
@@ -112,32 +118,36 @@ class ClockSampler:
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        t_end = time.time()
+        time.sleep(0.15)   # (a line stamped inside the region may still be on its way)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, smax, power, reasons = [], [], [], set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for ln in self.lines:
             parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                smax.append(float(parts[1]))
-                power.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]), float(parts[3]),
+                             [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "power_w_max": max(power), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        inside = [r for r in rows if self.t_begin is not None and self.t_begin <= r[0] <= t_end]
+        window = "timed region"
+        if not inside:   # (clock skew between nvidia-smi's stamps and this process, or a very short region)
+            inside, window = rows[-3:], "last samples before the end of the timed region"
+        sm = sorted(r[1] for r in inside)
+        reasons = sorted({n for r in inside for n in r[4]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in inside), "power_w_max": max(r[3] for r in inside),
+                "samples": len(inside), "samples_since_warmup": len(rows), "window": window, "reasons": reasons}
 
 
 def load_peaks():
@@ -317,14 +327,15 @@ def main():
         x = x_host.to(dev)
         c = c_host.to(dev) if c_host is not None else None
         out_px = B * H * r * W * r
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
         for _ in range(warmup):
             model.upscale(x, c)
         barrier()
         _native.check(eng.lib.mz_model_enable_timing(eng.handle, 1))
-        sampler = ClockSampler(local_rank)
-        if rank == 0 and sample_clocks:
-            sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.mark_begin()
         ev0.record()
         for _ in range(steps):
             model.upscale(x, c)
@@ -446,14 +457,15 @@ def main():
             for t in mine:
                 run_tile_into(model, x, c, t, r, frame)
 
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
         for _ in range(warmup):
             step()
         barrier()
         _native.check(eng.lib.mz_model_enable_timing(eng.handle, 1))
-        sampler = ClockSampler(local_rank)
-        if rank == 0 and sample_clocks:
-            sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.mark_begin()
         ev0.record()
         for _ in range(steps):
             step()

@@ -265,7 +265,7 @@ def test_head_shuffle_skip_clamp(dev, r, tol, cin, shape, use_tc, dt):
 @pytest.mark.parametrize("r,tol", [(2, 1e-4), (3, 2e-4), (4, 1e-4)])
 @pytest.mark.parametrize("cin,shape", [(48, (2, 7, 190)), (96, (1, 9, 129)), (54, (1, 4, 131)), (48, (1, 13, 300))])
 def test_head_with_stacked_taps(dev, r, tol, cin, shape):
-    """The head with its vertical filter taps stacked along N (`VAR 2`, four-row patches, tune.fuse = 1): one UMMA per input
+    """The head with its vertical filter taps stacked along N (`VAR 2`, four-row patches; the default, forced here): one UMMA per input
     row and filter column feeds up to three output rows.  Heights that are not multiples of four exercise the re-zeroing
     of accumulator rows below the image; both skip forms, clamp, and the plain shuffle match the PyTorch reference."""
     ops, native = _ops()

@@ -908,7 +908,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       MZ_TIMED(0, mbar_wait(bar_acc_full + 8 * as, pacc));
       __syncwarp();
       tc_fence_after();
-      for (int r = (MODE == 0 ? 0 : half), k = 0; r < ROWS; r += (MODE == 0 ? 1 : nh), ++k) {
+      bool rows_done = false;
+      if constexpr (MODE == 2 && ROWS == 4) {
+        // 2X head, eight epilogue warps: each warp finishes two ADJACENT rows of the patch in one pass (their bicubic
+        // neighbourhoods share four of five LR rows, and one load latency is exposed instead of two: epi_head2_pair)
+        if (nh == 2 && p.epi.r == 2 && !(p.dbg & 128)) {  // (warp-uniform; dbg 128: row-by-row form)
+          rows_done = true;
+          const int r0 = 2 * half, y = y0 + r0;
+          const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+          const uint32_t t0 = lane_base + (as * ROWS + (FUSE ? ROWS - 1 - r0 : r0)) * p.acc_stride;
+          const uint32_t t1 = lane_base + (as * ROWS + (FUSE ? ROWS - 2 - r0 : r0 + 1)) * p.acc_stride;
+          if (y >= p.epi.H || !live) {  // (warp-uniform) neither row is stored
+            if (FUSE) {
+              tmem_zero16(t0);
+              tmem_zero16(t1);
+            }
+          } else {
+            uint32_t v0[16], v1[16];
+            tmem_ld16(t0, v0);
+            tmem_ld16(t1, v1);
+            tmem_ld_wait();
+            if (FUSE) {
+              tmem_zero16(t0);
+              tmem_zero16(t1);
+            }
+            if (ok) {
+              const bool interior = xw >= 2 && xw + 33 < p.epi.W;  // (warp-uniform) no clamped column in this warp
+              const bool second = y + 1 < p.epi.H;
+              if (p.epi.x8 != nullptr)
+                epi_head2_pair<uint8_t>(p.epi, p.epi.x8, b, y, x, v0, v1, interior, second);
+              else
+                epi_head2_pair<float>(p.epi, p.epi.x, b, y, x, v0, v1, interior, second);
+            }
+          }
+        }
+      }
+      for (int r = (MODE == 0 ? 0 : half), k = 0; r < ROWS && !rows_done; r += (MODE == 0 ? 1 : nh), ++k) {
         const int y = y0 + r;
         // (FUSE keeps output row r in TMEM block ROWS-1-r so that the blocks of stacked vertical taps are adjacent)
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
@@ -1456,8 +1491,8 @@ int prepare_conv_tc(const ConvArgs& a, const ConvTcTune& tune, int device, ConvL
   // Automatic with three stacked taps (N <= 85: the 48-channel conv2, -19 % tensor-only time, -3.5 % on the whole 2X-Ctrl
   // step); with two (N = 96 | 128) the 2N-wide windows measured slower than they save: opt-in (tune.fuse = 1) only.
   // The head (mode 2, N = 16 / 32 / 48: every UMMA re-fetches its 4 KB activation tile for a few output columns) stacks
-  // its taps too, in four-row patches (six UMMAs per filter column and k-step instead of twelve): opt-in for now.
-  const bool head_fuse = e.mode == 2 && tune.fuse == 1 && e.H >= 4 && (tune.rows == 0 || tune.rows == 4);
+  // its taps too, in four-row patches (six UMMAs per filter column and k-step instead of twelve).
+  const bool head_fuse = e.mode == 2 && tune.fuse != 2 && e.H >= 4 && (tune.rows == 0 || tune.rows == 4);
   const bool fuse_ok = (e.mode != 2 || head_fuse) && tune.fuse != 2 && (fuse_g >= 3 || (tune.fuse == 1 && fuse_g >= 2)) &&
                        e.H >= 2 && (tune.rows == 0 || tune.rows >= 2) && tune.pair != 1;
   if (tune.pair == 1 && pair_ok) {

@@ -481,6 +481,124 @@ __device__ __forceinline__ void epi_head_r(const EpiParams& p, int b, int y, int
   else
     epi_head_rt<R, float>(p, p.x, b, y, x, acc, interior);
 }
+// r = 2, TWO vertically adjacent LR pixels (y, x) and (y + 1, x) per thread: their 5x5 neighbourhoods share four of
+// five rows, so the pair costs 6 x 5 loads and 6 x 2 horizontal interpolations per colour instead of 2 x (5 x 5) and
+// 2 x (5 x 2), and -- what matters for the latency-bound epilogue warps -- ONE exposed load latency instead of two.
+// Same FMA order per output as epi_head_rt<2>: the results are bit-identical.  v0 / v1: the twelve head channels of the
+// two pixels as they come out of TMEM; second: row y + 1 exists (y + 1 < H).
+template <typename T>
+__device__ __forceinline__ void epi_head2_pair(const EpiParams& p, const T* __restrict__ lr, int b, int y, int x,
+                                               const uint32_t (&v0)[16], const uint32_t (&v1)[16], bool interior,
+                                               bool second) {
+  const int H = p.H, W = p.W;
+  long long first[2];
+  first[0] = head_out_index(p, b, 0, y, x, 0, 0);
+  first[1] = second ? head_out_index(p, b, 0, y + 1, x, 0, 0) : -1;
+  if (first[0] < 0 && first[1] < 0) return;  // both outside the output window
+  const size_t row_pitch = p.y_row ? static_cast<size_t>(p.y_row) : static_cast<size_t>(W) * 2;
+  const size_t plane_pitch = p.y_plane ? static_cast<size_t>(p.y_plane) : static_cast<size_t>(H) * 2 * W * 2;
+  float out[2][3][2][2];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        out[0][c][i][j] = __uint_as_float(v0[c * 4 + i * 2 + j]);
+        out[1][c][i][j] = __uint_as_float(v1[c * 4 + i * 2 + j]);
+      }
+  if (p.skip_mode == 2) {
+    const size_t HW = static_cast<size_t>(H) * W;
+    const T* img = lr + static_cast<size_t>(b) * 3 * HW;
+    int xo[5], ro[6];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) xo[m] = min(max(x - 2 + m, 0), W - 1);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ro[k] = min(max(y - 2 + k, 0), H - 1) * W;
+    float nb[3][6][5];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const T* pl = img + c * HW;
+      if (interior) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const T* rp = pl + (ro[k] + (x - 2));
+#pragma unroll
+          for (int m = 0; m < 5; ++m) nb[c][k][m] = lr_px(rp + m);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+          for (int m = 0; m < 5; ++m) nb[c][k][m] = lr_px(pl + (ro[k] + xo[m]));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float hz[6][2];
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {  // phase j: first tap at x - 2 + j
+          float a = 0.f;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) a = fmaf(nb[c][k][j + m], p.bt.w[j][m], a);
+          hz[k][j] = a;
+        }
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {  // pixel row y + rr, phase i: first tap at LR row y + rr - 2 + i
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a = fmaf(hz[rr + i + k][j], p.bt.w[i][k], a);
+            out[rr][c][i][j] += a;
+          }
+    }
+  }
+  if (p.skip_mode == 1 && p.y8 == nullptr) {  // y already holds the bicubic image: every segment is read before the first store
+    float2 sk[2][3][2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          sk[rr][c][i] = first[rr] < 0 ? make_float2(0.f, 0.f)
+                                       : *reinterpret_cast<const float2*>(p.y + static_cast<size_t>(first[rr]) + c * plane_pitch +
+                                                                          static_cast<size_t>(i) * row_pitch);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          out[rr][c][i][0] += sk[rr][c][i].x;
+          out[rr][c][i][1] += sk[rr][c][i].y;
+        }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    if (first[rr] < 0) continue;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const size_t d = static_cast<size_t>(first[rr]) + c * plane_pitch + static_cast<size_t>(i) * row_pitch;
+        if (p.y8 != nullptr) {
+          const uint32_t w = static_cast<uint32_t>(to_u8(out[rr][c][i][0], p.u8_trunc)) |
+                             (static_cast<uint32_t>(to_u8(out[rr][c][i][1], p.u8_trunc)) << 8);
+          *reinterpret_cast<uint16_t*>(p.y8 + d) = static_cast<uint16_t>(w);
+        } else {
+          float a0 = out[rr][c][i][0], a1 = out[rr][c][i][1];
+          if (p.clamp01) a0 = fminf(fmaxf(a0, 0.f), 1.f), a1 = fminf(fmaxf(a1, 0.f), 1.f);
+          *reinterpret_cast<float2*>(p.y + d) = make_float2(a0, a1);
+        }
+      }
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace mz
