@@ -39,47 +39,63 @@ void make_bicubic_table(int r, BicubicTable* t) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// bicubic zoom.  One thread owns one LR column of a strip of kStrip LR rows and slides a 5-row window down it: each
-// new LR row costs five (coalesced, L1-resident) loads and R horizontal interpolations, then the R x R HR pixels of
-// the LR pixel leave as R row segments of R contiguous floats (a warp writes 32 * R contiguous floats per HR row).
-// ~2 loads per HR pixel at r = 2 (0.5 at r = 4) instead of 10 (5): the kernel is bound by the HR write.
+// bicubic zoom.  One thread owns one LR column of a strip of STRIP LR rows and slides a 5-row window of horizontally
+// interpolated values down it: each LR row costs five (coalesced, L1-resident) loads and R horizontal interpolations,
+// then the R x R HR pixels of the LR pixel leave as R row segments of R contiguous floats (a warp writes 32 * R
+// contiguous floats per HR row).  ~2 loads per HR pixel at r = 2 (0.5 at r = 4) instead of 10 (5).
+// A store stream (12 / r^2 B read, 12 B written per HR pixel).  Every tap of the strip -- STRIP + 4 rows x 5 columns --
+// is requested before the first FMA: each row is first touched by this very block, and with the loads of a row issued
+// when the window reached it a thread exposed one L2 / HBM round trip per row.  The strip loop is fully unrolled (the
+// window rotates through compile-time indices: no register moves) and blocks whose columns need no clamping read each
+// row through one pointer with immediate offsets; that halved the instruction count and, alone, changed nothing.
 // Arithmetic order follows ATen's upsample_bicubic2d: horizontal taps first, then vertical.
 // ----------------------------------------------------------------------------------------------
-constexpr int kStrip = 8;
-
-template <int R>
+template <int R, int STRIP>
 __global__ void __launch_bounds__(128) bicubic_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W,
-                                                      int n_strips, int strip_rows, BicubicTable bt) {
+                                                      int n_strips, BicubicTable bt) {
   const int lx = blockIdx.x * 128 + threadIdx.x;
   if (lx >= W) return;
   const int pl = blockIdx.y / n_strips, strip = blockIdx.y - pl * n_strips;
-  const int ly0 = strip * strip_rows, ly1 = min(ly0 + strip_rows, H);
+  const int ly0 = strip * STRIP, ly1 = min(ly0 + STRIP, H);
   const float* plane = x + static_cast<size_t>(pl) * H * W;
   const size_t WR = static_cast<size_t>(W) * R;
   float* out = y + static_cast<size_t>(pl) * H * R * WR + static_cast<size_t>(lx) * R;
+  const bool interior = blockIdx.x > 0 && static_cast<int>(blockIdx.x) * 128 + 129 < W;  // (block-uniform) no clamped column
   int xs[5];
 #pragma unroll
   for (int m = 0; m < 5; ++m) xs[m] = min(max(lx - 2 + m, 0), W - 1);
-  // horizontally interpolated values of LR row yy (clamped) at the R phases of this column
-  auto hrow = [&](int yy, float (&h)[R]) {
-    const float* row = plane + static_cast<size_t>(min(max(yy, 0), H - 1)) * W;
-    float v[5];
+  float raw[STRIP + 4][5];  // strip row n = LR row ly0 - 2 + n (clamped)
 #pragma unroll
-    for (int m = 0; m < 5; ++m) v[m] = __ldg(row + xs[m]);
+  for (int n = 0; n < STRIP + 4; ++n) {
+    const float* row = plane + static_cast<size_t>(min(max(ly0 - 2 + n, 0), H - 1)) * W;
+    if (interior) {
+      const float* rp = row + (lx - 2);
+#pragma unroll
+      for (int m = 0; m < 5; ++m) raw[n][m] = __ldg(rp + m);
+    } else {
+#pragma unroll
+      for (int m = 0; m < 5; ++m) raw[n][m] = __ldg(row + xs[m]);
+    }
+  }
+  // horizontally interpolated values of strip row n at the R phases of this column
+  auto hrow = [&](int n, float (&h)[R]) {
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int s = (2 * j + 1 < R) ? 0 : 1;  // first tap relative to lx-2 (phase offset -1 or 0)
       float a = 0.f;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) a = fmaf(v[s + m], bt.w[j][m], a);
+      for (int m = 0; m < 4; ++m) a = fmaf(raw[n][s + m], bt.w[j][m], a);
       h[j] = a;
     }
   };
-  float win[5][R];  // LR rows ly-2 .. ly+2
+  float win[5][R];  // a ring: strip row n lives in win[n % 5]
 #pragma unroll
-  for (int k = 0; k < 4; ++k) hrow(ly0 - 2 + k, win[k]);
-  for (int ly = ly0; ly < ly1; ++ly) {
-    hrow(ly + 2, win[4]);
+  for (int k = 0; k < 4; ++k) hrow(k, win[k]);
+#pragma unroll
+  for (int t = 0; t < STRIP; ++t) {
+    const int ly = ly0 + t;
+    if (ly >= ly1) break;  // (block-uniform)
+    hrow(t + 4, win[(t + 4) % 5]);
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       const int s = (2 * i + 1 < R) ? 0 : 1;
@@ -88,7 +104,7 @@ __global__ void __launch_bounds__(128) bicubic_kernel(const float* __restrict__ 
       for (int j = 0; j < R; ++j) {
         float a = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a = fmaf(win[s + k][j], bt.w[i][k], a);
+        for (int k = 0; k < 4; ++k) a = fmaf(win[(t + s + k) % 5][j], bt.w[i][k], a);
         o[j] = a;
       }
       float* dst = out + (static_cast<size_t>(ly) * R + i) * WR;
@@ -101,11 +117,18 @@ __global__ void __launch_bounds__(128) bicubic_kernel(const float* __restrict__ 
         for (int j = 0; j < R; ++j) dst[j] = o[j];
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-      for (int j = 0; j < R; ++j) win[k][j] = win[k + 1][j];
   }
+}
+
+template <int STRIP>
+static void launch_bicubic_strip(const float* x, float* y, int H, int W, int r, int n_strips, dim3 grid, const BicubicTable& bt,
+                                 cudaStream_t s) {
+  if (r == 2)
+    bicubic_kernel<2, STRIP><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, bt);
+  else if (r == 3)
+    bicubic_kernel<3, STRIP><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, bt);
+  else
+    bicubic_kernel<4, STRIP><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, bt);
 }
 
 int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cudaStream_t s) {
@@ -113,21 +136,17 @@ int launch_bicubic(const float* x, float* y, int planes, int H, int W, int r, cu
   MZ_REQUIRE(planes > 0 && H > 0 && W > 0, "bicubic: empty input (planes %d, H %d, W %d)", planes, H, W);
   BicubicTable bt;
   make_bicubic_table(r, &bt);
-  // strips of 8 LR rows (4 halo rows re-read per strip), shorter ones while the grid would not fill the GPU four times
-  // over: a pure store-bound kernel needs the stores of many threads in flight
-  int strip_rows = kStrip;
+  // strips of 8 LR rows (60 taps in flight per thread), of 4 while the grid would not fill the GPU four times over
   const long long bx = (W + 127) / 128;
-  while (strip_rows > 2 && bx * planes * ((H + strip_rows - 1) / strip_rows) < 148LL * 16 * 4) strip_rows /= 2;
+  const int strip_rows = bx * planes * ((H + 7) / 8) < 148LL * 16 * 4 ? 4 : 8;
   const int n_strips = (H + strip_rows - 1) / strip_rows;
   const long long gy = static_cast<long long>(planes) * n_strips;
   MZ_REQUIRE(gy <= 65535, "bicubic: planes x row strips (%lld) exceeds the grid limit", gy);
-  const dim3 grid((W + 127) / 128, static_cast<unsigned>(gy));
-  if (r == 2)
-    bicubic_kernel<2><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, strip_rows, bt);
-  else if (r == 3)
-    bicubic_kernel<3><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, strip_rows, bt);
+  const dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(gy));
+  if (strip_rows == 8)
+    launch_bicubic_strip<8>(x, y, H, W, r, n_strips, grid, bt, s);
   else
-    bicubic_kernel<4><<<grid, 128, 0, s>>>(x, y, H, W, n_strips, strip_rows, bt);
+    launch_bicubic_strip<4>(x, y, H, W, r, n_strips, grid, bt, s);
   MZ_CUDA(cudaGetLastError());
   return MZ_OK;
 }
