@@ -179,3 +179,22 @@ def test_refresh_rectangles_cover_every_halo_exactly_once():
             want[t.hy0:t.hy1, t.hx0:t.hx1] = 1
             want[t.y0:t.y1, t.x0:t.x1] = 0
             assert (cover == want).all()
+
+
+def test_bind_process_to_gpu_is_a_harmless_hint_without_a_gpu():
+    """`sharding.bind_process_to_gpu` pins a rank to the CPUs next to its GPU (node-local pinned buffers for the
+    end-to-end path); without NVML / a device it changes nothing and returns None instead of raising."""
+    import os
+
+    import torch
+
+    from ultrazoom_b200.sharding import bind_process_to_gpu
+
+    before = os.sched_getaffinity(0)
+    got = bind_process_to_gpu(0)
+    if not torch.cuda.is_available():
+        assert got is None and os.sched_getaffinity(0) == before
+    else:
+        assert got is None or set(got) == os.sched_getaffinity(0)
+        os.sched_setaffinity(0, before)
+
